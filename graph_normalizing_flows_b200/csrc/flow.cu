@@ -1,0 +1,673 @@
+// GRevNet flow object, fp32 layer-by-layer kernels, forward / inverse drivers, log-prob.
+// Reference path: GRevNet.f / GRevNet.g (gnn.py:304-373) over NodeBlockGNN (gnn.py:143-156)
+// with ConcatThenMLPBlock / AggThenMLPBlock (gnn.py:100-126) and make_mlp_model (gnn.py:159-180).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace gnf {
+
+// ---- error / bookkeeping -------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int64_t& launch_counter() {
+  static thread_local int64_t c = 0;
+  return c;
+}
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+namespace {
+
+static inline int pad_to(int x, int a) { return (x + a - 1) / a * a; }
+
+// ---- weight packing (fp32 path) ------------------------------------------------------------
+__global__ void k_pack32(const float* __restrict__ src, int in, int out, int in_pad, int out_pad,
+                         float* __restrict__ w, float* __restrict__ b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = in_pad * out_pad;
+  if (i < total) {
+    int r = i / out_pad, c = i - r * out_pad;
+    w[i] = (r < in && c < out) ? src[r * out + c] : 0.f;
+  }
+  if (i < out_pad) b[i] = (i < out) ? src[in * out + i] : 0.f;
+}
+
+// ---- planar split / merge ------------------------------------------------------------------
+__global__ void k_split(const float* __restrict__ x, int64_t n, int d, int h, int hp,
+                        float* __restrict__ x0, float* __restrict__ x1) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * hp) return;
+  int64_t node = i / hp;
+  int f = (int)(i - node * hp);
+  x0[i] = (f < h) ? x[node * d + f] : 0.f;
+  x1[i] = (f < h) ? x[node * d + h + f] : 0.f;
+}
+
+__global__ void k_merge(const float* __restrict__ x0, const float* __restrict__ x1, int64_t n,
+                        int d, int h, int hp, float* __restrict__ z) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * d) return;
+  int64_t node = i / d;
+  int f = (int)(i - node * d);
+  z[i] = (f < h) ? x0[node * hp + f] : x1[node * hp + f - h];
+}
+
+__global__ void k_pad_rows(const float* __restrict__ x, int64_t n, int h, int hp, float* __restrict__ xp) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * hp) return;
+  int64_t node = i / hp;
+  int f = (int)(i - node * hp);
+  xp[i] = (f < h) ? x[node * h + f] : 0.f;
+}
+
+__global__ void k_unpad_rows(const float* __restrict__ xp, int64_t n, int h, int hp, float* __restrict__ x) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * h) return;
+  int64_t node = i / h;
+  int f = (int)(i - node * h);
+  x[i] = xp[node * hp + f];
+}
+
+// ---- a3+a4+a5: aggregate and assemble the MLP input ------------------------------------------
+// thread per (node, feature<H); serial in-order accumulation over the stable CSR segment.
+__global__ void __launch_bounds__(256)
+k_agg_input(const float* __restrict__ xa, int h, int hp, const int32_t* __restrict__ rowptr,
+            const int32_t* __restrict__ csr_senders, int64_t n, int mean, int concat, float eps,
+            int in_pad, float* __restrict__ hbuf) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * h) return;
+  const int64_t node = i / h;
+  const int f = (int)(i - node * h);
+  int32_t e = rowptr[node];
+  const int32_t end = rowptr[node + 1];
+  const int32_t cnt = end - e;
+  float acc = 0.f;
+  for (; e + 4 <= end; e += 4) {
+    int32_t i0 = csr_senders[e], i1 = csr_senders[e + 1], i2 = csr_senders[e + 2], i3 = csr_senders[e + 3];
+    float v0 = xa[(int64_t)i0 * hp + f];
+    float v1 = xa[(int64_t)i1 * hp + f];
+    float v2 = xa[(int64_t)i2 * hp + f];
+    float v3 = xa[(int64_t)i3 * hp + f];
+    acc = __fadd_rn(acc, v0);
+    acc = __fadd_rn(acc, v1);
+    acc = __fadd_rn(acc, v2);
+    acc = __fadd_rn(acc, v3);
+  }
+  for (; e < end; ++e) acc = __fadd_rn(acc, xa[(int64_t)csr_senders[e] * hp + f]);
+  if (mean) acc = __fdiv_rn(acc, fmaxf((float)cnt, 1.f));
+  const float self = xa[node * hp + f];
+  if (concat) {
+    hbuf[node * in_pad + f] = self;          // tf.concat([nodes, agg], 1)   gnn.py:108-109
+    hbuf[node * in_pad + h + f] = acc;
+  } else {
+    hbuf[node * in_pad + f] = __fadd_rn(__fmul_rn(eps, self), acc);   // gnn.py:123-124
+  }
+}
+
+// ---- a6: one Sonnet Linear (+ activation), fp32 FFMA -----------------------------------------
+// C[M,N] = act(A[M,K] @ W[K,N] + b);  K % 8 == 0, N % 4 == 0 (zero-padded operands).
+constexpr int BM = 128, BK = 8;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 0) return fmaxf(v, 0.2f * v);   // tf.nn.leaky_relu, alpha = 0.2
+  if (act == 1) return fmaxf(v, 0.f);        // tf.nn.relu
+  return v;                                  // activate_final=False
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256)
+k_linear(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+         float* __restrict__ C, int64_t M, int N, int K, int act) {
+  constexpr int TN = BN / 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int a_row = tid >> 1, a_kq = (tid & 1) * 4;
+  const bool a_ok = (row0 + a_row) < M;
+  const float* a_ptr = A + (row0 + a_row) * K + a_kq;
+  // B tile: BK x BN floats = 8*BN; one float4 per thread covers BN=128; BN=16 needs 32 threads
+  constexpr int B_F4 = BK * BN / 4;
+  const int b_r = (tid * 4) / BN, b_c = (tid * 4) % BN;
+  const bool b_ok = tid < B_F4 && (col0 + b_c) < N;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    float4 av = a_ok ? *reinterpret_cast<const float4*>(a_ptr + k0) : make_float4(0, 0, 0, 0);
+    float4 bv = b_ok ? *reinterpret_cast<const float4*>(W + (int64_t)(k0 + b_r) * N + col0 + b_c)
+                     : make_float4(0, 0, 0, 0);
+    __syncthreads();
+    As[a_kq + 0][a_row] = av.x;
+    As[a_kq + 1][a_row] = av.y;
+    As[a_kq + 2][a_row] = av.z;
+    As[a_kq + 3][a_row] = av.w;
+    if (tid < B_F4) *reinterpret_cast<float4*>(&Bs[b_r][b_c]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int col = col0 + tx + 16 * j;
+    if (col >= N) continue;
+    const float bj = bias[col];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t row = row0 + ty * 8 + i;
+      if (row < M) C[row * N + col] = apply_act(acc[i][j] + bj, act);
+    }
+  }
+}
+
+// ---- a7: affine coupling update + log-det partials -------------------------------------------
+// forward: xb <- xb * exp(s) + t, ldj += sum(s)    (gnn.py:322-323,337-338)
+// inverse: xb <- (xb - t) * exp(-s)                (gnn.py:359,372)
+__global__ void __launch_bounds__(256)
+k_coupling_update(float* __restrict__ xb, const float* __restrict__ s, const float* __restrict__ t,
+                  int64_t n, int h, int hp, int sp, int inverse, double* __restrict__ partials) {
+  __shared__ double red[8];
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double local = 0.0;
+  if (i < n * h) {
+    int64_t node = i / h;
+    int f = (int)(i - node * h);
+    float sv = s[node * sp + f], tv = t[node * sp + f];
+    float x = xb[node * hp + f];
+    if (!inverse) {
+      xb[node * hp + f] = __fadd_rn(__fmul_rn(x, expf(sv)), tv);
+      local = (double)sv;
+    } else {
+      xb[node * hp + f] = __fmul_rn(__fsub_rn(x, tv), expf(-sv));
+    }
+  }
+  if (partials) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      partials[blockIdx.x] = tot;
+    }
+  }
+}
+
+// fixed-order reduction of partials; accum[0] (+)= total
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const double* __restrict__ partials, int n, double* __restrict__ accum, int add) {
+  __shared__ double red[256];
+  double local = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) local += partials[i];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) accum[0] = (add ? accum[0] : 0.0) + red[0];
+}
+
+// ---- a8: log-prob ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sumsq(const float* __restrict__ z, int64_t total, double* __restrict__ partials) {
+  __shared__ double red[8];
+  double local = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double v = (double)z[i];
+    local += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    partials[blockIdx.x] = tot;
+  }
+}
+
+__global__ void k_log_prob_final(const double* __restrict__ partials, int n, const double* __restrict__ ldj,
+                                 double n_nodes, int d, double* __restrict__ out) {
+  __shared__ double red[256];
+  double local = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) local += partials[i];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double kLog2Pi = 1.8378770664093454835606594728112;
+    double lpz = -0.5 * red[0] - 0.5 * (double)d * kLog2Pi * n_nodes;
+    double l = ldj ? ldj[0] : 0.0;
+    out[0] = lpz;
+    out[1] = l;
+    out[2] = lpz + l;
+    out[3] = n_nodes;
+  }
+}
+
+constexpr int kLogProbBlocks = 1184;  // 148 SMs x 8
+
+// ---- workspace carve-up --------------------------------------------------------------------
+struct Workspace {
+  float *x0, *x1, *hbuf, *act0, *act1, *sbuf, *tbuf;
+  double* partials;
+  int n_partials_cap;
+  size_t bytes;
+};
+
+Workspace carve(const Flow& f, int64_t n, int math, void* base) {
+  Workspace w{};
+  uint8_t* p = (uint8_t*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = base ? (void*)(p + off) : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  w.x0 = (float*)take(nn * f.HP * 4);
+  w.x1 = (float*)take(nn * f.HP * 4);
+  w.n_partials_cap = (int)ceil_div((int64_t)nn * f.H, 256);
+  if (w.n_partials_cap < 1024) w.n_partials_cap = 1024;
+  w.partials = (double*)take((size_t)w.n_partials_cap * 8);
+  if (math == GNF_MATH_FP32) {
+    const int lp = pad_to(f.L, 8);
+    w.hbuf = (float*)take(nn * f.in_pad * 4);
+    w.act0 = (float*)take(nn * lp * 4);
+    w.act1 = (float*)take(nn * lp * 4);
+    w.sbuf = (float*)take(nn * f.HP * 4);
+    w.tbuf = (float*)take(nn * f.HP * 4);
+  }
+  w.bytes = off;
+  return w;
+}
+
+int run_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K,
+               int act, cudaStream_t stream) {
+  if (N <= 16) {
+    dim3 grid((unsigned)ceil_div(M, BM), 1);
+    k_linear<16><<<grid, 256, 0, stream>>>(A, W, b, C, M, N, K, act);
+  } else {
+    dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, 128));
+    k_linear<128><<<grid, 256, 0, stream>>>(A, W, b, C, M, N, K, act);
+  }
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+// fp32 layered MLP: hbuf -> out (uses act0/act1 ping-pong)
+int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n, cudaStream_t stream) {
+  const float* base = f.w32 + (int64_t)mlp * f.w32_per_mlp;
+  const float* in = w.hbuf;
+  for (int l = 0; l < f.K; ++l) {
+    const bool last = (l == f.K - 1);
+    float* dst = last ? out : ((l & 1) ? w.act1 : w.act0);
+    int rc = run_linear(in, base + f.w32_layer_off[l], base + f.b32_layer_off[l], dst, n,
+                        f.out_pads[l], f.in_pads[l], last ? 2 : f.d.act, stream);
+    if (rc) return rc;
+    in = dst;
+  }
+  return GNF_OK;
+}
+
+// one half coupling step: (xa, xb) with the s/t GNNs of (half, step)
+int coupling_half(const Flow& f, int half, int step, int inverse, const float* xa, float* xb,
+                  int64_t n, const int32_t* rowptr, const int32_t* csr_senders, double* ldj_accum,
+                  int math, const Workspace& w, cudaStream_t stream) {
+  const int ms = f.mlp_index(0, half, step), mt = f.mlp_index(1, half, step);
+  if (n == 0) return GNF_OK;
+  if (math == GNF_MATH_FP32) {
+    const int64_t total = n * f.H;
+    const unsigned blocks = (unsigned)ceil_div(total, 256);
+    k_agg_input<<<blocks, 256, 0, stream>>>(xa, f.H, f.HP, rowptr, csr_senders, n,
+                                            f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT,
+                                            f.d.eps, f.in_pad, w.hbuf);
+    GNF_LAUNCH_CHECK();
+    int rc = run_mlp32(f, ms, w, w.sbuf, n, stream);
+    if (rc) return rc;
+    rc = run_mlp32(f, mt, w, w.tbuf, n, stream);
+    if (rc) return rc;
+    const bool want_ldj = (!inverse && ldj_accum);
+    k_coupling_update<<<blocks, 256, 0, stream>>>(xb, w.sbuf, w.tbuf, n, f.H, f.HP, f.HP, inverse,
+                                                  want_ldj ? w.partials : nullptr);
+    GNF_LAUNCH_CHECK();
+    if (want_ldj) {
+      k_reduce_partials<<<1, 256, 0, stream>>>(w.partials, (int)blocks, ldj_accum, 1);
+      GNF_LAUNCH_CHECK();
+    }
+    return GNF_OK;
+  }
+  int n_partials = 0;
+  int rc = tc_coupling_half(f, ms, mt, math, inverse, xa, xb, n, rowptr, csr_senders, w.partials,
+                            &n_partials, stream);
+  if (rc) return rc;
+  if (!inverse && ldj_accum) {
+    k_reduce_partials<<<1, 256, 0, stream>>>(w.partials, n_partials, ldj_accum, 1);
+    GNF_LAUNCH_CHECK();
+  }
+  return GNF_OK;
+}
+
+int check_math(const Flow& f, int math, const char* who) {
+  GNF_REQUIRE(math >= GNF_MATH_FP32 && math <= GNF_MATH_TC3X_BF16, GNF_EINVAL, "%s: bad math %d", who, math);
+  if (math != GNF_MATH_FP32)
+    GNF_REQUIRE(f.tc_ok, GNF_EUNSUPPORTED,
+                "%s: fused tcgen05 kernel needs latent_dim in {128,256}, MLP input dim <= 16, "
+                "D/2 <= 16, 2 <= num_layers <= %d (got L=%d in=%d H=%d K=%d); use GNF_MATH_FP32",
+                who, kMaxLayers, f.L, f.in_dim, f.H, f.K);
+  return GNF_OK;
+}
+
+}  // namespace
+}  // namespace gnf
+
+using namespace gnf;
+
+struct gnf_flow {
+  Flow f;
+};
+
+extern "C" int gnf_abi_version(void) { return GNF_ABI_VERSION; }
+extern "C" const char* gnf_last_error(void) { return g_err; }
+extern "C" int64_t gnf_launch_count(int reset) {
+  int64_t c = launch_counter();
+  if (reset) launch_counter() = 0;
+  return c;
+}
+extern "C" int32_t gnf_padded_half(int32_t h) { return pad_to(h, 4); }
+
+static int validate_desc(const gnf_flow_desc* d) {
+  GNF_REQUIRE(d, GNF_EINVAL, "null flow desc");
+  GNF_REQUIRE(d->num_timesteps >= 1, GNF_EINVAL, "num_timesteps must be >= 1");
+  GNF_REQUIRE(d->node_embedding_dim >= 2 && d->node_embedding_dim % 2 == 0, GNF_EINVAL,
+              "node_embedding_dim must be even (tf.split at gnn.py:306), got %d", d->node_embedding_dim);
+  GNF_REQUIRE(d->latent_dim >= 1, GNF_EINVAL, "latent_dim must be >= 1");
+  GNF_REQUIRE(d->num_layers >= 2 && d->num_layers <= kMaxLayers, GNF_EINVAL,
+              "num_layers must be in [2, %d]", kMaxLayers);
+  GNF_REQUIRE(d->agg == GNF_AGG_SUM || d->agg == GNF_AGG_MEAN, GNF_EINVAL, "bad agg");
+  GNF_REQUIRE(d->block == GNF_BLOCK_CONCAT || d->block == GNF_BLOCK_AGG_THEN, GNF_EINVAL, "bad block");
+  GNF_REQUIRE(d->act == GNF_ACT_LEAKY_RELU || d->act == GNF_ACT_RELU, GNF_EINVAL, "bad act");
+  return GNF_OK;
+}
+
+static int64_t params_per_mlp(const gnf_flow_desc* d) {
+  const int64_t H = d->node_embedding_dim / 2;
+  const int64_t in = d->block == GNF_BLOCK_CONCAT ? 2 * H : H;
+  const int64_t L = d->latent_dim, K = d->num_layers;
+  return in * L + L + (K - 2) * (L * L + L) + L * H + H;
+}
+
+extern "C" int64_t gnf_flow_param_count(const gnf_flow_desc* d) {
+  if (validate_desc(d)) return -1;
+  const int64_t n_mlps = 4ll * (d->weight_sharing ? 1 : d->num_timesteps);
+  return n_mlps * params_per_mlp(d);
+}
+
+extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
+  GNF_REQUIRE(out, GNF_EINVAL, "gnf_flow_create: null out");
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  gnf_flow* h = new gnf_flow();
+  Flow& f = h->f;
+  f.d = *d;
+  f.H = d->node_embedding_dim / 2;
+  f.HP = gnf_padded_half(f.H);
+  f.in_dim = d->block == GNF_BLOCK_CONCAT ? 2 * f.H : f.H;
+  f.in_pad = pad_to(f.in_dim, 8);
+  f.L = d->latent_dim;
+  f.K = d->num_layers;
+  f.n_mlps = 4 * (d->weight_sharing ? 1 : d->num_timesteps);
+  f.params_per_mlp = params_per_mlp(d);
+  const int lp = pad_to(f.L, 8);
+  int64_t off = 0;
+  for (int l = 0; l < f.K; ++l) {
+    f.ins[l] = l == 0 ? f.in_dim : f.L;
+    f.outs[l] = l == f.K - 1 ? f.H : f.L;
+    f.in_pads[l] = l == 0 ? f.in_pad : lp;
+    f.out_pads[l] = l == f.K - 1 ? f.HP : lp;
+    f.w32_layer_off[l] = off;
+    off += (int64_t)f.in_pads[l] * f.out_pads[l];
+    f.b32_layer_off[l] = off;
+    off += f.out_pads[l];
+    off = (off + 3) / 4 * 4;  // keep float4 alignment of the next W
+  }
+  f.w32_per_mlp = off;
+  cudaError_t e = cudaMalloc(&f.w32, (size_t)f.n_mlps * f.w32_per_mlp * 4);
+  if (e != cudaSuccess) {
+    delete h;
+    set_error("gnf_flow_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    return GNF_ECUDA;
+  }
+  f.tc_ok = tc_shape_supported(f);
+  if (f.tc_ok) {
+    f.wtc_per_mlp = (int64_t)tc_bytes_per_mlp(f.L, f.K);
+    cudaError_t e0 = cudaMalloc(&f.wtc[0], (size_t)f.n_mlps * f.wtc_per_mlp);
+    cudaError_t e1 = cudaMalloc(&f.wtc[1], (size_t)f.n_mlps * f.wtc_per_mlp);
+    cudaError_t e2 = cudaMalloc(&f.btc, (size_t)f.n_mlps * f.K * 256 * 4);
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
+      gnf_flow_destroy(h);
+      set_error("gnf_flow_create: cudaMalloc (tc weights) failed");
+      return GNF_ECUDA;
+    }
+  }
+  *out = h;
+  return GNF_OK;
+}
+
+extern "C" int gnf_flow_destroy(gnf_flow* h) {
+  if (!h) return GNF_OK;
+  cudaFree(h->f.w32);
+  cudaFree(h->f.wtc[0]);
+  cudaFree(h->f.wtc[1]);
+  cudaFree(h->f.btc);
+  delete h;
+  return GNF_OK;
+}
+
+extern "C" int gnf_flow_supports(const gnf_flow* h, int32_t math) {
+  if (!h) return 0;
+  if (math == GNF_MATH_FP32) return 1;
+  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC3X_BF16 && h->f.tc_ok) ? 1 : 0;
+}
+
+extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(h && params, GNF_EINVAL, "gnf_flow_set_params: null pointer");
+  Flow& f = h->f;
+  for (int m = 0; m < f.n_mlps; ++m) {
+    const float* src = params + (int64_t)m * f.params_per_mlp;
+    float* dst = f.w32 + (int64_t)m * f.w32_per_mlp;
+    for (int l = 0; l < f.K; ++l) {
+      int total = f.in_pads[l] * f.out_pads[l];
+      k_pack32<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
+          src, f.ins[l], f.outs[l], f.in_pads[l], f.out_pads[l], dst + f.w32_layer_off[l],
+          dst + f.b32_layer_off[l]);
+      GNF_LAUNCH_CHECK();
+      src += (int64_t)f.ins[l] * f.outs[l] + f.outs[l];
+    }
+    if (f.tc_ok) {
+      int rc = tc_pack_mlp(f, m, params + (int64_t)m * f.params_per_mlp, stream_);
+      if (rc) return rc;
+    }
+  }
+  return GNF_OK;
+}
+
+extern "C" size_t gnf_grevnet_workspace(const gnf_flow* h, int64_t n_nodes, int32_t math) {
+  if (!h || n_nodes < 0) return 0;
+  return carve(h->f, n_nodes, math, nullptr).bytes;
+}
+
+static int check_common(const gnf_flow* h, int64_t n, int64_t e, const int32_t* rowptr,
+                        const int32_t* csr, void* ws, size_t ws_bytes, int math, const char* who) {
+  GNF_REQUIRE(h, GNF_EINVAL, "%s: null flow", who);
+  GNF_REQUIRE(n >= 0 && e >= 0, GNF_EINVAL, "%s: negative size", who);
+  int rc = check_math(h->f, math, who);
+  if (rc) return rc;
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(rowptr && (e == 0 || csr), GNF_EINVAL, "%s: null CSR pointer", who);
+  GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0, GNF_EINVAL, "%s: workspace must be 256-byte aligned", who);
+  GNF_REQUIRE(ws_bytes >= carve(h->f, n, math, nullptr).bytes, GNF_EWORKSPACE, "%s: workspace too small", who);
+  return GNF_OK;
+}
+
+extern "C" int gnf_grevnet_forward(const gnf_flow* h, const float* x, int64_t n, int64_t e,
+                                   const int32_t* rowptr, const int32_t* csr, float* z, double* ldj,
+                                   int32_t math, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_common(h, n, e, rowptr, csr, ws, ws_bytes, math, "gnf_grevnet_forward");
+  if (rc) return rc;
+  GNF_REQUIRE(ldj, GNF_EINVAL, "gnf_grevnet_forward: null ldj");
+  GNF_CUDA(cudaMemsetAsync(ldj, 0, 8, stream));
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_forward: null x/z");
+  const Flow& f = h->f;
+  Workspace w = carve(f, n, math, ws);
+  const int D = f.d.node_embedding_dim;
+  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(x, n, D, f.H, f.HP, w.x0, w.x1);
+  GNF_LAUNCH_CHECK();
+  for (int i = 0; i < f.d.num_timesteps; ++i) {   // gnn.py:309
+    rc = coupling_half(f, 0, i, 0, w.x0, w.x1, n, rowptr, csr, ldj, math, w, stream);   // gnn.py:320-323
+    if (rc) return rc;
+    rc = coupling_half(f, 1, i, 0, w.x1, w.x0, n, rowptr, csr, ldj, math, w, stream);   // gnn.py:335-338
+    if (rc) return rc;
+  }
+  k_merge<<<(unsigned)ceil_div(n * D, 256), 256, 0, stream>>>(w.x0, w.x1, n, D, f.H, f.HP, z);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_grevnet_inverse(const gnf_flow* h, const float* z, int64_t n, int64_t e,
+                                   const int32_t* rowptr, const int32_t* csr, float* x, int32_t math,
+                                   void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_common(h, n, e, rowptr, csr, ws, ws_bytes, math, "gnf_grevnet_inverse");
+  if (rc) return rc;
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_inverse: null x/z");
+  const Flow& f = h->f;
+  Workspace w = carve(f, n, math, ws);
+  const int D = f.d.node_embedding_dim;
+  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(z, n, D, f.H, f.HP, w.x0, w.x1);
+  GNF_LAUNCH_CHECK();
+  for (int i = f.d.num_timesteps - 1; i >= 0; --i) {   // gnn.py:347
+    rc = coupling_half(f, 1, i, 1, w.x1, w.x0, n, rowptr, csr, nullptr, math, w, stream);  // gnn.py:353-359
+    if (rc) return rc;
+    rc = coupling_half(f, 0, i, 1, w.x0, w.x1, n, rowptr, csr, nullptr, math, w, stream);  // gnn.py:366-372
+    if (rc) return rc;
+  }
+  k_merge<<<(unsigned)ceil_div(n * D, 256), 256, 0, stream>>>(w.x0, w.x1, n, D, f.H, f.HP, x);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_coupling_step(const gnf_flow* h, int32_t step, int32_t inverse, float* x0, float* x1,
+                                 int64_t n, int64_t e, const int32_t* rowptr, const int32_t* csr,
+                                 double* ldj_accum, int32_t math, void* ws, size_t ws_bytes,
+                                 void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_common(h, n, e, rowptr, csr, ws, ws_bytes, math, "gnf_coupling_step");
+  if (rc) return rc;
+  GNF_REQUIRE(step >= 0 && step < h->f.d.num_timesteps, GNF_EINVAL, "gnf_coupling_step: bad step %d", step);
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x0 && x1, GNF_EINVAL, "gnf_coupling_step: null x0/x1");
+  const Flow& f = h->f;
+  Workspace w = carve(f, n, math, ws);
+  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  if (!inverse) {
+    rc = coupling_half(f, 0, step, 0, x0, x1, n, rowptr, csr, ldj_accum, math, w, stream);
+    if (rc) return rc;
+    return coupling_half(f, 1, step, 0, x1, x0, n, rowptr, csr, ldj_accum, math, w, stream);
+  }
+  rc = coupling_half(f, 1, step, 1, x1, x0, n, rowptr, csr, nullptr, math, w, stream);
+  if (rc) return rc;
+  return coupling_half(f, 0, step, 1, x0, x1, n, rowptr, csr, nullptr, math, w, stream);
+}
+
+extern "C" int gnf_gnn_forward(const gnf_flow* h, int32_t which, int32_t half, int32_t step, const float* x,
+                               int64_t n, int64_t e, const int32_t* rowptr, const int32_t* csr, float* out,
+                               void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_common(h, n, e, rowptr, csr, ws, ws_bytes, GNF_MATH_FP32, "gnf_gnn_forward");
+  if (rc) return rc;
+  const Flow& f = h->f;
+  GNF_REQUIRE((which == 0 || which == 1) && (half == 0 || half == 1) && step >= 0 &&
+                  step < f.d.num_timesteps, GNF_EINVAL, "gnf_gnn_forward: bad GNN selector");
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && out, GNF_EINVAL, "gnf_gnn_forward: null x/out");
+  Workspace w = carve(f, n, GNF_MATH_FP32, ws);
+  GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  k_pad_rows<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(x, n, f.H, f.HP, w.x0);
+  GNF_LAUNCH_CHECK();
+  k_agg_input<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(
+      w.x0, f.H, f.HP, rowptr, csr, n, f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps,
+      f.in_pad, w.hbuf);
+  GNF_LAUNCH_CHECK();
+  rc = run_mlp32(f, f.mlp_index(which, half, step), w, w.sbuf, n, stream);
+  if (rc) return rc;
+  k_unpad_rows<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(w.sbuf, n, f.H, f.HP, out);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" size_t gnf_log_prob_workspace(int64_t, int32_t) { return (size_t)kLogProbBlocks * 8; }
+
+extern "C" int gnf_log_prob(const float* z, int64_t n, int32_t d, const double* ldj, double* out,
+                            void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(out && n >= 0 && d > 0, GNF_EINVAL, "gnf_log_prob: bad argument");
+  GNF_REQUIRE(ws && ws_bytes >= (size_t)kLogProbBlocks * 8, GNF_EWORKSPACE, "gnf_log_prob: workspace too small");
+  GNF_REQUIRE(n == 0 || z, GNF_EINVAL, "gnf_log_prob: null z");
+  double* partials = (double*)ws;
+  const int64_t total = n * d;
+  int blocks = (int)(ceil_div(total, 256) < kLogProbBlocks ? ceil_div(total, 256) : kLogProbBlocks);
+  if (blocks < 1) blocks = 1;
+  k_sumsq<<<blocks, 256, 0, stream>>>(z, total, partials);
+  GNF_LAUNCH_CHECK();
+  k_log_prob_final<<<1, 256, 0, stream>>>(partials, blocks, ldj, (double)n, d, out);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}

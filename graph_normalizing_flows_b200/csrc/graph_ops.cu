@@ -1,0 +1,314 @@
+// Batch-structure and segment kernels.
+//
+// Bit-exactness contract: the reference's aggregator is tf.unsorted_segment_sum, whose CPU
+// kernel adds edge rows into their receiver segment serially in ascending edge index
+// (gnn.py:103-104 via graph_nets ReceivedEdgesToNodesAggregator).  We therefore build a
+// STABLE CSR-by-receiver once per batch and accumulate each (receiver, feature) serially in
+// that order.  Parallelism is across (node, feature), never across one segment's edges.
+#include "common.cuh"
+
+namespace gnf {
+namespace {
+
+constexpr int kScanItems = 4;
+constexpr int kScanThreads = 1024;
+constexpr int kScanTile = kScanItems * kScanThreads;
+
+__global__ void k_validate(const int32_t* __restrict__ senders, const int32_t* __restrict__ receivers,
+                           int64_t n_nodes, int64_t n_edges, int32_t* __restrict__ bad) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int local = 0;
+  for (; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    int32_t s = senders[e], r = receivers[e];
+    local += (s < 0 || s >= n_nodes) + (r < 0 || r >= n_nodes);
+  }
+  if (local) atomicAdd(bad, local);
+}
+
+__global__ void k_degree(const int32_t* __restrict__ receivers, int64_t n_edges,
+                         int32_t* __restrict__ deg) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < n_edges) atomicAdd(&deg[receivers[e]], 1);
+}
+
+// exclusive scan, pass 1: per-tile exclusive scan + tile totals
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_tiles(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out,
+             int32_t* __restrict__ tile_sums) {
+  __shared__ int32_t warp_sums[32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int32_t v[kScanItems];
+  int32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    sum += v[i];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int32_t w = warp_sums[lane];
+    int32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_sums[lane] = wi - w;  // exclusive
+    if (lane == 31) tile_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  int32_t excl = warp_sums[warp] + incl - sum;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = excl;
+    excl += v[i];
+  }
+}
+
+// pass 2: one block scans the tile totals in place (exclusive), serial carry over chunks
+__global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ sums, int n) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    int32_t v = (i < n) ? sums[i] : 0;
+    int32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    int32_t carry = carry_s;
+    int32_t excl = carry + warp_sums[warp] + incl - v;
+    if (i < n) sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+
+// pass 3: add tile offsets; also writes rowptr[n] = total
+__global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* __restrict__ tile_sums,
+                           int64_t n_edges) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] += tile_sums[i / kScanTile];
+  if (i == 0) out[n] = (int32_t)n_edges;
+}
+
+// unordered placement into segments
+__global__ void k_fill(const int32_t* __restrict__ receivers, int64_t n_edges,
+                       const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
+                       int32_t* __restrict__ tmp) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < n_edges) {
+    int32_t r = receivers[e];
+    int32_t pos = atomicAdd(&cursor[r], 1);
+    tmp[rowptr[r] + pos] = (int32_t)e;
+  }
+}
+
+// one warp per receiver: rank the segment's edge ids ascending (-> stable CSR), emit
+// perm and csr_senders.  deg <= 32: in registers; otherwise O(deg^2/32) counting.
+__global__ void k_sort_segments(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tmp,
+                                const int32_t* __restrict__ senders, int64_t n_nodes,
+                                int32_t* __restrict__ perm, int32_t* __restrict__ csr_senders) {
+  const int lane = threadIdx.x & 31;
+  int64_t node = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (node >= n_nodes) return;
+  const int32_t beg = rowptr[node], end = rowptr[node + 1];
+  const int deg = end - beg;
+  if (deg <= 32) {
+    int32_t mine = (lane < deg) ? tmp[beg + lane] : 0x7fffffff;
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      int32_t other = __shfl_sync(0xffffffffu, mine, j);
+      rank += (other < mine);
+    }
+    if (lane < deg) {
+      perm[beg + rank] = mine;
+      csr_senders[beg + rank] = senders[mine];
+    }
+  } else {
+    for (int i = lane; i < deg; i += 32) {
+      int32_t mine = tmp[beg + i];
+      int rank = 0;
+      for (int j = 0; j < deg; ++j) rank += (tmp[beg + j] < mine);
+      perm[beg + rank] = mine;
+      csr_senders[beg + rank] = senders[mine];
+    }
+  }
+}
+
+__global__ void k_gather_rows(const float* __restrict__ x, int h, const int32_t* __restrict__ senders,
+                              int64_t total, float* __restrict__ edges) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < total) {
+    int64_t e = i / h;
+    int f = (int)(i - e * h);
+    edges[i] = x[(int64_t)senders[e] * h + f];
+  }
+}
+
+// thread per (node, feature); serial in-order accumulation, 4 loads in flight
+template <bool kIndirectRows>
+__global__ void __launch_bounds__(256)
+k_segment_reduce(const float* __restrict__ src, int h, const int32_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ idx, int64_t total, int mean, float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t node = i / h;
+  const int f = (int)(i - node * h);
+  int32_t e = rowptr[node];
+  const int32_t end = rowptr[node + 1];
+  const int32_t cnt = end - e;
+  float acc = 0.f;
+  for (; e + 4 <= end; e += 4) {
+    int32_t i0 = idx[e], i1 = idx[e + 1], i2 = idx[e + 2], i3 = idx[e + 3];
+    float v0 = src[(int64_t)i0 * h + f];
+    float v1 = src[(int64_t)i1 * h + f];
+    float v2 = src[(int64_t)i2 * h + f];
+    float v3 = src[(int64_t)i3 * h + f];
+    acc = __fadd_rn(acc, v0);
+    acc = __fadd_rn(acc, v1);
+    acc = __fadd_rn(acc, v2);
+    acc = __fadd_rn(acc, v3);
+  }
+  for (; e < end; ++e) acc = __fadd_rn(acc, src[(int64_t)idx[e] * h + f]);
+  if (mean) acc = __fdiv_rn(acc, fmaxf((float)cnt, 1.f));
+  out[i] = acc;
+}
+
+}  // namespace
+}  // namespace gnf
+
+using namespace gnf;
+
+extern "C" size_t gnf_build_csr_workspace(int64_t n_nodes, int64_t n_edges) {
+  size_t tiles = (size_t)ceil_div(n_nodes + 1, kScanTile);
+  return align_up((size_t)(n_nodes + 1) * 4, 256)   // deg / cursor
+         + align_up((size_t)n_edges * 4, 256)        // tmp
+         + align_up(tiles * 4 + 4, 256);             // tile sums
+}
+
+extern "C" int gnf_build_csr(const int32_t* receivers, const int32_t* senders, int64_t n_nodes,
+                             int64_t n_edges, int32_t* rowptr, int32_t* perm, int32_t* csr_senders,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(n_nodes >= 0 && n_edges >= 0, GNF_EINVAL, "gnf_build_csr: negative size");
+  GNF_REQUIRE(n_nodes < (1ll << 31) - 1 && n_edges < (1ll << 31) - 1, GNF_EINVAL,
+              "gnf_build_csr: int32 index space exceeded");
+  GNF_REQUIRE(rowptr && (n_edges == 0 || (receivers && senders && perm && csr_senders)), GNF_EINVAL,
+              "gnf_build_csr: null pointer");
+  GNF_REQUIRE(n_edges == 0 || n_nodes > 0, GNF_EINVAL, "gnf_build_csr: edges without nodes");
+  GNF_REQUIRE(workspace_bytes >= gnf_build_csr_workspace(n_nodes, n_edges) &&
+                  (workspace || workspace_bytes == 0),
+              GNF_EWORKSPACE, "gnf_build_csr: workspace too small");
+  uint8_t* ws = (uint8_t*)workspace;
+  int32_t* deg = (int32_t*)ws;
+  ws += align_up((size_t)(n_nodes + 1) * 4, 256);
+  int32_t* tmp = (int32_t*)ws;
+  ws += align_up((size_t)n_edges * 4, 256);
+  int32_t* tile_sums = (int32_t*)ws;
+
+  const int64_t n1 = n_nodes + 1;
+  GNF_CUDA(cudaMemsetAsync(deg, 0, (size_t)n1 * 4, stream));
+  if (n_edges > 0) {
+    k_degree<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(receivers, n_edges, deg);
+    GNF_LAUNCH_CHECK();
+  }
+  const int tiles = (int)ceil_div(n1, kScanTile);
+  k_scan_tiles<<<tiles, kScanThreads, 0, stream>>>(deg, n1, rowptr, tile_sums);
+  GNF_LAUNCH_CHECK();
+  k_scan_sums<<<1, 1024, 0, stream>>>(tile_sums, tiles);
+  GNF_LAUNCH_CHECK();
+  k_scan_add<<<(unsigned)ceil_div(n1, 256), 256, 0, stream>>>(rowptr, n_nodes, tile_sums, n_edges);
+  GNF_LAUNCH_CHECK();
+  if (n_edges > 0) {
+    GNF_CUDA(cudaMemsetAsync(deg, 0, (size_t)n1 * 4, stream));  // reuse as cursor
+    k_fill<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(receivers, n_edges, rowptr, deg, tmp);
+    GNF_LAUNCH_CHECK();
+    k_sort_segments<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, stream>>>(
+        rowptr, tmp, senders, n_nodes, perm, csr_senders);
+    GNF_LAUNCH_CHECK();
+  }
+  return GNF_OK;
+}
+
+extern "C" int gnf_validate_indices(const int32_t* senders, const int32_t* receivers,
+                                    int64_t n_nodes, int64_t n_edges, int32_t* bad_count,
+                                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(bad_count, GNF_EINVAL, "gnf_validate_indices: null bad_count");
+  GNF_CUDA(cudaMemsetAsync(bad_count, 0, 4, stream));
+  if (n_edges > 0) {
+    GNF_REQUIRE(senders && receivers, GNF_EINVAL, "gnf_validate_indices: null pointer");
+    int blocks = (int)(ceil_div(n_edges, 256) < 4096 ? ceil_div(n_edges, 256) : 4096);
+    k_validate<<<blocks, 256, 0, stream>>>(senders, receivers, n_nodes, n_edges, bad_count);
+    GNF_LAUNCH_CHECK();
+  }
+  return GNF_OK;
+}
+
+extern "C" int gnf_gather_rows(const float* x, int32_t h, const int32_t* senders, int64_t n_edges,
+                               float* edges, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(h > 0 && n_edges >= 0, GNF_EINVAL, "gnf_gather_rows: bad shape");
+  if (n_edges == 0) return GNF_OK;
+  GNF_REQUIRE(x && senders && edges, GNF_EINVAL, "gnf_gather_rows: null pointer");
+  int64_t total = n_edges * h;
+  k_gather_rows<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(x, h, senders, total, edges);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+static int segment_common(const float* src, int32_t h, const int32_t* rowptr, const int32_t* idx,
+                          int64_t n_nodes, int32_t agg, float* out, cudaStream_t stream,
+                          const char* who) {
+  GNF_REQUIRE(h > 0 && n_nodes >= 0, GNF_EINVAL, "%s: bad shape", who);
+  GNF_REQUIRE(agg == GNF_AGG_SUM || agg == GNF_AGG_MEAN, GNF_EINVAL, "%s: bad agg %d", who, agg);
+  if (n_nodes == 0) return GNF_OK;
+  GNF_REQUIRE(rowptr && out, GNF_EINVAL, "%s: null pointer", who);
+  int64_t total = n_nodes * h;
+  k_segment_reduce<true><<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
+      src, h, rowptr, idx, total, agg == GNF_AGG_MEAN, out);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_segment_sum(const float* edges, int32_t h, const int32_t* rowptr,
+                               const int32_t* perm, int64_t n_nodes, int32_t agg, float* out,
+                               void* stream) {
+  return segment_common(edges, h, rowptr, perm, n_nodes, agg, out, (cudaStream_t)stream,
+                        "gnf_segment_sum");
+}
+
+extern "C" int gnf_gather_segment_sum(const float* x, int32_t h, const int32_t* rowptr,
+                                      const int32_t* csr_senders, int64_t n_nodes, int32_t agg,
+                                      float* out, void* stream) {
+  return segment_common(x, h, rowptr, csr_senders, n_nodes, agg, out, (cudaStream_t)stream,
+                        "gnf_gather_segment_sum");
+}

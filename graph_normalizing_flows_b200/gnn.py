@@ -1,0 +1,484 @@
+"""Host-side mirror of the reference's GRevNet / message-passing-GNN interface (gnn.py).
+
+Same names, constructor arguments, keyword semantics and return conventions as
+/root/reference/gnn.py for the hot path:
+
+    make_mlp_model (gnn.py:159-180)            ConcatThenMLPBlock (gnn.py:100-111)
+    AggThenMLPBlock (gnn.py:114-126)           NodeBlockGNN (gnn.py:143-156)
+    sum_concat_then_mlp_gnn / avg_concat_then_mlp_gnn / sum_then_mlp_gnn / avg_then_mlp_gnn
+    (gnn.py:238-257)                           GRevNet (gnn.py:273-381)
+
+The objects are thin parameter containers; all arithmetic runs in libgnf_b200.so
+(hand-written sm_100a kernels, include/gnf_b200.h).  There is no CPU or eager-PyTorch
+fallback: calling any of these without the library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .graphs import BatchStructure, GraphsTuple, structure_of
+
+# activation tokens (the reference passes tf.nn.leaky_relu / tf.nn.relu, run_grevnet.py:158, gnn.py:162)
+leaky_relu = "leaky_relu"
+relu = "relu"
+
+
+def _act_name(activation) -> str:
+    if activation in ("leaky_relu", "relu"):
+        return activation
+    name = getattr(activation, "__name__", None)
+    if name in ("leaky_relu", "relu"):
+        return name
+    raise ValueError(f"unsupported activation {activation!r}: the fused kernels implement "
+                     "leaky_relu(alpha=0.2) and relu")
+
+
+# reducer tokens (the reference passes tf.unsorted_segment_sum / tf.unsorted_segment_mean, gnn.py:239-257)
+def unsorted_segment_sum(data: torch.Tensor, segment_ids: torch.Tensor, num_segments: int) -> torch.Tensor:
+    """tf.unsorted_segment_sum on the device: serial in-order accumulation per segment
+    (bit-exact with the TF CPU kernel)."""
+    return _segment_reduce(data, segment_ids, num_segments, "sum")
+
+
+def unsorted_segment_mean(data: torch.Tensor, segment_ids: torch.Tensor, num_segments: int) -> torch.Tensor:
+    """tf.unsorted_segment_mean: segment_sum / max(count, 1)."""
+    return _segment_reduce(data, segment_ids, num_segments, "mean")
+
+
+unsorted_segment_sum.agg = "sum"
+unsorted_segment_mean.agg = "mean"
+
+
+def _agg_name(aggn_fn) -> str:
+    agg = getattr(aggn_fn, "agg", None) or (aggn_fn if aggn_fn in ("sum", "mean") else None)
+    if agg is None:
+        raise ValueError("aggn_fn must be unsorted_segment_sum or unsorted_segment_mean")
+    return agg
+
+
+def _segment_reduce(data, segment_ids, num_segments, agg):
+    lib = _lib.load()
+    _lib.require_cuda(data, "data", torch.float32)
+    _lib.require_cuda(segment_ids, "segment_ids", torch.int32)
+    if data.dim() != 2 or data.shape[0] != segment_ids.shape[0]:
+        raise ValueError("data must be [E, H] with one segment id per row")
+    st = BatchStructure(segment_ids, segment_ids, int(num_segments))
+    out = torch.empty(int(num_segments), data.shape[1], dtype=torch.float32, device=data.device)
+    _lib.check(lib.gnf_segment_sum(_lib.ptr(data), data.shape[1], _lib.ptr(st.rowptr), _lib.ptr(st.perm),
+                                   int(num_segments), _lib.AGG[agg], _lib.ptr(out), _lib.stream_ptr(data.device)),
+               "gnf_segment_sum")
+    return out
+
+
+def gather_segment_reduce(nodes: torch.Tensor, structure: BatchStructure, agg: str = "sum") -> torch.Tensor:
+    """EdgeBlock(use_sender_nodes) + ReceivedEdgesToNodesAggregator fused (gnn.py:151-156,103-104)."""
+    lib = _lib.load()
+    _lib.require_cuda(nodes, "nodes", torch.float32)
+    out = torch.empty_like(nodes)
+    _lib.check(lib.gnf_gather_segment_sum(_lib.ptr(nodes), nodes.shape[1], _lib.ptr(structure.rowptr),
+                                          _lib.ptr(structure.csr_senders), nodes.shape[0], _lib.AGG[agg],
+                                          _lib.ptr(out), _lib.stream_ptr(nodes.device)),
+               "gnf_gather_segment_sum")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# make_mlp_model  (gnn.py:159-180)
+# --------------------------------------------------------------------------------------------
+def _truncated_normal_(t: torch.Tensor, std: float, generator=None):
+    """tf truncated_normal: N(0, std) re-drawn outside 2 std."""
+    with torch.no_grad():
+        t.normal_(0.0, 1.0, generator=generator)
+        bad = t.abs() > 2.0
+        while bool(bad.any()):
+            t[bad] = torch.randn(int(bad.sum()), generator=generator, dtype=t.dtype, device=t.device)
+            bad = t.abs() > 2.0
+        t.mul_(std)
+    return t
+
+
+class MLP(nn.Module):
+    """snt.nets.MLP([latent]*(K-1)+[out], activate_final=False) with Glorot-normal weights and
+    truncated-normal biases (gnn.py:165-180).  The input width is bound on first use
+    (Sonnet infers it at connection time)."""
+
+    def __init__(self, latent_dim, output_dim, num_layers, activation=relu, l2_regularizer_weight=0.01,
+                 bias_init_stddev=0.1):
+        super().__init__()
+        self.latent_dim = int(latent_dim)
+        self.output_dim = int(output_dim)          # the scripts pass node_embedding_dim / 2 (a float)
+        self.num_layers = int(num_layers)
+        if self.num_layers < 2:
+            raise ValueError("num_layers must be >= 2")
+        self.activation = _act_name(activation)
+        self.l2_regularizer_weight = l2_regularizer_weight   # unused, as in the reference (commented out)
+        self.bias_init_stddev = float(bias_init_stddev)
+        self.input_dim: Optional[int] = None
+        self.weights: List[torch.Tensor] = []
+        self.biases: List[torch.Tensor] = []
+
+    def layer_shapes(self, input_dim):
+        sizes = [self.latent_dim] * (self.num_layers - 1) + [self.output_dim]
+        shapes, d = [], int(input_dim)
+        for o in sizes:
+            shapes.append((d, o))
+            d = o
+        return shapes
+
+    def param_count(self, input_dim):
+        return sum(i * o + o for i, o in self.layer_shapes(input_dim))
+
+    def bind(self, input_dim: int, flat: torch.Tensor, generator=None, init=True):
+        """Attach this MLP to a slice of a flat parameter buffer (layout of
+        include/gnf_b200.h: W0 b0 W1 b1 ...) and initialise it."""
+        self.input_dim = int(input_dim)
+        self.weights, self.biases = [], []
+        off = 0
+        for (i, o) in self.layer_shapes(input_dim):
+            w = flat[off:off + i * o].view(i, o)
+            off += i * o
+            b = flat[off:off + o]
+            off += o
+            if init:
+                # tf.initializers.glorot_normal = VarianceScaling(1, fan_avg, truncated_normal)
+                std = math.sqrt(2.0 / (i + o)) / 0.87962566103423978
+                _truncated_normal_(w, std, generator)
+                _truncated_normal_(b, self.bias_init_stddev, generator)
+            self.weights.append(w)
+            self.biases.append(b)
+        return off
+
+    def signature(self):
+        return (self.latent_dim, self.output_dim, self.num_layers, self.activation)
+
+
+def make_mlp_model(latent_dim, output_dim, num_layers, activation=relu, l2_regularizer_weight=0.01,
+                   bias_init_stddev=0.1) -> MLP:
+    return MLP(latent_dim, output_dim, num_layers, activation, l2_regularizer_weight, bias_init_stddev)
+
+
+# --------------------------------------------------------------------------------------------
+# node blocks and NodeBlockGNN  (gnn.py:100-156)
+# --------------------------------------------------------------------------------------------
+class ConcatThenMLPBlock(nn.Module):
+    """nodes <- MLP(concat([nodes, aggregate(received edges)], 1))   (gnn.py:100-111)"""
+    block = "concat"
+
+    def __init__(self, aggn_fn, make_mlp_fn, name="AggThenMLPBlock"):
+        super().__init__()
+        self.name = name
+        self.agg = _agg_name(aggn_fn)
+        self._mlp = make_mlp_fn()
+        self.epsilon = 1.0
+
+    def input_dim(self, half_dim):
+        return 2 * half_dim
+
+
+class AggThenMLPBlock(nn.Module):
+    """nodes <- MLP(epsilon * nodes + aggregate(received edges))   (gnn.py:114-126)"""
+    block = "agg_then"
+
+    def __init__(self, aggn_fn, make_mlp_fn, epsilon, name="AggThenMLPBlock"):
+        super().__init__()
+        self.name = name
+        self.agg = _agg_name(aggn_fn)
+        self._mlp = make_mlp_fn()
+        self.epsilon = float(epsilon)
+
+    def input_dim(self, half_dim):
+        return half_dim
+
+
+EDGE_BLOCK_OPT = {          # gnn.py:135-140: edges = nodes[senders], nothing else
+    "use_edges": False,
+    "use_receiver_nodes": False,
+    "use_sender_nodes": True,
+    "use_globals": False,
+}
+
+
+class _Flow:
+    """Owner of one gnf_flow handle (packed device weights)."""
+
+    def __init__(self, T, D, mlp: MLP, block: str, agg: str, eps: float, weight_sharing: bool):
+        self.lib = _lib.load()
+        self.desc = _lib.FlowDesc(
+            num_timesteps=T, node_embedding_dim=D, latent_dim=mlp.latent_dim, num_layers=mlp.num_layers,
+            agg=_lib.AGG[agg], block=_lib.BLOCK[block], act=_lib.ACT[mlp.activation],
+            weight_sharing=int(bool(weight_sharing)), eps=eps)
+        n = self.lib.gnf_flow_param_count(C.byref(self.desc))
+        if n < 0:
+            raise ValueError(_lib.last_error())
+        self.param_count = int(n)
+        self.handle = None
+        self._packed_version = None
+        self._packed_ptr = None
+
+    def ensure(self, flat: torch.Tensor):
+        """Create the handle on first use and (re)pack when the flat buffer changed."""
+        _lib.require_cuda(flat, "GRevNet parameters", torch.float32)
+        if self.handle is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device: the GRevNet hot path has no CPU fallback")
+            h = C.c_void_p()
+            with torch.cuda.device(flat.device):
+                _lib.check(self.lib.gnf_flow_create(C.byref(h), C.byref(self.desc)), "gnf_flow_create")
+            self.handle = h
+        if self._packed_version != flat._version or self._packed_ptr != flat.data_ptr():
+            _lib.check(self.lib.gnf_flow_set_params(self.handle, _lib.ptr(flat), _lib.stream_ptr(flat.device)),
+                       "gnf_flow_set_params")
+            self._packed_version, self._packed_ptr = flat._version, flat.data_ptr()
+        return self.handle
+
+    def supports(self, math_name: str) -> bool:
+        return bool(self.handle is not None and self.lib.gnf_flow_supports(self.handle, _lib.MATH[math_name]))
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                self.lib.gnf_flow_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class NodeBlockGNN(nn.Module):
+    """node_block(edge_block(graph)) with an identity edge model over sender nodes
+    (gnn.py:143-156).  Callable GraphsTuple -> GraphsTuple; inside a GRevNet its weights are
+    adopted into the flow's packed buffer and the fused kernels do the work."""
+
+    def __init__(self, node_block, edge_block_opt=EDGE_BLOCK_OPT, name="NodeBlockGNN"):
+        super().__init__()
+        self.name = name
+        self._node_block = node_block
+        self._flow: Optional[_Flow] = None
+        self.params: Optional[nn.Parameter] = None
+
+    @property
+    def mlp(self) -> MLP:
+        return self._node_block._mlp
+
+    def config(self):
+        nb = self._node_block
+        return (nb.block, nb.agg, nb.epsilon) + self.mlp.signature()
+
+    def _standalone(self, half_dim, device):
+        if self._flow is None:
+            nb, mlp = self._node_block, self.mlp
+            if mlp.output_dim != half_dim:
+                raise ValueError(f"MLP output_dim={mlp.output_dim} must equal the node width {half_dim}")
+            self._flow = _Flow(1, 2 * half_dim, mlp, nb.block, nb.agg, nb.epsilon, True)
+            per = mlp.param_count(nb.input_dim(half_dim))
+            flat = torch.empty(4 * per, dtype=torch.float32, device=device)
+            if mlp.input_dim is None:
+                mlp.bind(nb.input_dim(half_dim), flat[:per])
+            else:                      # already bound elsewhere (e.g. adopted by a GRevNet): copy
+                src = torch.cat([torch.cat([w.reshape(-1), b]) for w, b in zip(mlp.weights, mlp.biases)])
+                flat[:per].copy_(src)
+            for k in range(1, 4):
+                flat[k * per:(k + 1) * per].copy_(flat[:per])
+            self.params = nn.Parameter(flat, requires_grad=False)
+        return self._flow
+
+    def forward(self, graph: GraphsTuple) -> GraphsTuple:
+        nodes = _lib.require_cuda(graph.nodes, "graph.nodes", torch.float32)
+        n, h = nodes.shape
+        st = structure_of(graph)
+        flow = self._standalone(h, nodes.device)
+        handle = flow.ensure(self.params.data)
+        lib = flow.lib
+        wsb = lib.gnf_grevnet_workspace(handle, n, _lib.MATH["fp32"])
+        ws = _lib.workspace(wsb, nodes.device)
+        out = torch.empty_like(nodes)
+        _lib.check(lib.gnf_gnn_forward(handle, 0, 0, 0, _lib.ptr(nodes), n, st.n_edges, _lib.ptr(st.rowptr),
+                                       _lib.ptr(st.csr_senders), _lib.ptr(out), _lib.ptr(ws), wsb,
+                                       _lib.stream_ptr(nodes.device)), "gnf_gnn_forward")
+        return graph.replace(nodes=out)
+
+
+def avg_then_mlp_gnn(make_mlp_fn, epsilon):            # gnn.py:238-241
+    return NodeBlockGNN(AggThenMLPBlock(unsorted_segment_mean, make_mlp_fn, epsilon))
+
+
+def sum_then_mlp_gnn(make_mlp_fn, epsilon):            # gnn.py:244-247
+    return NodeBlockGNN(AggThenMLPBlock(unsorted_segment_sum, make_mlp_fn, epsilon))
+
+
+def sum_concat_then_mlp_gnn(make_mlp_fn):              # gnn.py:250-252
+    return NodeBlockGNN(ConcatThenMLPBlock(unsorted_segment_sum, make_mlp_fn))
+
+
+def avg_concat_then_mlp_gnn(make_mlp_fn):              # gnn.py:255-257
+    return NodeBlockGNN(ConcatThenMLPBlock(unsorted_segment_mean, make_mlp_fn))
+
+
+def get_gnns(num_timesteps, make_gnn_fn):              # gnn.py:266-267
+    return [make_gnn_fn() for _ in range(num_timesteps)]
+
+
+# --------------------------------------------------------------------------------------------
+# GRevNet  (gnn.py:273-381)
+# --------------------------------------------------------------------------------------------
+class GRevNet(nn.Module):
+    """Affine-coupling flow over node features.
+
+    grevnet(graph, inverse=True)  -> (GraphsTuple z, scalar log_det_jacobian)   [GRevNet.f]
+    grevnet(graph, inverse=False) -> GraphsTuple x                               [GRevNet.g]
+
+    NOTE the reference's naming: inverse=True is the data -> latent (density) direction
+    (gnn.py:379-381).
+
+    `math` selects the arithmetic of the MLP contraction: "tc3x" (tcgen05, fp16 hi/lo split,
+    fp32 accumulate; the default when the shape is supported), "fp32" (FFMA, any shape),
+    "bf16" (tcgen05 single pass), "tc3x_bf16".
+    """
+
+    def __init__(self, make_gnn_fn: Callable[[], NodeBlockGNN], num_timesteps, node_embedding_dim,
+                 use_batch_norm=False, weight_sharing=False, name="GRevNet", math: Optional[str] = None,
+                 device=None, seed: Optional[int] = None):
+        super().__init__()
+        self.name = name
+        self.num_timesteps = int(num_timesteps)
+        self.weight_sharing = bool(weight_sharing)
+        self.node_embedding_dim = int(node_embedding_dim)
+        if self.node_embedding_dim % 2:
+            raise ValueError("node_embedding_dim must be even (tf.split at gnn.py:306)")
+        if use_batch_norm:
+            raise NotImplementedError(
+                "use_batch_norm=True (TFP BatchNormalization bijector, gnn.py:260-263) is not part of the "
+                "accelerated path yet (SURVEY §8 row a9 / f4); construct with use_batch_norm=False")
+        self.use_batch_norm = False
+        T = self.num_timesteps
+        # construction order of gnn.py:283-299
+        if self.weight_sharing:
+            self.s = nn.ModuleList([make_gnn_fn(), make_gnn_fn()])
+            self.t = nn.ModuleList([make_gnn_fn(), make_gnn_fn()])
+            order = [self.s[0], self.s[1], self.t[0], self.t[1]]
+        else:
+            self.s = nn.ModuleList([nn.ModuleList(get_gnns(T, make_gnn_fn)), nn.ModuleList(get_gnns(T, make_gnn_fn))])
+            self.t = nn.ModuleList([nn.ModuleList(get_gnns(T, make_gnn_fn)), nn.ModuleList(get_gnns(T, make_gnn_fn))])
+            order = [g for which in (self.s, self.t) for half in which for g in half]
+        cfgs = {g.config() for g in order}
+        if len(cfgs) != 1:
+            raise ValueError("make_gnn_fn must return identically configured GNNs")
+        g0 = order[0]
+        if not isinstance(g0, NodeBlockGNN):
+            raise TypeError("make_gnn_fn must return a NodeBlockGNN (sum/avg concat_then_mlp or then_mlp)")
+        H = self.node_embedding_dim // 2
+        nb, mlp = g0._node_block, g0.mlp
+        if mlp.output_dim != H:
+            raise ValueError(f"MLP output_dim={mlp.output_dim} must be node_embedding_dim/2={H}")
+        self._flow = _Flow(T, self.node_embedding_dim, mlp, nb.block, nb.agg, nb.epsilon, self.weight_sharing)
+        in_dim = nb.input_dim(H)
+        per = mlp.param_count(in_dim)
+        assert per * len(order) == self._flow.param_count
+        dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device="cpu")
+            gen.manual_seed(int(seed))
+        flat = torch.empty(self._flow.param_count, dtype=torch.float32)
+        for k, g in enumerate(order):          # flat order: which -> half -> step (include/gnf_b200.h)
+            g.mlp.bind(in_dim, flat[k * per:(k + 1) * per], generator=gen)
+        self.params = nn.Parameter(flat.to(dev), requires_grad=False)
+        self._order = order
+        self._per = per
+        self._in_dim = in_dim
+        self._rebind()
+        self._math = math
+
+    # -- parameter plumbing -------------------------------------------------------------------
+    def _rebind(self):
+        for k, g in enumerate(self._order):
+            g.mlp.bind(self._in_dim, self.params.data[k * self._per:(k + 1) * self._per], init=False)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._rebind()
+        return out
+
+    def mlp_of(self, which: str, half: int, step: int) -> MLP:
+        grp = self.s if which == "s" else self.t
+        return (grp[half] if self.weight_sharing else grp[half][step]).mlp
+
+    def scale_last_layers_(self, factor: float):
+        """Damp the last layer of every MLP (synthetic benchmarks only: keeps the reference's
+        unclamped exp(s), gnn.py:323, finite; SURVEY §7 hard part 3)."""
+        with torch.no_grad():
+            for g in self._order:
+                g.mlp.weights[-1].mul_(factor)
+                g.mlp.biases[-1].mul_(factor)
+        return self
+
+    @property
+    def math(self) -> str:
+        if self._math is not None:
+            return self._math
+        self._flow.ensure(self.params.data)
+        return "tc3x" if self._flow.supports("tc3x") else "fp32"
+
+    @math.setter
+    def math(self, value):
+        if value is not None and value not in _lib.MATH:
+            raise ValueError(f"math must be one of {sorted(_lib.MATH)}")
+        self._math = value
+
+    # -- the hot path ---------------------------------------------------------------------------
+    def _run(self, x: GraphsTuple, inverse_kernel: bool):
+        nodes = _lib.require_cuda(x.nodes, "graph.nodes", torch.float32)
+        if nodes.dim() != 2 or nodes.shape[1] != self.node_embedding_dim:
+            raise ValueError(f"graph.nodes must be [N, {self.node_embedding_dim}], got {tuple(nodes.shape)}")
+        if nodes.device != self.params.device:
+            raise RuntimeError(f"graph is on {nodes.device} but the GRevNet parameters are on {self.params.device}")
+        st = structure_of(x)
+        handle = self._flow.ensure(self.params.data)
+        lib = self._flow.lib
+        m = _lib.MATH[self.math]
+        n = nodes.shape[0]
+        wsb = lib.gnf_grevnet_workspace(handle, n, m)
+        ws = _lib.workspace(wsb, nodes.device)
+        out = torch.empty_like(nodes)
+        stream = _lib.stream_ptr(nodes.device)
+        if not inverse_kernel:
+            ldj = torch.empty(1, dtype=torch.float64, device=nodes.device)
+            _lib.check(lib.gnf_grevnet_forward(handle, _lib.ptr(nodes), n, st.n_edges, _lib.ptr(st.rowptr),
+                                               _lib.ptr(st.csr_senders), _lib.ptr(out), _lib.ptr(ldj), m,
+                                               _lib.ptr(ws), wsb, stream), "gnf_grevnet_forward")
+            return out, ldj
+        _lib.check(lib.gnf_grevnet_inverse(handle, _lib.ptr(nodes), n, st.n_edges, _lib.ptr(st.rowptr),
+                                           _lib.ptr(st.csr_senders), _lib.ptr(out), m, _lib.ptr(ws), wsb,
+                                           stream), "gnf_grevnet_inverse")
+        return out, None
+
+    def f(self, x: GraphsTuple):
+        """x -> (z, log_det_jacobian)   (gnn.py:304-341)"""
+        z, ldj = self._run(x, inverse_kernel=False)
+        self._last_ldj64 = ldj
+        return x.replace(nodes=z), ldj[0].to(torch.float32)
+
+    def f64(self, x: GraphsTuple):
+        """As f, but returns the log-det as the device float64 [1] tensor the kernels produce."""
+        z, ldj = self._run(x, inverse_kernel=False)
+        return x.replace(nodes=z), ldj
+
+    def g(self, z: GraphsTuple):
+        """z -> x   (gnn.py:343-373)"""
+        x, _ = self._run(z, inverse_kernel=True)
+        return z.replace(nodes=x)
+
+    def log_prob(self, x: GraphsTuple):
+        """sum(prior.log_prob(z)) + log_det_jacobian with prior = N(0, I): what the dead
+        GRevNet.log_prob (gnn.py:375-377, self.prior is never set) was meant to compute and the
+        scripts inline (run_grevnet.py:291-295)."""
+        from .loss import log_prob as _log_prob
+        return _log_prob(self, x)["log_prob_xs"]
+
+    def forward(self, input: GraphsTuple, inverse=True):
+        func = self.f if inverse else self.g      # gnn.py:379-381
+        return func(input)

@@ -1,0 +1,183 @@
+/*
+ * gnf_b200.h -- C ABI of the B200-native GRevNet hot path (libgnf_b200.so).
+ *
+ * Drop-in boundary for the one path this repository accelerates: GRevNet forward
+ * (+log-det), inverse and log-prob over packed batches of graphs, with the
+ * message-passing GNN (sender gather -> segment reduce by receiver -> node MLP)
+ * inside every affine coupling.  Reference: jliu/graph-normalizing-flows @ d8b9256.
+ * Each entry point cites the reference interface (file:line under /root/reference)
+ * it replaces.  The arithmetic the reference delegates to graph_nets / Sonnet /
+ * TF / TFP (not vendored) is named where it applies.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer unless
+ *     the name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - all calls are asynchronous on `stream`; none synchronises the device, except
+ *     gnf_flow_create / gnf_flow_destroy (cudaMalloc / cudaFree).
+ *   - return value: 0 on success, a negative GNF_E* code otherwise;
+ *     gnf_last_error() returns a thread-local message for the last failure.
+ *   - inputs are never written; outputs never alias inputs unless stated.
+ *   - node features are row-major float32 [N, D] exactly as graph_nets' GraphsTuple.nodes
+ *     (train_grevnet_with_data.py:265-271); indices are int32 as GraphsTuple.senders/receivers.
+ */
+#ifndef GNF_B200_H_
+#define GNF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNF_ABI_VERSION 1
+
+/* status codes */
+#define GNF_OK            0
+#define GNF_EINVAL       -1   /* bad argument (shape, null pointer, unsupported size)        */
+#define GNF_ECUDA        -2   /* CUDA runtime error (message in gnf_last_error)              */
+#define GNF_EUNSUPPORTED -3   /* shape outside what the requested kernel family supports     */
+#define GNF_EWORKSPACE   -4   /* workspace too small                                         */
+
+/* aggregation reducers: tf.unsorted_segment_sum / tf.unsorted_segment_mean (gnn.py:239-257) */
+#define GNF_AGG_SUM  0
+#define GNF_AGG_MEAN 1
+/* node blocks: ConcatThenMLPBlock (gnn.py:100-111) / AggThenMLPBlock (gnn.py:114-126) */
+#define GNF_BLOCK_CONCAT   0
+#define GNF_BLOCK_AGG_THEN 1
+/* MLP activations: tf.nn.leaky_relu alpha=0.2 (run_grevnet.py:158) / tf.nn.relu (gnn.py:162) */
+#define GNF_ACT_LEAKY_RELU 0
+#define GNF_ACT_RELU       1
+/* arithmetic of the MLP contraction */
+#define GNF_MATH_FP32   0  /* FFMA fp32, layer-by-layer kernels, any supported shape           */
+#define GNF_MATH_TC3X   1  /* tcgen05 kind::f16, fp16 hi/lo split, 3 MMAs per product, fp32 acc */
+#define GNF_MATH_BF16   2  /* tcgen05 kind::f16, bf16 single pass, fp32 accumulate             */
+#define GNF_MATH_TC3X_BF16 3 /* as TC3X with a bf16 hi/lo split (no fp16 range limit)          */
+
+int         gnf_abi_version(void);
+const char* gnf_last_error(void);
+/* number of kernels this library launched on the calling thread since the last reset
+ * (bench.py's "gpu_launches") */
+int64_t     gnf_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  batch structure.  Replaces the per-call index handling of graph_nets' aggregator:
+ * CSR by receiver, STABLE (in-segment order = ascending edge index), so the in-order serial
+ * accumulation reproduces TF-CPU UnsortedSegmentSum bit for bit.
+ *   rowptr[N+1], perm[E] (edge ids in CSR order), csr_senders[E] = senders[perm[.]]
+ * workspace: gnf_build_csr_workspace(N, E) bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t gnf_build_csr_workspace(int64_t n_nodes, int64_t n_edges);
+int gnf_build_csr(const int32_t* receivers, const int32_t* senders, int64_t n_nodes, int64_t n_edges,
+                  int32_t* rowptr, int32_t* perm, int32_t* csr_senders,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Error behaviour of the reference (TF InvalidArgumentError on out-of-range gather/segment ids,
+ * gnn.py:151 / gnn.py:103): counts indices outside [0, n_nodes) into *bad_count (device int32). */
+int gnf_validate_indices(const int32_t* senders, const int32_t* receivers, int64_t n_nodes,
+                         int64_t n_edges, int32_t* bad_count, void* stream);
+
+/* a3  gn.blocks.EdgeBlock(IdentityModule, use_sender_nodes) (gnn.py:135-140,151-152):
+ * edges[e,:] = x[senders[e],:].  x [N,H] f32, edges [E,H] f32. */
+int gnf_gather_rows(const float* x, int32_t h, const int32_t* senders, int64_t n_edges,
+                    float* edges, void* stream);
+
+/* a4  gn.blocks.ReceivedEdgesToNodesAggregator(reducer) (gnn.py:103-104,117-118) on a
+ * materialised edge tensor: out[r,:] = sum_{e: receivers[e]=r} edges[e,:] in ascending e
+ * (mean: / max(count,1)).  Needs rowptr/perm from gnf_build_csr. */
+int gnf_segment_sum(const float* edges, int32_t h, const int32_t* rowptr, const int32_t* perm,
+                    int64_t n_nodes, int32_t agg, float* out, void* stream);
+
+/* a3+a4 fused (what NodeBlockGNN._build, gnn.py:155-156, amounts to before the MLP):
+ * out[r,:] = reduce_{e: receivers[e]=r} x[senders[e],:].  Same order, same bits as
+ * gnf_gather_rows followed by gnf_segment_sum. */
+int gnf_gather_segment_sum(const float* x, int32_t h, const int32_t* rowptr,
+                           const int32_t* csr_senders, int64_t n_nodes, int32_t agg,
+                           float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2  GRevNet.__init__ (gnn.py:274-302): the 4*T message-passing GNNs s[2][T], t[2][T]
+ * (4 when weight_sharing), each a NodeBlockGNN (gnn.py:143-156) around one
+ * make_mlp_model MLP (gnn.py:159-180).
+ *
+ * params: flat float32 DEVICE buffer, MLPs in the order
+ *     which (0 = s, 1 = t) -> half (0, 1) -> step (0..T-1; one entry when weight_sharing)
+ * each MLP as  W0[in,L] b0[L]  W1[L,L] b1[L] ... W_{K-1}[L,H] b_{K-1}[H],  row-major,
+ * Sonnet Linear convention y = x @ W + b;  in = D (concat) or D/2 (agg_then), H = D/2.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gnf_flow_desc {
+  int32_t num_timesteps;       /* T   GRevNet(num_timesteps)       gnn.py:276 */
+  int32_t node_embedding_dim;  /* D   GRevNet(node_embedding_dim)  gnn.py:277 (must be even) */
+  int32_t latent_dim;          /* L   make_mlp_model(latent_dim)   gnn.py:159 */
+  int32_t num_layers;          /* K   make_mlp_model(num_layers)   gnn.py:161 (>= 2) */
+  int32_t agg;                 /* GNF_AGG_*   */
+  int32_t block;               /* GNF_BLOCK_* */
+  int32_t act;                 /* GNF_ACT_*   */
+  int32_t weight_sharing;      /* gnn.py:279,283-286 */
+  float   eps;                 /* AggThenMLPBlock epsilon, gnn.py:121 */
+  int32_t reserved[3];
+} gnf_flow_desc;
+
+typedef struct gnf_flow gnf_flow;   /* opaque: packed device-side weights */
+
+int64_t gnf_flow_param_count(const gnf_flow_desc* desc);
+int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* desc);
+/* (re)pack weights from the flat buffer; call after every optimiser step */
+int gnf_flow_set_params(gnf_flow* flow, const float* params, void* stream);
+int gnf_flow_destroy(gnf_flow* flow);
+/* 1 if (flow shape, math) is served by the fused tcgen05 kernel, 0 if only GNF_MATH_FP32 is */
+int gnf_flow_supports(const gnf_flow* flow, int32_t math);
+
+/* ------------------------------------------------------------------------------------------
+ * a7  GRevNet.f (gnn.py:304-341) / GRevNet.g (gnn.py:343-373) / _build(inverse) (gnn.py:379-381),
+ * use_batch_norm = False.
+ *   x, z       [N, D] f32 row-major
+ *   ldj        device double[1]: sum over steps/halves/nodes/features of s  (gnn.py:322,337)
+ * workspace: gnf_grevnet_workspace(flow, N, math) bytes, 256-byte aligned.
+ * One fused kernel per half coupling step (aggregate + s-MLP + t-MLP + affine update +
+ * log-det partial) when math != GNF_MATH_FP32.
+ * ------------------------------------------------------------------------------------------ */
+size_t gnf_grevnet_workspace(const gnf_flow* flow, int64_t n_nodes, int32_t math);
+int gnf_grevnet_forward(const gnf_flow* flow, const float* x, int64_t n_nodes, int64_t n_edges,
+                        const int32_t* rowptr, const int32_t* csr_senders,
+                        float* z, double* ldj, int32_t math,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int gnf_grevnet_inverse(const gnf_flow* flow, const float* z, int64_t n_nodes, int64_t n_edges,
+                        const int32_t* rowptr, const int32_t* csr_senders,
+                        float* x, int32_t math,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* One full coupling step i (both halves) of f / g on planar halves: x0, x1 [N, HP] with
+ * HP = gnf_padded_half(D/2) floats per row (zero padded), updated in place.
+ * ldj_accum (device double[1]) is ADDED to (forward only; may be NULL for inverse). */
+int32_t gnf_padded_half(int32_t h);
+int gnf_coupling_step(const gnf_flow* flow, int32_t step, int32_t inverse,
+                      float* x0, float* x1, int64_t n_nodes, int64_t n_edges,
+                      const int32_t* rowptr, const int32_t* csr_senders,
+                      double* ldj_accum, int32_t math,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* One message-passing GNN of the flow on its own: NodeBlockGNN._build (gnn.py:155-156) =
+ * node_block(edge_block(graph)); x, out [N, D/2] f32.  which: 0 = s, 1 = t.  fp32 arithmetic.
+ * workspace: gnf_grevnet_workspace(flow, N, GNF_MATH_FP32). */
+int gnf_gnn_forward(const gnf_flow* flow, int32_t which, int32_t half, int32_t step,
+                    const float* x, int64_t n_nodes, int64_t n_edges,
+                    const int32_t* rowptr, const int32_t* csr_senders, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a8  log-prob assembly (run_grevnet.py:292-296, train_grevnet_with_data.py:348-350):
+ *   out[0] = log_prob_zs = sum_n ( -1/2 |z_n|^2 - D/2 ln 2pi )   (tfd.MultivariateNormalDiag)
+ *   out[1] = log_det_jacobian (copied from ldj)
+ *   out[2] = log_prob_xs = out[0] + out[1]
+ *   out[3] = N   (sum n_node, the per-node normaliser of run_grevnet.py:298)
+ * out: device double[4].  workspace: gnf_log_prob_workspace(N, D) bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t gnf_log_prob_workspace(int64_t n_nodes, int32_t d);
+int gnf_log_prob(const float* z, int64_t n_nodes, int32_t d, const double* ldj, double* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNF_B200_H_ */

@@ -1,0 +1,266 @@
+"""CPU oracle for the GRevNet hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product package never does: it fails loudly when
+the CUDA library is missing.
+
+PARITY UNPINNED: the reference (jliu/graph-normalizing-flows @ d8b9256) ships no
+tests and no golden vectors, and it cannot be imported here (needs TF 1.14,
+graph_nets, dm-sonnet 1.34, tensorflow-probability 0.7.0 -- none installed, no
+network).  This file restates the reference's algorithm op for op in numpy; what
+pins it are the known-answer tests K1..K8 in tests/ (round trip, zero weights,
+log-det vs. autograd Jacobian, graph independence, index formulas).
+
+Third-party semantics restated from their published behaviour (not in the tree):
+  graph_nets (unpinned, 1.0.x)   broadcast_sender_nodes_to_edges = gather(nodes, senders)
+                                 ReceivedEdgesToNodesAggregator(r) = r(edges, receivers, sum(n_node))
+  TF 1.14                        unsorted_segment_sum: CPU kernel accumulates serially in
+                                 ascending edge index; unsorted_segment_mean = sum / max(count, 1);
+                                 leaky_relu alpha = 0.2
+  dm-sonnet 1.34                 Linear: x @ W + b;  nets.MLP: act after every layer but the last
+  tensorflow-probability 0.7.0   MultivariateNormalDiag(0, I).log_prob(z) = -1/2 |z|^2 - D/2 ln(2 pi)
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import collections
+import math
+
+import numpy as np
+
+# graph_nets.graphs.GraphsTuple field order [upstream]; used at gnn.py:307-308
+# through .replace(nodes=...).
+_FIELDS = ("nodes", "edges", "receivers", "senders", "globals", "n_node", "n_edge")
+
+
+class GraphsTuple(collections.namedtuple("GraphsTuple", _FIELDS)):
+    def replace(self, **kwargs):
+        return self._replace(**kwargs)
+
+
+LOG_2PI = math.log(2.0 * math.pi)
+
+
+# --------------------------------------------------------------------------- #
+# a6  make_mlp_model  (gnn.py:159-180)
+# --------------------------------------------------------------------------- #
+def activation(x, kind):
+    """tf.nn.leaky_relu (alpha=0.2) for the *_then_mlp factories (run_grevnet.py:158,166,179),
+    tf.nn.relu is make_mlp_model's default (gnn.py:162)."""
+    if kind == "leaky_relu":
+        return np.maximum(x, x.dtype.type(0.2) * x)
+    if kind == "relu":
+        return np.maximum(x, x.dtype.type(0))
+    raise ValueError(kind)
+
+
+def mlp_forward(h, layers, act):
+    """snt.nets.MLP(activate_final=False): gnn.py:167-180.  layers = [(W[in,out], b[out]), ...]."""
+    last = len(layers) - 1
+    for i, (w, b) in enumerate(layers):
+        h = h @ w + b
+        if i != last:
+            h = activation(h, act)
+    return h
+
+
+def glorot_truncated_normal(rng, fan_in, fan_out, dtype=np.float32):
+    """tf.initializers.glorot_normal (gnn.py:172): VarianceScaling(1, fan_avg, truncated_normal):
+    stddev = sqrt(2/(fan_in+fan_out)) / 0.8796..., resampled outside 2 stddev."""
+    std = math.sqrt(2.0 / (fan_in + fan_out)) / 0.87962566103423978
+    return truncated_normal(rng, (fan_in, fan_out), std, dtype)
+
+
+def truncated_normal(rng, shape, std, dtype=np.float32):
+    """tf.initializers.truncated_normal (gnn.py:173): N(0, std) re-drawn beyond 2 std."""
+    out = rng.standard_normal(shape)
+    bad = np.abs(out) > 2.0
+    while bad.any():
+        out[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(out) > 2.0
+    return (out * std).astype(dtype)
+
+
+def init_mlp(rng, in_dim, latent_dim, out_dim, num_layers, bias_init_stddev=0.1,
+             last_layer_scale=1.0, dtype=np.float32):
+    """Layer sizes [latent]*(K-1)+[out] (gnn.py:165-166)."""
+    sizes = [latent_dim] * (num_layers - 1) + [out_dim]
+    layers = []
+    d = in_dim
+    for i, o in enumerate(sizes):
+        w = glorot_truncated_normal(rng, d, o, dtype)
+        b = truncated_normal(rng, (o,), bias_init_stddev, dtype)
+        if i == len(sizes) - 1:
+            w = (w * last_layer_scale).astype(dtype)
+            b = (b * last_layer_scale).astype(dtype)
+        layers.append((w, b))
+        d = o
+    return layers
+
+
+# --------------------------------------------------------------------------- #
+# a3 / a4  sender gather and received-edges aggregator
+# --------------------------------------------------------------------------- #
+def gather_senders(nodes, senders):
+    """EdgeBlock(IdentityModule, use_sender_nodes only), gnn.py:135-140,151-152:
+    edges[e,:] = nodes[senders[e],:]."""
+    return nodes[senders]
+
+
+def segment_sum_serial(edges, receivers, num_segments):
+    """tf.unsorted_segment_sum on CPU (gnn.py:239-257 pass it as the reducer): serial
+    accumulation in ascending edge index.  np.add.at is unbuffered and in index order,
+    so per (segment, feature) the floating-point add order is exactly that."""
+    out = np.zeros((num_segments, edges.shape[1]), dtype=edges.dtype)
+    np.add.at(out, receivers, edges)
+    return out
+
+
+def segment_mean_serial(edges, receivers, num_segments):
+    """tf.unsorted_segment_mean [upstream]: segment_sum / max(count, 1)."""
+    s = segment_sum_serial(edges, receivers, num_segments)
+    cnt = np.bincount(receivers, minlength=num_segments).astype(edges.dtype)
+    return s / np.maximum(cnt, edges.dtype.type(1))[:, None]
+
+
+def aggregate(nodes, senders, receivers, agg):
+    edges = gather_senders(nodes, senders)
+    if agg == "sum":
+        return segment_sum_serial(edges, receivers, nodes.shape[0])
+    if agg == "mean":
+        return segment_mean_serial(edges, receivers, nodes.shape[0])
+    raise ValueError(agg)
+
+
+# --------------------------------------------------------------------------- #
+# a5  node blocks  +  NodeBlockGNN
+# --------------------------------------------------------------------------- #
+def node_block_gnn(nodes, senders, receivers, layers, cfg):
+    """NodeBlockGNN._build (gnn.py:155-156) with ConcatThenMLPBlock (gnn.py:107-111)
+    or AggThenMLPBlock (gnn.py:122-126)."""
+    agg = aggregate(nodes, senders, receivers, cfg["agg"])
+    if cfg["block"] == "concat":
+        h = np.concatenate([nodes, agg], axis=1)
+    elif cfg["block"] == "agg_then":
+        h = nodes.dtype.type(cfg["eps"]) * nodes + agg
+    else:
+        raise ValueError(cfg["block"])
+    return mlp_forward(h, layers, cfg["act"])
+
+
+# --------------------------------------------------------------------------- #
+# a7  GRevNet.f / GRevNet.g   (gnn.py:304-373)
+# --------------------------------------------------------------------------- #
+def _st(params, which, half, i):
+    if params["weight_sharing"]:          # gnn.py:284-286,316-319
+        return params[which][half]
+    return params[which][half][i]         # gnn.py:320-321
+
+
+def grevnet_f(nodes, senders, receivers, params):
+    """GRevNet.f (gnn.py:304-341), use_batch_norm=False.  Returns (z, log_det_jacobian);
+    ldj accumulates in python order exactly as gnn.py:322,337 do."""
+    cfg = params["cfg"]
+    dt = nodes.dtype
+    h = nodes.shape[1] // 2
+    x0, x1 = nodes[:, :h].copy(), nodes[:, h:].copy()       # tf.split, gnn.py:306
+    ldj = dt.type(0)
+    for i in range(params["T"]):
+        s = node_block_gnn(x0, senders, receivers, _st(params, "s", 0, i), cfg)
+        t = node_block_gnn(x0, senders, receivers, _st(params, "t", 0, i), cfg)
+        ldj = ldj + np.sum(s, dtype=dt)                       # gnn.py:322
+        x1 = x1 * np.exp(s) + t                               # gnn.py:323
+        s = node_block_gnn(x1, senders, receivers, _st(params, "s", 1, i), cfg)
+        t = node_block_gnn(x1, senders, receivers, _st(params, "t", 1, i), cfg)
+        ldj = ldj + np.sum(s, dtype=dt)                       # gnn.py:337
+        x0 = x0 * np.exp(s) + t                               # gnn.py:338
+    return np.concatenate([x0, x1], axis=1), ldj              # gnn.py:340-341
+
+
+def grevnet_g(nodes, senders, receivers, params):
+    """GRevNet.g (gnn.py:343-373), use_batch_norm=False."""
+    cfg = params["cfg"]
+    h = nodes.shape[1] // 2
+    z0, z1 = nodes[:, :h].copy(), nodes[:, h:].copy()
+    for i in reversed(range(params["T"])):                   # gnn.py:347
+        s = node_block_gnn(z1, senders, receivers, _st(params, "s", 1, i), cfg)
+        t = node_block_gnn(z1, senders, receivers, _st(params, "t", 1, i), cfg)
+        z0 = (z0 - t) * np.exp(-s)                            # gnn.py:359
+        s = node_block_gnn(z0, senders, receivers, _st(params, "s", 0, i), cfg)
+        t = node_block_gnn(z0, senders, receivers, _st(params, "t", 0, i), cfg)
+        z1 = (z1 - t) * np.exp(-s)                            # gnn.py:372
+    return np.concatenate([z0, z1], axis=1)
+
+
+def grevnet_call(graph, params, inverse=True):
+    """GRevNet._build (gnn.py:379-381): inverse=True is the data->latent (density) direction."""
+    if inverse:
+        z, ldj = grevnet_f(graph.nodes, graph.senders, graph.receivers, params)
+        return graph.replace(nodes=z), ldj
+    return graph.replace(nodes=grevnet_g(graph.nodes, graph.senders, graph.receivers, params))
+
+
+# --------------------------------------------------------------------------- #
+# a8  log-prob assembly  (run_grevnet.py:290-302, train_grevnet_with_data.py:346-355)
+# --------------------------------------------------------------------------- #
+def log_prob(z_nodes, ldj, n_node):
+    """Returns the scalars the scripts log: log_prob_zs, log_prob_xs, total_loss and
+    the per-node normalisations by sum(n_node)."""
+    dt = z_nodes.dtype
+    d = z_nodes.shape[1]
+    per_node = dt.type(-0.5) * np.sum(z_nodes * z_nodes, axis=1, dtype=dt) - dt.type(0.5 * d * LOG_2PI)
+    log_prob_zs = np.sum(per_node, dtype=dt)                  # run_grevnet.py:294
+    log_prob_xs = log_prob_zs + dt.type(ldj)                  # run_grevnet.py:295
+    total_loss = -log_prob_xs                                 # run_grevnet.py:296
+    num_nodes = dt.type(np.sum(n_node))                       # run_grevnet.py:298
+    return {
+        "log_prob_zs": log_prob_zs,
+        "log_det_jacobian": dt.type(ldj),
+        "log_prob_xs": log_prob_xs,
+        "total_loss": total_loss,
+        "num_nodes": num_nodes,
+        "loss_per_node": total_loss / num_nodes,
+        "log_prob_xs_per_node": log_prob_xs / num_nodes,
+        "log_prob_zs_per_node": log_prob_zs / num_nodes,
+        "log_det_jacobian_per_node": dt.type(ldj) / num_nodes,
+    }
+
+
+# --------------------------------------------------------------------------- #
+# a2  GRevNet.__init__  (gnn.py:274-302): 4*T MLPs (or 4 when weight_sharing)
+# --------------------------------------------------------------------------- #
+def make_params(seed, T, D, latent_dim=256, num_layers=5, agg="sum", block="concat", eps=1.0,
+                act="leaky_relu", bias_init_stddev=0.1, last_layer_scale=1.0,
+                weight_sharing=False, dtype=np.float32):
+    if D % 2:
+        raise ValueError("node_embedding_dim must be even (tf.split, gnn.py:306)")
+    h = D // 2
+    in_dim = D if block == "concat" else h
+    rng = np.random.default_rng(seed)
+
+    def mk():
+        return init_mlp(rng, in_dim, latent_dim, h, num_layers, bias_init_stddev,
+                        last_layer_scale, dtype)
+
+    if weight_sharing:
+        s = [mk(), mk()]
+        t = [mk(), mk()]
+    else:                                   # construction order of gnn.py:292-299
+        s = [[mk() for _ in range(T)], [mk() for _ in range(T)]]
+        t = [[mk() for _ in range(T)], [mk() for _ in range(T)]]
+    return {"T": T, "D": D, "s": s, "t": t, "weight_sharing": weight_sharing,
+            "cfg": {"agg": agg, "block": block, "eps": float(eps), "act": act}}
+
+
+def cast_params(params, dtype):
+    def c(m):
+        return [(w.astype(dtype), b.astype(dtype)) for (w, b) in m]
+    out = dict(params)
+    for k in ("s", "t"):
+        if params["weight_sharing"]:
+            out[k] = [c(m) for m in params[k]]
+        else:
+            out[k] = [[c(m) for m in half] for half in params[k]]
+    return out
