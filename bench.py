@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- GRevNet fwd+logdet node-updates/sec (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference            # the CPU restatement of the reference path
+
+A "step" is one pass of the hot path over one batch: GRevNet.f (12 fused half-coupling kernels
+at T=6) + log-prob assembly.  Workload (BASELINE configs[1]): community_medium_4_128 graphs,
+B graphs per GPU drawn with replacement (rng 12345 + rank), D=14, T=6, sum_concat_then_mlp,
+L=256, K=5, leaky_relu, weights Glorot/trunc-normal seed 12345 with the last layer x0.05
+(keeps the reference's unclamped exp(s) finite).  node_updates = N * T * 2.
+
+value : device-resident throughput (batch + CSR already in HBM), CUDA events per step, L2 flushed
+        between steps, max over ranks.
+e2e   : same metric through the public API from pinned HOST buffers: H2D of the packed batch
+        (nodes, senders, receivers, n_node, n_edge), index validation + CSR build, f, log-prob,
+        D2H of the 4 scalars -- every step, host wall clock.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GRevNet fwd+logdet node-updates/sec"
+UNIT = "node-updates/s"
+D, T, L, K = 14, 6, 256, 5
+LAST_SCALE = 0.05
+SEED = 12345
+FLOPS_PER_NODE_UPDATE = 2 * 2 * (D * L + (K - 2) * L * L + L * (D // 2))      # 807 936  
+FAMILY = "community_medium_4_128"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_batch(n_graphs, seed):
+    from graph_normalizing_flows_b200 import graph_data as GD
+    npz = np.load(os.path.join(ROOT, "tests", "golden", f"graphs_{FAMILY}.npz"))
+    ds = GD.GraphDataset(None, D, structures=GD.structures_from_fixture(npz))
+    return ds.draw_batch(n_graphs, np.random.default_rng(seed))
+
+
+def make_oracle_params():
+    from oracle import gnf_oracle as O
+    return O.make_params(SEED, T, D, L, K, agg="sum", block="concat", act="leaky_relu",
+                         bias_init_stddev=0.1, last_layer_scale=LAST_SCALE)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=1)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_graphs, steps, warmup):
+    """The reference's CPU path (torch-CPU restatement, all host threads) on a bounded sample."""
+    import torch
+    from oracle import gnf_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = make_batch(n_graphs, SEED)
+    p = OT.params_to_torch(make_oracle_params())
+    nodes = torch.from_numpy(g.nodes)
+    s, r = torch.from_numpy(g.senders).long(), torch.from_numpy(g.receivers).long()
+    n = nodes.shape[0]
+    times = []
+    lp = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        z, ldj = OT.grevnet_f(nodes, s, r, p)
+        lp = float(OT.log_prob_xs(z, ldj))
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return {"value": n * T * 2 / sec, "sec_per_step": sec, "n_nodes": n, "n_edges": int(len(g.senders)),
+            "cores": torch.get_num_threads(), "log_prob_xs": lp,
+            "sample": f"{FAMILY} B={n_graphs} graphs (N={n} nodes), one GRevNet.f + log-prob per step, "
+                      f"{steps} timed steps after {warmup} warm-up, torch-CPU fp32"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs-per-gpu", type=int, default=4096)
+    ap.add_argument("--math", default="tc3x", choices=["tc3x", "fp32", "bf16", "tc3x_bf16"])
+    ap.add_argument("--cpu-graphs", type=int, default=1024, help="bounded CPU-baseline sample (graphs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seg-graphs", type=int, default=65536, help="batch for the scatter-reduce HBM roofline")
+    ap.add_argument("--profile", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    config = {"workload": f"{FAMILY} graphs, 6-step GRevNet, node_dim=14, sum_concat_then_mlp L=256 K=5 leaky_relu",
+              "graphs_per_gpu": args.graphs_per_gpu, "T": T, "D": D, "L": L, "K": K,
+              "parallelism": f"graph-sharded dp{world}", "last_layer_scale": LAST_SCALE}
+
+    # ---------------------------------------------------------------- reference arm (CPU) ---
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(args.cpu_graphs, args.steps, warmup)
+        config["cpu_sample_graphs"] = args.cpu_graphs
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": r["sec_per_step"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------------- B200 arm -------
+    import torch
+    import torch.distributed as dist
+    import graph_normalizing_flows_b200 as G
+    from graph_normalizing_flows_b200 import _lib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    host = make_batch(args.graphs_per_gpu, SEED + rank)          # each rank its own shard (weak scaling)
+    n_nodes, n_edges = int(host.nodes.shape[0]), int(len(host.senders))
+    node_updates = n_nodes * T * 2
+    net = H.make_grevnet(make_oracle_params(), L, K, device=dev, math=args.math)
+    graph = host.to(dev)
+    torch.cuda.synchronize()
+    G.graphs.structure_of(graph)                                  # CSR build, reported separately below
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(g):
+        out = G.loss.mvn_log_prob_sum(*_fz(net, g))
+        if world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)           # the one collective of the path
+        return out
+
+    def _fz(net, g):
+        z, ldj = net.f64(g)
+        return z.nodes, ldj
+
+    for _ in range(warmup):
+        out = step(graph)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    lib.gnf_launch_count(1)
+    if args.profile:
+        torch.cuda.profiler.start()
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)                                 # flush L2 (256 MB > 126 MB)
+        starts[i].record()
+        out = step(graph)
+        stops[i].record()
+    torch.cuda.synchronize()
+    if args.profile:
+        torch.cuda.profiler.stop()
+    launches = int(lib.gnf_launch_count(1))
+    if world > 1:
+        dist.barrier()
+    ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = torch.tensor([float(sum(ms))], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(node_updates)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = float(work.item()) / (ms_per_step * 1e-3)
+    log_prob_xs = float(out[2].item())
+
+    # ---- dominant kernel: one fused half-coupling launch (k_coupling_tc) ----------------------
+    roof = None
+    if args.math != "fp32":
+        handle = net._flow.ensure(net.params.data)
+        m = _lib.MATH[args.math]
+        wsb = lib.gnf_grevnet_workspace(handle, n_nodes, m)
+        ws = _lib.workspace(wsb, dev)
+        hp = lib.gnf_padded_half(D // 2)
+        x0 = torch.zeros(n_nodes, hp, device=dev)
+        x1 = torch.zeros(n_nodes, hp, device=dev)
+        x0[:, :D // 2] = graph.nodes[:, :D // 2]
+        x1[:, :D // 2] = graph.nodes[:, D // 2:]
+        st = G.graphs.structure_of(graph)
+        stream = _lib.stream_ptr(dev)
+        reps = 10
+
+        def one(stepi):
+            _lib.check(lib.gnf_coupling_step(handle, stepi % T, 0, _lib.ptr(x0), _lib.ptr(x1), n_nodes, n_edges,
+                                             _lib.ptr(st.rowptr), _lib.ptr(st.csr_senders), None, m, _lib.ptr(ws),
+                                             wsb, stream))
+        for i in range(3):
+            one(i)
+        x0[:, :D // 2] = graph.nodes[:, :D // 2]
+        x1[:, :D // 2] = graph.nodes[:, D // 2:]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            one(i)                                                # 2 launches of k_coupling_tc each
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / (2 * reps)
+        flops = n_nodes * FLOPS_PER_NODE_UPDATE
+        ach = flops / (k_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "k_coupling_tc (one fused half coupling step)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                "ms_per_launch": k_ms, "algorithmic_flops_per_launch": flops,
+                "executed_mma_flops_per_algorithmic_flop": 3 if args.math.startswith("tc3x") else 1,
+                "share_of_step": (2 * T * k_ms) / ms_per_step}
+
+    # ---- scatter-reduce sub-op against the HBM roofline (standalone gather+segment-sum) --------
+    seg = None
+    if rank == 0:
+        big = make_batch(args.seg_graphs, SEED)
+        nb, eb, h = int(big.nodes.shape[0]), int(len(big.senders)), D // 2
+        gb = big.replace(nodes=np.ascontiguousarray(big.nodes[:, :h])).to(dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stb = G.graphs.BatchStructure(gb.senders, gb.receivers, nb)
+        torch.cuda.synchronize()
+        csr_ms = (time.perf_counter() - t0) * 1e3
+        outb = torch.empty_like(gb.nodes)
+        stream = _lib.stream_ptr(dev)
+
+        def seg_once():
+            _lib.check(lib.gnf_gather_segment_sum(_lib.ptr(gb.nodes), h, _lib.ptr(stb.rowptr), _lib.ptr(stb.csr_senders),
+                                                  nb, 0, _lib.ptr(outb), stream))
+        for _ in range(3):
+            seg_once()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        reps = 10
+        for i in range(reps):
+            flush_buf.fill_(i)
+            e0.record()
+            seg_once()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        seg_ms = tot / reps
+        bytes_alg = eb * (8 + 4 * h) + 4 * nb * h                  # SURVEY §8d "THE figure"
+        ach = bytes_alg / (seg_ms * 1e-3) / 1e9
+        seg = {"bound": "hbm", "kernel": "k_segment_reduce (gather + segment-sum, standalone)",
+               "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+               "traffic": None, "ms_per_launch": seg_ms, "algorithmic_bytes_per_launch": bytes_alg,
+               "n_nodes": nb, "n_edges": eb, "csr_build_ms": csr_ms,
+               "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
+        del gb, outb, stb
+
+    # ---- end to end through the public API from pinned host memory ---------------------------
+    pinned = G.GraphsTuple(*[torch.from_numpy(np.ascontiguousarray(v)).pin_memory() if v is not None else None
+                             for v in host])
+    h2d = sum(v.numel() * v.element_size() for v in pinned if v is not None)
+
+    def e2e_step():
+        g = pinned.to(dev, non_blocking=True)
+        res = G.loss.log_prob(net, g)                             # validate + CSR + f + log-prob
+        vec = torch.stack([res["log_prob_zs"], res["log_det_jacobian"], res["log_prob_xs"], res["num_nodes"]])
+        if world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        return vec.cpu()                                          # D2H of the 4 scalars (sync)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vec = e2e_step()
+    torch.cuda.synchronize()
+    e2e_sec = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_sec, op=dist.ReduceOp.MAX)
+    e2e_value = float(work.item()) / float(e2e_sec.item())
+    clocks = sampler.stop()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ---------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.cpu_graphs, 3, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        config.update({"n_nodes_per_gpu": n_nodes, "n_edges_per_gpu": n_edges, "math": args.math,
+                       "l2": "flushed between timed steps (256 MB write)",
+                       "node_update": "one node through one half coupling (aggregate + s-MLP + t-MLP + affine)",
+                       "log_prob_xs": log_prob_xs})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": {"tc3x": "f16x2-split/f32-acc", "tc3x_bf16": "bf16x2-split/f32-acc",
+                                               "bf16": "bf16", "fp32": "f32"}[args.math],
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32},
+                "gpu_launches": launches, "roofline": roof, "roofline_segment_sum": seg, "cpu_baseline": cpu,
+                "effective_tflops": value * FLOPS_PER_NODE_UPDATE / 1e12}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,7 @@ SIGNATURES = {
     "gnf_abi_version": (C.c_int, []),
     "gnf_last_error": (C.c_char_p, []),
     "gnf_launch_count": (_i64, [C.c_int]),
+    "gnf_debug_set_trace": (C.c_int, [_p]),
     "gnf_build_csr_workspace": (_sz, [_i64, _i64]),
     "gnf_build_csr": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "gnf_validate_indices": (C.c_int, [_p, _p, _i64, _i64, _p, _p]),

@@ -90,6 +90,7 @@ struct Flow {
 size_t tc_bytes_per_mlp(int L, int K);
 int tc_pack_mlp(const Flow& f, int mlp, const float* params, void* stream);
 bool tc_shape_supported(const Flow& f);
+void tc_set_trace(void* buf);
 int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
                      const float* xa, float* xb, int64_t n_nodes,
                      const int32_t* rowptr, const int32_t* csr_senders,

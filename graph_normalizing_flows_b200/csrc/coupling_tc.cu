@@ -34,12 +34,14 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kK0 = 16;      // padded MLP input width  (in_dim <= 16)
 constexpr int kNOut = 16;    // padded MLP output width (H <= 16)
-constexpr int kStages = 5;
+constexpr int kStages = 4;
 constexpr int kStageBytes = 32768;
-constexpr int kThreads = 320;  // warp0 producer, warp1 MMA, warps2-5 epilogue, warps6-9 gather
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;   // two warps per TMEM lane quarter
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kGatherThreads = 128;
+constexpr int kThreads = 64 + kEpiThreads + kGatherThreads;  // warp0 producer, warp1 MMA, 8 epilogue, 4 gather
 constexpr int kNS = 2;
+constexpr int kMaxNA = 4;      // a_ready barriers: one per 64 converted feature columns
 
 template <int LAT>
 struct Geo {
@@ -52,6 +54,8 @@ struct Geo {
   static constexpr int L0_BYTES = 2 * L0_MAT_BYTES;
   static constexpr int LAST_MAT_BYTES = kNOut * LAT * 2;
   static constexpr int LAST_BYTES = 2 * LAST_MAT_BYTES;
+  static constexpr int NA = LAT / 64;                                    // a_ready groups
+  static constexpr int GPH = NH / 64;                                    // groups per acc half
   static_assert(CHUNK_BYTES <= kStageBytes && L0_BYTES <= kStageBytes && LAST_BYTES <= kStageBytes, "");
 };
 
@@ -85,6 +89,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+// one lane of a converged warp; ptxas recognises elect.sync and issues the tcgen05 ops that
+// follow once, with warp-uniform operands kept in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -182,10 +199,6 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   }
 }
 
-__device__ __forceinline__ float act_fn(float v, int act) {
-  return act == GNF_ACT_LEAKY_RELU ? fmaxf(v, 0.2f * v) : fmaxf(v, 0.f);
-}
-
 struct TcParams {
   const float* xa;
   float* xb;
@@ -198,29 +211,66 @@ struct TcParams {
   int K, H, HP, concat, mean, act, inverse;
   float eps;
   double* partials;
+  unsigned long long* trace;   // optional timeline of CTA 0 (gnf_debug_set_trace); null in production
+};
+
+// timeline entry: [63:56] event, [55:48] m*16+l, [47:40] ph*4+kc, [39:0] clock
+struct Tracer {
+  unsigned long long* buf;
+  int n;
+  __device__ __forceinline__ void init(unsigned long long* base, int role, bool on) {
+    buf = on && base ? base + role * 2048 : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void ev(int event, int ml, int pk) {
+    if (buf && n < 2047) {
+      buf[1 + n++] = ((unsigned long long)event << 56) | ((unsigned long long)(ml & 255) << 48) |
+                     ((unsigned long long)(pk & 255) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+      buf[0] = n;
+    }
+  }
 };
 
 struct __align__(8) Barriers {
   uint64_t full[kStages], empty[kStages];
-  uint64_t acc_full[kNS], a_ready[kNS];
+  uint64_t acc_full[kNS], a_ready[kMaxNA];
   uint64_t h_full[2], h_empty[2];
 };
 
 template <int LAT>
 constexpr size_t smem_bytes() {
   return 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * 2 * 4096 /*h tiles*/ +
-         2 * kMaxLayers * LAT * 4 /*bias*/ + kGatherThreads * 17 * 4 /*h staging*/ + sizeof(Barriers) + 64;
+         (kMaxLayers - 1) * 4096 /*selector A tiles*/ + 2 * LAT * 32 /*bias B tiles*/ +
+         2 * kNOut * 4 /*last-layer bias*/ + kGatherThreads * 17 * 4 /*h staging*/ + sizeof(Barriers) + 128;
 }
 
-template <int LAT, int NPROD, bool BF16>
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  return ACT == GNF_ACT_LEAKY_RELU ? fmaxf(v, 0.2f * v) : fmaxf(v, 0.f);
+}
+
+// activation + hi/lo split of one 32-column accumulator chunk, written back in place
+template <int NPROD, bool BF16, int ACT>
+__device__ __forceinline__ void convert_chunk(uint32_t taddr, const uint32_t (&v)[32]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    split_pair<BF16>(act_t<ACT>(__uint_as_float(v[2 * j])), act_t<ACT>(__uint_as_float(v[2 * j + 1])), hi[j], lo[j]);
+  tmem_st16(taddr, hi);
+  if (NPROD == 3) tmem_st16(taddr + 16, lo);
+}
+
+template <int LAT, int NPROD, bool BF16, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
   using G = Geo<LAT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
   uint8_t* hbuf = ring + kStages * kStageBytes;                 // [buf][hi|lo][4096]
-  float* bias_s = (float*)(hbuf + 2 * 2 * 4096);                // [2][kMaxLayers][LAT]
-  float* hstage = bias_s + 2 * kMaxLayers * LAT;                // [128][17]
+  uint8_t* sel = hbuf + 2 * 2 * 4096;                           // [kMaxLayers-1][4096] selector A tiles
+  uint8_t* btile = sel + (kMaxLayers - 1) * 4096;               // [2][LAT*32] bias B tiles (K-major, K=16)
+  float* blast = (float*)(btile + 2 * LAT * 32);                // [2][16] last-layer bias
+  float* hstage = blast + 2 * kNOut;                            // [128][17]
   Barriers* bars = (Barriers*)(hstage + kGatherThreads * 17);
   uint32_t* tmem_slot = (uint32_t*)(bars + 1);
   double* ldj_red = (double*)(tmem_slot + 2);                   // [4]
@@ -235,21 +285,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
-    for (int i = 0; i < kNS; ++i) {
-      mbar_init(smem_u32(&bars->acc_full[i]), 1);
-      mbar_init(smem_u32(&bars->a_ready[i]), kEpiThreads);
-    }
+    for (int i = 0; i < kNS; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1);
+    for (int i = 0; i < kMaxNA; ++i) mbar_init(smem_u32(&bars->a_ready[i]), kEpiThreads);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->h_full[i]), kGatherThreads);
       mbar_init(smem_u32(&bars->h_empty[i]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    fence_proxy_async();
   }
-  for (int i = tid; i < 2 * K * LAT; i += kThreads) {
-    int m = i / (K * LAT), r = i - m * (K * LAT);
-    int l = r / LAT, c = r - l * LAT;
-    bias_s[(m * kMaxLayers + l) * LAT + c] = p.bias[m][l * 256 + c];
+  // Biases ride on the tensor pipe: layer l (< K-1) adds  Sel_l[128x16] * BiasTile[N x 16]^T  where
+  // Sel_l has ones in K-columns 2l, 2l+1 and BiasTile holds (hi, lo) of b_l in those columns.
+  {
+    const uint16_t one = BF16 ? 0x3F80 : 0x3C00;
+    for (int i = tid; i < (K - 1) * 128 * 16; i += kThreads) {
+      const int l = i / 2048, r = i - l * 2048, m = r >> 4, k = r & 15;
+      *reinterpret_cast<uint16_t*>(sel + l * 4096 + (k >> 3) * 2048 + m * 16 + (k & 7) * 2) =
+          (k == 2 * l || k == 2 * l + 1) ? one : (uint16_t)0;
+    }
+    for (int i = tid; i < 2 * LAT * 8; i += kThreads) {          // (mlp, n, layer slot j): k = 2j, 2j+1
+      const int m = i / (LAT * 8), r = i - m * (LAT * 8), n = r >> 3, j = r & 7;
+      const float b = (j < K - 1) ? p.bias[m][j * 256 + n] : 0.f;
+      uint32_t hi, lo;
+      split_pair<BF16>(b, 0.f, hi, lo);
+      const uint32_t packed = (hi & 0xFFFFu) | (lo << 16);       // k = 2j -> hi(b), k = 2j+1 -> lo(b)
+      const int k = 2 * j;
+      *reinterpret_cast<uint32_t*>(btile + m * (LAT * 32) + (k >> 3) * (LAT * 16) + (n >> 3) * 128 + (n & 7) * 16 +
+                                   (k & 7) * 2) = packed;
+    }
+    if (tid < 2 * kNOut) blast[tid] = p.bias[tid >> 4][(K - 1) * 256 + (tid & 15)];
+    fence_proxy_async();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -260,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ===== weight producer =====================================================================
@@ -289,177 +353,211 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer ==========================================================================
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the schedule, one elected lane issues =============
+    {
       constexpr uint32_t idesc_l0 = make_idesc(LAT, BF16);
       constexpr uint32_t idesc_h = make_idesc(G::NH, BF16);
       constexpr uint32_t idesc_last = make_idesc(kNOut, BF16);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t aready_par[kNS] = {0, 0};
-      int region = 0;
+      const uint32_t bar_full = smem_u32(&bars->full[0]), bar_empty = smem_u32(&bars->empty[0]);
+      const uint32_t bar_acc = smem_u32(&bars->acc_full[0]), bar_ready = smem_u32(&bars->a_ready[0]);
+      const uint32_t bar_hfull = smem_u32(&bars->h_full[0]), bar_hempty = smem_u32(&bars->h_empty[0]);
+      const uint32_t ring_u = smem_u32(ring), sel_u = smem_u32(sel), btile_u = smem_u32(btile);
+      const uint32_t hbuf_u = smem_u32(hbuf);
+      uint32_t stage = 0, phase = 0;
+      uint32_t aready_par = 0;          // bit q = parity to wait for on a_ready[q]
+      uint32_t region = 0;
       int it = 0;
+      Tracer tr;
+      tr.init(p.trace, 0, blockIdx.x == 0 && lane == 0);
       // column of the packed hi half of feature k inside a region (lo is 16 columns further)
-      auto a_col = [](int k) { return (k >> 5) * 32 + ((k & 31) >> 4) * 8; };
+      auto a_col = [](int k) { return (uint32_t)((k >> 5) * 32 + ((k & 31) >> 4) * 8); };
+      auto wait_groups = [&](uint32_t& waited, int q_lo, int q_hi) {
+        for (int q = q_lo; q <= q_hi; ++q)
+          if (!(waited >> q & 1u)) {
+            mbar_wait(bar_ready + 8 * q, (aready_par >> q) & 1u);
+            aready_par ^= 1u << q;
+            waited |= 1u << q;
+          }
+      };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(smem_u32(&bars->h_full[buf]), (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t h_hi = smem_u32(hbuf + buf * 8192);
+        const uint32_t buf = it & 1;
+        mbar_wait(bar_hfull + 8 * buf, (it >> 1) & 1);
+        tr.ev(10, 0, 0);
+        const uint32_t h_hi = hbuf_u + buf * 8192;
         const uint32_t h_lo = h_hi + 4096;
         for (int m = 0; m < 2; ++m) {
-          // ---- layer 0: A = h (smem), B = W0 chunk, N = LAT, K = 16 ---------------------------
+          const uint32_t bt = btile_u + m * (LAT * 32);
+          // ---- layer 0: bias, then A = h (smem), B = W0 chunk, N = LAT, K = 16 ----------------
           {
-            mbar_wait(smem_u32(&bars->full[stage]), phase);
-            tc_fence_after();
-            const uint32_t sb = smem_u32(ring + stage * kStageBytes);
-            const uint64_t a_hi = smem_desc(h_hi, 2048, 128), a_lo = smem_desc(h_lo, 2048, 128);
-            const uint64_t b_hi = smem_desc(sb, LAT * 16, 128);
-            const uint64_t b_lo = smem_desc(sb + G::L0_MAT_BYTES, LAT * 16, 128);
             const uint32_t d = tmem_base + region * LAT;
-            mma_ss(d, a_hi, b_hi, idesc_l0, 0);
-            if (NPROD == 3) {
-              mma_ss(d, a_lo, b_hi, idesc_l0, 1);
-              mma_ss(d, a_hi, b_lo, idesc_l0, 1);
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sb = ring_u + stage * kStageBytes;
+            if (elect_one()) {
+              mma_ss(d, smem_desc(sel_u, 2048, 128), smem_desc(bt, LAT * 16, 128), idesc_l0, 0);
+              const uint64_t a_hi = smem_desc(h_hi, 2048, 128), a_lo = smem_desc(h_lo, 2048, 128);
+              const uint64_t b_hi = smem_desc(sb, LAT * 16, 128);
+              const uint64_t b_lo = smem_desc(sb + G::L0_MAT_BYTES, LAT * 16, 128);
+              mma_ss(d, a_hi, b_hi, idesc_l0, 1);
+              if (NPROD == 3) {
+                mma_ss(d, a_lo, b_hi, idesc_l0, 1);
+                mma_ss(d, a_hi, b_lo, idesc_l0, 1);
+              }
+              tc_commit(bar_empty + 8 * stage);
+              tc_commit(bar_acc);
+              tc_commit(bar_acc + 8);
+              if (m == 1) tc_commit(bar_hempty + 8 * buf);
             }
-            tc_commit(smem_u32(&bars->empty[stage]));
+            __syncwarp();
+            tr.ev(11, m * 16, 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
-            tc_commit(smem_u32(&bars->acc_full[0]));
-            tc_commit(smem_u32(&bars->acc_full[1]));
-            if (m == 1) tc_commit(smem_u32(&bars->h_empty[buf]));
             region ^= 1;
           }
           // ---- hidden layers: A from TMEM (previous region), N = NH per half -----------------
           for (int l = 1; l < K - 1; ++l) {
             const uint32_t in_col = tmem_base + (region ^ 1) * LAT;
             const uint32_t out_col = tmem_base + region * LAT;
-            bool waited[kNS] = {false, false};
+            const uint32_t sel_l = sel_u + l * 4096;
+            uint32_t waited = 0;
+#pragma unroll 1
             for (int ph = 0; ph < kNS; ++ph) {
+              const uint32_t d = out_col + ph * G::NH;
+#pragma unroll 1
               for (int kc = 0; kc < G::NKC; ++kc) {
-                const int q_lo = (kc * G::KC) / G::NH, q_hi = (kc * G::KC + G::KC - 1) / G::NH;
-                for (int q = q_lo; q <= q_hi; ++q)
-                  if (!waited[q]) {
-                    mbar_wait(smem_u32(&bars->a_ready[q]), aready_par[q]);
-                    aready_par[q] ^= 1;
-                    waited[q] = true;
-                  }
-                mbar_wait(smem_u32(&bars->full[stage]), phase);
+                wait_groups(waited, (kc * G::KC) >> 6, (kc * G::KC + G::KC - 1) >> 6);
+                mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                const uint32_t sb = smem_u32(ring + stage * kStageBytes);
+                const uint32_t sb = ring_u + stage * kStageBytes;
+                const uint32_t a0 = in_col + a_col(kc * G::KC);
+                tr.ev(12, m * 16 + l, ph * 4 + kc);
+                if (elect_one()) {
+                  if (kc == 0)   // bias first: it overwrites (accumulate = 0) the stale region contents
+                    mma_ss(d, smem_desc(sel_l, 2048, 128), smem_desc(bt + ph * G::NH * 16, LAT * 16, 128), idesc_h, 0);
+                  const uint64_t b_hi0 = smem_desc(sb, G::NH * 16, 128);
+                  const uint64_t b_lo0 = smem_desc(sb + G::MAT_BYTES, G::NH * 16, 128);
 #pragma unroll
-                for (int ks = 0; ks < G::KC / 16; ++ks) {
-                  const int kg = kc * G::KC + ks * 16;
-                  const uint32_t a_hi = in_col + a_col(kg);
-                  const uint64_t b_hi = smem_desc(sb + ks * 2 * (G::NH * 16), G::NH * 16, 128);
-                  const uint32_t acc = (kc | ks) ? 1u : 0u;
-                  const uint32_t d = out_col + ph * G::NH;
-                  mma_ts(d, a_hi, b_hi, idesc_h, acc);
-                  if (NPROD == 3) {
-                    const uint64_t b_lo =
-                        smem_desc(sb + G::MAT_BYTES + ks * 2 * (G::NH * 16), G::NH * 16, 128);
-                    mma_ts(d, a_hi + 16, b_hi, idesc_h, 1);
-                    mma_ts(d, a_hi, b_lo, idesc_h, 1);
+                  for (int ks = 0; ks < G::KC / 16; ++ks) {
+                    // K advances by 16 features = 2 core matrices = 2*LBO bytes (>>4 in the descriptor)
+                    const uint64_t koff = (uint64_t)((ks * 2 * (G::NH * 16)) >> 4);
+                    const uint32_t a_hi = a0 + a_col(ks * 16);
+                    mma_ts(d, a_hi, b_hi0 + koff, idesc_h, 1);
+                    if (NPROD == 3) {
+                      mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_h, 1);
+                      mma_ts(d, a_hi, b_lo0 + koff, idesc_h, 1);
+                    }
                   }
+                  tc_commit(bar_empty + 8 * stage);
+                  if (kc == G::NKC - 1) tc_commit(bar_acc + 8 * ph);
                 }
-                tc_commit(smem_u32(&bars->empty[stage]));
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
-              tc_commit(smem_u32(&bars->acc_full[ph]));
             }
             region ^= 1;
           }
-          // ---- last layer: N = 16, K = LAT, one chunk -----------------------------------------
+          // ---- last layer: N = 16, K = LAT, one chunk (bias added by the epilogue) -----------
           {
             const uint32_t in_col = tmem_base + (region ^ 1) * LAT;
             const uint32_t d = tmem_base + region * LAT;
-            for (int q = 0; q < kNS; ++q) {
-              mbar_wait(smem_u32(&bars->a_ready[q]), aready_par[q]);
-              aready_par[q] ^= 1;
-            }
-            mbar_wait(smem_u32(&bars->full[stage]), phase);
+            uint32_t waited = 0;
+            wait_groups(waited, 0, G::NA - 1);
+            mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
-            const uint32_t sb = smem_u32(ring + stage * kStageBytes);
-#pragma unroll 4
-            for (int ks = 0; ks < LAT / 16; ++ks) {
-              const uint32_t a_hi = in_col + a_col(ks * 16);
-              const uint64_t b_hi = smem_desc(sb + ks * 2 * (kNOut * 16), kNOut * 16, 128);
-              mma_ts(d, a_hi, b_hi, idesc_last, ks ? 1u : 0u);
-              if (NPROD == 3) {
-                const uint64_t b_lo =
-                    smem_desc(sb + G::LAST_MAT_BYTES + ks * 2 * (kNOut * 16), kNOut * 16, 128);
-                mma_ts(d, a_hi + 16, b_hi, idesc_last, 1);
-                mma_ts(d, a_hi, b_lo, idesc_last, 1);
+            const uint32_t sb = ring_u + stage * kStageBytes;
+            tr.ev(13, m * 16 + K - 1, 0);
+            if (elect_one()) {
+              const uint64_t b_hi0 = smem_desc(sb, kNOut * 16, 128);
+              const uint64_t b_lo0 = smem_desc(sb + G::LAST_MAT_BYTES, kNOut * 16, 128);
+#pragma unroll
+              for (int ks = 0; ks < LAT / 16; ++ks) {
+                const uint64_t koff = (uint64_t)((ks * 2 * (kNOut * 16)) >> 4);
+                const uint32_t a_hi = in_col + a_col(ks * 16);
+                mma_ts(d, a_hi, b_hi0 + koff, idesc_last, ks ? 1u : 0u);
+                if (NPROD == 3) {
+                  mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_last, 1);
+                  mma_ts(d, a_hi, b_lo0 + koff, idesc_last, 1);
+                }
               }
+              tc_commit(bar_empty + 8 * stage);
+              tc_commit(bar_acc);
             }
-            tc_commit(smem_u32(&bars->empty[stage]));
+            __syncwarp();
+            tr.ev(14, m * 16 + K - 1, 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
-            tc_commit(smem_u32(&bars->acc_full[0]));
             region ^= 1;
           }
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kEpiWarps) {
     // ===== epilogue warps ======================================================================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;             // which 32-column chunk of every 64-column group
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_par[kNS] = {0, 0};
+    uint32_t acc_par = 0;
     int region = 0;
     double ldj_local = 0.0;
     const int hp4 = p.HP >> 2;
+    Tracer tr;
+    tr.init(p.trace, 1 + (warp - 2), blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6));
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       float st[2][kNOut];
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
         for (int l = 0; l < K - 1; ++l) {
-          const float* bl = bias_s + (m * kMaxLayers + l) * LAT;
 #pragma unroll
           for (int ph = 0; ph < kNS; ++ph) {
-            mbar_wait(smem_u32(&bars->acc_full[ph]), acc_par[ph]);
-            acc_par[ph] ^= 1;
+            mbar_wait(smem_u32(&bars->acc_full[ph]), (acc_par >> ph) & 1u);
+            acc_par ^= 1u << ph;
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < G::NH / 32; ++c) {
-              const int col = ph * G::NH + c * 32;
-              const uint32_t taddr = lane_base + region * LAT + col;
-              uint32_t v[32];
-              tmem_ld32(taddr, v);
+            tr.ev(20, m * 16 + l, ph * 4);
+            const uint32_t t0 = lane_base + region * LAT + ph * G::NH + grp * 32;
+            if constexpr (G::GPH == 2) {
+              uint32_t v0[32], v1[32];
+              tmem_ld32(t0, v0);
+              tmem_ld32(t0 + 64, v1);
               tmem_wait_ld();
-              uint32_t hi[16], lo[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 bb = *reinterpret_cast<const float2*>(bl + col + 2 * j);
-                float a = act_fn(__uint_as_float(v[2 * j]) + bb.x, p.act);
-                float b = act_fn(__uint_as_float(v[2 * j + 1]) + bb.y, p.act);
-                split_pair<BF16>(a, b, hi[j], lo[j]);
-              }
-              tmem_st16(taddr, hi);
-              if (NPROD == 3) tmem_st16(taddr + 16, lo);
+              convert_chunk<NPROD, BF16, ACT>(t0, v0);
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(smem_u32(&bars->a_ready[ph * 2]));
+              convert_chunk<NPROD, BF16, ACT>(t0 + 64, v1);
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(smem_u32(&bars->a_ready[ph * 2 + 1]));
+              tr.ev(21, m * 16 + l, ph * 4);
+            } else {
+              uint32_t v0[32];
+              tmem_ld32(t0, v0);
+              tmem_wait_ld();
+              convert_chunk<NPROD, BF16, ACT>(t0, v0);
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(smem_u32(&bars->a_ready[ph]));
             }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->a_ready[ph]));
           }
           region ^= 1;
         }
-        // last layer: s (m == 0) or t (m == 1)
+        // last layer: s (m == 0) or t (m == 1); only the first warp of each lane quarter reads it
         {
-          const float* bl = bias_s + (m * kMaxLayers + (K - 1)) * LAT;
-          mbar_wait(smem_u32(&bars->acc_full[0]), acc_par[0]);
-          acc_par[0] ^= 1;
+          mbar_wait(smem_u32(&bars->acc_full[0]), acc_par & 1u);
+          acc_par ^= 1u;
           tc_fence_after();
-          uint32_t v[16];
-          tmem_ld16(lane_base + region * LAT, v);
-          tmem_wait_ld();
+          tr.ev(22, m * 16 + K - 1, 0);
+          if (grp == 0) {
+            uint32_t v[16];
+            tmem_ld16(lane_base + region * LAT, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < kNOut; ++j) st[m][j] = __uint_as_float(v[j]) + bl[j];
+            for (int j = 0; j < kNOut; ++j) st[m][j] = __uint_as_float(v[j]) + blast[m * kNOut + j];
+          }
           region ^= 1;
         }
       }
       // ---- affine coupling update + log-det partial (gnn.py:322-323 / :359) ------------------
       const int64_t node = (int64_t)tile * kTileM + row;
-      if (node < p.n_nodes) {
+      if (grp == 0 && node < p.n_nodes) {
         float* xrow = p.xb + node * p.HP;
 #pragma unroll
         for (int g4 = 0; g4 < kNOut / 4; ++g4) {
@@ -484,10 +582,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
         }
       }
     }
-    // fixed-order reduction of the log-det partial: lanes, then the 4 epilogue warps
+    tr.ev(23, 0, 0);
+    // fixed-order reduction of the log-det partial: lanes, then the 4 lane-quarter warps
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ldj_local += __shfl_down_sync(0xffffffffu, ldj_local, o);
-    if (lane == 0) ldj_red[warp - 2] = ldj_local;
+    if (lane == 0 && grp == 0) ldj_red[q] = ldj_local;
     asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
     if (warp == 2 && lane == 0 && p.partials)
       p.partials[blockIdx.x] = ((ldj_red[0] + ldj_red[1]) + ldj_red[2]) + ldj_red[3];
@@ -497,8 +596,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     float* my = hstage + row * 17;
     const int hp4 = p.HP >> 2;
     int it = 0;
+    Tracer tr;
+    tr.init(p.trace, 9, blockIdx.x == 0 && row == 0);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
+      tr.ev(30, 0, 0);
       const int64_t node = (int64_t)tile * kTileM + row;
       float self[kNOut], agg[kNOut];
 #pragma unroll
@@ -548,7 +650,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) split_pair<BF16>(my[2 * j], my[2 * j + 1], hi[j], lo[j]);
+      tr.ev(31, 0, 0);
       mbar_wait(smem_u32(&bars->h_empty[buf]), ((it >> 1) & 1) ^ 1);
+      tr.ev(32, 0, 0);
       uint8_t* hb = hbuf + buf * 8192;
       *reinterpret_cast<uint4*>(hb + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(hb + 2048 + row * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -633,9 +737,9 @@ int pack_mlp_t(const Flow& f, int mlp, const float* params, cudaStream_t stream)
   return GNF_OK;
 }
 
-template <int LAT, int NPROD, bool BF16>
-int launch_tc(const TcParams& p, int grid, cudaStream_t stream) {
-  auto kern = k_coupling_tc<LAT, NPROD, BF16>;
+template <int LAT, int NPROD, bool BF16, int ACT>
+int launch_tc_act(const TcParams& p, int grid, cudaStream_t stream) {
+  auto kern = k_coupling_tc<LAT, NPROD, BF16, ACT>;
   static bool configured = false;
   const size_t smem = smem_bytes<LAT>();
   if (!configured) {
@@ -647,7 +751,16 @@ int launch_tc(const TcParams& p, int grid, cudaStream_t stream) {
   return GNF_OK;
 }
 
+template <int LAT, int NPROD, bool BF16>
+int launch_tc(const TcParams& p, int grid, cudaStream_t stream) {
+  return p.act == GNF_ACT_LEAKY_RELU ? launch_tc_act<LAT, NPROD, BF16, GNF_ACT_LEAKY_RELU>(p, grid, stream)
+                                     : launch_tc_act<LAT, NPROD, BF16, GNF_ACT_RELU>(p, grid, stream);
+}
+
 }  // namespace
+
+static unsigned long long* g_trace = nullptr;
+void tc_set_trace(void* buf) { g_trace = (unsigned long long*)buf; }
 
 bool tc_shape_supported(const Flow& f) {
   return (f.L == 128 || f.L == 256) && f.in_dim <= kK0 && f.H <= kNOut && f.K >= 2 && f.K <= kMaxLayers;
@@ -685,6 +798,7 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   p.inverse = inverse;
   p.eps = f.d.eps;
   p.partials = ldj_partials;
+  p.trace = g_trace;
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   *n_partials = grid;
   if (f.L == 256) {

@@ -415,6 +415,10 @@ extern "C" int64_t gnf_launch_count(int reset) {
   if (reset) launch_counter() = 0;
   return c;
 }
+extern "C" int gnf_debug_set_trace(void* device_buf) {
+  tc_set_trace(device_buf);
+  return GNF_OK;
+}
 extern "C" int32_t gnf_padded_half(int32_t h) { return pad_to(h, 4); }
 
 static int validate_desc(const gnf_flow_desc* d) {

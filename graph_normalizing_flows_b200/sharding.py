@@ -1,0 +1,109 @@
+"""Graph-sharded data parallelism for the GRevNet hot path.
+
+Graphs in a packed batch never exchange data (gather / segment indices stay inside a graph's
+node range, the MLPs are row-wise, log-det and log-prob are plain sums; gnn.py:322,337 and
+run_grevnet.py:294), so whole graphs are assigned to ranks, each rank runs the fused kernels
+on its own packed sub-batch with replicated weights, and ONE all-reduce(SUM) of the fp64
+vector (log_prob_zs, log_det_jacobian, log_prob_xs, num_nodes) assembles the batch
+log-likelihood.  z stays sharded.  No data-path collective.  (use_batch_norm=True would couple
+graphs through batch statistics and is not on this path.)
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .graphs import GraphsTuple
+
+
+def graph_costs(n_node, n_edge, flops_per_node_update: float = 807936.0, alpha: float = 1.0,
+                beta: float = 64.0) -> np.ndarray:
+    """Per-graph cost model alpha * n_node * F + beta * n_edge (MLP FLOPs dominate; the edge term
+    keeps very dense graphs from piling up on one rank)."""
+    return alpha * np.asarray(n_node, np.float64) * flops_per_node_update + beta * np.asarray(n_edge, np.float64)
+
+
+def partition_graphs(n_node: Sequence[int], n_edge: Sequence[int], world_size: int, **cost_kw) -> List[np.ndarray]:
+    """Greedy longest-processing-time assignment of whole graphs to ranks.  Deterministic (stable
+    sort, lowest rank wins ties); each rank's graph ids are returned in ascending order."""
+    cost = graph_costs(n_node, n_edge, **cost_kw)
+    order = np.argsort(-cost, kind="stable")
+    load = np.zeros(world_size, np.float64)
+    buckets: List[List[int]] = [[] for _ in range(world_size)]
+    for gidx in order:
+        r = int(np.argmin(load))
+        buckets[r].append(int(gidx))
+        load[r] += cost[gidx]
+    return [np.array(sorted(b), dtype=np.int64) for b in buckets]
+
+
+def shard_graphs_tuple(graph: GraphsTuple, graph_ids: np.ndarray) -> GraphsTuple:
+    """Sub-batch of the selected graphs (host arrays), indices re-based to the shard's own packed
+    node array -- integer-exact, edge order inside every graph preserved."""
+    n_node = np.asarray(graph.n_node, np.int64)
+    n_edge = np.asarray(graph.n_edge, np.int64)
+    node_off = np.concatenate([[0], np.cumsum(n_node)])
+    edge_off = np.concatenate([[0], np.cumsum(n_edge)])
+    ids = np.asarray(graph_ids, np.int64)
+    if len(ids) == 0:
+        d = graph.nodes.shape[1] if graph.nodes is not None else 0
+        return GraphsTuple(np.zeros((0, d), np.float32), None, np.zeros(0, np.int32), np.zeros(0, np.int32), None,
+                           np.zeros(0, np.int32), np.zeros(0, np.int32))
+    node_idx = np.concatenate([np.arange(node_off[g], node_off[g + 1]) for g in ids])
+    edge_idx = np.concatenate([np.arange(edge_off[g], edge_off[g + 1]) for g in ids])
+    new_off = np.concatenate([[0], np.cumsum(n_node[ids])[:-1]])
+    shift = np.repeat(new_off - node_off[ids], n_edge[ids])
+    senders = (np.asarray(graph.senders, np.int64)[edge_idx] + shift).astype(np.int32)
+    receivers = (np.asarray(graph.receivers, np.int64)[edge_idx] + shift).astype(np.int32)
+    nodes = np.asarray(graph.nodes)[node_idx] if graph.nodes is not None else None
+    return GraphsTuple(nodes=nodes, edges=None, receivers=receivers, senders=senders, globals=None,
+                       n_node=n_node[ids].astype(np.int32), n_edge=n_edge[ids].astype(np.int32))
+
+
+def all_reduce_log_prob(vec4: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """In-place SUM of (log_prob_zs, ldj, log_prob_xs, num_nodes) over the ranks (fp64).  NCCL on
+    device tensors, gloo on host tensors (tests)."""
+    if vec4.dtype != torch.float64 or vec4.numel() != 4:
+        raise ValueError("expected a float64 4-vector")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec4, op=dist.ReduceOp.SUM, group=group)
+    return vec4
+
+
+class GraphShardedGRevNet:
+    """One process per GPU; weights replicated; graphs sharded.
+
+        sharded = GraphShardedGRevNet(grevnet)                    # after init_process_group("nccl")
+        local = sharded.local_shard(host_batch).to(device)        # this rank's graphs
+        scalars = sharded.log_prob(local)                          # global batch scalars on every rank
+    """
+
+    def __init__(self, grevnet, group: Optional[dist.ProcessGroup] = None):
+        self.grevnet = grevnet
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world_size = dist.get_world_size(group) if on else 1
+
+    def local_shard(self, host_batch: GraphsTuple) -> GraphsTuple:
+        parts = partition_graphs(host_batch.n_node, host_batch.n_edge, self.world_size)
+        return shard_graphs_tuple(host_batch, parts[self.rank])
+
+    def broadcast_parameters(self, src: int = 0):
+        if self.world_size > 1:
+            dist.broadcast(self.grevnet.params.data, src=src, group=self.group)
+
+    def log_prob(self, local_graph: GraphsTuple, return_z: bool = False) -> dict:
+        from .loss import mvn_log_prob_sum, scalars_from_vector
+        z, ldj64 = self.grevnet.f64(local_graph)
+        vec = all_reduce_log_prob(mvn_log_prob_sum(z.nodes, ldj64), self.group)
+        out = scalars_from_vector(vec)
+        if return_z:
+            out["z"] = z
+        return out
+
+    def sample(self, local_latent: GraphsTuple) -> GraphsTuple:
+        return self.grevnet.g(local_latent)

@@ -59,6 +59,9 @@ const char* gnf_last_error(void);
 /* number of kernels this library launched on the calling thread since the last reset
  * (bench.py's "gpu_launches") */
 int64_t     gnf_launch_count(int reset);
+/* Developer aid: when device_buf (>= 10*2048 uint64, zeroed) is non-NULL, CTA 0 of every fused
+ * coupling kernel records a clock64 timeline of its warp roles into it; NULL switches it off. */
+int         gnf_debug_set_trace(void* device_buf);
 
 /* ------------------------------------------------------------------------------------------
  * a1  batch structure.  Replaces the per-call index handling of graph_nets' aggregator:

@@ -1,0 +1,77 @@
+"""torch-CPU restatement of the reference path, used ONLY as the timed CPU baseline
+(bench.py cpu_baseline / --impl reference) and cross-checked against oracle/gnf_oracle.py in
+tests/.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.  PARITY UNPINNED (see gnf_oracle.py).
+
+Same op order as the reference executes on a CPU TensorFlow build (SURVEY §8d "CPU baseline"):
+tf.gather -> index_select, tf.unsorted_segment_sum -> index_add_ (serial over edges on CPU),
+snt.Linear -> addmm, s and t GNNs evaluated separately (gnn.py:320-321), x*exp(s)+t, scalar sum.
+All host threads torch can use (MKL / OpenMP), like TF's intra-op pool.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+
+def params_to_torch(params, dtype=torch.float32):
+    def c(m):
+        return [(torch.from_numpy(np.ascontiguousarray(w)).to(dtype), torch.from_numpy(np.ascontiguousarray(b)).to(dtype))
+                for (w, b) in m]
+    out = dict(params)
+    for k in ("s", "t"):
+        out[k] = [c(m) for m in params[k]] if params["weight_sharing"] else [[c(m) for m in half] for half in params[k]]
+    return out
+
+
+def _act(h, kind):
+    return torch.maximum(h, 0.2 * h) if kind == "leaky_relu" else torch.relu(h)   # tf.nn.leaky_relu alpha=0.2
+
+
+def _mlp(h, layers, act):                       # gnn.py:167-180
+    last = len(layers) - 1
+    for i, (w, b) in enumerate(layers):
+        h = torch.addmm(b, h, w)
+        if i != last:
+            h = _act(h, act)
+    return h
+
+
+def _gnn(nodes, senders, receivers, layers, cfg):   # gnn.py:155-156 + 107-111 / 122-126
+    edges = nodes.index_select(0, senders)                       # gnn.py:151 (use_sender_nodes)
+    agg = torch.zeros_like(nodes).index_add_(0, receivers, edges)  # gnn.py:103 unsorted_segment_sum
+    if cfg["agg"] == "mean":
+        cnt = torch.bincount(receivers, minlength=nodes.shape[0]).to(nodes.dtype).clamp_(min=1)
+        agg = agg / cnt[:, None]
+    h = torch.cat([nodes, agg], 1) if cfg["block"] == "concat" else cfg["eps"] * nodes + agg
+    return _mlp(h, layers, cfg["act"])
+
+
+def _st(p, which, half, i):
+    return p[which][half] if p["weight_sharing"] else p[which][half][i]
+
+
+@torch.no_grad()
+def grevnet_f(nodes, senders, receivers, p):
+    """GRevNet.f (gnn.py:304-341)."""
+    cfg = p["cfg"]
+    h = nodes.shape[1] // 2
+    x0, x1 = nodes[:, :h].contiguous(), nodes[:, h:].contiguous()
+    ldj = torch.zeros((), dtype=nodes.dtype)
+    for i in range(p["T"]):
+        s = _gnn(x0, senders, receivers, _st(p, "s", 0, i), cfg)
+        t = _gnn(x0, senders, receivers, _st(p, "t", 0, i), cfg)
+        ldj = ldj + s.sum()
+        x1 = x1 * torch.exp(s) + t
+        s = _gnn(x1, senders, receivers, _st(p, "s", 1, i), cfg)
+        t = _gnn(x1, senders, receivers, _st(p, "t", 1, i), cfg)
+        ldj = ldj + s.sum()
+        x0 = x0 * torch.exp(s) + t
+    return torch.cat([x0, x1], 1), ldj
+
+
+@torch.no_grad()
+def log_prob_xs(z, ldj):                       # run_grevnet.py:292-295
+    d = z.shape[1]
+    return (-0.5 * (z * z).sum(1) - 0.5 * d * math.log(2 * math.pi)).sum() + ldj

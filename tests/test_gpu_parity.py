@@ -1,0 +1,322 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs, against the committed golden fixtures, and -- at BASELINE's full size --
+through size-independent properties.
+
+Tolerances (north star): indexing and segment ops BIT-EXACT; floating-point log-prob within
+1e-5 relative (fp32 and tc3x modes).  The single-pass bf16 mode has its own, looser, stated
+tolerance (1e-4 relative on log-prob, 2e-2 absolute on z).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import gnf_oracle as O
+import graph_normalizing_flows_b200 as G
+from graph_normalizing_flows_b200 import _lib, sharding
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LOGPROB_RTOL = 1e-5
+CASES = sorted(glob.glob(os.path.join(H.GOLDEN, "golden_*.npz")))
+
+
+def dev_graph(g):
+    return H.to_device_graph(g, DEV)
+
+
+def load_case(path):
+    g = np.load(path, allow_pickle=False)
+    T, D, L, K, ws = [int(v) for v in g["spec"]]
+    params = O.make_params(int(g["seed"]), T, D, L, K, agg=str(g["agg"]), block=str(g["block"]),
+                           eps=float(g["eps"]), act=str(g["act"]), last_layer_scale=float(g["last_scale"]),
+                           weight_sharing=bool(ws))
+    graph = O.GraphsTuple(g["nodes"], None, g["receivers"], g["senders"], None, g["n_node"], g["n_edge"])
+    return g, graph, params, (T, D, L, K)
+
+
+# ------------------------------------------------------------------------------- a1: CSR -------
+@pytest.mark.parametrize("kind", ["random", "fc_big_degree", "isolated", "single_node"])
+def test_csr_is_stable_and_exact(kind):
+    rng = np.random.default_rng(0)
+    if kind == "random":
+        g = H.random_batch(rng, 40, 3, 60, D=2)
+    elif kind == "fc_big_degree":            # in-degree 70 > 32 exercises the long-segment path
+        s, r = G.utils.senders_receivers([70, 3, 45])
+        perm = rng.permutation(len(s))       # and an arbitrary (not sender-sorted) edge order
+        g = O.GraphsTuple(np.zeros((118, 2), np.float32), None, r[perm], s[perm], None,
+                          np.array([70, 3, 45], np.int32), np.array([4900, 9, 2025], np.int32))
+    elif kind == "isolated":
+        g = H.random_batch(rng, 10, 4, 20, D=2, isolated=True)
+    else:
+        g = O.GraphsTuple(np.zeros((1, 2), np.float32), None, np.zeros(1, np.int32), np.zeros(1, np.int32), None,
+                          np.ones(1, np.int32), np.ones(1, np.int32))
+    dg = dev_graph(g)
+    st = G.graphs.structure_of(dg)
+    n = g.nodes.shape[0]
+    order = np.argsort(g.receivers, kind="stable")
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(g.receivers, minlength=n))]).astype(np.int32)
+    assert np.array_equal(st.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(st.perm.cpu().numpy(), order.astype(np.int32))
+    assert np.array_equal(st.csr_senders.cpu().numpy(), g.senders[order])
+    assert G.graphs.structure_of(dg.replace(nodes=dg.nodes * 2)) is st        # cached across .replace
+
+
+def test_index_validation_raises_like_tf():
+    g = H.random_batch(np.random.default_rng(1), 3, 3, 6, D=4)
+    bad = g._replace(senders=g.senders.copy())
+    bad.senders[2] = g.nodes.shape[0]                      # out of range -> TF InvalidArgumentError
+    with pytest.raises(ValueError, match="outside"):
+        G.graphs.structure_of(dev_graph(bad))
+    neg = g._replace(receivers=g.receivers.copy())
+    neg.receivers[0] = -1
+    with pytest.raises(ValueError, match="outside"):
+        G.graphs.structure_of(dev_graph(neg))
+    wrong = g._replace(n_node=g.n_node + 1)
+    with pytest.raises(ValueError, match="n_node"):
+        G.graphs.structure_of(dev_graph(wrong))
+    with pytest.raises(ValueError):
+        G.graphs.BatchStructure(dev_graph(g).senders.long(), dev_graph(g).receivers, g.nodes.shape[0])
+
+
+# ---------------------------------------------------------------------- a3 / a4: segment ops ----
+@pytest.mark.parametrize("h", [1, 2, 7, 100])
+@pytest.mark.parametrize("agg", ["sum", "mean"])
+def test_segment_ops_bit_exact(h, agg):
+    """K6 + K7: serial in-edge-order fp32 accumulation, bit for bit; empty segments -> 0."""
+    rng = np.random.default_rng(h)
+    g = H.random_batch(rng, 30, 3, 50, D=2, isolated=True)
+    x = (rng.standard_normal((g.nodes.shape[0], h)) * 10).astype(np.float32)
+    want = O.aggregate(x, g.senders, g.receivers, agg)
+    dg = dev_graph(g._replace(nodes=x))
+    st = G.graphs.structure_of(dg)
+    lib = _lib.load()
+    fused = G.gnn.gather_segment_reduce(dg.nodes, st, agg)
+    assert np.array_equal(fused.cpu().numpy(), want)
+    # the two-step form of the reference: gather (a3) then aggregate (a4)
+    edges = torch.empty(len(g.senders), h, device=DEV)
+    _lib.check(lib.gnf_gather_rows(_lib.ptr(dg.nodes), h, _lib.ptr(dg.senders), len(g.senders), _lib.ptr(edges),
+                                   _lib.stream_ptr()))
+    assert np.array_equal(edges.cpu().numpy(), x[g.senders])
+    fn = G.gnn.unsorted_segment_sum if agg == "sum" else G.gnn.unsorted_segment_mean
+    two = fn(edges, dg.receivers, g.nodes.shape[0])
+    assert np.array_equal(two.cpu().numpy(), want)
+    iso = np.setdiff1d(np.arange(g.nodes.shape[0]), g.receivers)
+    assert len(iso) > 0 and not fused.cpu().numpy()[iso].any()
+
+
+# --------------------------------------------------------------------- a2-a8: golden parity -----
+@pytest.mark.parametrize("math", ["fp32", "tc3x", "tc3x_bf16"])
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[7:-4] for p in CASES])
+def test_golden_parity(path, math):
+    gold, graph, params, (T, D, L, K) = load_case(path)
+    net = H.make_grevnet(params, L, K, device=DEV, math=math)
+    if math != "fp32" and not (L in (128, 256)):
+        with pytest.raises(ValueError, match="GNF_MATH_FP32"):
+            net(dev_graph(graph), inverse=True)            # unsupported shape fails loudly
+        return
+    dg = dev_graph(graph)
+    out = G.loss.log_prob(net, dg, return_z=True)
+    z = out["z"].nodes.cpu().numpy()
+    assert np.abs(z - gold["z64"]).max() < 5e-5
+    assert np.abs(z - gold["z"]).max() < 5e-5
+    assert H.rel_err(out["log_prob_xs"], gold["log_prob_xs64"]) < LOGPROB_RTOL
+    assert H.rel_err(out["log_prob_xs"], gold["log_prob_xs"]) < LOGPROB_RTOL
+    assert H.rel_err(out["log_prob_zs"], gold["log_prob_zs64"]) < LOGPROB_RTOL
+    assert abs(float(out["log_det_jacobian"]) - float(gold["ldj64"])) < LOGPROB_RTOL * abs(float(gold["log_prob_xs64"]))
+    assert float(out["num_nodes"]) == graph.nodes.shape[0]
+    # reference API: (GraphsTuple, scalar) / GraphsTuple, inverse=True is the density direction
+    z2, ldj = net(dg, inverse=True)
+    assert isinstance(z2, G.GraphsTuple) and ldj.dim() == 0 and z2.senders is dg.senders
+    x_back = net(z2, inverse=False).nodes.cpu().numpy()
+    assert np.abs(x_back - graph.nodes).max() < 5e-5                     # K1
+    assert np.abs(x_back - gold["x_back"]).max() < 5e-5
+    assert H.rel_err(net.log_prob(dg), gold["log_prob_xs64"]) < LOGPROB_RTOL
+
+
+@pytest.mark.parametrize("path", [p for p in CASES if "caveman_small" in p or "concat_mean_d14" in p])
+def test_bf16_single_pass_has_its_own_tolerance(path):
+    gold, graph, params, (T, D, L, K) = load_case(path)
+    net = H.make_grevnet(params, L, K, device=DEV, math="bf16")
+    out = G.loss.log_prob(net, dev_graph(graph), return_z=True)
+    assert H.rel_err(out["log_prob_xs"], gold["log_prob_xs64"]) < 1e-4
+    assert np.abs(out["z"].nodes.cpu().numpy() - gold["z64"]).max() < 2e-2
+
+
+@pytest.mark.parametrize("math", ["fp32", "tc3x"])
+def test_k2_zero_last_layer_is_bit_exact_identity(math):
+    rng = np.random.default_rng(2)
+    g = H.random_batch(rng, 20, 5, 40, D=14)
+    params = O.make_params(1, 3, 14, 256, 4, last_layer_scale=0.0)
+    net = H.make_grevnet(params, 256, 4, device=DEV, math=math)
+    dg = dev_graph(g)
+    out = G.loss.log_prob(net, dg, return_z=True)
+    assert torch.equal(out["z"].nodes, dg.nodes)
+    assert float(out["log_det_jacobian"]) == 0.0
+    n, d = g.nodes.shape
+    want = -0.5 * float((g.nodes.astype(np.float64) ** 2).sum()) - 0.5 * n * d * np.log(2 * np.pi)
+    assert H.rel_err(out["log_prob_xs"], want) < 1e-12
+    assert torch.equal(net(out["z"], inverse=False).nodes, dg.nodes)
+
+
+@pytest.mark.parametrize("math", ["fp32", "tc3x"])
+def test_k4_graph_independence_and_shard_additivity(math):
+    rng = np.random.default_rng(3)
+    g = H.random_batch(rng, 37, 5, 40, D=14)
+    params = O.make_params(4, 2, 14, 256, 5, last_layer_scale=0.05)
+    net = H.make_grevnet(params, 256, 5, device=DEV, math=math)
+    full = G.loss.log_prob(net, dev_graph(g), return_z=True)
+    zfull = full["z"].nodes.cpu().numpy()
+    node_off = np.concatenate([[0], np.cumsum(g.n_node)])
+    tot = np.zeros(4)
+    for world in (3,):
+        parts = sharding.partition_graphs(g.n_node, g.n_edge, world)
+        for ids in parts:
+            sh = sharding.shard_graphs_tuple(G.GraphsTuple(*g), ids)
+            out = G.loss.log_prob(net, sh.to(DEV), return_z=True)
+            zs = out["z"].nodes.cpu().numpy()
+            rows = np.concatenate([np.arange(node_off[k], node_off[k + 1]) for k in ids])
+            assert np.abs(zs - zfull[rows]).max() < 1e-6          # other graphs in the batch do not matter
+            tot += np.array([float(out[k]) for k in ("log_prob_zs", "log_det_jacobian", "log_prob_xs", "num_nodes")])
+    want = np.array([float(full[k]) for k in ("log_prob_zs", "log_det_jacobian", "log_prob_xs", "num_nodes")])
+    assert np.all(np.abs(tot - want) <= 1e-7 * np.maximum(1.0, np.abs(want)))
+
+
+def test_sharded_wrapper_world_size_one():
+    rng = np.random.default_rng(5)
+    g = H.random_batch(rng, 10, 5, 20, D=14)
+    params = O.make_params(4, 2, 14, 128, 3, last_layer_scale=0.05)
+    net = H.make_grevnet(params, 128, 3, device=DEV)
+    assert net.math == "tc3x"
+    sh = sharding.GraphShardedGRevNet(net)
+    local = sh.local_shard(G.GraphsTuple(*g)).to(DEV)
+    out = sh.log_prob(local)
+    z, ldj = O.grevnet_f(g.nodes, g.senders, g.receivers, params)
+    assert H.rel_err(out["log_prob_xs"], O.log_prob(z, ldj, g.n_node)["log_prob_xs"]) < LOGPROB_RTOL
+
+
+@pytest.mark.parametrize("block,agg", [("concat", "sum"), ("concat", "mean"), ("agg_then", "sum"), ("agg_then", "mean")])
+def test_node_block_gnn_standalone(block, agg):
+    """NodeBlockGNN as a callable GraphsTuple -> GraphsTuple (gnn.py:155-156)."""
+    from functools import partial
+    rng = np.random.default_rng(6)
+    g = H.random_batch(rng, 8, 4, 20, D=7)                       # nodes are [N, H=7] here
+    mlp_fn = partial(G.make_mlp_model, 64, 7, 3, G.gnn.leaky_relu, 0.1, 0.1)
+    fac = {("concat", "sum"): G.sum_concat_then_mlp_gnn, ("concat", "mean"): G.avg_concat_then_mlp_gnn,
+           ("agg_then", "sum"): partial(G.sum_then_mlp_gnn, epsilon=0.7),
+           ("agg_then", "mean"): partial(G.avg_then_mlp_gnn, epsilon=0.7)}[(block, agg)]
+    gnn = fac(mlp_fn)
+    dg = dev_graph(g)
+    out = gnn(dg)
+    layers = [(w.cpu().numpy(), b.cpu().numpy()) for w, b in zip(gnn.mlp.weights, gnn.mlp.biases)]
+    want = O.node_block_gnn(g.nodes, g.senders, g.receivers, layers,
+                            {"agg": agg, "block": block, "eps": 0.7, "act": "leaky_relu"})
+    assert isinstance(out, G.GraphsTuple) and out.nodes.shape == dg.nodes.shape
+    assert np.abs(out.nodes.cpu().numpy() - want).max() < 1e-4
+
+
+def test_empty_and_tiny_batches():
+    params = O.make_params(4, 2, 14, 128, 3, last_layer_scale=0.05)
+    net = H.make_grevnet(params, 128, 3, device=DEV)
+    empty = G.GraphsTuple(torch.zeros(0, 14, device=DEV), None, torch.zeros(0, dtype=torch.int32, device=DEV),
+                          torch.zeros(0, dtype=torch.int32, device=DEV), None,
+                          torch.zeros(0, dtype=torch.int32, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV))
+    out = G.loss.log_prob(net, empty)
+    assert float(out["log_prob_xs"]) == 0.0 and float(out["num_nodes"]) == 0.0
+    one = O.GraphsTuple(np.ones((1, 14), np.float32), None, np.zeros(1, np.int32), np.zeros(1, np.int32), None,
+                        np.ones(1, np.int32), np.ones(1, np.int32))
+    z, ldj = O.grevnet_f(one.nodes, one.senders, one.receivers, params)
+    got = G.loss.log_prob(net, dev_graph(one))
+    assert H.rel_err(got["log_prob_xs"], O.log_prob(z, ldj, one.n_node)["log_prob_xs"]) < LOGPROB_RTOL
+    # no edges at all (segment ids never hit): agg = 0 everywhere
+    noedge = O.GraphsTuple(np.ones((5, 14), np.float32), None, np.zeros(0, np.int32), np.zeros(0, np.int32), None,
+                           np.full(1, 5, np.int32), np.zeros(1, np.int32))
+    z, ldj = O.grevnet_f(noedge.nodes, noedge.senders, noedge.receivers, params)
+    got = G.loss.log_prob(net, dev_graph(noedge))
+    assert H.rel_err(got["log_prob_xs"], O.log_prob(z, ldj, noedge.n_node)["log_prob_xs"]) < LOGPROB_RTOL
+
+
+def test_property_random_batches():
+    """K8: random small batches, D in {2,4,14}, T in {1,2}, every factory, both kernel families."""
+    rng = np.random.default_rng(8)
+    for trial in range(12):
+        D = int(rng.choice([2, 4, 14]))
+        T = int(rng.choice([1, 2]))
+        L = int(rng.choice([128, 256]))
+        K = int(rng.choice([2, 3, 5]))
+        block = str(rng.choice(["concat", "agg_then"]))
+        agg = str(rng.choice(["sum", "mean"]))
+        g = H.random_batch(rng, int(rng.integers(1, 12)), 1, 35, p_edge=float(rng.uniform(0.05, 0.6)), D=D,
+                           isolated=bool(rng.integers(0, 2)))
+        params = O.make_params(int(rng.integers(1 << 30)), T, D, L, K, agg=agg, block=block, eps=0.9,
+                               last_layer_scale=0.1)
+        p64 = O.cast_params(params, np.float64)
+        z64, ldj64 = O.grevnet_f(g.nodes.astype(np.float64), g.senders, g.receivers, p64)
+        want = O.log_prob(z64, ldj64, g.n_node)["log_prob_xs"]
+        for math in ("fp32", "tc3x"):
+            net = H.make_grevnet(params, L, K, device=DEV, math=math)
+            out = G.loss.log_prob(net, dev_graph(g), return_z=True)
+            assert H.rel_err(out["log_prob_xs"], want) < LOGPROB_RTOL, (trial, math)
+            assert np.abs(out["z"].nodes.cpu().numpy() - z64).max() < 1e-4, (trial, math)
+
+
+# ----------------------------------------------------------- BASELINE full size: properties -----
+def _community_batch(n_graphs, seed):
+    from graph_normalizing_flows_b200 import graph_data as GD
+    npz = np.load(os.path.join(H.GOLDEN, "graphs_community_medium_4_128.npz"))
+    ds = GD.GraphDataset(None, 14, structures=GD.structures_from_fixture(npz))
+    return ds.draw_batch(n_graphs, np.random.default_rng(seed))
+
+
+def test_full_size_community_medium_properties():
+    """BASELINE configs[1] at full size (B=4096, T=6, D=14, L=256, K=5): round trip, shard
+    additivity, permutation invariance of the batch scalars, fp32-vs-tc3x agreement."""
+    host = _community_batch(4096, 12345)
+    params = O.make_params(12345, 6, 14, 256, 5, last_layer_scale=0.05)
+    net = H.make_grevnet(params, 256, 5, device=DEV, math="tc3x")
+    dg = host.to(DEV)
+    full = G.loss.log_prob(net, dg, return_z=True)
+    assert torch.isfinite(full["z"].nodes).all()
+    x_back = net(full["z"], inverse=False).nodes
+    assert float((x_back - dg.nodes).abs().max()) < 1e-4
+    # two contiguous shards: scalars add up (what the NCCL all-reduce relies on)
+    half = 2048
+    ids = np.arange(4096)
+    tot = np.zeros(3)
+    for part in (ids[:half], ids[half:]):
+        sh = sharding.shard_graphs_tuple(host, part).to(DEV)
+        o = G.loss.log_prob(net, sh)
+        tot += np.array([float(o["log_prob_zs"]), float(o["log_det_jacobian"]), float(o["log_prob_xs"])])
+    want = np.array([float(full["log_prob_zs"]), float(full["log_det_jacobian"]), float(full["log_prob_xs"])])
+    assert np.all(np.abs(tot - want) <= 1e-8 * np.abs(want) + 1e-6)
+    # independent arithmetic (fp32 FFMA kernels) agrees with the tensor-core path
+    net32 = H.make_grevnet(params, 256, 5, device=DEV, math="fp32")
+    o32 = G.loss.log_prob(net32, dg, return_z=True)
+    assert H.rel_err(full["log_prob_xs"], o32["log_prob_xs"]) < LOGPROB_RTOL
+    assert float((o32["z"].nodes - full["z"].nodes).abs().max()) < 1e-4
+
+
+def test_oracle_parity_on_real_family_batches():
+    """Real graph families at sizes the oracle finishes in seconds."""
+    for fam, b, T in (("community_medium_4_128", 48, 6), ("grid_4_128", 6, 3), ("protein_4_128", 24, 2),
+                      ("citeseer_4_128", 6, 2), ("caveman_4_128", 8, 2)):
+        from graph_normalizing_flows_b200 import graph_data as GD
+        npz = np.load(os.path.join(H.GOLDEN, f"graphs_{fam}.npz"))
+        ds = GD.GraphDataset(None, 14, structures=GD.structures_from_fixture(npz))
+        host = ds.draw_batch(b, np.random.default_rng(7))
+        params = O.make_params(12345, T, 14, 256, 5, last_layer_scale=0.05)
+        p64 = O.cast_params(params, np.float64)
+        z64, ldj64 = O.grevnet_f(host.nodes.astype(np.float64), host.senders, host.receivers, p64)
+        want = O.log_prob(z64, ldj64, host.n_node)["log_prob_xs"]
+        agg = O.aggregate(np.ascontiguousarray(host.nodes[:, :7]), host.senders, host.receivers, "sum")
+        dg = host.to(DEV)
+        st = G.graphs.structure_of(dg)
+        got_agg = G.gnn.gather_segment_reduce(dg.nodes[:, :7].contiguous(), st, "sum")
+        assert np.array_equal(got_agg.cpu().numpy(), agg), fam
+        for math in ("tc3x", "fp32"):
+            net = H.make_grevnet(params, 256, 5, device=DEV, math=math)
+            out = G.loss.log_prob(net, dg)
+            assert H.rel_err(out["log_prob_xs"], want) < LOGPROB_RTOL, (fam, math)

@@ -1,0 +1,168 @@
+"""CPU suite: the oracle against the committed golden vectors and the known-answer tests
+K1-K5.  The reference ships no tests, so these are the pins ("parity unpinned")."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import data_oracle as DO
+from oracle import gnf_oracle as O
+
+CASES = sorted(glob.glob(os.path.join(H.GOLDEN, "golden_*.npz")))
+
+
+def load_case(path):
+    g = np.load(path, allow_pickle=False)
+    T, D, L, K, ws = [int(v) for v in g["spec"]]
+    params = O.make_params(int(g["seed"]), T, D, L, K, agg=str(g["agg"]), block=str(g["block"]),
+                           eps=float(g["eps"]), act=str(g["act"]), last_layer_scale=float(g["last_scale"]),
+                           weight_sharing=bool(ws))
+    return g, params, (T, D, L, K)
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[7:-4] for p in CASES])
+def test_oracle_reproduces_golden(path):
+    g, params, _ = load_case(path)
+    flat = H.flat_from_oracle(params)
+    # RNG stream drift would silently change every weight: pin it first
+    assert np.isclose(flat.astype(np.float64).sum(), float(g["params_checksum"]), rtol=0, atol=1e-9)
+    z, ldj = O.grevnet_f(g["nodes"], g["senders"], g["receivers"], params)
+    assert np.allclose(z, g["z"], rtol=1e-5, atol=1e-6)
+    assert abs(float(ldj) - float(g["ldj"])) <= 1e-5 * max(1.0, abs(float(g["ldj"])))
+    lp = O.log_prob(z, ldj, g["n_node"])
+    assert H.rel_err(lp["log_prob_xs"], g["log_prob_xs"]) < 1e-6
+    # segment op is integer-indexed fp32 adds in a fixed order: bit-exact
+    agg = O.aggregate(g["nodes"][:, :g["nodes"].shape[1] // 2].copy(), g["senders"], g["receivers"], str(g["agg"]))
+    assert np.array_equal(agg, g["agg_first_half"])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[7:-4] for p in CASES])
+def test_fp32_oracle_close_to_fp64(path):
+    g, _, _ = load_case(path)
+    assert H.rel_err(g["log_prob_xs"], g["log_prob_xs64"]) < 1e-6
+    assert np.abs(g["z"] - g["z64"]).max() < 1e-4
+
+
+def test_k1_round_trip():
+    rng = np.random.default_rng(0)
+    g = H.random_batch(rng, 6, 4, 15, D=14)
+    for block, agg in (("concat", "sum"), ("agg_then", "mean")):
+        p = O.make_params(5, 3, 14, 64, 4, agg=agg, block=block, last_layer_scale=0.1)
+        z, _ = O.grevnet_f(g.nodes, g.senders, g.receivers, p)
+        x = O.grevnet_g(z, g.senders, g.receivers, p)
+        assert np.abs(x - g.nodes).max() < 2e-5
+
+
+def test_k2_zero_last_layer_is_identity():
+    rng = np.random.default_rng(1)
+    g = H.random_batch(rng, 4, 4, 10, D=6)
+    p = O.make_params(5, 2, 6, 32, 3, last_layer_scale=0.0)
+    z, ldj = O.grevnet_f(g.nodes, g.senders, g.receivers, p)
+    assert np.array_equal(z, g.nodes) and float(ldj) == 0.0
+    lp = O.log_prob(z, ldj, g.n_node)
+    n, d = g.nodes.shape
+    want = -0.5 * float((g.nodes.astype(np.float64) ** 2).sum()) - 0.5 * n * d * np.log(2 * np.pi)
+    assert H.rel_err(lp["log_prob_xs"], want) < 1e-6
+
+
+def test_k3_logdet_is_the_jacobian_logdet():
+    """sum(s) == log|det d vec(z)/d vec(x)| (triangular coupling across nodes AND features):
+    central finite differences of the fp64 oracle on a tiny graph."""
+    rng = np.random.default_rng(2)
+    g = H.random_batch(rng, 2, 2, 3, p_edge=0.8, D=4)
+    p = O.cast_params(O.make_params(9, 2, 4, 16, 3, last_layer_scale=0.5), np.float64)
+    x = g.nodes.astype(np.float64)
+    z0, ldj = O.grevnet_f(x, g.senders, g.receivers, p)
+    n = x.size
+    J = np.zeros((n, n))
+    eps = 1e-6
+    for i in range(n):
+        dx = np.zeros(n)
+        dx[i] = eps
+        zp, _ = O.grevnet_f(x + dx.reshape(x.shape), g.senders, g.receivers, p)
+        zm, _ = O.grevnet_f(x - dx.reshape(x.shape), g.senders, g.receivers, p)
+        J[:, i] = ((zp - zm) / (2 * eps)).reshape(-1)
+    sign, logdet = np.linalg.slogdet(J)
+    assert sign > 0
+    assert abs(logdet - float(ldj)) < 1e-6 * max(1.0, abs(float(ldj)))
+
+
+def test_k4_graph_independence():
+    rng = np.random.default_rng(3)
+    g = H.random_batch(rng, 5, 4, 12, D=14)
+    p = O.make_params(5, 2, 14, 64, 3, last_layer_scale=0.1)
+    z, ldj = O.grevnet_f(g.nodes, g.senders, g.receivers, p)
+    node_off = np.concatenate([[0], np.cumsum(g.n_node)])
+    edge_off = np.concatenate([[0], np.cumsum(g.n_edge)])
+    total = 0.0
+    for k in range(len(g.n_node)):
+        s = g.senders[edge_off[k]:edge_off[k + 1]] - node_off[k]
+        r = g.receivers[edge_off[k]:edge_off[k + 1]] - node_off[k]
+        zk, lk = O.grevnet_f(g.nodes[node_off[k]:node_off[k + 1]], s, r, p)
+        assert np.allclose(zk, z[node_off[k]:node_off[k + 1]], rtol=1e-5, atol=1e-6)
+        total += float(lk)
+    assert abs(total - float(ldj)) < 1e-4 * max(1.0, abs(float(ldj)))
+
+
+def test_k5_index_formulas():
+    from graph_normalizing_flows_b200 import graph_data as GD, grevnet_synthetic_data as SD, utils as U
+    from graph_normalizing_flows_b200.graphs import networkxs_to_graphs_tuple
+    import networkx as nx
+    rng = np.random.default_rng(4)
+    graphs = []
+    for _ in range(6):
+        g = nx.gnp_random_graph(int(rng.integers(3, 12)), 0.4, seed=int(rng.integers(1 << 30)))
+        g = nx.relabel_nodes(g, {i: (i, i + 1) for i in g.nodes()})   # tuple ids like the grid family
+        if g.number_of_nodes() > 2:
+            first = list(g.nodes())[0]
+            g.add_edge(first, first)                                   # pre-existing self-loop (citeseer)
+        graphs.append(g)
+    want = DO.networkxs_to_graphs_tuple([DO.convert_nx_repr(g.to_directed()) for g in graphs], None)
+    from graph_normalizing_flows_b200.graphs import concat_structures
+    got = concat_structures([GD.convert_nx_repr(g.to_directed()) for g in graphs])
+    for f in ("senders", "receivers", "n_node", "n_edge"):
+        a, b = getattr(want, f), getattr(got, f)
+        assert a.dtype == b.dtype == np.int32 and np.array_equal(a, b), f
+    got2 = networkxs_to_graphs_tuple([DO.convert_nx_repr(g.to_directed()) for g in graphs])
+    assert np.array_equal(got2.senders, want.senders) and np.array_equal(got2.receivers, want.receivers)
+    for n_node in ([3, 1, 4, 0, 2], [1], [], [7, 7]):
+        a, b = DO.senders_receivers(n_node), U.senders_receivers(n_node)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and b[0].dtype == np.int32
+    for n in (1, 2, 5, 9):
+        a = DO.nx_to_arrays(DO.fully_connected_nx_graph(n))
+        s, r = SD.fully_connected_edges(n)
+        assert np.array_equal(a[1], s) and np.array_equal(a[2], r)
+
+
+def test_family_fixtures_are_consistent():
+    for path in sorted(glob.glob(os.path.join(H.GOLDEN, "graphs_*.npz"))):
+        f = np.load(path)
+        assert int(f["n_edge"].sum()) == len(f["senders_local"]) == len(f["receivers_local"])
+        rep = np.repeat(f["n_node"], f["n_edge"])
+        assert (f["senders_local"] < rep).all() and (f["receivers_local"] < rep).all()
+        # convert_nx_repr: every node has its self-loop, and it comes first for its sender
+        off = np.concatenate([[0], np.cumsum(f["n_edge"])])
+        for k in range(0, len(f["n_node"]), max(1, len(f["n_node"]) // 10)):
+            s = f["senders_local"][off[k]:off[k + 1]].astype(int)
+            r = f["receivers_local"][off[k]:off[k + 1]].astype(int)
+            assert (np.diff(s) >= 0).all()
+            first = np.r_[True, np.diff(s) > 0]
+            assert (r[first] == s[first]).all() and first.sum() == f["n_node"][k]
+
+
+def test_torch_baseline_matches_numpy_oracle():
+    import torch
+    from oracle import gnf_oracle_torch as OT
+    rng = np.random.default_rng(6)
+    g = H.random_batch(rng, 6, 4, 15, D=14)
+    for block, agg in (("concat", "sum"), ("agg_then", "mean")):
+        p = O.make_params(5, 2, 14, 64, 4, agg=agg, block=block, last_layer_scale=0.1)
+        z, ldj = O.grevnet_f(g.nodes, g.senders, g.receivers, p)
+        zt, lt = OT.grevnet_f(torch.from_numpy(g.nodes), torch.from_numpy(g.senders).long(),
+                              torch.from_numpy(g.receivers).long(), OT.params_to_torch(p))
+        assert np.allclose(zt.numpy(), z, rtol=1e-5, atol=1e-5)
+        assert abs(float(lt) - float(ldj)) < 1e-4 * max(1.0, abs(float(ldj)))
+        lp = O.log_prob(z, ldj, g.n_node)["log_prob_xs"]
+        assert H.rel_err(OT.log_prob_xs(zt, lt), lp) < 1e-5
