@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--graphs-per-gpu", type=int, default=4096)
-    ap.add_argument("--math", default="tc3x", choices=["tc3x", "fp32", "bf16", "tc3x_bf16"])
+    ap.add_argument("--math", default="tc3x", choices=["tc3x", "fp32", "bf16", "tc3x_bf16", "tc2x"])
     ap.add_argument("--cpu-graphs", type=int, default=1024, help="bounded CPU-baseline sample (graphs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seg-graphs", type=int, default=65536, help="batch for the scatter-reduce HBM roofline")
@@ -188,6 +188,8 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"                         # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -270,16 +272,19 @@ def main():
                                              wsb, stream))
         for i in range(3):
             one(i)
-        x0[:, :D // 2] = graph.nodes[:, :D // 2]
-        x1[:, :D // 2] = graph.nodes[:, D // 2:]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
         torch.cuda.synchronize()
-        e0.record()
-        for i in range(reps):
-            one(i)                                                # 2 launches of k_coupling_tc each
-        e1.record()
+        for r in range(reps):                                     # same cadence as a step: flush, then T steps
+            x0[:, :D // 2] = graph.nodes[:, :D // 2]
+            x1[:, :D // 2] = graph.nodes[:, D // 2:]
+            flush_buf.fill_(r)
+            e0[r].record()
+            for i in range(T):
+                one(i)                                            # 2 launches of k_coupling_tc each
+            e1[r].record()
         torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / (2 * reps)
+        k_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / (2 * T * reps)
         flops = n_nodes * FLOPS_PER_NODE_UPDATE
         ach = flops / (k_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
@@ -287,7 +292,7 @@ def main():
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                 "ms_per_launch": k_ms, "algorithmic_flops_per_launch": flops,
-                "executed_mma_flops_per_algorithmic_flop": 3 if args.math.startswith("tc3x") else 1,
+                "executed_mma_flops_per_algorithmic_flop": {"tc3x": 3, "tc3x_bf16": 3, "tc2x": 2}.get(args.math, 1),
                 "share_of_step": (2 * T * k_ms) / ms_per_step}
 
     # ---- scatter-reduce sub-op against the HBM roofline (standalone gather+segment-sum) --------
@@ -370,13 +375,14 @@ def main():
                        "log_prob_xs": log_prob_xs})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {"tc3x": "f16x2-split/f32-acc", "tc3x_bf16": "bf16x2-split/f32-acc",
+                "vs_baseline": None, "dtype": {"tc3x": "f16x2-split/f32-acc", "tc3x_bf16": "bf16x2-split/f32-acc", "tc2x": "f16 act x f16x2-split weights/f32-acc",
                                                "bf16": "bf16", "fp32": "f32"}[args.math],
                 "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32},
                 "gpu_launches": launches, "roofline": roof, "roofline_segment_sum": seg, "cpu_baseline": cpu,
                 "effective_tflops": value * FLOPS_PER_NODE_UPDATE / 1e12}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

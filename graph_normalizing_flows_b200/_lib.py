@@ -19,7 +19,7 @@ GNF_EINVAL, GNF_ECUDA, GNF_EUNSUPPORTED, GNF_EWORKSPACE = -1, -2, -3, -4
 AGG = {"sum": 0, "mean": 1}
 BLOCK = {"concat": 0, "agg_then": 1}
 ACT = {"leaky_relu": 0, "relu": 1}
-MATH = {"fp32": 0, "tc3x": 1, "bf16": 2, "tc3x_bf16": 3}
+MATH = {"fp32": 0, "tc3x": 1, "bf16": 2, "tc3x_bf16": 3, "tc2x": 4}
 
 
 class FlowDesc(C.Structure):
@@ -56,6 +56,12 @@ SIGNATURES = {
     "gnf_grevnet_inverse": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _i32, _p, _sz, _p]),
     "gnf_padded_half": (_i32, [_i32]),
     "gnf_coupling_step": (C.c_int, [_p, _i32, _i32, _p, _p, _i64, _i64, _p, _p, _p, _i32, _p, _sz, _p]),
+    "gnf_coupling_half": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i64, _i64, _p, _p, _p, _i32, _p, _sz, _p]),
+    "gnf_split_halves": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "gnf_merge_halves": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "gnf_bn_moments_workspace": (_sz, [_i32]),
+    "gnf_bn_moments": (C.c_int, [_p, _i64, _i32, _p, _p, _sz, _p]),
+    "gnf_affine_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "gnf_gnn_forward": (C.c_int, [_p, _i32, _i32, _i32, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "gnf_log_prob_workspace": (_sz, [_i64, _i32]),
     "gnf_log_prob": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),

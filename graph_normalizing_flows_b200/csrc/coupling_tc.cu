@@ -341,14 +341,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int m = 0; m < 2; ++m) {
           const uint8_t* src = p.w[m];
-          issue(src, NPROD == 3 ? G::L0_BYTES : G::L0_MAT_BYTES);
+          issue(src, NPROD >= 2 ? G::L0_BYTES : G::L0_MAT_BYTES);
           src += G::L0_BYTES;
           for (int l = 1; l < K - 1; ++l)
             for (int c = 0; c < kNS * G::NKC; ++c) {
-              issue(src, NPROD == 3 ? G::CHUNK_BYTES : G::MAT_BYTES);
+              issue(src, NPROD >= 2 ? G::CHUNK_BYTES : G::MAT_BYTES);
               src += G::CHUNK_BYTES;
             }
-          issue(src, NPROD == 3 ? G::LAST_BYTES : G::LAST_MAT_BYTES);
+          issue(src, NPROD >= 2 ? G::LAST_BYTES : G::LAST_MAT_BYTES);
         }
       }
     }
@@ -399,10 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
               const uint64_t b_hi = smem_desc(sb, LAT * 16, 128);
               const uint64_t b_lo = smem_desc(sb + G::L0_MAT_BYTES, LAT * 16, 128);
               mma_ss(d, a_hi, b_hi, idesc_l0, 1);
-              if (NPROD == 3) {
-                mma_ss(d, a_lo, b_hi, idesc_l0, 1);
-                mma_ss(d, a_hi, b_lo, idesc_l0, 1);
-              }
+              if (NPROD == 3) mma_ss(d, a_lo, b_hi, idesc_l0, 1);   // activation residual
+              if (NPROD >= 2) mma_ss(d, a_hi, b_lo, idesc_l0, 1);   // weight residual
               tc_commit(bar_empty + 8 * stage);
               tc_commit(bar_acc);
               tc_commit(bar_acc + 8);
@@ -441,10 +439,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
                     const uint64_t koff = (uint64_t)((ks * 2 * (G::NH * 16)) >> 4);
                     const uint32_t a_hi = a0 + a_col(ks * 16);
                     mma_ts(d, a_hi, b_hi0 + koff, idesc_h, 1);
-                    if (NPROD == 3) {
-                      mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_h, 1);
-                      mma_ts(d, a_hi, b_lo0 + koff, idesc_h, 1);
-                    }
+                    if (NPROD == 3) mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_h, 1);
+                    if (NPROD >= 2) mma_ts(d, a_hi, b_lo0 + koff, idesc_h, 1);
                   }
                   tc_commit(bar_empty + 8 * stage);
                   if (kc == G::NKC - 1) tc_commit(bar_acc + 8 * ph);
@@ -473,10 +469,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
                 const uint64_t koff = (uint64_t)((ks * 2 * (kNOut * 16)) >> 4);
                 const uint32_t a_hi = in_col + a_col(ks * 16);
                 mma_ts(d, a_hi, b_hi0 + koff, idesc_last, ks ? 1u : 0u);
-                if (NPROD == 3) {
-                  mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_last, 1);
-                  mma_ts(d, a_hi, b_lo0 + koff, idesc_last, 1);
-                }
+                if (NPROD == 3) mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_last, 1);
+                if (NPROD >= 2) mma_ts(d, a_hi, b_lo0 + koff, idesc_last, 1);
               }
               tc_commit(bar_empty + 8 * stage);
               tc_commit(bar_acc);
@@ -784,7 +778,7 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   p.csr = csr_senders;
   p.n_nodes = n_nodes;
   p.n_tiles = (int)ceil_div(n_nodes, kTileM);
-  const int img = (math == GNF_MATH_TC3X) ? 0 : 1;
+  const int img = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 0 : 1;
   p.w[0] = f.wtc[img] + (size_t)mlp_s * f.wtc_per_mlp;
   p.w[1] = f.wtc[img] + (size_t)mlp_t * f.wtc_per_mlp;
   p.bias[0] = f.btc + (size_t)mlp_s * f.K * 256;
@@ -802,10 +796,12 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   *n_partials = grid;
   if (f.L == 256) {
+    if (math == GNF_MATH_TC2X) return launch_tc<256, 2, false>(p, grid, stream);
     if (math == GNF_MATH_TC3X) return launch_tc<256, 3, false>(p, grid, stream);
     if (math == GNF_MATH_TC3X_BF16) return launch_tc<256, 3, true>(p, grid, stream);
     return launch_tc<256, 1, true>(p, grid, stream);
   }
+  if (math == GNF_MATH_TC2X) return launch_tc<128, 2, false>(p, grid, stream);
   if (math == GNF_MATH_TC3X) return launch_tc<128, 3, false>(p, grid, stream);
   if (math == GNF_MATH_TC3X_BF16) return launch_tc<128, 3, true>(p, grid, stream);
   return launch_tc<128, 1, true>(p, grid, stream);

@@ -242,6 +242,51 @@ k_reduce_partials(const double* __restrict__ partials, int n, double* __restrict
   if (threadIdx.x == 0) accum[0] = (add ? accum[0] : 0.0) + red[0];
 }
 
+// ---- a9: batch-norm bijector pieces (per-feature moments, in-place affine) ------------------
+// thread t owns feature t % hp (blockDim is a multiple of hp); fp64 partials, fixed order
+__global__ void k_bn_partial(const float* __restrict__ x, int64_t total, int hp, double* __restrict__ partials) {
+  extern __shared__ double sm[];                 // [2][blockDim]
+  double s = 0.0, ss = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const double v = (double)x[i];
+    s += v;
+    ss += v * v;
+  }
+  sm[threadIdx.x] = s;
+  sm[blockDim.x + threadIdx.x] = ss;
+  __syncthreads();
+  if ((int)threadIdx.x < hp) {
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < (int)blockDim.x; k += hp) {
+      a += sm[k];
+      b += sm[blockDim.x + k];
+    }
+    partials[(int64_t)blockIdx.x * 2 * hp + threadIdx.x] = a;
+    partials[(int64_t)blockIdx.x * 2 * hp + hp + threadIdx.x] = b;
+  }
+}
+
+__global__ void k_bn_final(const double* __restrict__ partials, int nblocks, int h, int hp, double* __restrict__ out) {
+  const int f = threadIdx.x;
+  if (f >= h) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nblocks; ++k) {
+    a += partials[(int64_t)k * 2 * hp + f];
+    b += partials[(int64_t)k * 2 * hp + hp + f];
+  }
+  out[f] = a;
+  out[h + f] = b;
+}
+
+__global__ void k_affine_rows(float* __restrict__ x, int64_t n, int h, int hp, const float* __restrict__ scale,
+                              const float* __restrict__ shift) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * hp) return;
+  const int f = (int)(i % hp);
+  if (f < h) x[i] = __fadd_rn(__fmul_rn(x[i], scale[f]), shift[f]);
+}
+
 // ---- a8: log-prob ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_sumsq(const float* __restrict__ z, int64_t total, double* __restrict__ partials) {
@@ -390,7 +435,7 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
 }
 
 int check_math(const Flow& f, int math, const char* who) {
-  GNF_REQUIRE(math >= GNF_MATH_FP32 && math <= GNF_MATH_TC3X_BF16, GNF_EINVAL, "%s: bad math %d", who, math);
+  GNF_REQUIRE(math >= GNF_MATH_FP32 && math <= GNF_MATH_TC2X, GNF_EINVAL, "%s: bad math %d", who, math);
   if (math != GNF_MATH_FP32)
     GNF_REQUIRE(f.tc_ok, GNF_EUNSUPPORTED,
                 "%s: fused tcgen05 kernel needs latent_dim in {128,256}, MLP input dim <= 16, "
@@ -512,7 +557,7 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
 extern "C" int gnf_flow_supports(const gnf_flow* h, int32_t math) {
   if (!h) return 0;
   if (math == GNF_MATH_FP32) return 1;
-  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC3X_BF16 && h->f.tc_ok) ? 1 : 0;
+  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && h->f.tc_ok) ? 1 : 0;
 }
 
 extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* stream_) {
@@ -653,6 +698,78 @@ extern "C" int gnf_gnn_forward(const gnf_flow* h, int32_t which, int32_t half, i
   rc = run_mlp32(f, f.mlp_index(which, half, step), w, w.sbuf, n, stream);
   if (rc) return rc;
   k_unpad_rows<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(w.sbuf, n, f.H, f.HP, out);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_coupling_half(const gnf_flow* h, int32_t half, int32_t step, int32_t inverse, const float* xa,
+                                 float* xb, int64_t n, int64_t e, const int32_t* rowptr, const int32_t* csr,
+                                 double* ldj_accum, int32_t math, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_common(h, n, e, rowptr, csr, ws, ws_bytes, math, "gnf_coupling_half");
+  if (rc) return rc;
+  GNF_REQUIRE((half == 0 || half == 1) && step >= 0 && step < h->f.d.num_timesteps, GNF_EINVAL,
+              "gnf_coupling_half: bad (half, step)");
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(xa && xb && xa != xb, GNF_EINVAL, "gnf_coupling_half: xa/xb must be distinct non-null buffers");
+  const Flow& f = h->f;
+  Workspace w = carve(f, n, math, ws);
+  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  return coupling_half(f, half, step, inverse, xa, xb, n, rowptr, csr, inverse ? nullptr : ldj_accum, math, w,
+                       stream);
+}
+
+extern "C" int gnf_split_halves(const float* x, int64_t n, int32_t d, float* x0, float* x1, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(d >= 2 && d % 2 == 0 && n >= 0, GNF_EINVAL, "gnf_split_halves: bad shape");
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && x0 && x1, GNF_EINVAL, "gnf_split_halves: null pointer");
+  const int hh = d / 2, hp = gnf_padded_half(hh);
+  k_split<<<(unsigned)ceil_div(n * hp, 256), 256, 0, stream>>>(x, n, d, hh, hp, x0, x1);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_merge_halves(const float* x0, const float* x1, int64_t n, int32_t d, float* x, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(d >= 2 && d % 2 == 0 && n >= 0, GNF_EINVAL, "gnf_merge_halves: bad shape");
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && x0 && x1, GNF_EINVAL, "gnf_merge_halves: null pointer");
+  const int hh = d / 2, hp = gnf_padded_half(hh);
+  k_merge<<<(unsigned)ceil_div(n * d, 256), 256, 0, stream>>>(x0, x1, n, d, hh, hp, x);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+constexpr int kBnBlocks = 296;
+extern "C" size_t gnf_bn_moments_workspace(int32_t h) { return (size_t)kBnBlocks * 2 * gnf_padded_half(h) * 8; }
+
+extern "C" int gnf_bn_moments(const float* x, int64_t n, int32_t hh, double* sums, void* ws, size_t ws_bytes,
+                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int hp = gnf_padded_half(hh);
+  GNF_REQUIRE(hh >= 1 && hp <= 256 && n >= 0 && sums, GNF_EINVAL, "gnf_bn_moments: bad argument (H <= 256)");
+  GNF_REQUIRE(ws && ws_bytes >= gnf_bn_moments_workspace(hh), GNF_EWORKSPACE, "gnf_bn_moments: workspace too small");
+  GNF_REQUIRE(n == 0 || x, GNF_EINVAL, "gnf_bn_moments: null x");
+  const int tpb = (256 / hp) * hp;
+  const int64_t total = n * hp;
+  int blocks = (int)(ceil_div(total, tpb) < kBnBlocks ? ceil_div(total, tpb) : kBnBlocks);
+  if (blocks < 1) blocks = 1;
+  k_bn_partial<<<blocks, tpb, 2 * tpb * sizeof(double), stream>>>(x, total, hp, (double*)ws);
+  GNF_LAUNCH_CHECK();
+  k_bn_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, hh, hp, sums);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_affine_rows(float* x, int64_t n, int32_t hh, const float* scale, const float* shift,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(hh >= 1 && n >= 0, GNF_EINVAL, "gnf_affine_rows: bad shape");
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && scale && shift, GNF_EINVAL, "gnf_affine_rows: null pointer");
+  const int hp = gnf_padded_half(hh);
+  k_affine_rows<<<(unsigned)ceil_div(n * hp, 256), 256, 0, stream>>>(x, n, hh, hp, scale, shift);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }

@@ -349,11 +349,7 @@ class GRevNet(nn.Module):
         self.node_embedding_dim = int(node_embedding_dim)
         if self.node_embedding_dim % 2:
             raise ValueError("node_embedding_dim must be even (tf.split at gnn.py:306)")
-        if use_batch_norm:
-            raise NotImplementedError(
-                "use_batch_norm=True (TFP BatchNormalization bijector, gnn.py:260-263) is not part of the "
-                "accelerated path yet (SURVEY §8 row a9 / f4); construct with use_batch_norm=False")
-        self.use_batch_norm = False
+        self.use_batch_norm = bool(use_batch_norm)
         T = self.num_timesteps
         # construction order of gnn.py:283-299
         if self.weight_sharing:
@@ -392,6 +388,17 @@ class GRevNet(nn.Module):
         self._in_dim = in_dim
         self._rebind()
         self._math = math
+        # bns[2][T] = make_batch_norm() (gnn.py:260-263,301-302): tf.layers.BatchNormalization(axis=-1)
+        # defaults gamma=1, beta=0, moving_mean=0, moving_variance=1, epsilon=1e-3, momentum=0.99,
+        # wrapped in tfb.BatchNormalization(training=True).  Always constructed, as in the reference.
+        self.bn_epsilon, self.bn_momentum = 1e-3, 0.99
+        self.bn_gamma = nn.Parameter(torch.ones(2, T, H, device=dev), requires_grad=False)
+        self.bn_beta = nn.Parameter(torch.zeros(2, T, H, device=dev), requires_grad=False)
+        self.register_buffer("bn_moving_mean", torch.zeros(2, T, H, device=dev))
+        self.register_buffer("bn_moving_var", torch.ones(2, T, H, device=dev))
+        self.bn_update_moving = True          # the scripts run UPDATE_OPS with every step (run_grevnet.py:362)
+        self.bn_group = None                  # process group for cross-rank batch statistics (sharding.py)
+        self.bn_sync = True                   # all-reduce the batch statistics when running sharded
 
     # -- parameter plumbing -------------------------------------------------------------------
     def _rebind(self):
@@ -431,6 +438,8 @@ class GRevNet(nn.Module):
 
     # -- the hot path ---------------------------------------------------------------------------
     def _run(self, x: GraphsTuple, inverse_kernel: bool):
+        if self.use_batch_norm:
+            return self._run_bn(x, inverse_kernel)
         nodes = _lib.require_cuda(x.nodes, "graph.nodes", torch.float32)
         if nodes.dim() != 2 or nodes.shape[1] != self.node_embedding_dim:
             raise ValueError(f"graph.nodes must be [N, {self.node_embedding_dim}], got {tuple(nodes.shape)}")
@@ -455,6 +464,90 @@ class GRevNet(nn.Module):
                                            _lib.ptr(st.csr_senders), _lib.ptr(out), m, _lib.ptr(ws), wsb,
                                            stream), "gnf_grevnet_inverse")
         return out, None
+
+    # -- a9: the batch-norm variant, half step by half step ---------------------------------------
+    def _bn_inverse_(self, xp, n_local, half, i, ldj):
+        """bn.inverse + bn.inverse_log_det_jacobian(x, 2) on a planar half, in place (gnn.py:310-313):
+        batch statistics over ALL nodes of the batch (all ranks when sharded)."""
+        lib, H, dev = self._flow.lib, self.node_embedding_dim // 2, xp.device
+        sums = torch.empty(2 * H + 1, dtype=torch.float64, device=dev)
+        wsb = lib.gnf_bn_moments_workspace(H)
+        ws = _lib.workspace(wsb, dev)
+        _lib.check(lib.gnf_bn_moments(_lib.ptr(xp), n_local, H, _lib.ptr(sums), _lib.ptr(ws), wsb,
+                                      _lib.stream_ptr(dev)), "gnf_bn_moments")
+        sums[2 * H] = float(n_local)
+        dist = torch.distributed
+        if self.bn_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.bn_group) > 1:
+            dist.all_reduce(sums, group=self.bn_group)                   # the extra [2H+1] all-reduce of row a9
+        n = sums[2 * H]
+        mean = sums[:H] / n
+        var = (sums[H:2 * H] / n - mean * mean).clamp_(min=0.0)         # biased, as tf.nn.moments
+        gamma = self.bn_gamma[half, i].double()
+        beta = self.bn_beta[half, i].double()
+        inv = torch.rsqrt(var + self.bn_epsilon)
+        scale = gamma * inv
+        shift = beta - mean * scale
+        # scalar ildj tiled over the node axis (event_ndims=2 vs forward_min_event_ndims=1): x N (local share)
+        ldj += float(n_local) * (torch.log(gamma) - 0.5 * torch.log(var + self.bn_epsilon)).sum()
+        sc, sh = scale.float().contiguous(), shift.float().contiguous()
+        _lib.check(lib.gnf_affine_rows(_lib.ptr(xp), n_local, H, _lib.ptr(sc), _lib.ptr(sh), _lib.stream_ptr(dev)),
+                   "gnf_affine_rows")
+        if self.bn_update_moving:
+            m = self.bn_momentum
+            self.bn_moving_mean[half, i].mul_(m).add_((1 - m) * mean.float())
+            self.bn_moving_var[half, i].mul_(m).add_((1 - m) * var.float())
+
+    def _bn_forward_(self, zp, n_local, half, i):
+        """bn.forward = de-normalise with the MOVING statistics (gnn.py:356-358,369-371)."""
+        lib, H, dev = self._flow.lib, self.node_embedding_dim // 2, zp.device
+        scale = torch.sqrt(self.bn_moving_var[half, i] + self.bn_epsilon) / self.bn_gamma[half, i]
+        shift = self.bn_moving_mean[half, i] - self.bn_beta[half, i] * scale
+        sc, sh = scale.float().contiguous(), shift.float().contiguous()
+        _lib.check(lib.gnf_affine_rows(_lib.ptr(zp), n_local, H, _lib.ptr(sc), _lib.ptr(sh), _lib.stream_ptr(dev)),
+                   "gnf_affine_rows")
+
+    def _run_bn(self, x: GraphsTuple, inverse_kernel: bool):
+        nodes = _lib.require_cuda(x.nodes, "graph.nodes", torch.float32)
+        D = self.node_embedding_dim
+        if nodes.dim() != 2 or nodes.shape[1] != D:
+            raise ValueError(f"graph.nodes must be [N, {D}], got {tuple(nodes.shape)}")
+        st = structure_of(x)
+        handle = self._flow.ensure(self.params.data)
+        lib, dev = self._flow.lib, nodes.device
+        m = _lib.MATH[self.math]
+        n = nodes.shape[0]
+        hp = lib.gnf_padded_half(D // 2)
+        wsb = lib.gnf_grevnet_workspace(handle, n, m)
+        ws = _lib.workspace(wsb, dev)
+        stream = _lib.stream_ptr(dev)
+        x0 = torch.empty(max(n, 1), hp, dtype=torch.float32, device=dev)
+        x1 = torch.empty(max(n, 1), hp, dtype=torch.float32, device=dev)
+        _lib.check(lib.gnf_split_halves(_lib.ptr(nodes), n, D, _lib.ptr(x0), _lib.ptr(x1), stream), "gnf_split_halves")
+        halves = (x0, x1)
+
+        def half_step(half, i, inverse, ldj):
+            xa, xb = halves[half], halves[1 - half]
+            _lib.check(lib.gnf_coupling_half(handle, half, i, int(inverse), _lib.ptr(xa), _lib.ptr(xb), n, st.n_edges,
+                                             _lib.ptr(st.rowptr), _lib.ptr(st.csr_senders), _lib.ptr(ldj), m,
+                                             _lib.ptr(ws), wsb, stream), "gnf_coupling_half")
+
+        ldj = None
+        if not inverse_kernel:
+            ldj = torch.zeros(1, dtype=torch.float64, device=dev)
+            for i in range(self.num_timesteps):                      # gnn.py:309-338
+                self._bn_inverse_(x0, n, 0, i, ldj)
+                half_step(0, i, False, ldj)
+                self._bn_inverse_(x1, n, 1, i, ldj)
+                half_step(1, i, False, ldj)
+        else:
+            for i in reversed(range(self.num_timesteps)):            # gnn.py:347-372
+                half_step(1, i, True, None)
+                self._bn_forward_(x1, n, 1, i)
+                half_step(0, i, True, None)
+                self._bn_forward_(x0, n, 0, i)
+        out = torch.empty_like(nodes)
+        _lib.check(lib.gnf_merge_halves(_lib.ptr(x0), _lib.ptr(x1), n, D, _lib.ptr(out), stream), "gnf_merge_halves")
+        return out, ldj
 
     def f(self, x: GraphsTuple):
         """x -> (z, log_det_jacobian)   (gnn.py:304-341)"""

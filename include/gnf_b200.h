@@ -53,6 +53,8 @@ extern "C" {
 #define GNF_MATH_TC3X   1  /* tcgen05 kind::f16, fp16 hi/lo split, 3 MMAs per product, fp32 acc */
 #define GNF_MATH_BF16   2  /* tcgen05 kind::f16, bf16 single pass, fp32 accumulate             */
 #define GNF_MATH_TC3X_BF16 3 /* as TC3X with a bf16 hi/lo split (no fp16 range limit)          */
+#define GNF_MATH_TC2X   4  /* fp16 activations (one rounding, unbiased) x fp16 hi/lo weights: 2 MMAs per
+                              product; log-prob parity holds, per-element z error ~1e-4            */
 
 int         gnf_abi_version(void);
 const char* gnf_last_error(void);
@@ -159,6 +161,31 @@ int gnf_coupling_step(const gnf_flow* flow, int32_t step, int32_t inverse,
                       const int32_t* rowptr, const int32_t* csr_senders,
                       double* ldj_accum, int32_t math,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* One HALF coupling step: the s/t GNNs of (half, step) read xa and update xb in place
+ * (forward: xb*exp(s)+t and *ldj_accum += sum(s); inverse: (xb-t)*exp(-s)).  gnn.py:320-323 is
+ * (half=0: xa=x0, xb=x1), gnn.py:335-338 is (half=1: xa=x1, xb=x0).  Used by the batch-norm
+ * variant of the flow, which interleaves gnf_bn_moments / gnf_affine_rows between half steps. */
+int gnf_coupling_half(const gnf_flow* flow, int32_t half, int32_t step, int32_t inverse,
+                      const float* xa, float* xb, int64_t n_nodes, int64_t n_edges,
+                      const int32_t* rowptr, const int32_t* csr_senders,
+                      double* ldj_accum, int32_t math,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* tf.split(x.nodes, 2, axis=1) (gnn.py:306) into planar zero-padded halves [N, HP], and
+ * tf.concat([x0, x1], 1) (gnn.py:340) back. */
+int gnf_split_halves(const float* x, int64_t n_nodes, int32_t d, float* x0, float* x1, void* stream);
+int gnf_merge_halves(const float* x0, const float* x1, int64_t n_nodes, int32_t d, float* x, void* stream);
+
+/* a9  pieces of tfb.BatchNormalization (gnn.py:260-263,310-313,325-328,356-358,369-371) on a
+ * planar half x [N, HP]:
+ *   gnf_bn_moments : sums[0:H] = sum_n x[n,f], sums[H:2H] = sum_n x[n,f]^2  (device double[2H];
+ *                    sums, not moments, so that ranks can all-reduce them before dividing)
+ *   gnf_affine_rows: x[n,f] <- x[n,f] * scale[f] + shift[f]  (normalise / de-normalise) */
+size_t gnf_bn_moments_workspace(int32_t h);
+int gnf_bn_moments(const float* x, int64_t n_nodes, int32_t h, double* sums,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int gnf_affine_rows(float* x, int64_t n_nodes, int32_t h, const float* scale, const float* shift, void* stream);
 
 /* One message-passing GNN of the flow on its own: NodeBlockGNN._build (gnn.py:155-156) =
  * node_block(edge_block(graph)); x, out [N, D/2] f32.  which: 0 = s, 1 = t.  fp32 arithmetic.

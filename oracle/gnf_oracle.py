@@ -194,6 +194,92 @@ def grevnet_g(nodes, senders, receivers, params):
     return np.concatenate([z0, z1], axis=1)
 
 
+# --------------------------------------------------------------------------- #
+# a9  TFP batch-norm bijector inside the coupling (gnn.py:260-263,310-313,325-328,356-358,369-371)
+# --------------------------------------------------------------------------- #
+BN_EPS = 1e-3         # tf.layers.BatchNormalization default epsilon
+BN_MOMENTUM = 0.99    # default momentum
+
+
+def make_bn_state(T, H, dtype=np.float32):
+    """bns[2][T] of make_batch_norm (gnn.py:260-263,301-302): gamma=1, beta=0, moving_mean=0,
+    moving_variance=1 (Keras defaults)."""
+    mk = lambda: {"gamma": np.ones(H, dtype), "beta": np.zeros(H, dtype),
+                  "moving_mean": np.zeros(H, dtype), "moving_var": np.ones(H, dtype)}
+    return [[mk() for _ in range(T)], [mk() for _ in range(T)]]
+
+
+def bn_inverse(x, bn, update=True):
+    """tfb.BatchNormalization(training=True): returns (inverse(x), inverse_log_det_jacobian(x, 2)).
+    [upstream, tensorflow-probability 0.7.0, restated; unverifiable here]
+      inverse  = batchnorm_layer(x, training=True): gamma*(x-mu_B)/sqrt(var_B+eps)+beta with the
+                 BIASED batch variance over the N nodes (tf.nn.moments); moving stats updated with
+                 momentum 0.99 (the scripts run UPDATE_OPS, run_grevnet.py:362).
+      ildj     = sum_f(log gamma_f - 1/2 log(var_B,f + eps)), a scalar, tiled over the extra event
+                 dimension (event_ndims=2, forward_min_event_ndims=1) -> multiplied by N."""
+    dt = x.dtype
+    n = x.shape[0]
+    mean = np.mean(x, axis=0, dtype=dt)
+    var = np.mean((x - mean) ** 2, axis=0, dtype=dt)
+    ildj = dt.type(n) * np.sum(np.log(bn["gamma"].astype(dt)) - dt.type(0.5) * np.log(var + dt.type(BN_EPS)), dtype=dt)
+    y = bn["gamma"].astype(dt) * (x - mean) / np.sqrt(var + dt.type(BN_EPS)) + bn["beta"].astype(dt)
+    if update:
+        bn["moving_mean"] = (bn["moving_mean"] * BN_MOMENTUM + mean * (1 - BN_MOMENTUM)).astype(bn["moving_mean"].dtype)
+        bn["moving_var"] = (bn["moving_var"] * BN_MOMENTUM + var * (1 - BN_MOMENTUM)).astype(bn["moving_var"].dtype)
+    return y, ildj
+
+
+def bn_forward(z, bn):
+    """bijector forward = de-normalise with the MOVING statistics:
+    sqrt(moving_var+eps)/gamma * (z - beta) + moving_mean."""
+    dt = z.dtype
+    return (np.sqrt(bn["moving_var"].astype(dt) + dt.type(BN_EPS)) / bn["gamma"].astype(dt)
+            * (z - bn["beta"].astype(dt)) + bn["moving_mean"].astype(dt))
+
+
+def grevnet_f_bn(nodes, senders, receivers, params, bns, update=True):
+    """GRevNet.f with use_batch_norm=True (gnn.py:304-341)."""
+    cfg = params["cfg"]
+    dt = nodes.dtype
+    h = nodes.shape[1] // 2
+    x0, x1 = nodes[:, :h].copy(), nodes[:, h:].copy()
+    ldj = dt.type(0)
+    for i in range(params["T"]):
+        y, ild = bn_inverse(x0, bns[0][i], update)            # gnn.py:310-313 (ildj on the un-normalised x0)
+        ldj = ldj + ild
+        x0 = y
+        s = node_block_gnn(x0, senders, receivers, _st(params, "s", 0, i), cfg)
+        t = node_block_gnn(x0, senders, receivers, _st(params, "t", 0, i), cfg)
+        ldj = ldj + np.sum(s, dtype=dt)
+        x1 = x1 * np.exp(s) + t
+        y, ild = bn_inverse(x1, bns[1][i], update)            # gnn.py:325-328
+        ldj = ldj + ild
+        x1 = y
+        s = node_block_gnn(x1, senders, receivers, _st(params, "s", 1, i), cfg)
+        t = node_block_gnn(x1, senders, receivers, _st(params, "t", 1, i), cfg)
+        ldj = ldj + np.sum(s, dtype=dt)
+        x0 = x0 * np.exp(s) + t
+    return np.concatenate([x0, x1], axis=1), ldj
+
+
+def grevnet_g_bn(nodes, senders, receivers, params, bns):
+    """GRevNet.g with use_batch_norm=True (gnn.py:343-373): s,t from the normalised-domain half,
+    THEN that half is de-normalised with the moving statistics."""
+    cfg = params["cfg"]
+    h = nodes.shape[1] // 2
+    z0, z1 = nodes[:, :h].copy(), nodes[:, h:].copy()
+    for i in reversed(range(params["T"])):
+        s = node_block_gnn(z1, senders, receivers, _st(params, "s", 1, i), cfg)
+        t = node_block_gnn(z1, senders, receivers, _st(params, "t", 1, i), cfg)
+        z1 = bn_forward(z1, bns[1][i])                        # gnn.py:356-358
+        z0 = (z0 - t) * np.exp(-s)
+        s = node_block_gnn(z0, senders, receivers, _st(params, "s", 0, i), cfg)
+        t = node_block_gnn(z0, senders, receivers, _st(params, "t", 0, i), cfg)
+        z0 = bn_forward(z0, bns[0][i])                        # gnn.py:369-371
+        z1 = (z1 - t) * np.exp(-s)
+    return np.concatenate([z0, z1], axis=1)
+
+
 def grevnet_call(graph, params, inverse=True):
     """GRevNet._build (gnn.py:379-381): inverse=True is the data->latent (density) direction."""
     if inverse:

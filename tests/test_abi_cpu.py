@@ -80,8 +80,8 @@ def test_scale_last_layers():
 def test_error_contract_on_host():
     with pytest.raises(ValueError, match="even"):
         G.GRevNet(mk(D=3), 2, 3, device="cpu")                         # tf.split failure at gnn.py:306
-    with pytest.raises(NotImplementedError):
-        G.GRevNet(mk(), 2, 14, use_batch_norm=True, device="cpu")
+    bn = G.GRevNet(mk(L=16, K=3, D=4), 2, 4, use_batch_norm=True, device="cpu")   # bns[2][T], gnn.py:301-302
+    assert bn.bn_gamma.shape == (2, 2, 2) and float(bn.bn_moving_var.min()) == 1.0
     with pytest.raises(ValueError):
         G.make_mlp_model(8, 2, 3, activation="tanh")
     with pytest.raises(ValueError):
