@@ -9,7 +9,8 @@ All arithmetic runs in libgnf_b200.so (include/gnf_b200.h).  No CPU fallback.
 """
 from . import _lib, gnn, graphs, loss, utils  # noqa: F401
 from .gnn import (GRevNet, NodeBlockGNN, ConcatThenMLPBlock, AggThenMLPBlock, make_mlp_model,  # noqa: F401
-                  sum_concat_then_mlp_gnn, avg_concat_then_mlp_gnn, sum_then_mlp_gnn, avg_then_mlp_gnn)
+                  sum_concat_then_mlp_gnn, avg_concat_then_mlp_gnn, sum_then_mlp_gnn, avg_then_mlp_gnn,
+                  dm_self_attn_gnn, DMSelfAttentionMLP)
 from .graphs import GraphsTuple  # noqa: F401
 
 __version__ = "0.1.0"

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libgnf_b200.so")
 GNF_OK = 0
 GNF_EINVAL, GNF_ECUDA, GNF_EUNSUPPORTED, GNF_EWORKSPACE = -1, -2, -3, -4
 AGG = {"sum": 0, "mean": 1}
-BLOCK = {"concat": 0, "agg_then": 1}
+BLOCK = {"concat": 0, "agg_then": 1, "dm_attn": 2}
+ATTN_CONCAT, ATTN_RESIDUAL, ATTN_KQ_DIV = 1, 2, 4
 ACT = {"leaky_relu": 0, "relu": 1}
 MATH = {"fp32": 0, "tc3x": 1, "bf16": 2, "tc3x_bf16": 3, "tc2x": 4}
 
@@ -27,7 +28,9 @@ class FlowDesc(C.Structure):
         ("num_timesteps", C.c_int32), ("node_embedding_dim", C.c_int32),
         ("latent_dim", C.c_int32), ("num_layers", C.c_int32),
         ("agg", C.c_int32), ("block", C.c_int32), ("act", C.c_int32),
-        ("weight_sharing", C.c_int32), ("eps", C.c_float), ("reserved", C.c_int32 * 3),
+        ("weight_sharing", C.c_int32), ("eps", C.c_float),
+        ("attn_num_heads", C.c_int32), ("attn_kq_dim", C.c_int32), ("attn_v_dim", C.c_int32),
+        ("attn_out_dim", C.c_int32), ("attn_flags", C.c_int32),
     ]
 
 
@@ -63,6 +66,9 @@ SIGNATURES = {
     "gnf_bn_moments": (C.c_int, [_p, _i64, _i32, _p, _p, _sz, _p]),
     "gnf_affine_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "gnf_gnn_forward": (C.c_int, [_p, _i32, _i32, _i32, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "gnf_grevnet_backward_workspace": (_sz, [_p, _i64]),
+    "gnf_grevnet_backward": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, C.c_double, _p, _p, _p, _sz, _p]),
+    "gnf_pred_adj": (C.c_int, [_p, _i32, _p, _p, _i64, C.c_float, C.c_float, _p, _p]),
     "gnf_log_prob_workspace": (_sz, [_i64, _i32]),
     "gnf_log_prob": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
 }

@@ -72,6 +72,19 @@ struct Flow {
   int64_t w32_layer_off[kMaxLayers];
   int64_t b32_layer_off[kMaxLayers];
   int in_pads[kMaxLayers], out_pads[kMaxLayers], ins[kMaxLayers], outs[kMaxLayers];
+  // transposed fp32 weights for the backward dX GEMMs: per layer W^T [out_pad8, in_pad]
+  float* w32T = nullptr;
+  int64_t w32T_per_mlp = 0;
+  int64_t w32T_layer_off[kMaxLayers];
+  int out_pad8[kMaxLayers];
+  int64_t flat_w_off[kMaxLayers], flat_b_off[kMaxLayers];   // offsets inside one MLP of the flat parameter vector
+  // f1 attention block (GNF_BLOCK_DM_ATTN): padded fp32 projections per GNN
+  int attn = 0, heads = 0, kq = 0, vd = 0, cho = 0, attn_flags = 0;
+  int hp8 = 0, qk_pad = 0, v_pad = 0, hv_pad = 0, cho_pad = 0;
+  int64_t mlp_off = 0;                    // offset of the MLP inside one GNN's flat parameters
+  float* wattn = nullptr;
+  int64_t wattn_per_mlp = 0, wq_off = 0, wk_off = 0, wv_off = 0, wo_off = 0;
+  float* zeros = nullptr;                 // zero bias for the bias-free projections
   // tensor-core packed weights (two images: fp16 and bf16 element type), per MLP a stream of
   // shared-memory chunk images in consumption order (see coupling_tc.cu)
   uint8_t* wtc[2] = {nullptr, nullptr};   // [0]=fp16 hi/lo, [1]=bf16 hi/lo
@@ -86,6 +99,12 @@ struct Flow {
   }
 };
 
+// flow.cu (shared with backward.cu)
+int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K, int act,
+               cudaStream_t stream);
+int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
+                  float* hbuf, cudaStream_t stream);
+
 // coupling_tc.cu
 size_t tc_bytes_per_mlp(int L, int K);
 int tc_pack_mlp(const Flow& f, int mlp, const float* params, void* stream);
@@ -97,3 +116,7 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
                      double* ldj_partials, int* n_partials, void* stream);
 
 }  // namespace gnf
+
+struct gnf_flow {
+  gnf::Flow f;
+};

@@ -757,7 +757,7 @@ static unsigned long long* g_trace = nullptr;
 void tc_set_trace(void* buf) { g_trace = (unsigned long long*)buf; }
 
 bool tc_shape_supported(const Flow& f) {
-  return (f.L == 128 || f.L == 256) && f.in_dim <= kK0 && f.H <= kNOut && f.K >= 2 && f.K <= kMaxLayers;
+  return !f.attn && (f.L == 128 || f.L == 256) && f.in_dim <= kK0 && f.H <= kNOut && f.K >= 2 && f.K <= kMaxLayers;
 }
 
 size_t tc_bytes_per_mlp(int L, int K) { return L == 256 ? bytes_per_mlp_t<256>(K) : bytes_per_mlp_t<128>(K); }

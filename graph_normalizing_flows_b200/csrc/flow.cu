@@ -118,6 +118,89 @@ k_agg_input(const float* __restrict__ xa, int h, int hp, const int32_t* __restri
   }
 }
 
+// ---- f1: DMSelfAttention (gnn.py:385-477) -----------------------------------------------------
+// thread per (receiver, head).  keys = project_q at the SENDER, queries = project_k at the RECEIVER
+// (the reference passes (values, project_q, project_k) into (values, keys, queries), gnn.py:531-532);
+// logits_e = <keys[s_e], queries[r]> (/ sqrt(kq)); softmax over the receiver's in-edges as
+// gn.modules._unsorted_segment_softmax (subtract segment max, exp, divide by segment sum);
+// attended = sum_e values[s_e] * w_e in ascending edge order.  Empty segments give 0.
+__global__ void __launch_bounds__(128)
+k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+          int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
+          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
+          float* __restrict__ att) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * heads) return;
+  const int64_t r = i / heads;
+  const int h = (int)(i - r * heads);
+  const int32_t beg = rowptr[r], end = rowptr[r + 1];
+  const float* qr = queries + r * qk_pad + h * kq;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  if (end > beg) {
+    float mx = -INFINITY;
+    for (int32_t e = beg; e < end; ++e) {
+      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+      mx = fmaxf(mx, l * inv_scale);
+    }
+    float sum = 0.f;
+    for (int32_t e = beg; e < end; ++e) {
+      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+      sum += expf(l * inv_scale - mx);
+    }
+    for (int32_t e = beg; e < end; ++e) {
+      const int32_t s = csr_senders[e];
+      const float* ks = keys + (int64_t)s * qk_pad + h * kq;
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+      const float w = expf(l * inv_scale - mx) / sum;
+      const float* vs = vals + (int64_t)s * v_pad;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < vd) acc[c] = __fadd_rn(acc[c], __fmul_rn(vs[c], w));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < vd) att[r * hv_pad + h * vd + c] = acc[c];
+}
+
+// MLP input of DMSelfAttentionMLP: concat([nodes, proj]) or proj (gnn.py:547-548)
+__global__ void k_attn_input(const float* __restrict__ xa, int h, int hp, const float* __restrict__ proj, int cho,
+                             int cho_pad, int concat, int in_pad, int64_t n, float* __restrict__ hbuf) {
+  const int width = concat ? h + cho : cho;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  const int64_t node = i / width;
+  const int c = (int)(i - node * width);
+  float v;
+  if (concat) v = c < h ? xa[node * hp + c] : proj[node * cho_pad + c - h];
+  else v = proj[node * cho_pad + c];
+  hbuf[node * in_pad + c] = v;
+}
+
+__global__ void k_add_rows(float* __restrict__ out, const float* __restrict__ x, int h, int hp, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * h) return;
+  const int64_t node = i / h;
+  const int f = (int)(i - node * h);
+  out[node * hp + f] = __fadd_rn(out[node * hp + f], x[node * hp + f]);
+}
+
+__global__ void k_pack_mat(const float* __restrict__ src, int in, int out, int in_pad, int out_pad,
+                           float* __restrict__ w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < in_pad * out_pad) {
+    int r = i / out_pad, c = i - r * out_pad;
+    w[i] = (r < in && c < out) ? src[r * out + c] : 0.f;
+  }
+}
+
 // ---- a6: one Sonnet Linear (+ activation), fp32 FFMA -----------------------------------------
 // C[M,N] = act(A[M,K] @ W[K,N] + b);  K % 8 == 0, N % 4 == 0 (zero-padded operands).
 constexpr int BM = 128, BK = 8;
@@ -336,6 +419,7 @@ constexpr int kLogProbBlocks = 1184;  // 148 SMs x 8
 // ---- workspace carve-up --------------------------------------------------------------------
 struct Workspace {
   float *x0, *x1, *hbuf, *act0, *act1, *sbuf, *tbuf;
+  float *xq, *qbuf, *kbuf, *vbuf, *att, *proj;     // attention block only
   double* partials;
   int n_partials_cap;
   size_t bytes;
@@ -363,6 +447,14 @@ Workspace carve(const Flow& f, int64_t n, int math, void* base) {
     w.act1 = (float*)take(nn * lp * 4);
     w.sbuf = (float*)take(nn * f.HP * 4);
     w.tbuf = (float*)take(nn * f.HP * 4);
+    if (f.attn) {
+      w.xq = (float*)take(nn * f.hp8 * 4);
+      w.qbuf = (float*)take(nn * f.qk_pad * 4);
+      w.kbuf = (float*)take(nn * f.qk_pad * 4);
+      w.vbuf = (float*)take(nn * f.v_pad * 4);
+      w.att = (float*)take(nn * f.hv_pad * 4);
+      w.proj = (float*)take(nn * f.cho_pad * 4);
+    }
   }
   w.bytes = off;
   return w;
@@ -396,6 +488,55 @@ int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n,
   return GNF_OK;
 }
 
+// MLP input of GNN `mlp` from the half xa: aggregation blocks (shared by s and t) or attention
+int build_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
+                     const int32_t* csr_senders, const Workspace& w, cudaStream_t stream) {
+  const float* wa = f.wattn + (int64_t)mlp * f.wattn_per_mlp;
+  k_pad_rows<<<(unsigned)ceil_div(n * f.hp8, 256), 256, 0, stream>>>(xa, n, f.HP < f.hp8 ? f.HP : f.hp8, f.hp8, w.xq);
+  GNF_LAUNCH_CHECK();
+  // xa rows are [HP] wide with zero padding, so reading min(HP, hp8) columns and zero-filling is exact
+  int rc = run_linear(w.xq, wa + f.wq_off, f.zeros, w.qbuf, n, f.qk_pad, f.hp8, 2, stream);   // project_q  gnn.py:509-512
+  if (rc) return rc;
+  rc = run_linear(w.xq, wa + f.wk_off, f.zeros, w.kbuf, n, f.qk_pad, f.hp8, 2, stream);       // project_k  gnn.py:513-516
+  if (rc) return rc;
+  rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
+  if (rc) return rc;
+  const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
+  k_dm_attn<<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
+                                                                      f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
+                                                                      csr_senders, n, w.att);
+  GNF_LAUNCH_CHECK();
+  rc = run_linear(w.att, wa + f.wo_off, f.zeros, w.proj, n, f.cho_pad, f.hv_pad, 2, stream);  // new_node_proj gnn.py:543-545
+  if (rc) return rc;
+  const int concat = (f.attn_flags & GNF_ATTN_CONCAT) ? 1 : 0;
+  const int width = concat ? f.H + f.cho : f.cho;
+  k_attn_input<<<(unsigned)ceil_div(n * width, 256), 256, 0, stream>>>(xa, f.H, f.HP, w.proj, f.cho, f.cho_pad, concat,
+                                                                       f.in_pad, n, w.hbuf);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+int gnn_forward32(const Flow& f, int mlp, bool build_agg, const float* xa, int64_t n, const int32_t* rowptr,
+                  const int32_t* csr_senders, const Workspace& w, float* out, cudaStream_t stream) {
+  int rc = GNF_OK;
+  if (f.attn) {
+    rc = build_attn_input(f, mlp, xa, n, rowptr, csr_senders, w, stream);
+  } else if (build_agg) {
+    k_agg_input<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(
+        xa, f.H, f.HP, rowptr, csr_senders, n, f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps,
+        f.in_pad, w.hbuf);
+    GNF_LAUNCH_CHECK();
+  }
+  if (rc) return rc;
+  rc = run_mlp32(f, mlp, w, out, n, stream);
+  if (rc) return rc;
+  if (f.attn && (f.attn_flags & GNF_ATTN_RESIDUAL)) {                                          // gnn.py:551-552
+    k_add_rows<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(out, xa, f.H, f.HP, n);
+    GNF_LAUNCH_CHECK();
+  }
+  return GNF_OK;
+}
+
 // one half coupling step: (xa, xb) with the s/t GNNs of (half, step)
 int coupling_half(const Flow& f, int half, int step, int inverse, const float* xa, float* xb,
                   int64_t n, const int32_t* rowptr, const int32_t* csr_senders, double* ldj_accum,
@@ -405,13 +546,9 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
   if (math == GNF_MATH_FP32) {
     const int64_t total = n * f.H;
     const unsigned blocks = (unsigned)ceil_div(total, 256);
-    k_agg_input<<<blocks, 256, 0, stream>>>(xa, f.H, f.HP, rowptr, csr_senders, n,
-                                            f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT,
-                                            f.d.eps, f.in_pad, w.hbuf);
-    GNF_LAUNCH_CHECK();
-    int rc = run_mlp32(f, ms, w, w.sbuf, n, stream);
+    int rc = gnn_forward32(f, ms, true, xa, n, rowptr, csr_senders, w, w.sbuf, stream);
     if (rc) return rc;
-    rc = run_mlp32(f, mt, w, w.tbuf, n, stream);
+    rc = gnn_forward32(f, mt, false, xa, n, rowptr, csr_senders, w, w.tbuf, stream);   // aggregation input is shared
     if (rc) return rc;
     const bool want_ldj = (!inverse && ldj_accum);
     k_coupling_update<<<blocks, 256, 0, stream>>>(xb, w.sbuf, w.tbuf, n, f.H, f.HP, f.HP, inverse,
@@ -444,14 +581,45 @@ int check_math(const Flow& f, int math, const char* who) {
   return GNF_OK;
 }
 
+__global__ void k_pack32T(const float* __restrict__ src, int in, int out, int in_pad, int out_pad8,
+                          float* __restrict__ wt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < in_pad * out_pad8) {
+    int r = i / in_pad, c = i - r * in_pad;          // wt[r = out index][c = in index]
+    wt[i] = (r < out && c < in) ? src[c * out + r] : 0.f;
+  }
+}
+
 }  // namespace
+
+int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K, int act,
+               cudaStream_t stream) {
+  return run_linear(A, W, b, C, M, N, K, act, stream);
+}
+
+int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
+                  float* hbuf, cudaStream_t stream) {
+  k_agg_input<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(
+      xa, f.H, f.HP, rowptr, csr_senders, n, f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps,
+      f.in_pad, hbuf);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+int pack_w32T(const Flow& f, int mlp, const float* src, cudaStream_t stream) {
+  float* dst = f.w32T + (int64_t)mlp * f.w32T_per_mlp;
+  for (int l = 0; l < f.K; ++l) {
+    int total = f.in_pads[l] * f.out_pad8[l];
+    k_pack32T<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src + f.flat_w_off[l], f.ins[l], f.outs[l],
+                                                                 f.in_pads[l], f.out_pad8[l], dst + f.w32T_layer_off[l]);
+    GNF_LAUNCH_CHECK();
+  }
+  return GNF_OK;
+}
+
 }  // namespace gnf
 
 using namespace gnf;
-
-struct gnf_flow {
-  Flow f;
-};
 
 extern "C" int gnf_abi_version(void) { return GNF_ABI_VERSION; }
 extern "C" const char* gnf_last_error(void) { return g_err; }
@@ -475,16 +643,27 @@ static int validate_desc(const gnf_flow_desc* d) {
   GNF_REQUIRE(d->num_layers >= 2 && d->num_layers <= kMaxLayers, GNF_EINVAL,
               "num_layers must be in [2, %d]", kMaxLayers);
   GNF_REQUIRE(d->agg == GNF_AGG_SUM || d->agg == GNF_AGG_MEAN, GNF_EINVAL, "bad agg");
-  GNF_REQUIRE(d->block == GNF_BLOCK_CONCAT || d->block == GNF_BLOCK_AGG_THEN, GNF_EINVAL, "bad block");
+  GNF_REQUIRE(d->block == GNF_BLOCK_CONCAT || d->block == GNF_BLOCK_AGG_THEN || d->block == GNF_BLOCK_DM_ATTN,
+              GNF_EINVAL, "bad block");
+  if (d->block == GNF_BLOCK_DM_ATTN)
+    GNF_REQUIRE(d->attn_num_heads >= 1 && d->attn_kq_dim >= 1 && d->attn_kq_dim <= 64 && d->attn_v_dim >= 1 &&
+                    d->attn_v_dim <= 32 && d->attn_out_dim >= 1,
+                GNF_EINVAL, "dm_self_attn: need heads >= 1, 1 <= kq_dim <= 64, 1 <= v_dim <= 32, out_dim >= 1");
   GNF_REQUIRE(d->act == GNF_ACT_LEAKY_RELU || d->act == GNF_ACT_RELU, GNF_EINVAL, "bad act");
   return GNF_OK;
 }
 
 static int64_t params_per_mlp(const gnf_flow_desc* d) {
   const int64_t H = d->node_embedding_dim / 2;
-  const int64_t in = d->block == GNF_BLOCK_CONCAT ? 2 * H : H;
+  int64_t in = d->block == GNF_BLOCK_CONCAT ? 2 * H : H;
+  int64_t attn = 0;
+  if (d->block == GNF_BLOCK_DM_ATTN) {
+    const int64_t qk = (int64_t)d->attn_num_heads * d->attn_kq_dim, hv = (int64_t)d->attn_num_heads * d->attn_v_dim;
+    attn = 2 * H * qk + H * d->attn_v_dim + hv * d->attn_out_dim;
+    in = (d->attn_flags & GNF_ATTN_CONCAT) ? H + d->attn_out_dim : d->attn_out_dim;
+  }
   const int64_t L = d->latent_dim, K = d->num_layers;
-  return in * L + L + (K - 2) * (L * L + L) + L * H + H;
+  return attn + in * L + L + (K - 2) * (L * L + L) + L * H + H;
 }
 
 extern "C" int64_t gnf_flow_param_count(const gnf_flow_desc* d) {
@@ -503,6 +682,20 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
   f.H = d->node_embedding_dim / 2;
   f.HP = gnf_padded_half(f.H);
   f.in_dim = d->block == GNF_BLOCK_CONCAT ? 2 * f.H : f.H;
+  if (d->block == GNF_BLOCK_DM_ATTN) {
+    f.attn = 1;
+    f.heads = d->attn_num_heads; f.kq = d->attn_kq_dim; f.vd = d->attn_v_dim; f.cho = d->attn_out_dim;
+    f.attn_flags = d->attn_flags;
+    f.hp8 = pad_to(f.H, 8); f.qk_pad = pad_to(f.heads * f.kq, 8); f.v_pad = pad_to(f.vd, 8);
+    f.hv_pad = pad_to(f.heads * f.vd, 8); f.cho_pad = pad_to(f.cho, 8);
+    f.in_dim = (f.attn_flags & GNF_ATTN_CONCAT) ? f.H + f.cho : f.cho;
+    f.wq_off = 0;
+    f.wk_off = f.wq_off + (int64_t)f.hp8 * f.qk_pad;
+    f.wv_off = f.wk_off + (int64_t)f.hp8 * f.qk_pad;
+    f.wo_off = f.wv_off + (int64_t)f.hp8 * f.v_pad;
+    f.wattn_per_mlp = f.wo_off + (int64_t)f.hv_pad * f.cho_pad;
+    f.mlp_off = 2ll * f.H * f.heads * f.kq + (int64_t)f.H * f.vd + (int64_t)f.heads * f.vd * f.cho;
+  }
   f.in_pad = pad_to(f.in_dim, 8);
   f.L = d->latent_dim;
   f.K = d->num_layers;
@@ -522,7 +715,26 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
     off = (off + 3) / 4 * 4;  // keep float4 alignment of the next W
   }
   f.w32_per_mlp = off;
+  int64_t offT = 0, offF = 0;
+  for (int l = 0; l < f.K; ++l) {
+    f.out_pad8[l] = pad_to(f.out_pads[l], 8);
+    f.w32T_layer_off[l] = offT;
+    offT += (int64_t)f.out_pad8[l] * f.in_pads[l];
+    f.flat_w_off[l] = offF;
+    offF += (int64_t)f.ins[l] * f.outs[l];
+    f.flat_b_off[l] = offF;
+    offF += f.outs[l];
+  }
+  f.w32T_per_mlp = offT;
+  for (int l = 0; l < f.K; ++l) {   // flat offsets are relative to the GNN's parameter block
+    f.flat_w_off[l] += f.mlp_off;
+    f.flat_b_off[l] += f.mlp_off;
+  }
   cudaError_t e = cudaMalloc(&f.w32, (size_t)f.n_mlps * f.w32_per_mlp * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&f.w32T, (size_t)f.n_mlps * f.w32T_per_mlp * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&f.zeros, 8192 * 4);
+  if (e == cudaSuccess) e = cudaMemset(f.zeros, 0, 8192 * 4);
+  if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wattn, (size_t)f.n_mlps * f.wattn_per_mlp * 4);
   if (e != cudaSuccess) {
     delete h;
     set_error("gnf_flow_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -547,6 +759,9 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
 extern "C" int gnf_flow_destroy(gnf_flow* h) {
   if (!h) return GNF_OK;
   cudaFree(h->f.w32);
+  cudaFree(h->f.w32T);
+  cudaFree(h->f.zeros);
+  cudaFree(h->f.wattn);
   cudaFree(h->f.wtc[0]);
   cudaFree(h->f.wtc[1]);
   cudaFree(h->f.btc);
@@ -566,6 +781,22 @@ extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* strea
   Flow& f = h->f;
   for (int m = 0; m < f.n_mlps; ++m) {
     const float* src = params + (int64_t)m * f.params_per_mlp;
+    if (f.attn) {
+      float* wa = f.wattn + (int64_t)m * f.wattn_per_mlp;
+      const int qk = f.heads * f.kq, hv = f.heads * f.vd;
+      auto pack = [&](const float* s_, int in, int out, int in_pad, int out_pad, float* d_) {
+        k_pack_mat<<<(unsigned)ceil_div((int64_t)in_pad * out_pad, 256), 256, 0, stream>>>(s_, in, out, in_pad, out_pad, d_);
+      };
+      pack(src, f.H, qk, f.hp8, f.qk_pad, wa + f.wq_off);
+      GNF_LAUNCH_CHECK();
+      pack(src + (int64_t)f.H * qk, f.H, qk, f.hp8, f.qk_pad, wa + f.wk_off);
+      GNF_LAUNCH_CHECK();
+      pack(src + 2ll * f.H * qk, f.H, f.vd, f.hp8, f.v_pad, wa + f.wv_off);
+      GNF_LAUNCH_CHECK();
+      pack(src + 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, f.hv_pad, f.cho_pad, wa + f.wo_off);
+      GNF_LAUNCH_CHECK();
+      src += f.mlp_off;
+    }
     float* dst = f.w32 + (int64_t)m * f.w32_per_mlp;
     for (int l = 0; l < f.K; ++l) {
       int total = f.in_pads[l] * f.out_pads[l];
@@ -575,8 +806,12 @@ extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* strea
       GNF_LAUNCH_CHECK();
       src += (int64_t)f.ins[l] * f.outs[l] + f.outs[l];
     }
+    {
+      int rc = pack_w32T(f, m, params + (int64_t)m * f.params_per_mlp, stream);
+      if (rc) return rc;
+    }
     if (f.tc_ok) {
-      int rc = tc_pack_mlp(f, m, params + (int64_t)m * f.params_per_mlp, stream_);
+      int rc = tc_pack_mlp(f, m, params + (int64_t)m * f.params_per_mlp + f.mlp_off, stream_);
       if (rc) return rc;
     }
   }
@@ -691,11 +926,7 @@ extern "C" int gnf_gnn_forward(const gnf_flow* h, int32_t which, int32_t half, i
   GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
   k_pad_rows<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(x, n, f.H, f.HP, w.x0);
   GNF_LAUNCH_CHECK();
-  k_agg_input<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(
-      w.x0, f.H, f.HP, rowptr, csr, n, f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps,
-      f.in_pad, w.hbuf);
-  GNF_LAUNCH_CHECK();
-  rc = run_mlp32(f, f.mlp_index(which, half, step), w, w.sbuf, n, stream);
+  rc = gnn_forward32(f, f.mlp_index(which, half, step), true, w.x0, n, rowptr, csr, w, w.sbuf, stream);
   if (rc) return rc;
   k_unpad_rows<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(w.sbuf, n, f.H, f.HP, out);
   GNF_LAUNCH_CHECK();

@@ -202,10 +202,49 @@ k_segment_reduce(const float* __restrict__ src, int h, const int32_t* __restrict
   out[i] = acc;
 }
 
+// f3  pred_adj(graph, scaled_hacky_sigmoid_l2) (loss.py:154-159,45-53,131-151,83-85), block-diagonal:
+// one CTA per graph writes its [n, n] block  sigmoid(10 * (1 - D_ij / sqrt(dim))),  D_ij = r_i - 2 x_i.x_j + r_j,
+// diagonal zeroed.  The reference builds the dense [N, N] matrix and multiplies by a block mask.
+__global__ void __launch_bounds__(256)
+k_pred_adj(const float* __restrict__ x, int d, const int64_t* __restrict__ node_off,
+           const int64_t* __restrict__ adj_off, float temp, float shift, float* __restrict__ out) {
+  const int g = blockIdx.x;
+  const int64_t lo = node_off[g];
+  const int n = (int)(node_off[g + 1] - lo);
+  float* blk = out + adj_off[g];
+  const float inv_sqrt_d = 1.f / sqrtf((float)d);
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx / n, j = idx - i * n;
+    const float* xi = x + (lo + i) * d;
+    const float* xj = x + (lo + j) * d;
+    float ri = 0.f, rj = 0.f, dot = 0.f;
+    for (int k = 0; k < d; ++k) {
+      const float a = xi[k], b = xj[k];
+      ri = fmaf(a, a, ri);
+      rj = fmaf(b, b, rj);
+      dot = fmaf(a, b, dot);
+    }
+    float dist = (ri - 2.f * dot + rj) * inv_sqrt_d;
+    float v = 1.f / (1.f + expf(-temp * (shift - dist)));
+    blk[idx] = (i == j) ? 0.f : v;
+  }
+}
+
 }  // namespace
 }  // namespace gnf
 
 using namespace gnf;
+
+extern "C" int gnf_pred_adj(const float* nodes, int32_t d, const int64_t* node_off, const int64_t* adj_off,
+                            int64_t n_graphs, float temp, float shift, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(d > 0 && n_graphs >= 0, GNF_EINVAL, "gnf_pred_adj: bad shape");
+  if (n_graphs == 0) return GNF_OK;
+  GNF_REQUIRE(nodes && node_off && adj_off && out, GNF_EINVAL, "gnf_pred_adj: null pointer");
+  k_pred_adj<<<(unsigned)n_graphs, 256, 0, stream>>>(nodes, d, node_off, adj_off, temp, shift, out);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
 
 extern "C" size_t gnf_build_csr_workspace(int64_t n_nodes, int64_t n_edges) {
   size_t tiles = (size_t)ceil_div(n_nodes + 1, kScanTile);

@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .graphs import BatchStructure, GraphsTuple, structure_of
+from .graphs import BatchStructure, GraphsTuple, structure_of, transposed_structure_of
 
 # activation tokens (the reference passes tf.nn.leaky_relu / tf.nn.relu, run_grevnet.py:158, gnn.py:162)
 leaky_relu = "leaky_relu"
@@ -207,12 +207,15 @@ EDGE_BLOCK_OPT = {          # gnn.py:135-140: edges = nodes[senders], nothing el
 class _Flow:
     """Owner of one gnf_flow handle (packed device weights)."""
 
-    def __init__(self, T, D, mlp: MLP, block: str, agg: str, eps: float, weight_sharing: bool):
+    def __init__(self, T, D, mlp: MLP, block: str, agg: str, eps: float, weight_sharing: bool, attn=None):
         self.lib = _lib.load()
+        attn = attn or {}
         self.desc = _lib.FlowDesc(
             num_timesteps=T, node_embedding_dim=D, latent_dim=mlp.latent_dim, num_layers=mlp.num_layers,
             agg=_lib.AGG[agg], block=_lib.BLOCK[block], act=_lib.ACT[mlp.activation],
-            weight_sharing=int(bool(weight_sharing)), eps=eps)
+            weight_sharing=int(bool(weight_sharing)), eps=eps,
+            attn_num_heads=attn.get("num_heads", 0), attn_kq_dim=attn.get("kq_dim", 0),
+            attn_v_dim=attn.get("v_dim", 0), attn_out_dim=attn.get("out_dim", 0), attn_flags=attn.get("flags", 0))
         n = self.lib.gnf_flow_param_count(C.byref(self.desc))
         if n < 0:
             raise ValueError(_lib.last_error())
@@ -268,19 +271,30 @@ class NodeBlockGNN(nn.Module):
         nb = self._node_block
         return (nb.block, nb.agg, nb.epsilon) + self.mlp.signature()
 
+    # -- what a flow needs from one of its GNNs ----------------------------------------------------
+    def flow_kwargs(self):
+        nb = self._node_block
+        return dict(block=nb.block, agg=nb.agg, eps=nb.epsilon, attn=None)
+
+    def gnn_param_count(self, half_dim):
+        return self.mlp.param_count(self._node_block.input_dim(half_dim))
+
+    def bind_params(self, half_dim, flat, generator=None, init=True):
+        self._bound = flat
+        return self.mlp.bind(self._node_block.input_dim(half_dim), flat, generator=generator, init=init)
+
     def _standalone(self, half_dim, device):
         if self._flow is None:
-            nb, mlp = self._node_block, self.mlp
+            mlp = self.mlp
             if mlp.output_dim != half_dim:
                 raise ValueError(f"MLP output_dim={mlp.output_dim} must equal the node width {half_dim}")
-            self._flow = _Flow(1, 2 * half_dim, mlp, nb.block, nb.agg, nb.epsilon, True)
-            per = mlp.param_count(nb.input_dim(half_dim))
+            self._flow = _Flow(1, 2 * half_dim, mlp, weight_sharing=True, **self.flow_kwargs())
+            per = self.gnn_param_count(half_dim)
             flat = torch.empty(4 * per, dtype=torch.float32, device=device)
-            if mlp.input_dim is None:
-                mlp.bind(nb.input_dim(half_dim), flat[:per])
+            if getattr(self, "_bound", None) is None:
+                self.bind_params(half_dim, flat[:per])
             else:                      # already bound elsewhere (e.g. adopted by a GRevNet): copy
-                src = torch.cat([torch.cat([w.reshape(-1), b]) for w, b in zip(mlp.weights, mlp.biases)])
-                flat[:per].copy_(src)
+                flat[:per].copy_(self._bound.detach().to(device))
             for k in range(1, 4):
                 flat[k * per:(k + 1) * per].copy_(flat[:per])
             self.params = nn.Parameter(flat, requires_grad=False)
@@ -291,7 +305,7 @@ class NodeBlockGNN(nn.Module):
         n, h = nodes.shape
         st = structure_of(graph)
         flow = self._standalone(h, nodes.device)
-        handle = flow.ensure(self.params.data)
+        handle = flow.ensure(self.params.detach())
         lib = flow.lib
         wsb = lib.gnf_grevnet_workspace(handle, n, _lib.MATH["fp32"])
         ws = _lib.workspace(wsb, nodes.device)
@@ -316,6 +330,79 @@ def sum_concat_then_mlp_gnn(make_mlp_fn):              # gnn.py:250-252
 
 def avg_concat_then_mlp_gnn(make_mlp_fn):              # gnn.py:255-257
     return NodeBlockGNN(ConcatThenMLPBlock(unsorted_segment_mean, make_mlp_fn))
+
+
+class DMSelfAttentionMLP(NodeBlockGNN):
+    """DMSelfAttentionMLP (gnn.py:480-553), the default GNN of both GRevNet scripts
+    (run_grevnet.py:56, train_grevnet_with_data.py:42): bias-free q/k/v projections, multi-head
+    edge-softmax attention over each receiver's in-edges (DMSelfAttention, gnn.py:385-477; the value
+    projection is shared by all heads, gnn.py:528), head-concat projection to
+    `concat_heads_output_dim`, concat with the input, MLP.  fp32 kernels (SURVEY §8 row f1);
+    layer_norm=True is not supported."""
+
+    def __init__(self, kq_dim, v_dim, make_mlp_fn, num_heads=8, concat_heads_output_dim=20, concat=True,
+                 residual=False, layer_norm=False, kq_dim_division=False, name="dm_self_attention"):
+        nn.Module.__init__(self)
+        if layer_norm:
+            raise NotImplementedError("dm_self_attn_gnn(layer_norm=True) (snt.LayerNorm, gnn.py:554-556) is not built")
+        self.name = name
+        self.kq_dim, self.v_dim, self.num_heads = int(kq_dim), int(v_dim), int(num_heads)
+        self.concat_heads_output_dim = int(concat_heads_output_dim)
+        self.concat, self.residual, self.layer_norm = bool(concat), bool(residual), False
+        self.kq_dim_division = bool(kq_dim_division)
+        self._mlp = make_mlp_fn()
+        self._flow = None
+        self.params = None
+        self.wq = self.wk = self.wv = self.wo = None
+
+    @property
+    def mlp(self) -> MLP:
+        return self._mlp
+
+    def config(self):
+        return ("dm_attn", self.kq_dim, self.v_dim, self.num_heads, self.concat_heads_output_dim, self.concat,
+                self.residual, self.kq_dim_division) + self.mlp.signature()
+
+    def flow_kwargs(self):
+        flags = (_lib.ATTN_CONCAT if self.concat else 0) | (_lib.ATTN_RESIDUAL if self.residual else 0) | \
+                (_lib.ATTN_KQ_DIV if self.kq_dim_division else 0)
+        return dict(block="dm_attn", agg="sum", eps=1.0,
+                    attn=dict(num_heads=self.num_heads, kq_dim=self.kq_dim, v_dim=self.v_dim,
+                              out_dim=self.concat_heads_output_dim, flags=flags))
+
+    def mlp_input_dim(self, half_dim):
+        return half_dim + self.concat_heads_output_dim if self.concat else self.concat_heads_output_dim
+
+    def _attn_shapes(self, half_dim):
+        qk, hv = self.num_heads * self.kq_dim, self.num_heads * self.v_dim
+        return [(half_dim, qk), (half_dim, qk), (half_dim, self.v_dim), (hv, self.concat_heads_output_dim)]
+
+    def gnn_param_count(self, half_dim):
+        return sum(i * o for i, o in self._attn_shapes(half_dim)) + self.mlp.param_count(self.mlp_input_dim(half_dim))
+
+    def bind_params(self, half_dim, flat, generator=None, init=True):
+        self._bound = flat
+        off, mats = 0, []
+        for k, (i, o) in enumerate(self._attn_shapes(half_dim)):
+            w = flat[off:off + i * o].view(i, o)
+            off += i * o
+            if init:
+                with torch.no_grad():
+                    if k < 3:      # tf.contrib.layers.xavier_initializer(uniform=True)  gnn.py:504-506
+                        lim = math.sqrt(6.0 / (i + o))
+                        w.uniform_(-lim, lim, generator=generator)
+                    else:          # snt.Linear default: truncated normal, stddev 1/sqrt(input_size)
+                        _truncated_normal_(w, 1.0 / math.sqrt(i), generator)
+            mats.append(w)
+        self.wq, self.wk, self.wv, self.wo = mats
+        return off + self.mlp.bind(self.mlp_input_dim(half_dim), flat[off:], generator=generator, init=init)
+
+
+def dm_self_attn_gnn(kq_dim, v_dim, make_mlp_fn, num_heads, concat_heads_output_dim, concat=True, residual=False,
+                     layer_norm=False, kq_dim_division=False):            # gnn.py:555-573
+    return DMSelfAttentionMLP(kq_dim=kq_dim, v_dim=v_dim, make_mlp_fn=make_mlp_fn, num_heads=num_heads,
+                              concat_heads_output_dim=concat_heads_output_dim, concat=concat, residual=residual,
+                              layer_norm=layer_norm, kq_dim_division=kq_dim_division)
 
 
 def get_gnns(num_timesteps, make_gnn_fn):              # gnn.py:266-267
@@ -365,15 +452,16 @@ class GRevNet(nn.Module):
             raise ValueError("make_gnn_fn must return identically configured GNNs")
         g0 = order[0]
         if not isinstance(g0, NodeBlockGNN):
-            raise TypeError("make_gnn_fn must return a NodeBlockGNN (sum/avg concat_then_mlp or then_mlp)")
+            raise TypeError("make_gnn_fn must return a NodeBlockGNN (sum/avg concat_then_mlp or then_mlp) "
+                            "or a dm_self_attn_gnn")
         H = self.node_embedding_dim // 2
-        nb, mlp = g0._node_block, g0.mlp
+        mlp = g0.mlp
         if mlp.output_dim != H:
             raise ValueError(f"MLP output_dim={mlp.output_dim} must be node_embedding_dim/2={H}")
-        self._flow = _Flow(T, self.node_embedding_dim, mlp, nb.block, nb.agg, nb.epsilon, self.weight_sharing)
-        in_dim = nb.input_dim(H)
-        per = mlp.param_count(in_dim)
-        assert per * len(order) == self._flow.param_count
+        self._flow = _Flow(T, self.node_embedding_dim, mlp, weight_sharing=self.weight_sharing, **g0.flow_kwargs())
+        in_dim = H
+        per = g0.gnn_param_count(H)
+        assert per * len(order) == self._flow.param_count, (per, len(order), self._flow.param_count)
         dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
         gen = None
         if seed is not None:
@@ -381,7 +469,7 @@ class GRevNet(nn.Module):
             gen.manual_seed(int(seed))
         flat = torch.empty(self._flow.param_count, dtype=torch.float32)
         for k, g in enumerate(order):          # flat order: which -> half -> step (include/gnf_b200.h)
-            g.mlp.bind(in_dim, flat[k * per:(k + 1) * per], generator=gen)
+            g.bind_params(H, flat[k * per:(k + 1) * per], generator=gen)
         self.params = nn.Parameter(flat.to(dev), requires_grad=False)
         self._order = order
         self._per = per
@@ -403,7 +491,7 @@ class GRevNet(nn.Module):
     # -- parameter plumbing -------------------------------------------------------------------
     def _rebind(self):
         for k, g in enumerate(self._order):
-            g.mlp.bind(self._in_dim, self.params.data[k * self._per:(k + 1) * self._per], init=False)
+            g.bind_params(self._in_dim, self.params.detach()[k * self._per:(k + 1) * self._per], init=False)
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -427,7 +515,7 @@ class GRevNet(nn.Module):
     def math(self) -> str:
         if self._math is not None:
             return self._math
-        self._flow.ensure(self.params.data)
+        self._flow.ensure(self.params.detach())
         return "tc3x" if self._flow.supports("tc3x") else "fp32"
 
     @math.setter
@@ -446,7 +534,7 @@ class GRevNet(nn.Module):
         if nodes.device != self.params.device:
             raise RuntimeError(f"graph is on {nodes.device} but the GRevNet parameters are on {self.params.device}")
         st = structure_of(x)
-        handle = self._flow.ensure(self.params.data)
+        handle = self._flow.ensure(self.params.detach())
         lib = self._flow.lib
         m = _lib.MATH[self.math]
         n = nodes.shape[0]
@@ -512,7 +600,7 @@ class GRevNet(nn.Module):
         if nodes.dim() != 2 or nodes.shape[1] != D:
             raise ValueError(f"graph.nodes must be [N, {D}], got {tuple(nodes.shape)}")
         st = structure_of(x)
-        handle = self._flow.ensure(self.params.data)
+        handle = self._flow.ensure(self.params.detach())
         lib, dev = self._flow.lib, nodes.device
         m = _lib.MATH[self.math]
         n = nodes.shape[0]
@@ -564,6 +652,44 @@ class GRevNet(nn.Module):
         """z -> x   (gnn.py:343-373)"""
         x, _ = self._run(z, inverse_kernel=True)
         return z.replace(nodes=x)
+
+    # -- f2: training-step gradients (reversible, nothing stored by the forward pass) --------------
+    def backward_from_z(self, graph: GraphsTuple, z_nodes: torch.Tensor, loss_scale: float,
+                        grads: Optional[torch.Tensor] = None, return_x: bool = False):
+        """d(-loss_scale * log_prob_xs)/d(params), accumulated into `grads` (flat, same layout as
+        self.params).  `z_nodes` must be f(graph).nodes."""
+        if self.use_batch_norm:
+            raise NotImplementedError("backward with use_batch_norm=True is not implemented")
+        lib = self._flow.lib
+        _lib.require_cuda(z_nodes, "z.nodes", torch.float32)
+        handle = self._flow.ensure(self.params.detach())
+        st, stt = structure_of(graph), transposed_structure_of(graph)
+        n, dev = z_nodes.shape[0], z_nodes.device
+        if grads is None:
+            grads = torch.zeros_like(self.params.detach())
+        _lib.require_cuda(grads, "grads", torch.float32)
+        x_out = torch.empty_like(z_nodes) if return_x else None
+        wsb = lib.gnf_grevnet_backward_workspace(handle, n)
+        ws = _lib.workspace(wsb, dev)
+        _lib.check(lib.gnf_grevnet_backward(handle, _lib.ptr(z_nodes), n, st.n_edges, _lib.ptr(st.rowptr),
+                                            _lib.ptr(st.csr_senders), _lib.ptr(stt.rowptr), _lib.ptr(stt.csr_senders),
+                                            float(loss_scale), _lib.ptr(grads), _lib.ptr(x_out), _lib.ptr(ws), wsb,
+                                            _lib.stream_ptr(dev)), "gnf_grevnet_backward")
+        return (grads, x_out) if return_x else grads
+
+    def loss_and_grad(self, graph: GraphsTuple, per_node: bool = True):
+        """One training-step evaluation: the scalars of run_grevnet.py:292-302 and the gradient of
+        total_loss (per_node=False, run_grevnet.py:362-364) or loss_per_node (per_node=True,
+        train_grevnet_with_data.py:353-380) w.r.t. the flat parameter vector; also stored in
+        self.params.grad for torch optimisers."""
+        from .loss import mvn_log_prob_sum, scalars_from_vector
+        z, ldj64 = self.f64(graph)
+        out = scalars_from_vector(mvn_log_prob_sum(z.nodes, ldj64))
+        n = max(int(z.nodes.shape[0]), 1)
+        grads = self.backward_from_z(graph, z.nodes, 1.0 / n if per_node else 1.0)
+        self.params.grad = grads
+        out["z"] = z
+        return out, grads
 
     def log_prob(self, x: GraphsTuple):
         """sum(prior.log_prob(z)) + log_det_jacobian with prior = N(0, I): what the dead

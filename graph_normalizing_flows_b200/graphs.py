@@ -86,9 +86,11 @@ class BatchStructure:
     """Device-side, per-batch index structure: stable CSR by receiver.  Built once per batch
     (cached on the senders/receivers tensors) and shared by all 2T half steps."""
 
-    __slots__ = ("n_nodes", "n_edges", "rowptr", "perm", "csr_senders", "device")
+    __slots__ = ("n_nodes", "n_edges", "rowptr", "perm", "csr_senders", "device", "_bad")
 
-    def __init__(self, senders: torch.Tensor, receivers: torch.Tensor, n_nodes: int, validate: bool = True):
+    def __init__(self, senders: torch.Tensor, receivers: torch.Tensor, n_nodes: int, validate=True):
+        """validate: True = count out-of-range ids and raise now (one host sync); "deferred" = launch
+        the check but read it later with .check() (prefetch path); False = trust the caller."""
         lib = _lib.load()
         _lib.require_cuda(senders, "senders", torch.int32)
         _lib.require_cuda(receivers, "receivers", torch.int32)
@@ -97,15 +99,15 @@ class BatchStructure:
         dev = senders.device
         n, e = int(n_nodes), int(senders.numel())
         st = _lib.stream_ptr(dev)
+        self.n_nodes, self.n_edges, self.device = n, e, dev
+        self._bad = None
         if validate:
             # reference behaviour: TF raises InvalidArgumentError on out-of-range ids (CPU)
-            bad = torch.zeros(1, dtype=torch.int32, device=dev)
-            _lib.check(lib.gnf_validate_indices(_lib.ptr(senders), _lib.ptr(receivers), n, e, _lib.ptr(bad), st),
+            self._bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.check(lib.gnf_validate_indices(_lib.ptr(senders), _lib.ptr(receivers), n, e, _lib.ptr(self._bad), st),
                        "gnf_validate_indices")
-            nbad = int(bad.item())
-            if nbad:
-                raise ValueError(f"{nbad} sender/receiver indices outside [0, {n})")
-        self.n_nodes, self.n_edges, self.device = n, e, dev
+            if validate != "deferred":
+                self.check()
         self.rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
         self.perm = torch.empty(e, dtype=torch.int32, device=dev)
         self.csr_senders = torch.empty(e, dtype=torch.int32, device=dev)
@@ -114,6 +116,55 @@ class BatchStructure:
         _lib.check(lib.gnf_build_csr(_lib.ptr(receivers), _lib.ptr(senders), n, e, _lib.ptr(self.rowptr),
                                      _lib.ptr(self.perm), _lib.ptr(self.csr_senders), _lib.ptr(ws), wsb, st),
                    "gnf_build_csr")
+
+
+    def check(self):
+        """Raise if the (possibly deferred) index validation found ids outside [0, N)."""
+        if self._bad is not None:
+            nbad = int(self._bad.item())
+            self._bad = None
+            if nbad:
+                raise ValueError(f"{nbad} sender/receiver indices outside [0, {self.n_nodes})")
+
+
+class BatchPrefetcher:
+    """Stages the NEXT batch while the current one computes: pinned-host -> device copies, index
+    validation and the CSR build run on a side stream; `wait` hands the batch to the current stream.
+
+        pf = BatchPrefetcher(device)
+        ticket = pf.submit(host_batch)                 # host_batch: GraphsTuple of (pinned) CPU tensors / numpy
+        ...                                            # compute on the previous batch
+        graph = pf.wait(ticket)                        # device GraphsTuple, structure cached, ids validated
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+
+    def submit(self, host: GraphsTuple):
+        n = int(host.nodes.shape[0])
+        for name, tot in (("n_node", n), ("n_edge", int(len(host.senders)))):
+            v = getattr(host, name)
+            if v is not None and int(np.asarray(v).sum()) != tot:       # host side of the error contract
+                raise ValueError(f"sum({name})={int(np.asarray(v).sum())} does not match {tot}")
+        with torch.cuda.stream(self.stream):
+            g = host.to(self.device, non_blocking=True)
+            st = BatchStructure(g.senders, g.receivers, n, validate="deferred")
+            s, r = g.senders, g.receivers
+            s._gnf_structure = ((id(r), r._version, s._version, n), weakref.ref(r), st)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return g, st, ev
+
+    def wait(self, ticket) -> GraphsTuple:
+        g, st, ev = ticket
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in list(g) + [st.rowptr, st.perm, st.csr_senders]:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(cur)
+        st.check()
+        return g
 
 
 def structure_of(graph: GraphsTuple) -> BatchStructure:
@@ -140,4 +191,18 @@ def structure_of(graph: GraphsTuple) -> BatchStructure:
             raise ValueError(f"sum(n_edge)={tot} does not match len(senders)={int(s.numel())}")
     st = BatchStructure(s, r, n)
     s._gnf_structure = (key, weakref.ref(r), st)
+    return st
+
+
+def transposed_structure_of(graph: GraphsTuple) -> BatchStructure:
+    """CSR by SENDER (rowptr over out-edges, payload = receivers): the transpose the backward of
+    gather + segment-reduce walks.  Cached on the receivers tensor."""
+    s, r = graph.senders, graph.receivers
+    n = int(graph.nodes.shape[0])
+    key = (id(s), s._version, r._version, n)
+    hit = getattr(r, "_gnf_structure_t", None)
+    if hit is not None and hit[0] == key and hit[1]() is s:
+        return hit[2]
+    st = BatchStructure(r, s, n, validate=False)      # roles swapped: keyed by sender, carries receivers
+    r._gnf_structure_t = (key, weakref.ref(s), st)
     return st

@@ -63,3 +63,42 @@ def log_prob(grevnet, graph: GraphsTuple, return_z: bool = False):
     if return_z:
         out["z"] = z
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# f3  decode tail of the sampling pass (train_grevnet_with_data.py:414-416, 529-548)
+# ------------------------------------------------------------------------------------------------
+def pred_adj(gnn_output: GraphsTuple, temp: float = 10.0, shift: float = 1.0):
+    """pred_adj(graph, scaled_hacky_sigmoid_l2) (loss.py:154-159,45-53): per graph the [n, n] block
+    sigmoid(temp * (shift - |x_i - x_j|^2 / sqrt(d))) with a zero diagonal.  Returns (blocks, adj_off):
+    a flat float32 device tensor holding the blocks back to back and the int64 offsets [G+1].  The
+    reference materialises the dense [N, N] matrix times a block mask; `dense_pred_adj` rebuilds that
+    view for small batches."""
+    lib = _lib.load()
+    nodes = _lib.require_cuda(gnn_output.nodes, "graph.nodes", torch.float32)
+    n_node = torch.as_tensor(gnn_output.n_node).to(nodes.device, torch.int64)
+    zero = torch.zeros(1, dtype=torch.int64, device=nodes.device)
+    node_off = torch.cat([zero, torch.cumsum(n_node, 0)]).contiguous()
+    adj_off = torch.cat([zero, torch.cumsum(n_node * n_node, 0)]).contiguous()
+    out = torch.empty(int(adj_off[-1].item()), dtype=torch.float32, device=nodes.device)
+    _lib.check(lib.gnf_pred_adj(_lib.ptr(nodes), nodes.shape[1], _lib.ptr(node_off), _lib.ptr(adj_off),
+                                int(n_node.numel()), float(temp), float(shift), _lib.ptr(out),
+                                _lib.stream_ptr(nodes.device)), "gnf_pred_adj")
+    return out, adj_off
+
+
+def dense_pred_adj(blocks: torch.Tensor, adj_off: torch.Tensor, n_node) -> torch.Tensor:
+    """The reference's dense [N, N] layout (zeros off the block diagonal) from the packed blocks."""
+    n_node = [int(v) for v in torch.as_tensor(n_node).tolist()]
+    off = [int(v) for v in adj_off.tolist()]
+    return torch.block_diag(*[blocks[off[g]:off[g + 1]].view(n, n) for g, n in enumerate(n_node)])
+
+
+def sampled_graphs(blocks: torch.Tensor, adj_off: torch.Tensor, n_node, threshold: float = 0.5):
+    """train_grevnet_with_data.py:529-548: adjacency = pred_adj > 0.5 per sampled graph -> networkx."""
+    import networkx as nx
+    n_node = [int(v) for v in torch.as_tensor(n_node).tolist()]
+    off = [int(v) for v in adj_off.tolist()]
+    host = blocks.cpu().numpy()
+    return [nx.from_numpy_array((host[off[g]:off[g + 1]].reshape(n, n) > threshold).astype(float))
+            for g, n in enumerate(n_node)]

@@ -105,5 +105,21 @@ class GraphShardedGRevNet:
             out["z"] = z
         return out
 
+    def loss_and_grad(self, local_graph: GraphsTuple, per_node: bool = True):
+        """Sharded training-step evaluation: local density pass, all-reduce of the 4-vector (gives the
+        global node count the per-node loss is normalised by), local reversible backward, then the
+        gradient all-reduce(SUM) -- every rank ends with the global-batch gradient."""
+        from .loss import mvn_log_prob_sum, scalars_from_vector
+        net = self.grevnet
+        z, ldj64 = net.f64(local_graph)
+        vec = all_reduce_log_prob(mvn_log_prob_sum(z.nodes, ldj64), self.group)
+        out = scalars_from_vector(vec)
+        n_global = max(float(vec[3].item()), 1.0)
+        grads = net.backward_from_z(local_graph, z.nodes, 1.0 / n_global if per_node else 1.0)
+        if self.world_size > 1:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=self.group)
+        net.params.grad = grads
+        return out, grads
+
     def sample(self, local_latent: GraphsTuple) -> GraphsTuple:
         return self.grevnet.g(local_latent)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GNF_ABI_VERSION 1
+#define GNF_ABI_VERSION 2
 
 /* status codes */
 #define GNF_OK            0
@@ -45,6 +45,12 @@ extern "C" {
 /* node blocks: ConcatThenMLPBlock (gnn.py:100-111) / AggThenMLPBlock (gnn.py:114-126) */
 #define GNF_BLOCK_CONCAT   0
 #define GNF_BLOCK_AGG_THEN 1
+/* f1  DMSelfAttentionMLP (gnn.py:480-573): edge-softmax multi-head attention over the in-edges,
+ * head-concat projection, then concat-with-input + MLP.  fp32 arithmetic only. */
+#define GNF_BLOCK_DM_ATTN  2
+#define GNF_ATTN_CONCAT    1   /* concat=True   gnn.py:547-548 */
+#define GNF_ATTN_RESIDUAL  2   /* residual=True gnn.py:551-552 */
+#define GNF_ATTN_KQ_DIV    4   /* kq_dim_division=True gnn.py:462-464 */
 /* MLP activations: tf.nn.leaky_relu alpha=0.2 (run_grevnet.py:158) / tf.nn.relu (gnn.py:162) */
 #define GNF_ACT_LEAKY_RELU 0
 #define GNF_ACT_RELU       1
@@ -109,6 +115,8 @@ int gnf_gather_segment_sum(const float* x, int32_t h, const int32_t* rowptr,
  *     which (0 = s, 1 = t) -> half (0, 1) -> step (0..T-1; one entry when weight_sharing)
  * each MLP as  W0[in,L] b0[L]  W1[L,L] b1[L] ... W_{K-1}[L,H] b_{K-1}[H],  row-major,
  * Sonnet Linear convention y = x @ W + b;  in = D (concat) or D/2 (agg_then), H = D/2.
+ * GNF_BLOCK_DM_ATTN: every GNN is  Wq[H, heads*kq]  Wk[H, heads*kq]  Wv[H, v]  Wo[heads*v, out]
+ * (all without bias, gnn.py:509-545) followed by its MLP with in = H + out (concat) or out.
  * ------------------------------------------------------------------------------------------ */
 typedef struct gnf_flow_desc {
   int32_t num_timesteps;       /* T   GRevNet(num_timesteps)       gnn.py:276 */
@@ -120,7 +128,12 @@ typedef struct gnf_flow_desc {
   int32_t act;                 /* GNF_ACT_*   */
   int32_t weight_sharing;      /* gnn.py:279,283-286 */
   float   eps;                 /* AggThenMLPBlock epsilon, gnn.py:121 */
-  int32_t reserved[3];
+  /* GNF_BLOCK_DM_ATTN only (dm_self_attn_gnn arguments, gnn.py:555-573); zero otherwise */
+  int32_t attn_num_heads;      /* num_heads               */
+  int32_t attn_kq_dim;         /* kq_dim   (<= 64)        */
+  int32_t attn_v_dim;          /* v_dim    (<= 32)        */
+  int32_t attn_out_dim;        /* concat_heads_output_dim */
+  int32_t attn_flags;          /* GNF_ATTN_* */
 } gnf_flow_desc;
 
 typedef struct gnf_flow gnf_flow;   /* opaque: packed device-side weights */
@@ -194,6 +207,38 @@ int gnf_gnn_forward(const gnf_flow* flow, int32_t which, int32_t half, int32_t s
                     const float* x, int64_t n_nodes, int64_t n_edges,
                     const int32_t* rowptr, const int32_t* csr_senders, float* out,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f2  Training-step gradients, reversible (what GNFBlock(use_efficient_backprop=True),
+ * run_grevnet.py:46,288, did by name; the optimiser side is run_grevnet.py:345-377).
+ *   loss = -loss_scale * (sum_n log N(z_n; 0, I) + log_det_jacobian)      run_grevnet.py:292-296
+ *          (loss_scale = 1 for total_loss, 1/N for loss_per_node, train_grevnet_with_data.py:353-355)
+ * Input is z = f(x) from gnf_grevnet_forward; nothing else is kept from the forward pass: each half
+ * step is undone with the inverse update and its MLP activations are recomputed.
+ *   grads     float[gnf_flow_param_count], same layout as params; ACCUMULATED into (zero it first)
+ *   x_out     optional [N, D]: the reconstructed input (equals x up to rounding)
+ *   rowptr / csr_senders            CSR by receiver (gnf_build_csr(receivers, senders))
+ *   rowptr_by_sender / csr_receivers CSR by sender   (gnf_build_csr(senders, receivers)): the
+ *                                   transpose the aggregation's backward walks
+ * fp32 arithmetic (use_batch_norm = False).  workspace: gnf_grevnet_backward_workspace(flow, N).
+ * ------------------------------------------------------------------------------------------ */
+size_t gnf_grevnet_backward_workspace(const gnf_flow* flow, int64_t n_nodes);
+int gnf_grevnet_backward(const gnf_flow* flow, const float* z, int64_t n_nodes, int64_t n_edges,
+                         const int32_t* rowptr, const int32_t* csr_senders,
+                         const int32_t* rowptr_by_sender, const int32_t* csr_receivers,
+                         double loss_scale, float* grads, float* x_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f3  Decode tail of the sampling pass (train_grevnet_with_data.py:414-416):
+ * pred_adj(graph, scaled_hacky_sigmoid_l2) = sigmoid(temp * (shift - D / sqrt(d))) with the pairwise
+ * squared L2 distance D, masked to the block diagonal and with a zero diagonal
+ * (loss.py:154-159,45-53,131-151,83-85; temp = 10, shift = 1 for scaled_hacky_sigmoid_l2,
+ * loss.py:56-62 sigmoid_l2 for other values).  Written per graph: out[adj_off[g] + i*n_g + j];
+ * node_off[G+1], adj_off[G+1] are device int64 prefix sums of n_node and n_node^2.
+ * ------------------------------------------------------------------------------------------ */
+int gnf_pred_adj(const float* nodes, int32_t d, const int64_t* node_off, const int64_t* adj_off,
+                 int64_t n_graphs, float temp, float shift, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a8  log-prob assembly (run_grevnet.py:292-296, train_grevnet_with_data.py:348-350):

@@ -137,9 +137,45 @@ def aggregate(nodes, senders, receivers, agg):
 # --------------------------------------------------------------------------- #
 # a5  node blocks  +  NodeBlockGNN
 # --------------------------------------------------------------------------- #
+def dm_self_attention_mlp(nodes, senders, receivers, gnn, cfg):
+    """DMSelfAttentionMLP._build (gnn.py:501-558) around DMSelfAttention._build (gnn.py:419-477).
+    gnn = {"wq","wk","wv","wo","mlp"};  cfg carries num_heads, kq_dim, v_dim, concat, residual,
+    kq_dim_division.  [graph_nets _unsorted_segment_softmax: subtract segment max, exp, / segment sum]"""
+    dt = nodes.dtype
+    n, heads, kq, vd = nodes.shape[0], cfg["num_heads"], cfg["kq_dim"], cfg["v_dim"]
+    project_q = (nodes @ gnn["wq"]).reshape(n, heads, kq)           # gnn.py:509-520
+    project_k = (nodes @ gnn["wk"]).reshape(n, heads, kq)
+    project_v = np.repeat((nodes @ gnn["wv"])[:, None, :], heads, axis=1)    # keras.backend.repeat, gnn.py:528
+    # attn_module(project_v, project_q, project_k, graph): keys = project_q, queries = project_k (gnn.py:531-532)
+    sender_keys = project_q[senders]                                 # gnn.py:445-446
+    sender_values = project_v[senders]
+    receiver_queries = project_k[receivers]                          # gnn.py:453-454
+    logits = np.sum(sender_keys * receiver_queries, axis=-1, dtype=dt)            # [E, heads]
+    if cfg["kq_dim_division"]:
+        logits = logits / np.sqrt(dt.type(kq))
+    seg_max = np.full((n, heads), -np.inf, dt)
+    np.maximum.at(seg_max, receivers, logits)
+    ex = np.exp(logits - seg_max[receivers])
+    seg_sum = np.zeros((n, heads), dt)
+    np.add.at(seg_sum, receivers, ex)
+    w = ex / seg_sum[receivers]
+    attended = sender_values * w[..., None]                          # gnn.py:467
+    agg = np.zeros((n, heads, vd), dt)
+    np.add.at(agg, receivers, attended)                              # unsorted_segment_sum, gnn.py:471-475
+    new_nodes = agg.reshape(n, heads * vd) @ gnn["wo"]               # gnn.py:541-545
+    if cfg["concat"]:
+        new_nodes = np.concatenate([nodes, new_nodes], axis=1)       # gnn.py:547-548
+    new_nodes = mlp_forward(new_nodes, gnn["mlp"], cfg["act"])
+    if cfg["residual"]:
+        new_nodes = new_nodes + nodes                                # gnn.py:551-552
+    return new_nodes
+
+
 def node_block_gnn(nodes, senders, receivers, layers, cfg):
     """NodeBlockGNN._build (gnn.py:155-156) with ConcatThenMLPBlock (gnn.py:107-111)
     or AggThenMLPBlock (gnn.py:122-126)."""
+    if cfg["block"] == "dm_attn":
+        return dm_self_attention_mlp(nodes, senders, receivers, layers, cfg)
     agg = aggregate(nodes, senders, receivers, cfg["agg"])
     if cfg["block"] == "concat":
         h = np.concatenate([nodes, agg], axis=1)
@@ -319,14 +355,27 @@ def log_prob(z_nodes, ldj, n_node):
 # --------------------------------------------------------------------------- #
 def make_params(seed, T, D, latent_dim=256, num_layers=5, agg="sum", block="concat", eps=1.0,
                 act="leaky_relu", bias_init_stddev=0.1, last_layer_scale=1.0,
-                weight_sharing=False, dtype=np.float32):
+                weight_sharing=False, dtype=np.float32, attn=None):
+    """attn (block == "dm_attn"): dict(num_heads, kq_dim, v_dim, out_dim, concat, residual, kq_dim_division)."""
     if D % 2:
         raise ValueError("node_embedding_dim must be even (tf.split, gnn.py:306)")
     h = D // 2
     in_dim = D if block == "concat" else h
     rng = np.random.default_rng(seed)
+    if block == "dm_attn":
+        in_dim = h + attn["out_dim"] if attn["concat"] else attn["out_dim"]
+
+    def xavier(i, o):        # tf.contrib.layers.xavier_initializer(uniform=True), gnn.py:504-506
+        lim = math.sqrt(6.0 / (i + o))
+        return rng.uniform(-lim, lim, (i, o)).astype(dtype)
 
     def mk():
+        if block == "dm_attn":
+            qk, hv = attn["num_heads"] * attn["kq_dim"], attn["num_heads"] * attn["v_dim"]
+            g = {"wq": xavier(h, qk), "wk": xavier(h, qk), "wv": xavier(h, attn["v_dim"]),
+                 "wo": truncated_normal(rng, (hv, attn["out_dim"]), 1.0 / math.sqrt(hv), dtype)}
+            g["mlp"] = init_mlp(rng, in_dim, latent_dim, h, num_layers, bias_init_stddev, last_layer_scale, dtype)
+            return g
         return init_mlp(rng, in_dim, latent_dim, h, num_layers, bias_init_stddev,
                         last_layer_scale, dtype)
 
@@ -336,12 +385,18 @@ def make_params(seed, T, D, latent_dim=256, num_layers=5, agg="sum", block="conc
     else:                                   # construction order of gnn.py:292-299
         s = [[mk() for _ in range(T)], [mk() for _ in range(T)]]
         t = [[mk() for _ in range(T)], [mk() for _ in range(T)]]
-    return {"T": T, "D": D, "s": s, "t": t, "weight_sharing": weight_sharing,
-            "cfg": {"agg": agg, "block": block, "eps": float(eps), "act": act}}
+    cfg = {"agg": agg, "block": block, "eps": float(eps), "act": act}
+    if block == "dm_attn":
+        cfg.update(attn)
+    return {"T": T, "D": D, "s": s, "t": t, "weight_sharing": weight_sharing, "cfg": cfg}
 
 
 def cast_params(params, dtype):
     def c(m):
+        if isinstance(m, dict):
+            out = {k: m[k].astype(dtype) for k in ("wq", "wk", "wv", "wo")}
+            out["mlp"] = [(w.astype(dtype), b.astype(dtype)) for (w, b) in m["mlp"]]
+            return out
         return [(w.astype(dtype), b.astype(dtype)) for (w, b) in m]
     out = dict(params)
     for k in ("s", "t"):
@@ -350,3 +405,33 @@ def cast_params(params, dtype):
         else:
             out[k] = [[c(m) for m in half] for half in params[k]]
     return out
+
+
+# --------------------------------------------------------------------------- #
+# f3  decode tail: pred_adj + scaled_hacky_sigmoid_l2   (loss.py:154-159,45-53,131-151,83-85)
+# --------------------------------------------------------------------------- #
+def scaled_hacky_sigmoid_l2(nodes):
+    """loss.py:45-53."""
+    dt = nodes.dtype
+    dim = nodes.shape[1]
+    r = np.sum(np.square(nodes), 1, dtype=dt).reshape(-1, 1)
+    D = r - dt.type(2) * (nodes @ nodes.T) + r.T
+    D = D / np.sqrt(dt.type(dim))
+    return dt.type(1) / (dt.type(1) + np.exp(-dt.type(10) * (dt.type(1) - D)))
+
+
+def loss_mask(n_node):
+    """loss.py:131-151: block-diagonal ones."""
+    n = int(np.sum(n_node))
+    m = np.zeros((n, n), np.float32)
+    lo = 0
+    for k in n_node:
+        m[lo:lo + int(k), lo:lo + int(k)] = 1
+        lo += int(k)
+    return m
+
+
+def pred_adj(nodes, n_node):
+    """loss.py:154-159: distance_fn(nodes) * loss_mask, diagonal removed (loss.py:83-85)."""
+    p = scaled_hacky_sigmoid_l2(nodes) * loss_mask(n_node).astype(nodes.dtype)
+    return p * (1 - np.eye(p.shape[0], dtype=nodes.dtype))

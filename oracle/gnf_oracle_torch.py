@@ -52,9 +52,8 @@ def _st(p, which, half, i):
     return p[which][half] if p["weight_sharing"] else p[which][half][i]
 
 
-@torch.no_grad()
-def grevnet_f(nodes, senders, receivers, p):
-    """GRevNet.f (gnn.py:304-341)."""
+def grevnet_f_autograd(nodes, senders, receivers, p):
+    """GRevNet.f (gnn.py:304-341), differentiable (tests: reference gradients by autograd)."""
     cfg = p["cfg"]
     h = nodes.shape[1] // 2
     x0, x1 = nodes[:, :h].contiguous(), nodes[:, h:].contiguous()
@@ -72,6 +71,35 @@ def grevnet_f(nodes, senders, receivers, p):
 
 
 @torch.no_grad()
-def log_prob_xs(z, ldj):                       # run_grevnet.py:292-295
+def grevnet_f(nodes, senders, receivers, p):
+    return grevnet_f_autograd(nodes, senders, receivers, p)
+
+
+def log_prob_xs_autograd(z, ldj):              # run_grevnet.py:292-295
     d = z.shape[1]
     return (-0.5 * (z * z).sum(1) - 0.5 * d * math.log(2 * math.pi)).sum() + ldj
+
+
+@torch.no_grad()
+def log_prob_xs(z, ldj):
+    return log_prob_xs_autograd(z, ldj)
+
+
+def loss_and_grads(nodes, senders, receivers, params, scale=1.0, dtype=torch.float64):
+    """loss = -scale * log_prob_xs and its gradient w.r.t. every (W, b), by autograd, flattened in the
+    include/gnf_b200.h parameter order (which -> half -> step; W0 b0 W1 b1 ...)."""
+    p = params_to_torch(params, dtype)
+    leaves = []
+    for which in ("s", "t"):
+        for half in range(2):
+            mlps = [p[which][half]] if p["weight_sharing"] else p[which][half]
+            for mlp in mlps:
+                for i, (w, b) in enumerate(mlp):
+                    w.requires_grad_(True)
+                    b.requires_grad_(True)
+                    leaves += [w, b]
+    z, ldj = grevnet_f_autograd(torch.as_tensor(nodes).to(dtype), torch.as_tensor(senders).long(),
+                                torch.as_tensor(receivers).long(), p)
+    loss = -scale * log_prob_xs_autograd(z, ldj)
+    grads = torch.autograd.grad(loss, leaves)
+    return float(loss.detach()), torch.cat([g.reshape(-1) for g in grads]).numpy()

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gnf_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.gnf_abi_version() == 1
+    assert lib.gnf_abi_version() == 2
 
 
 def test_param_count_matches_reference_formula():
@@ -75,6 +75,19 @@ def test_scale_last_layers():
     w = net.mlp_of("t", 1, 1).weights[-1].clone()
     net.scale_last_layers_(0.05)
     assert torch.allclose(net.mlp_of("t", 1, 1).weights[-1], w * 0.05)
+
+
+def test_parameter_edits_invalidate_the_packed_weights():
+    """The device-side packed weights are refreshed whenever the flat parameter's in-place version
+    changes: optimiser steps, copy_, and edits through the per-MLP views all bump it."""
+    net = G.GRevNet(mk(L=16, K=3, D=4), 2, 4, seed=1, device="cpu")
+    v0 = net.params._version
+    net.scale_last_layers_(0.5)
+    v1 = net.params._version
+    assert v1 > v0
+    net.params.grad = torch.ones_like(net.params)
+    torch.optim.SGD([net.params], lr=0.1).step()
+    assert net.params._version > v1 and net.params.detach()._version == net.params._version
 
 
 def test_error_contract_on_host():

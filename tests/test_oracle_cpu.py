@@ -166,3 +166,43 @@ def test_torch_baseline_matches_numpy_oracle():
         assert abs(float(lt) - float(ldj)) < 1e-4 * max(1.0, abs(float(ldj)))
         lp = O.log_prob(z, ldj, g.n_node)["log_prob_xs"]
         assert H.rel_err(OT.log_prob_xs(zt, lt), lp) < 1e-5
+
+
+def test_f4_embedding_pickle_readers(tmp_path):
+    """GrevnetDatasetFixed / Variable (train_grevnet_with_data.py:145-234) + transform_example (:237-271)."""
+    import pickle
+    from graph_normalizing_flows_b200 import train_grevnet_with_data as TD
+    rng = np.random.default_rng(0)
+    files = []
+    for k in range(2):
+        n_node = rng.integers(3, 9, size=10)
+        emb = rng.standard_normal((int(n_node.sum()), 6)).astype(np.float32)
+        pickle.dump((emb, n_node), open(tmp_path / f"part{k}.p", "wb"))
+        files.append((emb, n_node))
+    ds = TD.GrevnetDatasetFixed(str(tmp_path), 4)
+    e, n = ds.train_batch()
+    assert np.array_equal(n, files[0][1][:4]) and np.array_equal(e, files[0][0][:n.sum()])
+    e, n = ds.train_batch()
+    assert np.array_equal(n, files[0][1][4:8])
+    e, n = ds.train_batch()                      # 2 graphs left < batch: next file (reference behaviour)
+    assert np.array_equal(n, files[1][1][:4]) and np.array_equal(e, files[1][0][:n.sum()])
+    dv = TD.GrevnetDatasetVariable(str(tmp_path), 20)
+    seen = []
+    for _ in range(3):
+        e, n = dv.train_batch()
+        assert e.shape[0] == n.sum() and n.sum() < 20
+        seen.append(n)
+    assert np.array_equal(np.concatenate(seen), files[0][1][:sum(len(s) for s in seen)])
+    g = TD.transform_example(e, n)
+    s, r = DO.senders_receivers(n)
+    assert np.array_equal(g.senders, s) and np.array_equal(g.receivers, r)
+    assert np.array_equal(g.n_edge, (n ** 2).astype(np.int32)) and g.nodes.dtype == np.float32
+
+
+def test_f3_oracle_pred_adj_properties():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((9, 4))
+    p = O.pred_adj(x, [4, 5])
+    assert not np.diag(p).any() and not p[:4, 4:].any() and np.allclose(p, p.T)
+    d01 = ((x[0] - x[1]) ** 2).sum() / 2.0
+    assert np.isclose(p[0, 1], 1 / (1 + np.exp(-10 * (1 - d01))))

@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 lib = _lib.load()
 buf = torch.zeros(10 * 2048, dtype=torch.int64, device="cuda")
 lib.gnf_debug_set_trace(_lib.ptr(buf))
-handle = net._flow.ensure(net.params.data)
+handle = net._flow.ensure(net.params.detach())
 st = G.graphs.structure_of(g)
 n = g.nodes.shape[0]
 m = _lib.MATH[math]
