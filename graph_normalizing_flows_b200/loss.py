@@ -65,6 +65,47 @@ def log_prob(grevnet, graph: GraphsTuple, return_z: bool = False):
     return out
 
 
+class GraphedLogProb:
+    """The density pass + log-prob assembly of ONE batch structure captured in a CUDA graph: the
+    2T fused coupling kernels, the reductions and the log-prob kernels replay with a single launch
+    (small batches are launch-bound: ~30 kernels of a few microseconds each).
+
+        runner = GraphedLogProb(grevnet, graph)        # warm-up + capture on a side stream
+        vec = runner(new_nodes)                         # float64 [4]: log_prob_zs, ldj, log_prob_xs, N
+        z = runner.z                                    # [N, D] latent of the last replay
+
+    Node features may change between replays (they are copied into the captured input buffer);
+    the structure (senders / receivers) and the parameters' packed image are the captured ones --
+    re-create the runner after an optimiser step or for a different batch structure."""
+
+    def __init__(self, grevnet, graph: GraphsTuple, warmup: int = 2):
+        from .graphs import structure_of
+        structure_of(graph)                                        # validation + CSR outside the capture
+        grevnet._flow.ensure(grevnet.params.detach())              # pack weights outside the capture
+        _ = grevnet.math
+        self.grevnet = grevnet
+        self.graph = graph.replace(nodes=graph.nodes.clone())
+        dev = graph.nodes.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                z, ldj = grevnet.f64(self.graph)
+                mvn_log_prob_sum(z.nodes, ldj)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.cuda_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.cuda_graph):
+            z, ldj = grevnet.f64(self.graph)
+            self.vec = mvn_log_prob_sum(z.nodes, ldj)
+        self.z = z.nodes
+
+    def __call__(self, nodes: torch.Tensor = None) -> torch.Tensor:
+        if nodes is not None:
+            self.graph.nodes.copy_(nodes, non_blocking=True)
+        self.cuda_graph.replay()
+        return self.vec
+
+
 # ------------------------------------------------------------------------------------------------
 # f3  decode tail of the sampling pass (train_grevnet_with_data.py:414-416, 529-548)
 # ------------------------------------------------------------------------------------------------
