@@ -354,27 +354,76 @@ int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_t
 }
 
 }  // namespace
+
+int bwd_agg_transpose(const Flow& f, const float* gh, int gh_stride, const int32_t* rowptr_s,
+                      const int32_t* csr_receivers, const int32_t* rowptr_r, int64_t n, float* gxa,
+                      cudaStream_t stream) {
+  k_agg_bwd<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(gh, gh_stride, f.H, f.HP, rowptr_s, csr_receivers,
+                                                                 rowptr_r, n, f.d.agg == GNF_AGG_MEAN,
+                                                                 f.d.block == GNF_BLOCK_CONCAT, f.d.eps, gxa);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+int bwd_split_scale(const float* z, int64_t n, int d, int h, int hp, float scale, float* x0, float* x1, float* g0,
+                    float* g1, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)ceil_div(n * hp, 256);
+  k_split_p<<<blocks, 256, 0, stream>>>(z, n, d, h, hp, x0, x1);
+  GNF_LAUNCH_CHECK();
+  k_scale_rows<<<blocks, 256, 0, stream>>>(x0, n * hp, scale, g0);      // dL/dz = scale * z
+  GNF_LAUNCH_CHECK();
+  k_scale_rows<<<blocks, 256, 0, stream>>>(x1, n * hp, scale, g1);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp, float* x, cudaStream_t stream) {
+  k_merge_p<<<(unsigned)ceil_div(n * d, 256), 256, 0, stream>>>(x0, x1, n, d, h, hp, x);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
 }  // namespace gnf
 
 using namespace gnf;
 
-extern "C" size_t gnf_grevnet_backward_workspace(const gnf_flow* h, int64_t n_nodes) {
+static bool bwd_use_tc(const Flow& f, int math) { return math != GNF_MATH_FP32 && tc_bwd_supported(f); }
+
+extern "C" size_t gnf_grevnet_backward_workspace(const gnf_flow* h, int64_t n_nodes, int32_t math) {
   if (!h || n_nodes < 0) return 0;
+  if (bwd_use_tc(h->f, math)) return tc_bwd_workspace(h->f, n_nodes);
   return carve_bwd(h->f, n_nodes, nullptr).bytes;
 }
+
+extern "C" int gnf_debug_dw_gemm(const float* a, const float* b, int64_t n, int32_t fa, int32_t fb, int32_t parts,
+                                 int32_t n_splits, float* out, void* ws, size_t ws_bytes, void* stream) {
+  GNF_REQUIRE(a && b && out && n > 0, GNF_EINVAL, "gnf_debug_dw_gemm: null pointer / empty");
+  return tc_dw_gemm_test(a, b, n, fa, fb, parts, n_splits, out, ws, ws_bytes, stream);
+}
+
 
 extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n, int64_t e,
                                     const int32_t* rowptr, const int32_t* csr_senders,
                                     const int32_t* rowptr_by_sender, const int32_t* csr_receivers, double loss_scale,
-                                    float* grads, float* x_out, void* ws, size_t ws_bytes, void* stream_) {
+                                    float* grads, float* x_out, int32_t math, void* ws, size_t ws_bytes,
+                                    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GNF_REQUIRE(h && grads, GNF_EINVAL, "gnf_grevnet_backward: null flow/grads");
   GNF_REQUIRE(n >= 0 && e >= 0, GNF_EINVAL, "gnf_grevnet_backward: negative size");
+  GNF_REQUIRE(math >= GNF_MATH_FP32 && math <= GNF_MATH_TC2X, GNF_EINVAL, "gnf_grevnet_backward: bad math %d", math);
   if (n == 0) return GNF_OK;
   GNF_REQUIRE(z && rowptr && rowptr_by_sender && (e == 0 || (csr_senders && csr_receivers)), GNF_EINVAL,
               "gnf_grevnet_backward: null pointer");
   const Flow& f = h->f;
   GNF_REQUIRE(!f.attn, GNF_EUNSUPPORTED, "gnf_grevnet_backward: the dm_self_attn block has no backward yet");
+  if (math != GNF_MATH_FP32) {
+    GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED,
+                "gnf_grevnet_backward: the tensor-core backward needs a flow shape the fused kernel supports "
+                "(gnf_flow_supports); use GNF_MATH_FP32");
+    const int dw_parts = (math == GNF_MATH_TC3X || math == GNF_MATH_TC3X_BF16) ? 2 : 1;
+    return tc_grevnet_backward(f, z, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, loss_scale, grads, x_out,
+                               ws, ws_bytes, dw_parts, stream_);
+  }
   GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0 && ws_bytes >= carve_bwd(f, n, nullptr).bytes, GNF_EWORKSPACE,
               "gnf_grevnet_backward: workspace too small or misaligned");
   BwdWs w = carve_bwd(f, n, ws);

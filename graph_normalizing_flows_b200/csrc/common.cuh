@@ -90,6 +90,7 @@ struct Flow {
   uint8_t* wtc[2] = {nullptr, nullptr};   // [0]=fp16 hi/lo, [1]=bf16 hi/lo
   int64_t wtc_per_mlp = 0;
   float* btc = nullptr;        // biases for the TC kernel: per MLP K*256 floats
+  uint8_t* wtcT = nullptr;     // bf16 hi/lo images of the TRANSPOSED MLP chains (backward dX), same geometry
   bool tc_ok = false;
 
   int mlp_index(int which, int half, int step) const {
@@ -105,7 +106,25 @@ int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t
 int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                   float* hbuf, cudaStream_t stream);
 
+// backward.cu (shared with backward_tc.cu)
+int bwd_agg_transpose(const Flow& f, const float* gh, int gh_stride, const int32_t* rowptr_s,
+                      const int32_t* csr_receivers, const int32_t* rowptr_r, int64_t n, float* gxa,
+                      cudaStream_t stream);
+int bwd_split_scale(const float* z, int64_t n, int d, int h, int hp, float scale, float* x0, float* x1, float* g0,
+                    float* g1, cudaStream_t stream);
+int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp, float* x, cudaStream_t stream);
+
+// backward_tc.cu
+bool tc_bwd_supported(const Flow& f);
+size_t tc_bwd_workspace(const Flow& f, int64_t n);
+int tc_grevnet_backward(const Flow& f, const float* z, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
+                        const int32_t* rowptr_s, const int32_t* csr_receivers, double loss_scale, float* grads,
+                        float* x_out, void* ws, size_t ws_bytes, int dw_parts, void* stream);
+int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, int parts, int n_splits, float* out,
+                    void* ws, size_t ws_bytes, void* stream);
+
 // coupling_tc.cu
+int tc_pack_mlp_T(const Flow& f, int mlp, const float* params, void* stream);
 size_t tc_bytes_per_mlp(int L, int K);
 int tc_pack_mlp(const Flow& f, int mlp, const float* params, void* stream);
 bool tc_shape_supported(const Flow& f);

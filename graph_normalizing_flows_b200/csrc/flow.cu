@@ -746,6 +746,7 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
     cudaError_t e0 = cudaMalloc(&f.wtc[0], (size_t)f.n_mlps * f.wtc_per_mlp);
     cudaError_t e1 = cudaMalloc(&f.wtc[1], (size_t)f.n_mlps * f.wtc_per_mlp);
     cudaError_t e2 = cudaMalloc(&f.btc, (size_t)f.n_mlps * f.K * 256 * 4);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&f.wtcT, (size_t)f.n_mlps * f.wtc_per_mlp);
     if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
       gnf_flow_destroy(h);
       set_error("gnf_flow_create: cudaMalloc (tc weights) failed");
@@ -765,6 +766,7 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.wtc[0]);
   cudaFree(h->f.wtc[1]);
   cudaFree(h->f.btc);
+  cudaFree(h->f.wtcT);
   delete h;
   return GNF_OK;
 }
@@ -812,6 +814,8 @@ extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* strea
     }
     if (f.tc_ok) {
       int rc = tc_pack_mlp(f, m, params + (int64_t)m * f.params_per_mlp + f.mlp_off, stream_);
+      if (rc) return rc;
+      rc = tc_pack_mlp_T(f, m, params + (int64_t)m * f.params_per_mlp + f.mlp_off, stream_);
       if (rc) return rc;
     }
   }

@@ -655,9 +655,10 @@ class GRevNet(nn.Module):
 
     # -- f2: training-step gradients (reversible, nothing stored by the forward pass) --------------
     def backward_from_z(self, graph: GraphsTuple, z_nodes: torch.Tensor, loss_scale: float,
-                        grads: Optional[torch.Tensor] = None, return_x: bool = False):
+                        grads: Optional[torch.Tensor] = None, return_x: bool = False, math: Optional[str] = None):
         """d(-loss_scale * log_prob_xs)/d(params), accumulated into `grads` (flat, same layout as
-        self.params).  `z_nodes` must be f(graph).nodes."""
+        self.params).  `z_nodes` must be f(graph).nodes.  `math` defaults to the forward's mode:
+        "fp32" = layered FFMA kernels, anything else = the tcgen05 backward (backward_tc.cu)."""
         if self.use_batch_norm:
             raise NotImplementedError("backward with use_batch_norm=True is not implemented")
         lib = self._flow.lib
@@ -669,15 +670,16 @@ class GRevNet(nn.Module):
             grads = torch.zeros_like(self.params.detach())
         _lib.require_cuda(grads, "grads", torch.float32)
         x_out = torch.empty_like(z_nodes) if return_x else None
-        wsb = lib.gnf_grevnet_backward_workspace(handle, n)
+        m = _lib.MATH[math if math is not None else self.math]
+        wsb = lib.gnf_grevnet_backward_workspace(handle, n, m)
         ws = _lib.workspace(wsb, dev)
         _lib.check(lib.gnf_grevnet_backward(handle, _lib.ptr(z_nodes), n, st.n_edges, _lib.ptr(st.rowptr),
                                             _lib.ptr(st.csr_senders), _lib.ptr(stt.rowptr), _lib.ptr(stt.csr_senders),
-                                            float(loss_scale), _lib.ptr(grads), _lib.ptr(x_out), _lib.ptr(ws), wsb,
+                                            float(loss_scale), _lib.ptr(grads), _lib.ptr(x_out), m, _lib.ptr(ws), wsb,
                                             _lib.stream_ptr(dev)), "gnf_grevnet_backward")
         return (grads, x_out) if return_x else grads
 
-    def loss_and_grad(self, graph: GraphsTuple, per_node: bool = True):
+    def loss_and_grad(self, graph: GraphsTuple, per_node: bool = True, backward_math: Optional[str] = None):
         """One training-step evaluation: the scalars of run_grevnet.py:292-302 and the gradient of
         total_loss (per_node=False, run_grevnet.py:362-364) or loss_per_node (per_node=True,
         train_grevnet_with_data.py:353-380) w.r.t. the flat parameter vector; also stored in
@@ -686,7 +688,7 @@ class GRevNet(nn.Module):
         z, ldj64 = self.f64(graph)
         out = scalars_from_vector(mvn_log_prob_sum(z.nodes, ldj64))
         n = max(int(z.nodes.shape[0]), 1)
-        grads = self.backward_from_z(graph, z.nodes, 1.0 / n if per_node else 1.0)
+        grads = self.backward_from_z(graph, z.nodes, 1.0 / n if per_node else 1.0, math=backward_math)
         self.params.grad = grads
         out["z"] = z
         return out, grads

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GNF_ABI_VERSION 2
+#define GNF_ABI_VERSION 3
 
 /* status codes */
 #define GNF_OK            0
@@ -220,14 +220,29 @@ int gnf_gnn_forward(const gnf_flow* flow, int32_t which, int32_t half, int32_t s
  *   rowptr / csr_senders            CSR by receiver (gnf_build_csr(receivers, senders))
  *   rowptr_by_sender / csr_receivers CSR by sender   (gnf_build_csr(senders, receivers)): the
  *                                   transpose the aggregation's backward walks
- * fp32 arithmetic (use_batch_norm = False).  workspace: gnf_grevnet_backward_workspace(flow, N).
+ * math (use_batch_norm = False):
+ *   GNF_MATH_FP32                     layered FFMA kernels, any supported shape;
+ *   GNF_MATH_TC3X / GNF_MATH_TC3X_BF16 tcgen05 path (flows gnf_flow_supports() accepts): per half step one
+ *                                     fused kernel (recompute s,t; undo the update; dX chain with the
+ *                                     transposed weights) + one weight-gradient GEMM kernel; every operand
+ *                                     a bf16 hi/lo split, 3 MMAs per product, fp32 accumulate;
+ *   GNF_MATH_TC2X / GNF_MATH_BF16     same, but the weight-gradient GEMM reads only the bf16 hi parts
+ *                                     (one MMA per product; its rounding errors average over the nodes).
+ * workspace: gnf_grevnet_backward_workspace(flow, N, math), 256-byte aligned.
  * ------------------------------------------------------------------------------------------ */
-size_t gnf_grevnet_backward_workspace(const gnf_flow* flow, int64_t n_nodes);
+size_t gnf_grevnet_backward_workspace(const gnf_flow* flow, int64_t n_nodes, int32_t math);
 int gnf_grevnet_backward(const gnf_flow* flow, const float* z, int64_t n_nodes, int64_t n_edges,
                          const int32_t* rowptr, const int32_t* csr_senders,
                          const int32_t* rowptr_by_sender, const int32_t* csr_receivers,
-                         double loss_scale, float* grads, float* x_out,
+                         double loss_scale, float* grads, float* x_out, int32_t math,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Weight-gradient GEMM of the tensor-core backward on its own (unit tests, profiling):
+ * out[fa, fb] = a^T b for row-major fp32 a [n, fa], b [n, fb]; fa in {128,256}, fb in {16,128,256};
+ * parts 2 = bf16 hi/lo split (3 MMAs per product), 1 = single bf16 pass; n_splits node ranges (one CTA
+ * each) reduced in fixed order.  workspace >= 4*ceil(n/128)*128*(fa+fb) + 4*n_splits*fa*fb + 2048 bytes. */
+int gnf_debug_dw_gemm(const float* a, const float* b, int64_t n, int32_t fa, int32_t fb, int32_t parts,
+                      int32_t n_splits, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * f3  Decode tail of the sampling pass (train_grevnet_with_data.py:414-416):

@@ -270,12 +270,19 @@ def test_a9_batch_norm_bijector(math):
     assert np.abs(x - x_ref).max() < 1e-3 * max(1.0, np.abs(x_ref).max())
 
 
+# backward arithmetic -> (max-norm tolerance, 1 - cosine tolerance); see include/gnf_b200.h (f2)
+BWD_TOL = {"fp32": (2e-4, 1e-6), "tc3x": (4e-3, 2e-6), "bf16": (1e-2, 1e-4)}
+
+
+@pytest.mark.parametrize("bmath", ["fp32", "tc3x", "bf16"])
 @pytest.mark.parametrize("block,agg,ws,act", [("concat", "sum", False, "leaky_relu"), ("concat", "mean", False, "relu"),
                                               ("agg_then", "sum", True, "leaky_relu"), ("agg_then", "mean", False, "leaky_relu")])
-def test_f2_reversible_backward_matches_autograd(block, agg, ws, act):
+def test_f2_reversible_backward_matches_autograd(block, agg, ws, act, bmath):
     """Row f2: analytic reversible backward (gnf_grevnet_backward) vs torch autograd of the fp64
-    torch restatement of the reference.  Stated tolerance: 2e-4 of the gradient's max-norm per
-    parameter tensor family (fp32 FFMA arithmetic, fp32 split-K reductions)."""
+    torch restatement of the reference.  Stated tolerances (of the gradient's max-norm over the
+    whole parameter vector): fp32 FFMA kernels 2e-4; tensor-core backward with bf16 hi/lo split
+    operands ("tc3x": 2^-17 per operand, systematic weight rounding that does not average over the
+    nodes, ~20 chained GEMMs) 4e-3; the same with a single-bf16 weight-gradient GEMM ("bf16") 1e-2."""
     from oracle import gnf_oracle_torch as OT
     rng = np.random.default_rng(21)
     D, T, L, K = (14, 2, 128, 4) if block == "concat" else (6, 3, 128, 3)
@@ -283,23 +290,70 @@ def test_f2_reversible_backward_matches_autograd(block, agg, ws, act):
     params = O.make_params(8, T, D, L, K, agg=agg, block=block, eps=0.8, act=act, last_layer_scale=0.2,
                            weight_sharing=ws)
     n = g.nodes.shape[0]
+    tol, ctol = BWD_TOL[bmath]
     for per_node in (True, False):
         scale = 1.0 / n if per_node else 1.0
         loss_ref, grad_ref = OT.loss_and_grads(g.nodes, g.senders, g.receivers, params, scale)
         net = H.make_grevnet(params, L, K, device=DEV)
-        out, grads = net.loss_and_grad(dev_graph(g), per_node=per_node)
+        out, grads = net.loss_and_grad(dev_graph(g), per_node=per_node, backward_math=bmath)
         got = grads.cpu().numpy().astype(np.float64)
         loss = float(out["loss_per_node"] if per_node else out["total_loss"])
         assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
         assert got.shape == grad_ref.shape and np.isfinite(got).all()
-        assert np.abs(got - grad_ref).max() <= 2e-4 * np.abs(grad_ref).max()
+        assert np.abs(got - grad_ref).max() <= tol * np.abs(grad_ref).max()
         # cosine of the whole gradient vector
-        assert float(got @ grad_ref) / (np.linalg.norm(got) * np.linalg.norm(grad_ref)) > 1 - 1e-6
+        assert float(got @ grad_ref) / (np.linalg.norm(got) * np.linalg.norm(grad_ref)) > 1 - ctol
         assert net.params.grad is grads
     # the backward reconstructs the input on its way (reversibility)
     z = out["z"]
-    _, x_rec = net.backward_from_z(dev_graph(g), z.nodes, 1.0, return_x=True)
+    _, x_rec = net.backward_from_z(dev_graph(g), z.nodes, 1.0, return_x=True, math=bmath)
     assert np.abs(x_rec.cpu().numpy() - g.nodes).max() < 5e-5
+
+
+@pytest.mark.parametrize("bmath", ["tc3x", "bf16"])
+def test_f2_tensor_core_backward_many_tiles(bmath):
+    """More tiles than SMs (every CTA walks several 128-node tiles; the weight-gradient GEMM splits
+    over node ranges) at the bench shape L=256, K=5: tensor-core backward vs the fp32 FFMA backward
+    on the same device, and determinism (fixed-order reductions -> bit-identical reruns)."""
+    rng = np.random.default_rng(23)
+    g = H.random_batch(rng, 1200, 10, 30, p_edge=0.2, D=14)
+    params = O.make_params(5, 2, 14, 256, 5, last_layer_scale=0.1)
+    net = H.make_grevnet(params, 256, 5, device=DEV)
+    dg = dev_graph(g)
+    n = g.nodes.shape[0]
+    assert n > 148 * 128
+    z, _ = net.f64(dg)
+    ref, x_ref = net.backward_from_z(dg, z.nodes, 1.0 / n, return_x=True, math="fp32")
+    got, x_got = net.backward_from_z(dg, z.nodes, 1.0 / n, return_x=True, math=bmath)
+    again = net.backward_from_z(dg, z.nodes, 1.0 / n, math=bmath)
+    ref, got = ref.double().cpu().numpy(), got.double().cpu().numpy()
+    tol, ctol = BWD_TOL[bmath]
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= tol * np.abs(ref).max()
+    assert float(got @ ref) / (np.linalg.norm(got) * np.linalg.norm(ref)) > 1 - ctol
+    assert torch.equal(again.cpu(), torch.from_numpy(got).float())
+    assert (x_got - x_ref).abs().max().item() < 5e-5
+    assert np.abs(x_got.cpu().numpy() - g.nodes).max() < 5e-5
+
+
+def test_f2_weight_gradient_gemm():
+    """k_dw_tc on its own (gnf_debug_dw_gemm): a^T b over the node dimension from the MN-major bf16
+    hi/lo tile images; split parts=2 is fp32-class (2^-17 operands), parts=1 is one bf16 rounding."""
+    from graph_normalizing_flows_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    for (fa, fb, n, parts, splits, tol) in [(256, 256, 128, 2, 1, 3e-5), (256, 256, 128, 1, 1, 8e-3),
+                                            (256, 16, 300, 2, 2, 3e-5), (128, 128, 1000, 2, 3, 3e-5),
+                                            (128, 16, 77, 1, 1, 8e-3), (256, 256, 5000, 2, 7, 3e-5)]:
+        a = torch.randn(n, fa, generator=gen).to(DEV)
+        b = (torch.randn(n, fb, generator=gen) * 1e-3).to(DEV)
+        out = torch.empty(fa, fb, device=DEV)
+        wsb = 4 * ((n + 127) // 128) * 128 * (fa + fb) + 4 * splits * fa * fb + 4096
+        ws = _lib.workspace(wsb, torch.device(DEV))
+        _lib.check(lib.gnf_debug_dw_gemm(_lib.ptr(a), _lib.ptr(b), n, fa, fb, parts, splits, _lib.ptr(out),
+                                         _lib.ptr(ws), wsb, _lib.stream_ptr(torch.device(DEV))), "gnf_debug_dw_gemm")
+        ref = a.double().T @ b.double()
+        assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol, (fa, fb, n, parts)
 
 
 def test_f2_training_steps_reduce_the_loss():
