@@ -68,6 +68,7 @@ SIGNATURES = {
     "gnf_gnn_forward": (C.c_int, [_p, _i32, _i32, _i32, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "gnf_grevnet_backward_workspace": (_sz, [_p, _i64, _i32]),
     "gnf_grevnet_backward": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, C.c_double, _p, _p, _i32, _p, _sz, _p]),
+    "gnf_debug_bwd_layout": (C.c_int, [_p, _i64, _p]),
     "gnf_debug_dw_gemm": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "gnf_pred_adj": (C.c_int, [_p, _i32, _p, _p, _i64, C.c_float, C.c_float, _p, _p]),
     "gnf_log_prob_workspace": (_sz, [_i64, _i32]),

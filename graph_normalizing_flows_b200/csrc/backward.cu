@@ -395,6 +395,12 @@ extern "C" size_t gnf_grevnet_backward_workspace(const gnf_flow* h, int64_t n_no
   return carve_bwd(h->f, n_nodes, nullptr).bytes;
 }
 
+extern "C" int gnf_debug_bwd_layout(const gnf_flow* h, int64_t n_nodes, int64_t* out8) {
+  GNF_REQUIRE(h && out8 && n_nodes > 0 && tc_bwd_supported(h->f), GNF_EINVAL, "gnf_debug_bwd_layout: bad argument");
+  tc_bwd_layout(h->f, n_nodes, out8);
+  return GNF_OK;
+}
+
 extern "C" int gnf_debug_dw_gemm(const float* a, const float* b, int64_t n, int32_t fa, int32_t fb, int32_t parts,
                                  int32_t n_splits, float* out, void* ws, size_t ws_bytes, void* stream) {
   GNF_REQUIRE(a && b && out && n > 0, GNF_EINVAL, "gnf_debug_dw_gemm: null pointer / empty");
@@ -421,8 +427,9 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
                 "gnf_grevnet_backward: the tensor-core backward needs a flow shape the fused kernel supports "
                 "(gnf_flow_supports); use GNF_MATH_FP32");
     const int dw_parts = (math == GNF_MATH_TC3X || math == GNF_MATH_TC3X_BF16) ? 2 : 1;
+    const int fwd_f16 = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 1 : 0;
     return tc_grevnet_backward(f, z, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, loss_scale, grads, x_out,
-                               ws, ws_bytes, dw_parts, stream_);
+                               ws, ws_bytes, dw_parts, fwd_f16, stream_);
   }
   GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0 && ws_bytes >= carve_bwd(f, n, nullptr).bytes, GNF_EWORKSPACE,
               "gnf_grevnet_backward: workspace too small or misaligned");

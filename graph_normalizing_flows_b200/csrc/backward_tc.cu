@@ -28,7 +28,10 @@ namespace {
 
 using namespace tcx;
 
-constexpr bool kBF = true;      // element type of every backward operand: bf16 (gradients underflow fp16)
+constexpr bool kBF = true;      // element type of every GRADIENT operand: bf16 (gradients underflow fp16)
+// The recomputed forward chains (template flag F16F) use the fp16 hi/lo split when the math mode is
+// tc3x / tc2x: 2^-22 operands keep the recomputed pre-activations at fp32 accuracy, so the sign masks of
+// act' flip no more often than in fp32 arithmetic (bf16 hi/lo, 2^-17, flips ~40x more near the kink).
 
 struct BwdParams {
   const float* xa;
@@ -49,6 +52,7 @@ struct BwdParams {
   uint16_t* g_img;           // [2][tiles][2][16*128]
   float* gh;                 // [tiles*128][16]
   float* db_part;            // [grid][4][2][kMaxLayers][256]   (zeroed by the caller)
+  int write_lo;              // 0: the weight-gradient GEMM reads only the hi parts, skip the lo images
 };
 
 struct __align__(8) BwdBarriers {
@@ -95,8 +99,9 @@ __device__ __forceinline__ float colsum32(float (&d)[32], int lane) {
   return d[0];
 }
 
-template <int LAT, int ACT>
+template <int LAT, int ACT, bool F16F>
 __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
+  constexpr bool kFB = !F16F;   // forward chains: bf16 split?
   using G = Geo<LAT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {   // bias selector / bias tiles: as in the forward kernel
-    const uint16_t one = 0x3F80;
+    const uint16_t one = F16F ? 0x3C00 : 0x3F80;
     for (int i = tid; i < (K - 1) * 128 * 16; i += kThreads) {
       const int l = i / 2048, r = i - l * 2048, m = r >> 4, k = r & 15;
       *reinterpret_cast<uint16_t*>(sel + l * 4096 + (k >> 3) * 2048 + m * 16 + (k & 7) * 2) =
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
       const int m = i / (LAT * 8), r = i - m * (LAT * 8), n = r >> 3, j = r & 7;
       const float b = (j < K - 1) ? p.bias[m][j * 256 + n] : 0.f;
       uint32_t hi, lo;
-      split_pair<kBF>(b, 0.f, hi, lo);
+      split_pair<kFB>(b, 0.f, hi, lo);
       const uint32_t packed = (hi & 0xFFFFu) | (lo << 16);
       const int k = 2 * j;
       *reinterpret_cast<uint32_t*>(btile + m * (LAT * 32) + (k >> 3) * (LAT * 16) + (n >> 3) * 128 + (n & 7) * 16 +
@@ -190,9 +195,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
     }
   } else if (warp == 1) {
     // ===== MMA issuer ==============================================================================
-    constexpr uint32_t idesc_l0 = make_idesc(LAT, kBF);
-    constexpr uint32_t idesc_h = make_idesc(G::NH, kBF);
-    constexpr uint32_t idesc_last = make_idesc(kNOut, kBF);
+    constexpr uint32_t idesc_l0_f = make_idesc(LAT, kFB), idesc_l0_b = make_idesc(LAT, kBF);
+    constexpr uint32_t idesc_h_f = make_idesc(G::NH, kFB), idesc_h_b = make_idesc(G::NH, kBF);
+    constexpr uint32_t idesc_last_f = make_idesc(kNOut, kFB), idesc_last_b = make_idesc(kNOut, kBF);
     const uint32_t bar_full = smem_u32(&bars->full[0]), bar_empty = smem_u32(&bars->empty[0]);
     const uint32_t bar_acc = smem_u32(&bars->acc_full[0]), bar_ready = smem_u32(&bars->a_ready[0]);
     const uint32_t bar_hfull = smem_u32(&bars->h_full[0]), bar_hempty = smem_u32(&bars->h_empty[0]);
@@ -222,6 +227,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
         const uint32_t a0_hi = bwd ? gbuf_u + m * 8192 : hbuf_u + buf * 8192;
         const uint32_t a0_lo = a0_hi + 4096;
         const uint32_t bt = btile_u + m * (LAT * 32);
+        const uint32_t idesc_l0 = bwd ? idesc_l0_b : idesc_l0_f, idesc_h = bwd ? idesc_h_b : idesc_h_f;
+        const uint32_t idesc_last = bwd ? idesc_last_b : idesc_last_f;
         // ---- chain layer 0: A from smem (K = 16), N = LAT --------------------------------------
         {
           const uint32_t d = tmem_base + region * LAT;
@@ -378,20 +385,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
                 for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * dact_f<ACT>((pos[ch] >> j) & 1u);
               }
               uint32_t hi[16], lo[16];
+              if (bwd) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) split_pair<kBF>(d[2 * j], d[2 * j + 1], hi[j], lo[j]);
+                for (int j = 0; j < 16; ++j) split_pair<kBF>(d[2 * j], d[2 * j + 1], hi[j], lo[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) split_pair<kFB>(d[2 * j], d[2 * j + 1], hi[j], lo[j]);
+              }
               tmem_st16(t0, hi);
               tmem_st16(t0 + 16, lo);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(smem_u32(&bars->a_ready[NCH == 2 ? ph * 2 + ch : ph]));
-              // image for the weight-gradient GEMM
+              // image for the weight-gradient GEMM: always bf16 (tcgen05 kind::f16 needs one operand format)
+              if (F16F && !bwd) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) split_pair<kBF>(d[2 * j], d[2 * j + 1], hi[j], lo[j]);
+              }
               uint4* oh = reinterpret_cast<uint4*>(out_img + img_off(LAT, col0 >> 3, row));
               uint4* ol = reinterpret_cast<uint4*>(out_img + img_elems + img_off(LAT, col0 >> 3, row));
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 oh[g * 8] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-                ol[g * 8] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+                if (p.write_lo) ol[g * 8] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
               }
               if (bwd) {   // bias gradient of layer li: column sums over this warp's 32 rows
                 const float cs = colsum32(d, lane);
@@ -562,6 +578,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
         ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         ol[8] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       }
+      if (F16F) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_pair<kFB>(my[2 * j], my[2 * j + 1], hi[j], lo[j]);
+      }
       mbar_wait(smem_u32(&bars->h_empty[buf]), ((it >> 1) & 1) ^ 1);
       uint8_t* hb = hbuf + buf * 8192;
       *reinterpret_cast<uint4*>(hb + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -596,6 +616,7 @@ struct DwPair {
   float* part;             // [n_splits][a_feats][b_feats]
   int a_feats, b_feats;
   int first_cta, n_splits;
+  int a_bf16, b_bf16;      // element type of each operand's images (0 = fp16)
 };
 struct DwParams {
   DwPair pair[kDwMaxPairs];
@@ -606,9 +627,10 @@ struct __align__(8) DwBarriers {
   uint64_t full[kDwStages], empty[kDwStages], acc_full;
 };
 
-__host__ __device__ constexpr uint32_t make_idesc_mn(int n) {   // bf16 x bf16 -> f32, both operands MN-major
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(kTileM >> 4) << 24);
+// 16-bit x 16-bit -> f32, both operands MN-major; the two operand formats are independent fields
+__host__ __device__ constexpr uint32_t make_idesc_mn(int n, bool a_bf16, bool b_bf16) {
+  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
 template <int PARTS>   // 2: hi/lo split, 3 MMAs per product; 1: single bf16 pass
@@ -675,7 +697,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_mn(FB);
+    const uint32_t idesc = make_idesc_mn(FB, pr.a_bf16 != 0, pr.b_bf16 != 0);
     // MN-major no-swizzle: SBO = stride between 8-feature groups, LBO = stride between 8-node groups
     const uint32_t a_lbo = FA * 16u, a_sbo = 128u, b_lbo = FB * 16u, b_sbo = 128u;
     uint32_t stage = 0, phase = 0;
@@ -767,9 +789,13 @@ __global__ void k_dw_reduce(const DwReduceParams p) {
   const int a = i / r.fb, b = i - a * r.fb;
   const int in = r.transposed ? b : a, out = r.transposed ? a : b;
   if (in >= r.in_dim || out >= r.out_dim) return;
-  float s = 0.f;
-  for (int z = 0; z < r.n_splits; ++z) s += r.part[(size_t)z * r.fa * r.fb + i];
-  r.grad[(size_t)in * r.out_dim + out] += s;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int z0 = 0; z0 < r.n_splits; z0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (z0 + u < r.n_splits) acc[u] += r.part[(size_t)(z0 + u) * r.fa * r.fb + i];
+  }
+  r.grad[(size_t)in * r.out_dim + out] += (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 // bias gradients: fixed-order sum over (cta, lane quarter) of the per-CTA column sums
@@ -783,9 +809,16 @@ __global__ void k_db_reduce(const DbReduceParams p) {
   const int m = blockIdx.y / p.K, l = blockIdx.y - m * p.K;
   const int col = threadIdx.x;
   if (col >= p.out_dim[l]) return;
-  float s = 0.f;
-  for (int z = 0; z < p.grid * 4; ++z) s += p.part[(((size_t)z * 2 + m) * kMaxLayers + l) * 256 + col];
-  p.grad_b[m][l][col] += s;
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  const int nz = p.grid * 4;
+  for (int z0 = 0; z0 < nz; z0 += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (z0 + u < nz) acc[u] += p.part[(((size_t)(z0 + u) * 2 + m) * kMaxLayers + l) * 256 + col];
+  }
+  p.grad_b[m][l][col] += ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 // ---- debug / unit-test helper: fp32 [n, F] row-major -> bf16 hi/lo tile images ----------------
@@ -818,9 +851,9 @@ int launch_dw(const DwParams& p, int grid, int parts, cudaStream_t stream) {
   return GNF_OK;
 }
 
-template <int LAT, int ACT>
+template <int LAT, int ACT, bool F16F>
 int launch_chain_t(const BwdParams& p, int grid, cudaStream_t stream) {
-  auto kern = k_bwd_chain<LAT, ACT>;
+  auto kern = k_bwd_chain<LAT, ACT, F16F>;
   static bool configured = false;
   const size_t smem = bwd_smem_bytes<LAT>();
   if (!configured) {
@@ -926,11 +959,25 @@ bool tc_bwd_supported(const Flow& f) { return f.tc_ok && f.wtcT != nullptr && f.
 
 size_t tc_bwd_workspace(const Flow& f, int64_t n) { return carve_bwd_tc(f, n, nullptr).bytes; }
 
+// byte offsets of the per-half-step buffers inside the workspace (bring-up / tests decode the images)
+void tc_bwd_layout(const Flow& f, int64_t n, int64_t* out) {
+  BwdTcWs w = carve_bwd_tc(f, n, (void*)4096);
+  const uint8_t* b = (const uint8_t*)4096;
+  out[0] = (const uint8_t*)w.act_img - b;
+  out[1] = (const uint8_t*)w.dlt_img - b;
+  out[2] = (const uint8_t*)w.h_img - b;
+  out[3] = (const uint8_t*)w.g_img - b;
+  out[4] = (const uint8_t*)w.gh - b;
+  out[5] = (const uint8_t*)w.x0 - b;
+  out[6] = (const uint8_t*)w.g0 - b;
+  out[7] = (int64_t)w.bytes;
+}
+
 // one reversed half step: (xa, xb', g_xa, g_xb') -> (xb, g_xa += ..., g_xb), grads += ...
 static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb, float* ga, float* gb, int64_t n,
                        const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
                        const int32_t* csr_receivers, float scale, float* grads, const BwdTcWs& w, int dw_parts,
-                       cudaStream_t stream) {
+                       bool fwd_f16, cudaStream_t stream) {
   const int K = f.K, L = f.L;
   const int n_tiles = (int)ceil_div(n, kTileM);
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
@@ -939,8 +986,8 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
   p.xa = xa; p.xb = xb; p.gxb = gb;
   p.rowptr = rowptr; p.csr = csr_senders;
   p.n_nodes = n; p.n_tiles = n_tiles;
-  p.wf[0] = f.wtc[1] + (size_t)ms * f.wtc_per_mlp;
-  p.wf[1] = f.wtc[1] + (size_t)mt * f.wtc_per_mlp;
+  p.wf[0] = f.wtc[fwd_f16 ? 0 : 1] + (size_t)ms * f.wtc_per_mlp;
+  p.wf[1] = f.wtc[fwd_f16 ? 0 : 1] + (size_t)mt * f.wtc_per_mlp;
   p.wb[0] = f.wtcT + (size_t)ms * f.wtc_per_mlp;
   p.wb[1] = f.wtcT + (size_t)mt * f.wtc_per_mlp;
   p.bias[0] = f.btc + (size_t)ms * f.K * 256;
@@ -951,13 +998,20 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
   p.eps = f.d.eps; p.scale = scale;
   p.act_img = w.act_img; p.dlt_img = w.dlt_img; p.h_img = w.h_img; p.g_img = w.g_img;
   p.gh = w.gh; p.db_part = w.db_part;
+  p.write_lo = dw_parts == 2;
   int rc;
-  if (L == 256)
-    rc = f.d.act == GNF_ACT_LEAKY_RELU ? launch_chain_t<256, GNF_ACT_LEAKY_RELU>(p, grid, stream)
-                                       : launch_chain_t<256, GNF_ACT_RELU>(p, grid, stream);
-  else
-    rc = f.d.act == GNF_ACT_LEAKY_RELU ? launch_chain_t<128, GNF_ACT_LEAKY_RELU>(p, grid, stream)
-                                       : launch_chain_t<128, GNF_ACT_RELU>(p, grid, stream);
+  const bool leaky = f.d.act == GNF_ACT_LEAKY_RELU;
+  if (L == 256) {
+    if (fwd_f16) rc = leaky ? launch_chain_t<256, GNF_ACT_LEAKY_RELU, true>(p, grid, stream)
+                            : launch_chain_t<256, GNF_ACT_RELU, true>(p, grid, stream);
+    else rc = leaky ? launch_chain_t<256, GNF_ACT_LEAKY_RELU, false>(p, grid, stream)
+                    : launch_chain_t<256, GNF_ACT_RELU, false>(p, grid, stream);
+  } else {
+    if (fwd_f16) rc = leaky ? launch_chain_t<128, GNF_ACT_LEAKY_RELU, true>(p, grid, stream)
+                            : launch_chain_t<128, GNF_ACT_RELU, true>(p, grid, stream);
+    else rc = leaky ? launch_chain_t<128, GNF_ACT_LEAKY_RELU, false>(p, grid, stream)
+                    : launch_chain_t<128, GNF_ACT_RELU, false>(p, grid, stream);
+  }
   if (rc) return rc;
   rc = bwd_agg_transpose(f, w.gh, kK0, rowptr_s, csr_receivers, rowptr, n, ga, stream);
   if (rc) return rc;
@@ -985,14 +1039,17 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
         pr.A = w.dlt_img + ((size_t)m * (K - 1) + 0) * layer_stride;
         pr.B = w.h_img;
         pr.b_feats = 16;
+        pr.a_bf16 = 1; pr.b_bf16 = 1;
       } else if (l == K - 1) {            // dW_{K-1} = a_{K-2}^T g_top
         pr.A = w.act_img + ((size_t)m * (K - 1) + (K - 2)) * layer_stride;
         pr.B = w.g_img + (size_t)m * n_tiles * 2 * 16 * 128;
         pr.b_feats = 16;
+        pr.a_bf16 = 1; pr.b_bf16 = 1;
       } else {                            // dW_l = a_{l-1}^T delta_l
         pr.A = w.act_img + ((size_t)m * (K - 1) + (l - 1)) * layer_stride;
         pr.B = w.dlt_img + ((size_t)m * (K - 1) + l) * layer_stride;
         pr.b_feats = L;
+        pr.a_bf16 = 1; pr.b_bf16 = 1;
       }
       rr.part = pr.part;
       rr.grad = gm + f.flat_w_off[l];
@@ -1033,7 +1090,7 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
 
 int tc_grevnet_backward(const Flow& f, const float* z, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                         const int32_t* rowptr_s, const int32_t* csr_receivers, double loss_scale, float* grads,
-                        float* x_out, void* ws, size_t ws_bytes, int dw_parts, void* stream_) {
+                        float* x_out, void* ws, size_t ws_bytes, int dw_parts, int fwd_f16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED, "tensor-core backward: unsupported flow shape");
   GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0 && ws_bytes >= carve_bwd_tc(f, n, nullptr).bytes, GNF_EWORKSPACE,
@@ -1051,7 +1108,7 @@ int tc_grevnet_backward(const Flow& f, const float* z, int64_t n, const int32_t*
       float* gb = half == 0 ? w.g1 : w.g0;
       const int ms = f.mlp_index(0, half, i), mt = f.mlp_index(1, half, i);
       rc = bwd_half_tc(f, ms, mt, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_s, csr_receivers, scale, grads, w,
-                       dw_parts, stream);
+                       dw_parts, fwd_f16 != 0, stream);
       if (rc) return rc;
     }
   }
@@ -1085,7 +1142,7 @@ int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, i
   DwParams dp{};
   dp.n_pairs = 1;
   dp.n_tiles = n_tiles;
-  dp.pair[0] = DwPair{ai, bi, part, fa, fb, 0, n_splits};
+  dp.pair[0] = DwPair{ai, bi, part, fa, fb, 0, n_splits, 1, 1};
   int rc = launch_dw(dp, n_splits, parts, stream);
   if (rc) return rc;
   GNF_CUDA(cudaMemsetAsync(out, 0, (size_t)fa * fb * 4, stream));

@@ -117,9 +117,10 @@ int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp,
 // backward_tc.cu
 bool tc_bwd_supported(const Flow& f);
 size_t tc_bwd_workspace(const Flow& f, int64_t n);
+void tc_bwd_layout(const Flow& f, int64_t n, int64_t* out);
 int tc_grevnet_backward(const Flow& f, const float* z, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                         const int32_t* rowptr_s, const int32_t* csr_receivers, double loss_scale, float* grads,
-                        float* x_out, void* ws, size_t ws_bytes, int dw_parts, void* stream);
+                        float* x_out, void* ws, size_t ws_bytes, int dw_parts, int fwd_f16, void* stream);
 int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, int parts, int n_splits, float* out,
                     void* ws, size_t ws_bytes, void* stream);
 

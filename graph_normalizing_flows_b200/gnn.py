@@ -677,6 +677,7 @@ class GRevNet(nn.Module):
                                             _lib.ptr(st.csr_senders), _lib.ptr(stt.rowptr), _lib.ptr(stt.csr_senders),
                                             float(loss_scale), _lib.ptr(grads), _lib.ptr(x_out), m, _lib.ptr(ws), wsb,
                                             _lib.stream_ptr(dev)), "gnf_grevnet_backward")
+        self._last_backward_workspace = ws if getattr(self, "_keep_backward_workspace", False) else None
         return (grads, x_out) if return_x else grads
 
     def loss_and_grad(self, graph: GraphsTuple, per_node: bool = True, backward_math: Optional[str] = None):

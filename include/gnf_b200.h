@@ -222,12 +222,16 @@ int gnf_gnn_forward(const gnf_flow* flow, int32_t which, int32_t half, int32_t s
  *                                   transpose the aggregation's backward walks
  * math (use_batch_norm = False):
  *   GNF_MATH_FP32                     layered FFMA kernels, any supported shape;
- *   GNF_MATH_TC3X / GNF_MATH_TC3X_BF16 tcgen05 path (flows gnf_flow_supports() accepts): per half step one
- *                                     fused kernel (recompute s,t; undo the update; dX chain with the
- *                                     transposed weights) + one weight-gradient GEMM kernel; every operand
- *                                     a bf16 hi/lo split, 3 MMAs per product, fp32 accumulate;
- *   GNF_MATH_TC2X / GNF_MATH_BF16     same, but the weight-gradient GEMM reads only the bf16 hi parts
- *                                     (one MMA per product; its rounding errors average over the nodes).
+ *   any other mode                    tcgen05 path (flows gnf_flow_supports() accepts): per half step one fused
+ *                                     kernel (recompute s,t; undo the update; dX chain with the transposed
+ *                                     weights; bias gradients) + one weight-gradient GEMM kernel, fp32
+ *                                     accumulate, hi/lo split 16-bit operands, 3 MMAs per product.  Gradient
+ *                                     operands are always bf16 hi/lo (fp16 would underflow); the recomputed
+ *                                     forward chains are fp16 hi/lo for GNF_MATH_TC3X / GNF_MATH_TC2X (fp32-class
+ *                                     pre-activations, so act' masks match fp32 arithmetic) and bf16 hi/lo for
+ *                                     GNF_MATH_TC3X_BF16 / GNF_MATH_BF16.  GNF_MATH_TC2X / GNF_MATH_BF16
+ *                                     additionally run the weight-gradient GEMM on the hi parts only (one MMA
+ *                                     per product; its rounding errors average over the nodes).
  * workspace: gnf_grevnet_backward_workspace(flow, N, math), 256-byte aligned.
  * ------------------------------------------------------------------------------------------ */
 size_t gnf_grevnet_backward_workspace(const gnf_flow* flow, int64_t n_nodes, int32_t math);
@@ -241,6 +245,9 @@ int gnf_grevnet_backward(const gnf_flow* flow, const float* z, int64_t n_nodes, 
  * out[fa, fb] = a^T b for row-major fp32 a [n, fa], b [n, fb]; fa in {128,256}, fb in {16,128,256};
  * parts 2 = bf16 hi/lo split (3 MMAs per product), 1 = single bf16 pass; n_splits node ranges (one CTA
  * each) reduced in fixed order.  workspace >= 4*ceil(n/128)*128*(fa+fb) + 4*n_splits*fa*fb + 2048 bytes. */
+/* Byte offsets inside the tensor-core backward workspace (tests decode the tile images left by the last
+ * half step): out8 = {act_img, dlt_img, h_img, g_img, g_h, x0, g0, total bytes}. */
+int gnf_debug_bwd_layout(const gnf_flow* flow, int64_t n_nodes, int64_t* out8);
 int gnf_debug_dw_gemm(const float* a, const float* b, int64_t n, int32_t fa, int32_t fb, int32_t parts,
                       int32_t n_splits, float* out, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -271,7 +271,7 @@ def test_a9_batch_norm_bijector(math):
 
 
 # backward arithmetic -> (max-norm tolerance, 1 - cosine tolerance); see include/gnf_b200.h (f2)
-BWD_TOL = {"fp32": (2e-4, 1e-6), "tc3x": (4e-3, 2e-6), "bf16": (1e-2, 1e-4)}
+BWD_TOL = {"fp32": (2e-4, 1e-6), "tc3x": (5e-4, 1e-6), "bf16": (1e-2, 1e-4)}
 
 
 @pytest.mark.parametrize("bmath", ["fp32", "tc3x", "bf16"])
@@ -280,9 +280,10 @@ BWD_TOL = {"fp32": (2e-4, 1e-6), "tc3x": (4e-3, 2e-6), "bf16": (1e-2, 1e-4)}
 def test_f2_reversible_backward_matches_autograd(block, agg, ws, act, bmath):
     """Row f2: analytic reversible backward (gnf_grevnet_backward) vs torch autograd of the fp64
     torch restatement of the reference.  Stated tolerances (of the gradient's max-norm over the
-    whole parameter vector): fp32 FFMA kernels 2e-4; tensor-core backward with bf16 hi/lo split
-    operands ("tc3x": 2^-17 per operand, systematic weight rounding that does not average over the
-    nodes, ~20 chained GEMMs) 4e-3; the same with a single-bf16 weight-gradient GEMM ("bf16") 1e-2."""
+    whole parameter vector): fp32 FFMA kernels 2e-4; tensor-core backward "tc3x" (fp16 hi/lo
+    recomputed forward chains, bf16 hi/lo gradient operands) 5e-4; "bf16" (bf16 hi/lo forward chains:
+    pre-activations good to ~4e-5, so a few act' masks flip at the leaky-relu kink -- each flip is a
+    1/N effect, visible at these tiny N -- and a single-bf16 weight-gradient GEMM) 1e-2."""
     from oracle import gnf_oracle_torch as OT
     rng = np.random.default_rng(21)
     D, T, L, K = (14, 2, 128, 4) if block == "concat" else (6, 3, 128, 3)
