@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--math", default="tc3x", choices=["tc3x", "fp32", "bf16", "tc3x_bf16", "tc2x"])
     ap.add_argument("--cpu-graphs", type=int, default=1024, help="bounded CPU-baseline sample (graphs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the row-f2 backward timing")
     ap.add_argument("--seg-graphs", type=int, default=65536, help="batch for the scatter-reduce HBM roofline")
     ap.add_argument("--profile", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
@@ -335,6 +336,30 @@ def main():
                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
         del gb, outb, stb
 
+    # ---- row f2: reversible backward / training-step evaluation (forward + gradients) -----------
+    train = None
+    if rank == 0 and args.math != "fp32" and not args.no_train:
+        grads = torch.zeros_like(net.params.detach())
+        z, _ = net.f64(graph)
+        reps = 5
+        for _ in range(2):
+            net.backward_from_z(graph, z.nodes, 1.0 / n_nodes, grads=grads)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            net.backward_from_z(graph, z.nodes, 1.0 / n_nodes, grads=grads)
+        e1.record()
+        torch.cuda.synchronize()
+        bwd_ms = e0.elapsed_time(e1) / reps
+        # executed-algorithm FLOPs of the backward: recompute (1x) + dX chain (1x) + dW (1x) of the forward's
+        train = {"backward_ms": bwd_ms, "forward_ms": ms_per_step, "math": args.math,
+                 "node_updates_per_s_fwd_bwd": node_updates / ((bwd_ms + ms_per_step) * 1e-3),
+                 "backward_algorithmic_tflops": 3 * n_nodes * 2 * T * FLOPS_PER_NODE_UPDATE / (bwd_ms * 1e-3) / 1e12,
+                 "what": "gnf_grevnet_backward (reversible: recompute + dX chain + dW GEMM per half step), "
+                         "device-resident, CUDA events, mean of %d" % reps}
+        del grads
+
     # ---- end to end through the public API from pinned host memory ---------------------------
     pinned = G.GraphsTuple(*[torch.from_numpy(np.ascontiguousarray(v)).pin_memory() if v is not None else None
                              for v in host])
@@ -392,7 +417,7 @@ def main():
                                                "bf16": "bf16", "fp32": "f32"}[args.math],
                 "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32},
-                "gpu_launches": launches, "roofline": roof, "roofline_segment_sum": seg, "cpu_baseline": cpu,
+                "gpu_launches": launches, "roofline": roof, "roofline_segment_sum": seg, "cpu_baseline": cpu, "train_step": train,
                 "effective_tflops": value * FLOPS_PER_NODE_UPDATE / 1e12}
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
