@@ -50,6 +50,22 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summary
+    (profiles/, written by tools/summarize_ncu.py); None if the file is absent."""
+    try:
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for line in open(path):
+            c = line.strip().split(",")
+            if c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals = [float(v) for v in c[2:]]
+                tot += unit[c[1]] * sum(vals) / len(vals)
+        return tot or None
+    except Exception:
+        return None
+
+
 def make_batch(n_graphs, seed):
     from graph_normalizing_flows_b200 import graph_data as GD
     npz = np.load(os.path.join(ROOT, "tests", "golden", f"graphs_{FAMILY}.npz"))
@@ -259,31 +275,29 @@ def main():
         m = _lib.MATH[args.math]
         wsb = lib.gnf_grevnet_workspace(handle, n_nodes, m)
         ws = _lib.workspace(wsb, dev)
-        hp = lib.gnf_padded_half(D // 2)
-        x0 = torch.zeros(n_nodes, hp, device=dev)
-        x1 = torch.zeros(n_nodes, hp, device=dev)
-        x0[:, :D // 2] = graph.nodes[:, :D // 2]
-        x1[:, :D // 2] = graph.nodes[:, D // 2:]
         st = G.graphs.structure_of(graph)
         stream = _lib.stream_ptr(dev)
         reps = 10
 
-        def one(stepi):
-            _lib.check(lib.gnf_coupling_step(handle, stepi % T, 0, _lib.ptr(x0), _lib.ptr(x1), n_nodes, n_edges,
-                                             _lib.ptr(st.rowptr), _lib.ptr(st.csr_senders), None, m, _lib.ptr(ws),
-                                             wsb, stream))
+        z_out = torch.empty_like(graph.nodes)
+        ldj_out = torch.empty(1, dtype=torch.float64, device=dev)
+
+        def fwd_only():
+            # the step's own call path: ONE gnf_grevnet_forward = k_split + 2T x (k_coupling_tc + k_reduce_partials)
+            # + k_merge; the 2T fused launches are >96 % of it (profiles/r1_launches_bench_tc3x.csv), so dividing
+            # by 2T slightly OVERstates the kernel's duration (conservative for the roofline fraction)
+            _lib.check(lib.gnf_grevnet_forward(handle, _lib.ptr(graph.nodes), n_nodes, n_edges, _lib.ptr(st.rowptr),
+                                               _lib.ptr(st.csr_senders), _lib.ptr(z_out), _lib.ptr(ldj_out), m,
+                                               _lib.ptr(ws), wsb, stream))
         for i in range(3):
-            one(i)
+            fwd_only()
         e0 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
         torch.cuda.synchronize()
-        for r in range(reps):                                     # same cadence as a step: flush, then T steps
-            x0[:, :D // 2] = graph.nodes[:, :D // 2]
-            x1[:, :D // 2] = graph.nodes[:, D // 2:]
+        for r in range(reps):                                     # same cadence as a step: flush, then the 2T launches
             flush_buf.fill_(r)
             e0[r].record()
-            for i in range(T):
-                one(i)                                            # 2 launches of k_coupling_tc each
+            fwd_only()
             e1[r].record()
         torch.cuda.synchronize()
         k_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / (2 * T * reps)
@@ -291,7 +305,11 @@ def main():
         ach = flops / (k_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "k_coupling_tc (one fused half coupling step)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": ncu_traffic(os.path.join(ROOT, "profiles", "r1_ncu_full_k_coupling_tc.csv"))
+                if args.math == "tc3x" else None,
+                "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r1_ncu_full_k_coupling_tc.csv); the "
+                                "kernel is tensor-bound and lives in L2/smem/TMEM",
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                 "ms_per_launch": k_ms, "algorithmic_flops_per_launch": flops,
                 "executed_mma_flops_per_algorithmic_flop": {"tc3x": 3, "tc3x_bf16": 3, "tc2x": 2}.get(args.math, 1),
@@ -382,9 +400,10 @@ def main():
         last = None
         for i in range(k):
             g = prefetch.wait(ticket)
+            vec_dev = e2e_compute(g)                              # enqueue this step's kernels first ...
             if i + 1 < k:
-                ticket = prefetch.submit(pinned)
-            last = e2e_compute(g).cpu()                           # D2H of the 4 scalars (sync)
+                ticket = prefetch.submit(pinned)                  # ... then stage the next batch while they run
+            last = vec_dev.cpu()                                  # D2H of this step's 4 scalars (sync)
         return last
 
     e2e_loop(3)

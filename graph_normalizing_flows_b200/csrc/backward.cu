@@ -238,9 +238,175 @@ __global__ void k_merge_p(const float* __restrict__ x0, const float* __restrict_
   z[i] = (f < h) ? x0[node * hp + f] : x1[node * hp + f - h];
 }
 
+
+// ---- f1: backward of DMSelfAttention (gnn.py:419-477) -----------------------------------------
+// keys = project_q (at the sender), queries = project_k (at the receiver), as in k_dm_attn.
+// Pass 1, thread per (receiver r, head): softmax statistics, dot = sum_e w_e g_w_e with
+// g_w_e = <g_att[r,h,:], values[s_e,:]>, and g_queries[r,h,:] = sum_e g_l_e keys[s_e,h,:],
+// g_l_e = w_e (g_w_e - dot) * inv_scale.
+__global__ void __launch_bounds__(128)
+k_attn_bwd_recv(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+                const float* __restrict__ gatt, int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd,
+                float inv_scale, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
+                float* __restrict__ stats, float* __restrict__ gqueries) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * heads) return;
+  const int64_t r = i / heads;
+  const int h = (int)(i - r * heads);
+  const int32_t beg = rowptr[r], end = rowptr[r + 1];
+  const float* qr = queries + r * qk_pad + h * kq;
+  const float* ga = gatt + r * hv_pad + h * vd;
+  float acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+  float mx = 0.f, sum = 1.f, dot = 0.f;
+  if (end > beg) {
+    mx = -INFINITY;
+    for (int32_t e = beg; e < end; ++e) {
+      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+      mx = fmaxf(mx, l * inv_scale);
+    }
+    sum = 0.f;
+    for (int32_t e = beg; e < end; ++e) {
+      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+      sum += expf(l * inv_scale - mx);
+    }
+    for (int32_t e = beg; e < end; ++e) {
+      const int32_t s = csr_senders[e];
+      const float* ks = keys + (int64_t)s * qk_pad + h * kq;
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+      const float w = expf(l * inv_scale - mx) / sum;
+      const float* vs = vals + (int64_t)s * v_pad;
+      float gw = 0.f;
+      for (int c = 0; c < vd; ++c) gw = fmaf(ga[c], vs[c], gw);
+      dot = fmaf(w, gw, dot);
+    }
+    for (int32_t e = beg; e < end; ++e) {
+      const int32_t s = csr_senders[e];
+      const float* ks = keys + (int64_t)s * qk_pad + h * kq;
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+      const float w = expf(l * inv_scale - mx) / sum;
+      const float* vs = vals + (int64_t)s * v_pad;
+      float gw = 0.f;
+      for (int c = 0; c < vd; ++c) gw = fmaf(ga[c], vs[c], gw);
+      const float gl = w * (gw - dot) * inv_scale;
+#pragma unroll
+      for (int d = 0; d < 64; ++d)
+        if (d < kq) acc[d] = fmaf(gl, ks[d], acc[d]);
+    }
+  }
+  stats[i * 3] = mx;
+  stats[i * 3 + 1] = sum;
+  stats[i * 3 + 2] = dot;
+#pragma unroll
+  for (int d = 0; d < 64; ++d)
+    if (d < kq) gqueries[r * qk_pad + h * kq + d] = acc[d];
+}
+
+// Pass 2, thread per (sender s, head): walks the out-edges (CSR by sender) and rebuilds each edge's
+// weight from the receiver's statistics:  g_keys[s,h,:] = sum g_l_e queries[r_e,h,:],
+// g_vh[s,h,:] = sum w_e g_att[r_e,h,:]  (the value projection is shared by the heads: summed after).
+__global__ void __launch_bounds__(128)
+k_attn_bwd_send(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+                const float* __restrict__ gatt, const float* __restrict__ stats, int qk_pad, int v_pad, int hv_pad,
+                int heads, int kq, int vd, float inv_scale, const int32_t* __restrict__ rowptr_s,
+                const int32_t* __restrict__ csr_receivers, int64_t n, float* __restrict__ gkeys,
+                float* __restrict__ gvh) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * heads) return;
+  const int64_t s = i / heads;
+  const int h = (int)(i - s * heads);
+  const float* ks = keys + s * qk_pad + h * kq;
+  const float* vs = vals + s * v_pad;
+  float acc[64], accv[32];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) accv[c] = 0.f;
+  const int32_t end = rowptr_s[s + 1];
+  for (int32_t e = rowptr_s[s]; e < end; ++e) {
+    const int64_t r = csr_receivers[e];
+    const float* qr = queries + r * qk_pad + h * kq;
+    const float* ga = gatt + r * hv_pad + h * vd;
+    const float* st = stats + (r * heads + h) * 3;
+    float l = 0.f;
+    for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+    const float w = expf(l * inv_scale - st[0]) / st[1];
+    float gw = 0.f;
+    for (int c = 0; c < vd; ++c) gw = fmaf(ga[c], vs[c], gw);
+    const float gl = w * (gw - st[2]) * inv_scale;
+#pragma unroll
+    for (int d = 0; d < 64; ++d)
+      if (d < kq) acc[d] = fmaf(gl, qr[d], acc[d]);
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < vd) accv[c] = fmaf(w, ga[c], accv[c]);
+  }
+#pragma unroll
+  for (int d = 0; d < 64; ++d)
+    if (d < kq) gkeys[s * qk_pad + h * kq + d] = acc[d];
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < vd) gvh[s * hv_pad + h * vd + c] = accv[c];
+}
+
+// g_v[s, c] = sum over heads of g_vh[s, h, c]   (keras.backend.repeat, gnn.py:528)
+__global__ void k_sum_heads(const float* __restrict__ gvh, int hv_pad, int heads, int vd, int v_pad, int64_t n,
+                            float* __restrict__ gv) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * v_pad) return;
+  const int64_t s = i / v_pad;
+  const int c = (int)(i - s * v_pad);
+  float a = 0.f;
+  if (c < vd)
+    for (int h = 0; h < heads; ++h) a += gvh[s * hv_pad + h * vd + c];
+  gv[i] = a;
+}
+
+// dst[n, dpad] = src[n, off : off + cols] zero padded
+__global__ void k_take_cols(const float* __restrict__ src, int spad, int off, int cols, int dpad, int64_t n,
+                            float* __restrict__ dst) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * dpad) return;
+  const int64_t r = i / dpad;
+  const int c = (int)(i - r * dpad);
+  dst[i] = c < cols ? src[r * spad + off + c] : 0.f;
+}
+
+// g_xa += [concat: g_h direct columns] + [residual: top gradient] + g_xq
+__global__ void k_attn_gxa(float* __restrict__ gxa, int h, int hp, const float* __restrict__ gh, int in_pad, int concat,
+                           const float* __restrict__ gtop, int gp, int residual, const float* __restrict__ gxq, int hp8,
+                           int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * h) return;
+  const int64_t node = i / h;
+  const int f = (int)(i - node * h);
+  float v = gxq[node * hp8 + f];
+  if (concat) v += gh[node * in_pad + f];
+  if (residual) v += gtop[node * gp + f];
+  gxa[node * hp + f] += v;
+}
+
+__global__ void k_add_rows_p(float* __restrict__ out, const float* __restrict__ x, int h, int hp, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * h) return;
+  const int64_t node = i / h;
+  const int f = (int)(i - node * h);
+  out[node * hp + f] = __fadd_rn(out[node * hp + f], x[node * hp + f]);
+}
+
 struct BwdWs {
   float *x0, *x1, *g0, *g1, *hbuf, *gh, *sbuf, *tbuf, *gs, *gt, *d0, *d1, *part;
   float* act[2][kMaxLayers];
+  // f1 attention block: per-GNN forward intermediates, shared gradient temporaries
+  AttnBufs ab[2];
+  float *hbuf2, *gproj, *gatt, *gkeys, *gqueries, *gvh, *gv, *gxq, *stats;
   size_t bytes;
 };
 
@@ -271,7 +437,30 @@ BwdWs carve_bwd(const Flow& f, int64_t n, void* base) {
   for (int m = 0; m < 2; ++m)
     for (int l = 0; l < f.K - 1; ++l) w.act[m][l] = take(nn * lp * 4);
   const int mmax = lp > f.in_pad ? lp : f.in_pad;
-  w.part = take((size_t)kSplit * mmax * lp * 4);
+  size_t part_elems = (size_t)mmax * lp;
+  if (f.attn) {
+    for (int m = 0; m < 2; ++m) {
+      w.ab[m].xq = take(nn * f.hp8 * 4);
+      w.ab[m].qbuf = take(nn * f.qk_pad * 4);
+      w.ab[m].kbuf = take(nn * f.qk_pad * 4);
+      w.ab[m].vbuf = take(nn * f.v_pad * 4);
+      w.ab[m].att = take(nn * f.hv_pad * 4);
+      w.ab[m].proj = take(nn * f.cho_pad * 4);
+    }
+    w.hbuf2 = take(nn * f.in_pad * 4);
+    w.gproj = take(nn * f.cho_pad * 4);
+    w.gatt = take(nn * f.hv_pad * 4);
+    w.gkeys = take(nn * f.qk_pad * 4);
+    w.gqueries = take(nn * f.qk_pad * 4);
+    w.gvh = take(nn * f.hv_pad * 4);
+    w.gv = take(nn * f.v_pad * 4);
+    w.gxq = take(nn * f.hp8 * 4);
+    w.stats = take(nn * f.heads * 3 * 4);
+    const size_t a1 = (size_t)f.hp8 * f.qk_pad, a2 = (size_t)f.hv_pad * f.cho_pad;
+    if (a1 > part_elems) part_elems = a1;
+    if (a2 > part_elems) part_elems = a2;
+  }
+  w.part = take((size_t)kSplit * part_elems * 4);
   w.bytes = off;
   return w;
 }
@@ -312,10 +501,28 @@ int run_dw(const Flow& f, int l, const float* a_in, int lda, const float* delta,
   return GNF_OK;
 }
 
+// part/grad of one bias-free projection: grad[in, out] += a_in^T delta
+int run_dw_generic(const float* a_in, int lda, int in_real, const float* delta, int ldd, int out_real, int64_t n,
+                   float* part, float* grad, cudaStream_t stream) {
+  if (ldd <= 16) {
+    dim3 grid((unsigned)ceil_div(lda, BM), 1, kSplit);
+    k_dw<16><<<grid, 256, 0, stream>>>(a_in, lda, delta, ldd, n, lda, ldd, part);
+  } else {
+    dim3 grid((unsigned)ceil_div(lda, BM), (unsigned)ceil_div(ldd, 128), kSplit);
+    k_dw<128><<<grid, 256, 0, stream>>>(a_in, lda, delta, ldd, n, lda, ldd, part);
+  }
+  GNF_LAUNCH_CHECK();
+  k_reduce_split<<<(unsigned)ceil_div((int64_t)in_real * out_real, 256), 256, 0, stream>>>(part, kSplit, lda, ldd,
+                                                                                          in_real, out_real, grad);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
 // forward of one MLP keeping every hidden activation
-int mlp_forward_keep(const Flow& f, int mlp, const BwdWs& w, int m, float* out, int64_t n, cudaStream_t stream) {
+int mlp_forward_keep(const Flow& f, int mlp, const BwdWs& w, int m, const float* h_in, float* out, int64_t n,
+                     cudaStream_t stream) {
   const float* base = f.w32 + (int64_t)mlp * f.w32_per_mlp;
-  const float* in = w.hbuf;
+  const float* in = h_in;
   for (int l = 0; l < f.K; ++l) {
     const bool last = l == f.K - 1;
     float* dst = last ? out : w.act[m][l];
@@ -328,7 +535,7 @@ int mlp_forward_keep(const Flow& f, int mlp, const BwdWs& w, int m, float* out, 
 }
 
 // backward of one MLP: top gradient g_top [n, gp]; accumulates into gh and the flat grads
-int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_top, int gp, int64_t n,
+int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* h_in, const float* g_top, int gp, int64_t n,
                  int accumulate_gh, float* grads, cudaStream_t stream) {
   const float* wt = f.w32T + (int64_t)mlp * f.w32T_per_mlp;
   float* grad_mlp = grads + (int64_t)mlp * f.params_per_mlp;
@@ -336,7 +543,7 @@ int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_t
   const float* delta = g_top;
   int ldd = gp;
   for (int l = f.K - 1; l >= 0; --l) {
-    const float* a_in = l == 0 ? w.hbuf : w.act[m][l - 1];
+    const float* a_in = l == 0 ? h_in : w.act[m][l - 1];
     const int lda = f.in_pads[l];
     // weight gradient needs delta with leading dimension == out_pads[l]: the top gradient buffer is
     // [n, gp] with gp = pad8(HP) >= HP; its extra columns are zero, so Ndim = ldd works for both
@@ -350,6 +557,53 @@ int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_t
     delta = dst;
     ldd = f.in_pads[l];
   }
+  return GNF_OK;
+}
+
+// backward of the attention front end of GNN `mlp` (m = 0: s, 1: t): w.gh holds dL/d(MLP input)
+int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_top, int gp, int64_t n,
+                  const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
+                  const int32_t* csr_receivers, float* ga, float* grads, cudaStream_t stream) {
+  const AttnBufs& b = w.ab[m];
+  const float* wt = f.wattnT + (int64_t)mlp * f.wattnT_per_mlp;
+  float* gm = grads + (int64_t)mlp * f.params_per_mlp;
+  const int concat = (f.attn_flags & GNF_ATTN_CONCAT) ? 1 : 0, residual = (f.attn_flags & GNF_ATTN_RESIDUAL) ? 1 : 0;
+  const int qk = f.heads * f.kq, hv = f.heads * f.vd;
+  const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
+  // g_proj = columns of g_h that multiplied new_node_proj's output (gnn.py:547-548)
+  k_take_cols<<<(unsigned)ceil_div(n * f.cho_pad, 256), 256, 0, stream>>>(w.gh, f.in_pad, concat ? f.H : 0, f.cho,
+                                                                         f.cho_pad, n, w.gproj);
+  GNF_LAUNCH_CHECK();
+  int rc = run_dw_generic(b.att, f.hv_pad, hv, w.gproj, f.cho_pad, f.cho, n, w.part,
+                          gm + 2ll * f.H * qk + (int64_t)f.H * f.vd, stream);                    // dWo
+  if (rc) return rc;
+  rc = run_dx(w.gproj, wt + f.woT_off, nullptr, w.gatt, n, f.hv_pad, f.cho_pad, 0, 0, stream);   // g_att = g_proj Wo^T
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)ceil_div(n * f.heads, 128);
+  k_attn_bwd_recv<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq,
+                                              f.vd, inv_scale, rowptr, csr_senders, n, w.stats, w.gqueries);
+  GNF_LAUNCH_CHECK();
+  k_attn_bwd_send<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, w.stats, f.qk_pad, f.v_pad, f.hv_pad,
+                                              f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys, w.gvh);
+  GNF_LAUNCH_CHECK();
+  k_sum_heads<<<(unsigned)ceil_div(n * f.v_pad, 256), 256, 0, stream>>>(w.gvh, f.hv_pad, f.heads, f.vd, f.v_pad, n, w.gv);
+  GNF_LAUNCH_CHECK();
+  // keys = project_q, queries = project_k (gnn.py:531-532)
+  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gkeys, f.qk_pad, qk, n, w.part, gm, stream);                          // dWq
+  if (rc) return rc;
+  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gqueries, f.qk_pad, qk, n, w.part, gm + (int64_t)f.H * qk, stream);   // dWk
+  if (rc) return rc;
+  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gv, f.v_pad, f.vd, n, w.part, gm + 2ll * f.H * qk, stream);           // dWv
+  if (rc) return rc;
+  rc = run_dx(w.gkeys, wt + f.wqT_off, nullptr, w.gxq, n, f.hp8, f.qk_pad, 0, 0, stream);
+  if (rc) return rc;
+  rc = run_dx(w.gqueries, wt + f.wkT_off, nullptr, w.gxq, n, f.hp8, f.qk_pad, 0, 1, stream);
+  if (rc) return rc;
+  rc = run_dx(w.gv, wt + f.wvT_off, nullptr, w.gxq, n, f.hp8, f.v_pad, 0, 1, stream);
+  if (rc) return rc;
+  k_attn_gxa<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(ga, f.H, f.HP, w.gh, f.in_pad, concat, g_top, gp,
+                                                                  residual, w.gxq, f.hp8, n);
+  GNF_LAUNCH_CHECK();
   return GNF_OK;
 }
 
@@ -421,7 +675,6 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
   GNF_REQUIRE(z && rowptr && rowptr_by_sender && (e == 0 || (csr_senders && csr_receivers)), GNF_EINVAL,
               "gnf_grevnet_backward: null pointer");
   const Flow& f = h->f;
-  GNF_REQUIRE(!f.attn, GNF_EUNSUPPORTED, "gnf_grevnet_backward: the dm_self_attn block has no backward yet");
   if (math != GNF_MATH_FP32) {
     GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED,
                 "gnf_grevnet_backward: the tensor-core backward needs a flow shape the fused kernel supports "
@@ -456,17 +709,46 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
       float* ga = half == 0 ? w.g0 : w.g1;
       float* gb = half == 0 ? w.g1 : w.g0;
       const int ms = f.mlp_index(0, half, i), mt = f.mlp_index(1, half, i);
-      int rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, w.hbuf, stream);
+      int rc;
+      if (f.attn) {
+        // f1: every GNN has its own attention front end, so s and t have different MLP inputs
+        float* hin[2] = {w.hbuf, w.hbuf2};
+        float* outs[2] = {w.sbuf, w.tbuf};
+        const int mm[2] = {ms, mt};
+        for (int m = 0; m < 2; ++m) {
+          GNF_CUDA(cudaMemsetAsync(hin[m], 0, (size_t)n * f.in_pad * 4, stream));
+          rc = fwd_attn_input(f, mm[m], xa, n, rowptr, csr_senders, w.ab[m], hin[m], stream);
+          if (rc) return rc;
+          rc = mlp_forward_keep(f, mm[m], w, m, hin[m], outs[m], n, stream);
+          if (rc) return rc;
+          if (f.attn_flags & GNF_ATTN_RESIDUAL) {                                     // gnn.py:551-552
+            k_add_rows_p<<<eb, 256, 0, stream>>>(outs[m], xa, H, HP, n);
+            GNF_LAUNCH_CHECK();
+          }
+        }
+        k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
+        GNF_LAUNCH_CHECK();
+        float* gtop[2] = {w.gs, w.gt};
+        for (int m = 0; m < 2; ++m) {
+          rc = mlp_backward(f, mm[m], w, m, hin[m], gtop[m], gp, n, 0, grads, stream);
+          if (rc) return rc;
+          rc = attn_backward(f, mm[m], w, m, gtop[m], gp, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, ga,
+                             grads, stream);
+          if (rc) return rc;
+        }
+        continue;
+      }
+      rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, w.hbuf, stream);
       if (rc) return rc;
-      rc = mlp_forward_keep(f, ms, w, 0, w.sbuf, n, stream);
+      rc = mlp_forward_keep(f, ms, w, 0, w.hbuf, w.sbuf, n, stream);
       if (rc) return rc;
-      rc = mlp_forward_keep(f, mt, w, 1, w.tbuf, n, stream);
+      rc = mlp_forward_keep(f, mt, w, 1, w.hbuf, w.tbuf, n, stream);
       if (rc) return rc;
       k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
       GNF_LAUNCH_CHECK();
-      rc = mlp_backward(f, ms, w, 0, w.gs, gp, n, 0, grads, stream);
+      rc = mlp_backward(f, ms, w, 0, w.hbuf, w.gs, gp, n, 0, grads, stream);
       if (rc) return rc;
-      rc = mlp_backward(f, mt, w, 1, w.gt, gp, n, 1, grads, stream);
+      rc = mlp_backward(f, mt, w, 1, w.hbuf, w.gt, gp, n, 1, grads, stream);
       if (rc) return rc;
       k_agg_bwd<<<eb, 256, 0, stream>>>(w.gh, f.in_pad, H, HP, rowptr_by_sender, csr_receivers, rowptr, n,
                                         f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps, ga);

@@ -85,6 +85,8 @@ struct Flow {
   float* wattn = nullptr;
   int64_t wattn_per_mlp = 0, wq_off = 0, wk_off = 0, wv_off = 0, wo_off = 0;
   float* zeros = nullptr;                 // zero bias for the bias-free projections
+  float* wattnT = nullptr;                // transposed projections for the backward dX GEMMs: W^T [out_pad, in_pad]
+  int64_t wattnT_per_mlp = 0, wqT_off = 0, wkT_off = 0, wvT_off = 0, woT_off = 0;
   // tensor-core packed weights (two images: fp16 and bf16 element type), per MLP a stream of
   // shared-memory chunk images in consumption order (see coupling_tc.cu)
   uint8_t* wtc[2] = {nullptr, nullptr};   // [0]=fp16 hi/lo, [1]=bf16 hi/lo
@@ -103,6 +105,11 @@ struct Flow {
 // flow.cu (shared with backward.cu)
 int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K, int act,
                cudaStream_t stream);
+struct AttnBufs {      // per-GNN intermediates of the f1 attention block (all [n, *_pad] fp32)
+  float *xq, *qbuf, *kbuf, *vbuf, *att, *proj;
+};
+int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
+                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream);
 int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                   float* hbuf, cudaStream_t stream);
 

@@ -461,6 +461,12 @@ Workspace carve(const Flow& f, int64_t n, int math, void* base) {
 }
 
 int run_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K,
+               int act, cudaStream_t stream);
+}  // namespace
+int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
+                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream);
+namespace {
+int run_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K,
                int act, cudaStream_t stream) {
   if (N <= 16) {
     dim3 grid((unsigned)ceil_div(M, BM), 1);
@@ -491,29 +497,8 @@ int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n,
 // MLP input of GNN `mlp` from the half xa: aggregation blocks (shared by s and t) or attention
 int build_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
                      const int32_t* csr_senders, const Workspace& w, cudaStream_t stream) {
-  const float* wa = f.wattn + (int64_t)mlp * f.wattn_per_mlp;
-  k_pad_rows<<<(unsigned)ceil_div(n * f.hp8, 256), 256, 0, stream>>>(xa, n, f.HP < f.hp8 ? f.HP : f.hp8, f.hp8, w.xq);
-  GNF_LAUNCH_CHECK();
-  // xa rows are [HP] wide with zero padding, so reading min(HP, hp8) columns and zero-filling is exact
-  int rc = run_linear(w.xq, wa + f.wq_off, f.zeros, w.qbuf, n, f.qk_pad, f.hp8, 2, stream);   // project_q  gnn.py:509-512
-  if (rc) return rc;
-  rc = run_linear(w.xq, wa + f.wk_off, f.zeros, w.kbuf, n, f.qk_pad, f.hp8, 2, stream);       // project_k  gnn.py:513-516
-  if (rc) return rc;
-  rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
-  if (rc) return rc;
-  const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
-  k_dm_attn<<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
-                                                                      f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
-                                                                      csr_senders, n, w.att);
-  GNF_LAUNCH_CHECK();
-  rc = run_linear(w.att, wa + f.wo_off, f.zeros, w.proj, n, f.cho_pad, f.hv_pad, 2, stream);  // new_node_proj gnn.py:543-545
-  if (rc) return rc;
-  const int concat = (f.attn_flags & GNF_ATTN_CONCAT) ? 1 : 0;
-  const int width = concat ? f.H + f.cho : f.cho;
-  k_attn_input<<<(unsigned)ceil_div(n * width, 256), 256, 0, stream>>>(xa, f.H, f.HP, w.proj, f.cho, f.cho_pad, concat,
-                                                                       f.in_pad, n, w.hbuf);
-  GNF_LAUNCH_CHECK();
-  return GNF_OK;
+  AttnBufs b{w.xq, w.qbuf, w.kbuf, w.vbuf, w.att, w.proj};
+  return fwd_attn_input(f, mlp, xa, n, rowptr, csr_senders, b, w.hbuf, stream);
 }
 
 int gnn_forward32(const Flow& f, int mlp, bool build_agg, const float* xa, int64_t n, const int32_t* rowptr,
@@ -595,6 +580,33 @@ __global__ void k_pack32T(const float* __restrict__ src, int in, int out, int in
 int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K, int act,
                cudaStream_t stream) {
   return run_linear(A, W, b, C, M, N, K, act, stream);
+}
+
+int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
+                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream) {
+  const float* wa = f.wattn + (int64_t)mlp * f.wattn_per_mlp;
+  k_pad_rows<<<(unsigned)ceil_div(n * f.hp8, 256), 256, 0, stream>>>(xa, n, f.HP < f.hp8 ? f.HP : f.hp8, f.hp8, w.xq);
+  GNF_LAUNCH_CHECK();
+  // xa rows are [HP] wide with zero padding, so reading min(HP, hp8) columns and zero-filling is exact
+  int rc = run_linear(w.xq, wa + f.wq_off, f.zeros, w.qbuf, n, f.qk_pad, f.hp8, 2, stream);   // project_q  gnn.py:509-512
+  if (rc) return rc;
+  rc = run_linear(w.xq, wa + f.wk_off, f.zeros, w.kbuf, n, f.qk_pad, f.hp8, 2, stream);       // project_k  gnn.py:513-516
+  if (rc) return rc;
+  rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
+  if (rc) return rc;
+  const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
+  k_dm_attn<<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
+                                                                      f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
+                                                                      csr_senders, n, w.att);
+  GNF_LAUNCH_CHECK();
+  rc = run_linear(w.att, wa + f.wo_off, f.zeros, w.proj, n, f.cho_pad, f.hv_pad, 2, stream);  // new_node_proj gnn.py:543-545
+  if (rc) return rc;
+  const int concat = (f.attn_flags & GNF_ATTN_CONCAT) ? 1 : 0;
+  const int width = concat ? f.H + f.cho : f.cho;
+  k_attn_input<<<(unsigned)ceil_div(n * width, 256), 256, 0, stream>>>(xa, f.H, f.HP, w.proj, f.cho, f.cho_pad, concat,
+                                                                       f.in_pad, n, hbuf);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
 }
 
 int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
@@ -694,6 +706,11 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
     f.wv_off = f.wk_off + (int64_t)f.hp8 * f.qk_pad;
     f.wo_off = f.wv_off + (int64_t)f.hp8 * f.v_pad;
     f.wattn_per_mlp = f.wo_off + (int64_t)f.hv_pad * f.cho_pad;
+    f.wqT_off = 0;
+    f.wkT_off = f.wqT_off + (int64_t)f.qk_pad * f.hp8;
+    f.wvT_off = f.wkT_off + (int64_t)f.qk_pad * f.hp8;
+    f.woT_off = f.wvT_off + (int64_t)f.v_pad * f.hp8;
+    f.wattnT_per_mlp = f.woT_off + (int64_t)f.cho_pad * f.hv_pad;
     f.mlp_off = 2ll * f.H * f.heads * f.kq + (int64_t)f.H * f.vd + (int64_t)f.heads * f.vd * f.cho;
   }
   f.in_pad = pad_to(f.in_dim, 8);
@@ -735,6 +752,7 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
   if (e == cudaSuccess) e = cudaMalloc(&f.zeros, 8192 * 4);
   if (e == cudaSuccess) e = cudaMemset(f.zeros, 0, 8192 * 4);
   if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wattn, (size_t)f.n_mlps * f.wattn_per_mlp * 4);
+  if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wattnT, (size_t)f.n_mlps * f.wattnT_per_mlp * 4);
   if (e != cudaSuccess) {
     delete h;
     set_error("gnf_flow_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -763,6 +781,7 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.w32T);
   cudaFree(h->f.zeros);
   cudaFree(h->f.wattn);
+  cudaFree(h->f.wattnT);
   cudaFree(h->f.wtc[0]);
   cudaFree(h->f.wtc[1]);
   cudaFree(h->f.btc);
@@ -796,6 +815,18 @@ extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* strea
       pack(src + 2ll * f.H * qk, f.H, f.vd, f.hp8, f.v_pad, wa + f.wv_off);
       GNF_LAUNCH_CHECK();
       pack(src + 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, f.hv_pad, f.cho_pad, wa + f.wo_off);
+      GNF_LAUNCH_CHECK();
+      float* wt = f.wattnT + (int64_t)m * f.wattnT_per_mlp;
+      auto packT = [&](const float* s_, int in, int out, int in_pad, int out_pad, float* d_) {   // d_[out_pad][in_pad]
+        k_pack32T<<<(unsigned)ceil_div((int64_t)in_pad * out_pad, 256), 256, 0, stream>>>(s_, in, out, in_pad, out_pad, d_);
+      };
+      packT(src, f.H, qk, f.hp8, f.qk_pad, wt + f.wqT_off);
+      GNF_LAUNCH_CHECK();
+      packT(src + (int64_t)f.H * qk, f.H, qk, f.hp8, f.qk_pad, wt + f.wkT_off);
+      GNF_LAUNCH_CHECK();
+      packT(src + 2ll * f.H * qk, f.H, f.vd, f.hp8, f.v_pad, wt + f.wvT_off);
+      GNF_LAUNCH_CHECK();
+      packT(src + 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, f.hv_pad, f.cho_pad, wt + f.woT_off);
       GNF_LAUNCH_CHECK();
       src += f.mlp_off;
     }

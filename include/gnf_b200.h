@@ -221,7 +221,9 @@ int gnf_gnn_forward(const gnf_flow* flow, int32_t which, int32_t half, int32_t s
  *   rowptr_by_sender / csr_receivers CSR by sender   (gnf_build_csr(senders, receivers)): the
  *                                   transpose the aggregation's backward walks
  * math (use_batch_norm = False):
- *   GNF_MATH_FP32                     layered FFMA kernels, any supported shape;
+ *   GNF_MATH_FP32                     layered FFMA kernels, any supported shape, including GNF_BLOCK_DM_ATTN
+ *                                     (attention backward: softmax statistics per receiver, then a gather
+ *                                     over the CSR by sender; projections Wq Wk Wv Wo get gradients too);
  *   any other mode                    tcgen05 path (flows gnf_flow_supports() accepts): per half step one fused
  *                                     kernel (recompute s,t; undo the update; dX chain with the transposed
  *                                     weights; bias gradients) + one weight-gradient GEMM kernel, fp32

@@ -16,9 +16,15 @@ import torch
 
 
 def params_to_torch(params, dtype=torch.float32):
+    def t(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+
     def c(m):
-        return [(torch.from_numpy(np.ascontiguousarray(w)).to(dtype), torch.from_numpy(np.ascontiguousarray(b)).to(dtype))
-                for (w, b) in m]
+        if isinstance(m, dict):                  # dm_self_attn GNN: projections + MLP (oracle/gnf_oracle.py)
+            out = {k: t(m[k]) for k in ("wq", "wk", "wv", "wo")}
+            out["mlp"] = [(t(w), t(b)) for (w, b) in m["mlp"]]
+            return out
+        return [(t(w), t(b)) for (w, b) in m]
     out = dict(params)
     for k in ("s", "t"):
         out[k] = [c(m) for m in params[k]] if params["weight_sharing"] else [[c(m) for m in half] for half in params[k]]
@@ -38,7 +44,34 @@ def _mlp(h, layers, act):                       # gnn.py:167-180
     return h
 
 
+def _dm_attn(nodes, senders, receivers, gnn, cfg):
+    """DMSelfAttentionMLP._build (gnn.py:501-558), same restatement as oracle/gnf_oracle.py::dm_self_attention_mlp,
+    differentiable."""
+    n, heads, kq, vd = nodes.shape[0], cfg["num_heads"], cfg["kq_dim"], cfg["v_dim"]
+    project_q = (nodes @ gnn["wq"]).reshape(n, heads, kq)
+    project_k = (nodes @ gnn["wk"]).reshape(n, heads, kq)
+    project_v = (nodes @ gnn["wv"])[:, None, :].expand(n, heads, vd)
+    logits = (project_q[senders] * project_k[receivers]).sum(-1)          # keys = project_q, queries = project_k
+    if cfg["kq_dim_division"]:
+        logits = logits / math.sqrt(kq)
+    idx = receivers[:, None].expand(-1, heads)
+    seg_max = torch.full((n, heads), -float("inf"), dtype=nodes.dtype).scatter_reduce(0, idx, logits.detach(), "amax")
+    ex = torch.exp(logits - seg_max[receivers])
+    seg_sum = torch.zeros((n, heads), dtype=nodes.dtype).index_add_(0, receivers, ex)
+    w = ex / seg_sum[receivers]
+    agg = torch.zeros((n, heads, vd), dtype=nodes.dtype).index_add_(0, receivers, project_v[senders] * w[..., None])
+    new_nodes = agg.reshape(n, heads * vd) @ gnn["wo"]
+    if cfg["concat"]:
+        new_nodes = torch.cat([nodes, new_nodes], 1)
+    new_nodes = _mlp(new_nodes, gnn["mlp"], cfg["act"])
+    if cfg["residual"]:
+        new_nodes = new_nodes + nodes
+    return new_nodes
+
+
 def _gnn(nodes, senders, receivers, layers, cfg):   # gnn.py:155-156 + 107-111 / 122-126
+    if cfg["block"] == "dm_attn":
+        return _dm_attn(nodes, senders, receivers, layers, cfg)
     edges = nodes.index_select(0, senders)                       # gnn.py:151 (use_sender_nodes)
     agg = torch.zeros_like(nodes).index_add_(0, receivers, edges)  # gnn.py:103 unsorted_segment_sum
     if cfg["agg"] == "mean":
@@ -94,6 +127,11 @@ def loss_and_grads(nodes, senders, receivers, params, scale=1.0, dtype=torch.flo
         for half in range(2):
             mlps = [p[which][half]] if p["weight_sharing"] else p[which][half]
             for mlp in mlps:
+                if isinstance(mlp, dict):
+                    for k in ("wq", "wk", "wv", "wo"):
+                        mlp[k].requires_grad_(True)
+                        leaves.append(mlp[k])
+                    mlp = mlp["mlp"]
                 for i, (w, b) in enumerate(mlp):
                     w.requires_grad_(True)
                     b.requires_grad_(True)

@@ -495,6 +495,41 @@ def test_f1_dm_self_attn_gnn(variant):
     assert np.abs(got - ref).max() < 1e-4
 
 
+@pytest.mark.parametrize("variant", ["concat_kqdiv", "noconcat_residual_shared"])
+def test_f1_dm_self_attn_backward_matches_autograd(variant):
+    """Row f1 + f2: reversible backward THROUGH the attention GNN (fp32 kernels: k_attn_bwd_recv / k_attn_bwd_send,
+    projection dW/dX GEMMs) vs torch autograd of the fp64 restatement.  Tolerance as the fp32 MLP backward (2e-4
+    of the max-norm), cosine > 1 - 1e-6; the input is reconstructed on the way."""
+    from oracle import gnf_oracle_torch as OT
+    rng = np.random.default_rng(53)
+    if variant == "concat_kqdiv":
+        D, T, L, K, ws = 6, 2, 64, 3, False
+        attn = dict(num_heads=4, kq_dim=16, v_dim=8, out_dim=20, concat=True, residual=False, kq_dim_division=True)
+        g = H.random_batch(rng, 8, 4, 25, D=D, isolated=True)
+    else:
+        D, T, L, K, ws = 14, 2, 32, 4, True
+        attn = dict(num_heads=3, kq_dim=5, v_dim=7, out_dim=12, concat=False, residual=True, kq_dim_division=False)
+        g = H.random_batch(rng, 9, 4, 30, D=D)
+        g = g._replace(nodes=(g.nodes * 0.1).astype(np.float32))
+    params = O.make_params(17, T, D, L, K, block="dm_attn", act="leaky_relu", attn=attn, last_layer_scale=0.1,
+                           weight_sharing=ws)
+    n = g.nodes.shape[0]
+    net = H.make_grevnet(params, L, K, device=DEV)
+    dg = dev_graph(g)
+    for per_node in (True, False):
+        scale = 1.0 / n if per_node else 1.0
+        loss_ref, grad_ref = OT.loss_and_grads(g.nodes, g.senders, g.receivers, params, scale)
+        out, grads = net.loss_and_grad(dg, per_node=per_node)
+        got = grads.double().cpu().numpy()
+        loss = float(out["loss_per_node"] if per_node else out["total_loss"])
+        assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+        assert got.shape == grad_ref.shape and np.isfinite(got).all()
+        assert np.abs(got - grad_ref).max() <= 2e-4 * np.abs(grad_ref).max()
+        assert float(got @ grad_ref) / (np.linalg.norm(got) * np.linalg.norm(grad_ref)) > 1 - 1e-6
+    _, x_rec = net.backward_from_z(dg, out["z"].nodes, 1.0, return_x=True)
+    assert np.abs(x_rec.cpu().numpy() - g.nodes).max() < 5e-5
+
+
 def test_cuda_graph_replay_matches_eager():
     rng = np.random.default_rng(61)
     g = H.random_batch(rng, 10, 5, 30, D=14)

@@ -168,6 +168,26 @@ def test_torch_baseline_matches_numpy_oracle():
         assert H.rel_err(OT.log_prob_xs(zt, lt), lp) < 1e-5
 
 
+def test_torch_attention_restatement_matches_numpy_oracle():
+    """f1: the differentiable torch restatement of DMSelfAttentionMLP (reference gradients for the GPU
+    backward test) agrees with the numpy oracle it mirrors; its autograd runs (isolated receivers too)."""
+    import torch
+    from oracle import gnf_oracle_torch as OT
+    rng = np.random.default_rng(7)
+    g = H.random_batch(rng, 5, 4, 12, D=6, isolated=True)
+    g = g._replace(nodes=(g.nodes * 0.1).astype(np.float32))       # residual adds x to s: keep exp(s) tame
+    for attn in (dict(num_heads=3, kq_dim=5, v_dim=4, out_dim=9, concat=True, residual=False, kq_dim_division=True),
+                 dict(num_heads=2, kq_dim=3, v_dim=6, out_dim=5, concat=False, residual=True, kq_dim_division=False)):
+        p = O.make_params(5, 2, 6, 32, 3, block="dm_attn", act="relu", attn=attn, last_layer_scale=0.1)
+        z, ldj = O.grevnet_f(g.nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(p, np.float64))
+        zt, lt = OT.grevnet_f(torch.from_numpy(g.nodes).double(), torch.from_numpy(g.senders).long(),
+                              torch.from_numpy(g.receivers).long(), OT.params_to_torch(p, torch.float64))
+        assert np.allclose(zt.numpy(), z, rtol=1e-10, atol=1e-10)
+        assert abs(float(lt) - float(ldj)) < 1e-9 * max(1.0, abs(float(ldj)))
+        loss, grads = OT.loss_and_grads(g.nodes, g.senders, g.receivers, p, 1.0 / g.nodes.shape[0])
+        assert np.isfinite(grads).all() and grads.shape == (H.flat_from_oracle(p).shape[0],)
+
+
 def test_f4_embedding_pickle_readers(tmp_path):
     """GrevnetDatasetFixed / Variable (train_grevnet_with_data.py:145-234) + transform_example (:237-271)."""
     import pickle
