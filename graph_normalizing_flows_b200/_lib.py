@@ -43,6 +43,8 @@ SIGNATURES = {
     "gnf_last_error": (C.c_char_p, []),
     "gnf_launch_count": (_i64, [C.c_int]),
     "gnf_debug_set_trace": (C.c_int, [_p]),
+    "gnf_debug_kernel_timing": (C.c_int, [_i32]),
+    "gnf_debug_kernel_time": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gnf_build_csr_workspace": (_sz, [_i64, _i64]),
     "gnf_build_csr": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "gnf_validate_indices": (C.c_int, [_p, _p, _i64, _i64, _p, _p]),
@@ -65,6 +67,10 @@ SIGNATURES = {
     "gnf_bn_moments_workspace": (_sz, [_i32]),
     "gnf_bn_moments": (C.c_int, [_p, _i64, _i32, _p, _p, _sz, _p]),
     "gnf_affine_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "gnf_bn_backward_sums": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "gnf_bn_backward_apply": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "gnf_coupling_half_backward": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, C.c_double, _p,
+                                             _i32, _p, _sz, _p]),
     "gnf_gnn_forward": (C.c_int, [_p, _i32, _i32, _i32, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "gnf_grevnet_backward_workspace": (_sz, [_p, _i64, _i32]),
     "gnf_grevnet_backward": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, C.c_double, _p, _p, _i32, _p, _sz, _p]),

@@ -641,6 +641,60 @@ int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp,
 
 using namespace gnf;
 
+// one reversed half step on the fp32 FFMA path: (xa, xb', g_xa, g_xb') -> (xb, g_xa += ..., g_xb), grads += ...
+static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const float* xa, float* xb, float* ga, float* gb,
+                         int64_t n, const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_by_sender,
+                         const int32_t* csr_receivers, float scale, float* grads, cudaStream_t stream) {
+  const int H = f.H, HP = f.HP, gp = pad_to(HP, 8);
+  const unsigned eb = (unsigned)ceil_div(n * H, 256);
+  const int ms = f.mlp_index(0, half, i), mt = f.mlp_index(1, half, i);
+  int rc;
+  if (f.attn) {
+    // f1: every GNN has its own attention front end, so s and t have different MLP inputs
+    float* hin[2] = {w.hbuf, w.hbuf2};
+    float* outs[2] = {w.sbuf, w.tbuf};
+    const int mm[2] = {ms, mt};
+    for (int m = 0; m < 2; ++m) {
+      GNF_CUDA(cudaMemsetAsync(hin[m], 0, (size_t)n * f.in_pad * 4, stream));
+      rc = fwd_attn_input(f, mm[m], xa, n, rowptr, csr_senders, w.ab[m], hin[m], stream);
+      if (rc) return rc;
+      rc = mlp_forward_keep(f, mm[m], w, m, hin[m], outs[m], n, stream);
+      if (rc) return rc;
+      if (f.attn_flags & GNF_ATTN_RESIDUAL) {                                     // gnn.py:551-552
+        k_add_rows_p<<<eb, 256, 0, stream>>>(outs[m], xa, H, HP, n);
+        GNF_LAUNCH_CHECK();
+      }
+    }
+    k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
+    GNF_LAUNCH_CHECK();
+    float* gtop[2] = {w.gs, w.gt};
+    for (int m = 0; m < 2; ++m) {
+      rc = mlp_backward(f, mm[m], w, m, hin[m], gtop[m], gp, n, 0, grads, stream);
+      if (rc) return rc;
+      rc = attn_backward(f, mm[m], w, m, gtop[m], gp, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, ga,
+                         grads, stream);
+      if (rc) return rc;
+    }
+    return GNF_OK;
+  }
+  rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, w.hbuf, stream);
+  if (rc) return rc;
+  rc = mlp_forward_keep(f, ms, w, 0, w.hbuf, w.sbuf, n, stream);
+  if (rc) return rc;
+  rc = mlp_forward_keep(f, mt, w, 1, w.hbuf, w.tbuf, n, stream);
+  if (rc) return rc;
+  k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
+  GNF_LAUNCH_CHECK();
+  rc = mlp_backward(f, ms, w, 0, w.hbuf, w.gs, gp, n, 0, grads, stream);
+  if (rc) return rc;
+  rc = mlp_backward(f, mt, w, 1, w.hbuf, w.gt, gp, n, 1, grads, stream);
+  if (rc) return rc;
+  k_agg_bwd<<<eb, 256, 0, stream>>>(w.gh, f.in_pad, H, HP, rowptr_by_sender, csr_receivers, rowptr, n,
+                                    f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps, ga);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
 static bool bwd_use_tc(const Flow& f, int math) { return math != GNF_MATH_FP32 && tc_bwd_supported(f); }
 
 extern "C" size_t gnf_grevnet_backward_workspace(const gnf_flow* h, int64_t n_nodes, int32_t math) {
@@ -708,51 +762,9 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
       float* xb = half == 0 ? w.x1 : w.x0;
       float* ga = half == 0 ? w.g0 : w.g1;
       float* gb = half == 0 ? w.g1 : w.g0;
-      const int ms = f.mlp_index(0, half, i), mt = f.mlp_index(1, half, i);
-      int rc;
-      if (f.attn) {
-        // f1: every GNN has its own attention front end, so s and t have different MLP inputs
-        float* hin[2] = {w.hbuf, w.hbuf2};
-        float* outs[2] = {w.sbuf, w.tbuf};
-        const int mm[2] = {ms, mt};
-        for (int m = 0; m < 2; ++m) {
-          GNF_CUDA(cudaMemsetAsync(hin[m], 0, (size_t)n * f.in_pad * 4, stream));
-          rc = fwd_attn_input(f, mm[m], xa, n, rowptr, csr_senders, w.ab[m], hin[m], stream);
-          if (rc) return rc;
-          rc = mlp_forward_keep(f, mm[m], w, m, hin[m], outs[m], n, stream);
-          if (rc) return rc;
-          if (f.attn_flags & GNF_ATTN_RESIDUAL) {                                     // gnn.py:551-552
-            k_add_rows_p<<<eb, 256, 0, stream>>>(outs[m], xa, H, HP, n);
-            GNF_LAUNCH_CHECK();
-          }
-        }
-        k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
-        GNF_LAUNCH_CHECK();
-        float* gtop[2] = {w.gs, w.gt};
-        for (int m = 0; m < 2; ++m) {
-          rc = mlp_backward(f, mm[m], w, m, hin[m], gtop[m], gp, n, 0, grads, stream);
-          if (rc) return rc;
-          rc = attn_backward(f, mm[m], w, m, gtop[m], gp, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, ga,
-                             grads, stream);
-          if (rc) return rc;
-        }
-        continue;
-      }
-      rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, w.hbuf, stream);
+      int rc = bwd_half_fp32(f, w, half, i, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers,
+                             scale, grads, stream);
       if (rc) return rc;
-      rc = mlp_forward_keep(f, ms, w, 0, w.hbuf, w.sbuf, n, stream);
-      if (rc) return rc;
-      rc = mlp_forward_keep(f, mt, w, 1, w.hbuf, w.tbuf, n, stream);
-      if (rc) return rc;
-      k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
-      GNF_LAUNCH_CHECK();
-      rc = mlp_backward(f, ms, w, 0, w.hbuf, w.gs, gp, n, 0, grads, stream);
-      if (rc) return rc;
-      rc = mlp_backward(f, mt, w, 1, w.hbuf, w.gt, gp, n, 1, grads, stream);
-      if (rc) return rc;
-      k_agg_bwd<<<eb, 256, 0, stream>>>(w.gh, f.in_pad, H, HP, rowptr_by_sender, csr_receivers, rowptr, n,
-                                        f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps, ga);
-      GNF_LAUNCH_CHECK();
     }
   }
   if (x_out) {
@@ -760,4 +772,36 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
     GNF_LAUNCH_CHECK();
   }
   return GNF_OK;
+}
+
+extern "C" int gnf_coupling_half_backward(const gnf_flow* h, int32_t half, int32_t step, const float* xa, float* xb,
+                                          float* ga, float* gb, int64_t n, int64_t e, const int32_t* rowptr,
+                                          const int32_t* csr_senders, const int32_t* rowptr_by_sender,
+                                          const int32_t* csr_receivers, double loss_scale, float* grads, int32_t math,
+                                          void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(h && grads, GNF_EINVAL, "gnf_coupling_half_backward: null flow/grads");
+  GNF_REQUIRE(n >= 0 && e >= 0 && (half == 0 || half == 1), GNF_EINVAL, "gnf_coupling_half_backward: bad argument");
+  GNF_REQUIRE(step >= 0 && step < h->f.d.num_timesteps, GNF_EINVAL, "gnf_coupling_half_backward: bad step %d", step);
+  GNF_REQUIRE(math >= GNF_MATH_FP32 && math <= GNF_MATH_TC2X, GNF_EINVAL, "gnf_coupling_half_backward: bad math %d", math);
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(xa && xb && ga && gb && rowptr && rowptr_by_sender && (e == 0 || (csr_senders && csr_receivers)),
+              GNF_EINVAL, "gnf_coupling_half_backward: null pointer");
+  const Flow& f = h->f;
+  GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0 && ws_bytes >= gnf_grevnet_backward_workspace(h, n, math), GNF_EWORKSPACE,
+              "gnf_coupling_half_backward: workspace too small or misaligned");
+  if (math != GNF_MATH_FP32) {
+    GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED, "gnf_coupling_half_backward: flow shape needs GNF_MATH_FP32");
+    const int dw_parts = (math == GNF_MATH_TC3X || math == GNF_MATH_TC3X_BF16) ? 2 : 1;
+    const int fwd_f16 = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 1 : 0;
+    return tc_half_backward(f, half, step, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers,
+                            loss_scale, grads, ws, dw_parts, fwd_f16, stream_);
+  }
+  BwdWs w = carve_bwd(f, n, ws);
+  const int gp = pad_to(f.HP, 8);
+  GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  GNF_CUDA(cudaMemsetAsync(w.gs, 0, (size_t)n * gp * 4, stream));
+  GNF_CUDA(cudaMemsetAsync(w.gt, 0, (size_t)n * gp * 4, stream));
+  return bwd_half_fp32(f, w, half, step, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers,
+                       (float)loss_scale, grads, stream);
 }

@@ -1119,6 +1119,16 @@ int tc_grevnet_backward(const Flow& f, const float* z, int64_t n, const int32_t*
   return GNF_OK;
 }
 
+int tc_half_backward(const Flow& f, int half, int step, const float* xa, float* xb, float* ga, float* gb, int64_t n,
+                     const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
+                     const int32_t* csr_receivers, double loss_scale, float* grads, void* ws, int dw_parts, int fwd_f16,
+                     void* stream_) {
+  BwdTcWs w = carve_bwd_tc(f, n, ws);
+  const int ms = f.mlp_index(0, half, step), mt = f.mlp_index(1, half, step);
+  return bwd_half_tc(f, ms, mt, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_s, csr_receivers, (float)loss_scale,
+                     grads, w, dw_parts, fwd_f16 != 0, (cudaStream_t)stream_);
+}
+
 // unit-test entry: out[fa][fb] = A^T B for fp32 A [n, fa], B [n, fb] through the image format + k_dw_tc
 int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, int parts, int n_splits, float* out,
                     void* ws, size_t ws_bytes, void* stream_) {

@@ -128,6 +128,10 @@ void tc_bwd_layout(const Flow& f, int64_t n, int64_t* out);
 int tc_grevnet_backward(const Flow& f, const float* z, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                         const int32_t* rowptr_s, const int32_t* csr_receivers, double loss_scale, float* grads,
                         float* x_out, void* ws, size_t ws_bytes, int dw_parts, int fwd_f16, void* stream);
+int tc_half_backward(const Flow& f, int half, int step, const float* xa, float* xb, float* ga, float* gb, int64_t n,
+                     const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
+                     const int32_t* csr_receivers, double loss_scale, float* grads, void* ws, int dw_parts, int fwd_f16,
+                     void* stream);
 int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, int parts, int n_splits, float* out,
                     void* ws, size_t ws_bytes, void* stream);
 
@@ -137,6 +141,8 @@ size_t tc_bytes_per_mlp(int L, int K);
 int tc_pack_mlp(const Flow& f, int mlp, const float* params, void* stream);
 bool tc_shape_supported(const Flow& f);
 void tc_set_trace(void* buf);
+int tc_kernel_timing(int enable);
+int tc_kernel_time(double* total_ms, int64_t* launches);
 int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
                      const float* xa, float* xb, int64_t n_nodes,
                      const int32_t* rowptr, const int32_t* csr_senders,

@@ -370,6 +370,46 @@ __global__ void k_affine_rows(float* __restrict__ x, int64_t n, int h, int hp, c
   if (f < h) x[i] = __fadd_rn(__fmul_rn(x[i], scale[f]), shift[f]);
 }
 
+// backward of the batch-norm bijector, phase 1: per-feature sums of G_y and G_y * xhat, xhat = (y - beta) / gamma
+__global__ void k_bn_bwd_partial(const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ beta,
+                                 const float* __restrict__ inv_gamma, int64_t total, int h, int hp,
+                                 double* __restrict__ partials) {
+  extern __shared__ double sm[];                 // [2][blockDim]
+  double s = 0.0, ss = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int f = threadIdx.x % hp;                // stride and blockDim are multiples of hp
+  const float b = f < h ? beta[f] : 0.f, ig = f < h ? inv_gamma[f] : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const double gv = (double)g[i];
+    s += gv;
+    ss += gv * (double)((y[i] - b) * ig);
+  }
+  sm[threadIdx.x] = s;
+  sm[blockDim.x + threadIdx.x] = ss;
+  __syncthreads();
+  if ((int)threadIdx.x < hp) {
+    double a = 0.0, c = 0.0;
+    for (int k = threadIdx.x; k < (int)blockDim.x; k += hp) {
+      a += sm[k];
+      c += sm[blockDim.x + k];
+    }
+    partials[(int64_t)blockIdx.x * 2 * hp + threadIdx.x] = a;
+    partials[(int64_t)blockIdx.x * 2 * hp + hp + threadIdx.x] = c;
+  }
+}
+
+// phase 2: xhat = (y - beta)/gamma;  g <- c1*g + c2*xhat + c3;  y <- xhat*s + mu   (coef rows: beta, 1/gamma, c1, c2, c3, s, mu)
+__global__ void k_bn_bwd_apply(float* __restrict__ y, float* __restrict__ g, int64_t n, int h, int hp,
+                               const float* __restrict__ coef) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * hp) return;
+  const int f = (int)(i % hp);
+  if (f >= h) return;
+  const float xh = (y[i] - coef[f]) * coef[h + f];
+  g[i] = fmaf(coef[2 * h + f], g[i], fmaf(coef[3 * h + f], xh, coef[4 * h + f]));
+  y[i] = fmaf(xh, coef[5 * h + f], coef[6 * h + f]);
+}
+
 // ---- a8: log-prob ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_sumsq(const float* __restrict__ z, int64_t total, double* __restrict__ partials) {
@@ -644,6 +684,8 @@ extern "C" int gnf_debug_set_trace(void* device_buf) {
   tc_set_trace(device_buf);
   return GNF_OK;
 }
+extern "C" int gnf_debug_kernel_timing(int32_t enable) { return tc_kernel_timing(enable); }
+extern "C" int gnf_debug_kernel_time(double* total_ms, int64_t* launches) { return tc_kernel_time(total_ms, launches); }
 extern "C" int32_t gnf_padded_half(int32_t h) { return pad_to(h, 4); }
 
 static int validate_desc(const gnf_flow_desc* d) {
@@ -1024,6 +1066,36 @@ extern "C" int gnf_bn_moments(const float* x, int64_t n, int32_t hh, double* sum
   k_bn_partial<<<blocks, tpb, 2 * tpb * sizeof(double), stream>>>(x, total, hp, (double*)ws);
   GNF_LAUNCH_CHECK();
   k_bn_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, hh, hp, sums);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_bn_backward_sums(const float* y, const float* g, int64_t n, int32_t hh, const float* beta,
+                                    const float* inv_gamma, double* sums, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int hp = gnf_padded_half(hh);
+  GNF_REQUIRE(hh >= 1 && hp <= 256 && n >= 0 && sums && beta && inv_gamma, GNF_EINVAL,
+              "gnf_bn_backward_sums: bad argument (H <= 256)");
+  GNF_REQUIRE(ws && ws_bytes >= gnf_bn_moments_workspace(hh), GNF_EWORKSPACE, "gnf_bn_backward_sums: workspace too small");
+  GNF_REQUIRE(n == 0 || (y && g), GNF_EINVAL, "gnf_bn_backward_sums: null y/g");
+  const int tpb = (256 / hp) * hp;
+  const int64_t total = n * hp;
+  int blocks = (int)(ceil_div(total, tpb) < kBnBlocks ? ceil_div(total, tpb) : kBnBlocks);
+  if (blocks < 1) blocks = 1;
+  k_bn_bwd_partial<<<blocks, tpb, 2 * tpb * sizeof(double), stream>>>(y, g, beta, inv_gamma, total, hh, hp, (double*)ws);
+  GNF_LAUNCH_CHECK();
+  k_bn_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, hh, hp, sums);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_bn_backward_apply(float* y, float* g, int64_t n, int32_t hh, const float* coef, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(hh >= 1 && n >= 0 && coef, GNF_EINVAL, "gnf_bn_backward_apply: bad argument");
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(y && g, GNF_EINVAL, "gnf_bn_backward_apply: null y/g");
+  const int hp = gnf_padded_half(hh);
+  k_bn_bwd_apply<<<(unsigned)ceil_div(n * hp, 256), 256, 0, stream>>>(y, g, n, hh, hp, coef);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }

@@ -480,11 +480,14 @@ class GRevNet(nn.Module):
         # defaults gamma=1, beta=0, moving_mean=0, moving_variance=1, epsilon=1e-3, momentum=0.99,
         # wrapped in tfb.BatchNormalization(training=True).  Always constructed, as in the reference.
         self.bn_epsilon, self.bn_momentum = 1e-3, 0.99
-        self.bn_gamma = nn.Parameter(torch.ones(2, T, H, device=dev), requires_grad=False)
-        self.bn_beta = nn.Parameter(torch.zeros(2, T, H, device=dev), requires_grad=False)
+        # trainable, like the tf.layers variables they stand for, when the bijector is in use (gradients come from
+        # _backward_bn); the gamma constraint relu(gamma)+1e-6 is a Keras constraint = a projection after each update
+        self.bn_gamma = nn.Parameter(torch.ones(2, T, H, device=dev), requires_grad=bool(use_batch_norm))
+        self.bn_beta = nn.Parameter(torch.zeros(2, T, H, device=dev), requires_grad=bool(use_batch_norm))
         self.register_buffer("bn_moving_mean", torch.zeros(2, T, H, device=dev))
         self.register_buffer("bn_moving_var", torch.ones(2, T, H, device=dev))
         self.bn_update_moving = True          # the scripts run UPDATE_OPS with every step (run_grevnet.py:362)
+        self._bn_saved = {}                   # (half, step) -> (mean, var, N) of the last density pass
         self.bn_group = None                  # process group for cross-rank batch statistics (sharding.py)
         self.bn_sync = True                   # all-reduce the batch statistics when running sharded
 
@@ -570,13 +573,14 @@ class GRevNet(nn.Module):
         n = sums[2 * H]
         mean = sums[:H] / n
         var = (sums[H:2 * H] / n - mean * mean).clamp_(min=0.0)         # biased, as tf.nn.moments
-        gamma = self.bn_gamma[half, i].double()
-        beta = self.bn_beta[half, i].double()
+        gamma = self.bn_gamma.detach()[half, i].double()
+        beta = self.bn_beta.detach()[half, i].double()
         inv = torch.rsqrt(var + self.bn_epsilon)
         scale = gamma * inv
         shift = beta - mean * scale
         # scalar ildj tiled over the node axis (event_ndims=2 vs forward_min_event_ndims=1): x N (local share)
         ldj += float(n_local) * (torch.log(gamma) - 0.5 * torch.log(var + self.bn_epsilon)).sum()
+        self._bn_saved[(half, i)] = (mean, var, n)        # the backward undoes the bijector with these
         sc, sh = scale.float().contiguous(), shift.float().contiguous()
         _lib.check(lib.gnf_affine_rows(_lib.ptr(xp), n_local, H, _lib.ptr(sc), _lib.ptr(sh), _lib.stream_ptr(dev)),
                    "gnf_affine_rows")
@@ -588,8 +592,8 @@ class GRevNet(nn.Module):
     def _bn_forward_(self, zp, n_local, half, i):
         """bn.forward = de-normalise with the MOVING statistics (gnn.py:356-358,369-371)."""
         lib, H, dev = self._flow.lib, self.node_embedding_dim // 2, zp.device
-        scale = torch.sqrt(self.bn_moving_var[half, i] + self.bn_epsilon) / self.bn_gamma[half, i]
-        shift = self.bn_moving_mean[half, i] - self.bn_beta[half, i] * scale
+        scale = torch.sqrt(self.bn_moving_var[half, i] + self.bn_epsilon) / self.bn_gamma.detach()[half, i]
+        shift = self.bn_moving_mean[half, i] - self.bn_beta.detach()[half, i] * scale
         sc, sh = scale.float().contiguous(), shift.float().contiguous()
         _lib.check(lib.gnf_affine_rows(_lib.ptr(zp), n_local, H, _lib.ptr(sc), _lib.ptr(sh), _lib.stream_ptr(dev)),
                    "gnf_affine_rows")
@@ -660,7 +664,7 @@ class GRevNet(nn.Module):
         self.params).  `z_nodes` must be f(graph).nodes.  `math` defaults to the forward's mode:
         "fp32" = layered FFMA kernels, anything else = the tcgen05 backward (backward_tc.cu)."""
         if self.use_batch_norm:
-            raise NotImplementedError("backward with use_batch_norm=True is not implemented")
+            return self._backward_bn(graph, z_nodes, loss_scale, grads, return_x, math)
         lib = self._flow.lib
         _lib.require_cuda(z_nodes, "z.nodes", torch.float32)
         handle = self._flow.ensure(self.params.detach())
@@ -679,6 +683,85 @@ class GRevNet(nn.Module):
                                             _lib.stream_ptr(dev)), "gnf_grevnet_backward")
         self._last_backward_workspace = ws if getattr(self, "_keep_backward_workspace", False) else None
         return (grads, x_out) if return_x else grads
+
+    def _backward_bn(self, graph, z_nodes, loss_scale, grads, return_x, math):
+        """backward_from_z with use_batch_norm=True: the reversed half steps (gnf_coupling_half_backward)
+        interleaved with the backward of the TFP batch-norm bijector in training mode.  The bijector is undone
+        with the batch statistics the density pass saved (`f` must have been called on this batch); its gamma
+        and beta get gradients in `self.bn_gamma.grad` / `self.bn_beta.grad`:
+            y = gamma * xhat + beta,  xhat = (x - mu) / s,  s = sqrt(var + eps),  ldj += N (log gamma - log s)
+            dL/dbeta = S1,  dL/dgamma = S2 - loss_scale * N / gamma          (S1 = sum G_y, S2 = sum G_y xhat)
+            dL/dx = (gamma G_y - gamma S1/N - xhat gamma S2/N) / s + loss_scale * xhat / s
+        Sharded runs all-reduce (S1, S2) like the forward's moments."""
+        lib = self._flow.lib
+        _lib.require_cuda(z_nodes, "z.nodes", torch.float32)
+        T, D = self.num_timesteps, self.node_embedding_dim
+        H = D // 2
+        if len(self._bn_saved) != 2 * T:
+            raise RuntimeError("backward with use_batch_norm=True needs the batch statistics of the density pass: "
+                               "call f(graph) (or loss_and_grad) on this batch first")
+        handle = self._flow.ensure(self.params.detach())
+        st, stt = structure_of(graph), transposed_structure_of(graph)
+        n, dev = z_nodes.shape[0], z_nodes.device
+        if grads is None:
+            grads = torch.zeros_like(self.params.detach())
+        _lib.require_cuda(grads, "grads", torch.float32)
+        m = _lib.MATH[math if math is not None else self.math]
+        stream = _lib.stream_ptr(dev)
+        hp = lib.gnf_padded_half(H)
+        wsb = lib.gnf_grevnet_backward_workspace(handle, n, m)
+        ws = _lib.workspace(wsb, dev)
+        bwsb = lib.gnf_bn_moments_workspace(H)
+        bws = _lib.workspace(bwsb, dev)
+        x = [torch.empty(max(n, 1), hp, dtype=torch.float32, device=dev) for _ in range(2)]
+        _lib.check(lib.gnf_split_halves(_lib.ptr(z_nodes), n, D, _lib.ptr(x[0]), _lib.ptr(x[1]), stream), "gnf_split_halves")
+        g = [x[0] * float(loss_scale), x[1] * float(loss_scale)]          # dL/dz = loss_scale * z
+        g_gamma = torch.zeros_like(self.bn_gamma.detach(), dtype=torch.float64)
+        g_beta = torch.zeros_like(self.bn_beta.detach(), dtype=torch.float64)
+        dist = torch.distributed
+        sync = self.bn_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.bn_group) > 1
+
+        def bn_backward(half, i):
+            mean, var, n_glob = self._bn_saved[(half, i)]
+            gamma, beta = self.bn_gamma.detach()[half, i].double(), self.bn_beta.detach()[half, i].double()
+            s = torch.sqrt(var + self.bn_epsilon)
+            sums = torch.empty(2 * H, dtype=torch.float64, device=dev)
+            bt, ig = beta.float().contiguous(), (1.0 / gamma).float().contiguous()
+            _lib.check(lib.gnf_bn_backward_sums(_lib.ptr(x[half]), _lib.ptr(g[half]), n, H, _lib.ptr(bt), _lib.ptr(ig),
+                                                _lib.ptr(sums), _lib.ptr(bws), bwsb, stream), "gnf_bn_backward_sums")
+            if sync:
+                dist.all_reduce(sums, group=self.bn_group)
+            s1, s2 = sums[:H], sums[H:]
+            g_beta[half, i] += s1
+            g_gamma[half, i] += s2 - float(loss_scale) * n_glob / gamma
+            coef = torch.stack([beta, 1.0 / gamma, gamma / s, (float(loss_scale) - gamma * s2 / n_glob) / s,
+                                -gamma * s1 / (n_glob * s), s, mean]).float().contiguous()
+            _lib.check(lib.gnf_bn_backward_apply(_lib.ptr(x[half]), _lib.ptr(g[half]), n, H, _lib.ptr(coef), stream),
+                       "gnf_bn_backward_apply")
+
+        def half_backward(half, i):
+            a, b = half, 1 - half
+            _lib.check(lib.gnf_coupling_half_backward(handle, half, i, _lib.ptr(x[a]), _lib.ptr(x[b]), _lib.ptr(g[a]),
+                                                      _lib.ptr(g[b]), n, st.n_edges, _lib.ptr(st.rowptr),
+                                                      _lib.ptr(st.csr_senders), _lib.ptr(stt.rowptr),
+                                                      _lib.ptr(stt.csr_senders), float(loss_scale), _lib.ptr(grads), m,
+                                                      _lib.ptr(ws), wsb, stream), "gnf_coupling_half_backward")
+
+        for i in reversed(range(T)):                                  # gnn.py:309-338 reversed
+            half_backward(1, i)
+            bn_backward(1, i)
+            half_backward(0, i)
+            bn_backward(0, i)
+        # a sharded caller all-reduces parameter gradients itself; gamma/beta data terms were already global sums
+        self.bn_gamma.requires_grad_(True)
+        self.bn_beta.requires_grad_(True)
+        self.bn_gamma.grad = g_gamma.float()
+        self.bn_beta.grad = g_beta.float()
+        if return_x:
+            x_out = torch.empty_like(z_nodes)
+            _lib.check(lib.gnf_merge_halves(_lib.ptr(x[0]), _lib.ptr(x[1]), n, D, _lib.ptr(x_out), stream), "gnf_merge_halves")
+            return grads, x_out
+        return grads
 
     def loss_and_grad(self, graph: GraphsTuple, per_node: bool = True, backward_math: Optional[str] = None):
         """One training-step evaluation: the scalars of run_grevnet.py:292-302 and the gradient of

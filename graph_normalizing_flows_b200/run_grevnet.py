@@ -3,14 +3,16 @@ B200 hot path.  Same flag names and defaults for everything that reaches the hot
 optimiser (run_grevnet.py:39-132); TF-1 session / summary / checkpoint plumbing is replaced by a
 plain loop, python logging and torch.save.
 
-    python -m graph_normalizing_flows_b200.run_grevnet --dataset mog_4 --make_gnn_fn sum_concat_then_mlp \
-        --num_train_iters 200 --use_batch_norm=False
+    python -m graph_normalizing_flows_b200.run_grevnet --dataset mog_4 --num_train_iters 200
+    python -m graph_normalizing_flows_b200.run_grevnet --make_gnn_fn sum_concat_then_mlp --use_batch_norm=False
 
-Differences, stated: `--make_gnn_fn` accepts the four message-passing factories this repository
-accelerates (avg_then_mlp, sum_then_mlp, avg_concat_then_mlp, sum_concat_then_mlp; the reference's
-default dm_self_attn is SURVEY §8 row f1, not built); `--use_gnf` / GNFBlock does not exist in the
-reference tree (grevnet.py is missing) -- GRevNet is always used and its backward is already the
-reversible one; training with --use_batch_norm=True is not supported (forward only).
+Differences, stated: `--make_gnn_fn` accepts the reference default dm_self_attn (SURVEY §8 row f1, fp32 kernels)
+and the four message-passing factories on the fused tcgen05 path (avg_then_mlp, sum_then_mlp,
+avg_concat_then_mlp, sum_concat_then_mlp); the dense-attention / GRU factories of run_grevnet.py:254-266 are
+out of scope.  `--use_gnf` / GNFBlock does not exist in the reference tree (grevnet.py is missing) -- GRevNet is
+always used and its backward is already the reversible one.  With --use_batch_norm (reference default True)
+the batch-norm bijector's gamma/beta are trained too; the reference's gamma constraint relu(gamma)+1e-6
+(gnn.py:261-262, a Keras constraint) is applied as a projection after every optimiser step.
 """
 from __future__ import annotations
 
@@ -33,15 +35,23 @@ flags.DEFINE_integer("node_embedding_dim", 2, "Number of dimensions in node embe
 flags.DEFINE_integer("num_coupling_layers", 12, "Number of coupling layers in GRevNet.")
 flags.DEFINE_bool("weight_sharing", False, "")
 # GNN params (:55-72)
-flags.DEFINE_string("make_gnn_fn", "sum_concat_then_mlp", "avg_then_mlp | sum_then_mlp | avg_concat_then_mlp | "
+flags.DEFINE_string("make_gnn_fn", "dm_self_attn", "dm_self_attn | avg_then_mlp | sum_then_mlp | avg_concat_then_mlp | "
                     "sum_concat_then_mlp")
 flags.DEFINE_integer("gnn_num_layers", 5, "Number of layers to use in MLP in GRevNet.")
 flags.DEFINE_integer("gnn_latent_dim", 256, "Latent dim for GNN used in GRevNet.")
 flags.DEFINE_float("gnn_bias_init_stddev", 0.1, "Used to initialize biases in GRevNet MLPs.")
 flags.DEFINE_float("gnn_l2_regularizer_weight", 0.1, "Unused (as in the reference).")
 flags.DEFINE_float("gnn_avg_then_mlp_epsilon", 1.0, "Weight of the node's own embedding vs. its neighbours'.")
+# Attention params (:74-80)
+flags.DEFINE_integer("attn_kq_dim", 10, "")
+flags.DEFINE_integer("attn_v_dim", 10, "")
+flags.DEFINE_integer("attn_num_heads", 8, "")
+flags.DEFINE_integer("attn_concat_heads_output_dim", 80, "")
+flags.DEFINE_bool("attn_concat", True, "")
+flags.DEFINE_bool("attn_residual", False, "")
+flags.DEFINE_bool("attn_layer_norm", False, "snt.LayerNorm on the GNN output: not built (raises).")
 # Training params (:82-109)
-flags.DEFINE_bool("use_batch_norm", False, "Reference default is True; training through BN is not supported here.")
+flags.DEFINE_bool("use_batch_norm", True, "TFP batch-norm bijector between half steps (reference default).")
 flags.DEFINE_string("dataset", "mog_4", "Which dataset to use.")
 flags.DEFINE_string("logdir", "test_runs/test_grevnet", "Where to write training files.")
 flags.DEFINE_integer("train_batch_size", 32, "Batch size used at training.")
@@ -70,7 +80,13 @@ def make_gnn_fn_map():
     half = FLAGS.node_embedding_dim / 2          # run_grevnet.py:157: a float under true division
     mlp = partial(gnn.make_mlp_model, FLAGS.gnn_latent_dim, half, FLAGS.gnn_num_layers, gnn.leaky_relu,
                   FLAGS.gnn_l2_regularizer_weight, FLAGS.gnn_bias_init_stddev)
-    return {                                     # run_grevnet.py:254-266 (message-passing entries)
+    relu_mlp = partial(gnn.make_mlp_model, FLAGS.gnn_latent_dim, half, FLAGS.gnn_num_layers, gnn.relu,
+                       FLAGS.gnn_l2_regularizer_weight, FLAGS.gnn_bias_init_stddev)      # run_grevnet.py:203-206
+    return {                                     # run_grevnet.py:254-266 (in-scope entries)
+        "dm_self_attn": lambda: gnn.dm_self_attn_gnn(                                    # run_grevnet.py:199-211
+            kq_dim=FLAGS.attn_kq_dim, v_dim=FLAGS.attn_v_dim, make_mlp_fn=relu_mlp, num_heads=FLAGS.attn_num_heads,
+            concat_heads_output_dim=FLAGS.attn_concat_heads_output_dim, concat=FLAGS.attn_concat,
+            residual=FLAGS.attn_residual, layer_norm=FLAGS.attn_layer_norm),
         "avg_then_mlp": lambda: gnn.avg_then_mlp_gnn(mlp, FLAGS.gnn_avg_then_mlp_epsilon),
         "sum_then_mlp": lambda: gnn.sum_then_mlp_gnn(mlp, FLAGS.gnn_avg_then_mlp_epsilon),
         "avg_concat_then_mlp": lambda: gnn.avg_concat_then_mlp_gnn(mlp),
@@ -93,7 +109,8 @@ def main(argv):
                           seed=FLAGS.random_seed, math=FLAGS.math or None)          # run_grevnet.py:277-281
     if FLAGS.last_layer_init_scale != 1.0:
         grevnet.scale_last_layers_(FLAGS.last_layer_init_scale)
-    opt = torch.optim.Adam([grevnet.params], lr=FLAGS.lr, betas=(FLAGS.adam_beta1, FLAGS.adam_beta2),
+    train_vars = [grevnet.params] + ([grevnet.bn_gamma, grevnet.bn_beta] if FLAGS.use_batch_norm else [])
+    opt = torch.optim.Adam(train_vars, lr=FLAGS.lr, betas=(FLAGS.adam_beta1, FLAGS.adam_beta2),
                            eps=FLAGS.adam_epsilon)                                   # run_grevnet.py:357-361
     t0 = time.time()
     for step in range(1, FLAGS.num_train_iters + 1):
@@ -103,10 +120,15 @@ def main(argv):
         graph = dataset.get_next_batch(FLAGS.train_batch_size).to("cuda")
         scalars, grads = grevnet.loss_and_grad(graph, per_node=False)               # total_loss, :296,362-364
         if FLAGS.clip_gradient_by_value:                                             # :365-370
-            grads.clamp_(FLAGS.clip_gradient_value_lower, FLAGS.clip_gradient_value_upper)
+            for v in train_vars:
+                v.grad.clamp_(FLAGS.clip_gradient_value_lower, FLAGS.clip_gradient_value_upper)
         if FLAGS.clip_gradient_by_norm:                                              # :372-375 (per-variable in TF)
-            torch.nn.utils.clip_grad_norm_([grevnet.params], FLAGS.clip_gradient_norm)
+            for v in train_vars:
+                torch.nn.utils.clip_grad_norm_([v], FLAGS.clip_gradient_norm)
         opt.step()
+        if FLAGS.use_batch_norm:                                                     # gamma_constraint, gnn.py:261-262
+            with torch.no_grad():
+                grevnet.bn_gamma.copy_(torch.relu(grevnet.bn_gamma) + 1e-6)
         if step % FLAGS.log_every_n_steps == 0 or step == 1:                         # scalars of :385-392
             z = scalars["z"].nodes
             logging.info("step %d loss_per_node %.5f log_prob_zs_per_node %.5f log_det_jacobian_per_node %.5f "

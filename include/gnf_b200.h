@@ -70,6 +70,12 @@ int64_t     gnf_launch_count(int reset);
 /* Developer aid: when device_buf (>= 10*2048 uint64, zeroed) is non-NULL, CTA 0 of every fused
  * coupling kernel records a clock64 timeline of its warp roles into it; NULL switches it off. */
 int         gnf_debug_set_trace(void* device_buf);
+/* CUDA-event bracket around every fused coupling launch (k_coupling_tc): enable = 1 resets the counters and
+ * starts recording (up to 4096 launches), 0 stops.  gnf_debug_kernel_time synchronises the recorded events and
+ * returns their summed duration and count, so a benchmark can report the kernel's average duration inside its
+ * own timed steps.  Host-side state, not thread safe. */
+int         gnf_debug_kernel_timing(int32_t enable);
+int         gnf_debug_kernel_time(double* total_ms, int64_t* launches);
 
 /* ------------------------------------------------------------------------------------------
  * a1  batch structure.  Replaces the per-call index handling of graph_nets' aggregator:
@@ -199,6 +205,17 @@ size_t gnf_bn_moments_workspace(int32_t h);
 int gnf_bn_moments(const float* x, int64_t n_nodes, int32_t h, double* sums,
                    void* workspace, size_t workspace_bytes, void* stream);
 int gnf_affine_rows(float* x, int64_t n_nodes, int32_t h, const float* scale, const float* shift, void* stream);
+/* Backward of the bijector in training mode (batch statistics depend on x), for loss = -loss_scale * log_prob_xs:
+ *   gnf_bn_backward_sums : sums[0:H] = sum_n G_y[n,f], sums[H:2H] = sum_n G_y[n,f] * xhat[n,f],
+ *                          xhat = (y - beta) * inv_gamma   (device double[2H]; all-reduce across ranks before use;
+ *                          also d/d beta and the data term of d/d gamma).  workspace: gnf_bn_moments_workspace(H).
+ *   gnf_bn_backward_apply: in place, coef = 7 rows of H floats {beta, 1/gamma, c1, c2, c3, s, mu}:
+ *                          g <- c1*g + c2*xhat + c3   (c1 = gamma/s, c2 = (loss_scale - gamma*S2/N)/s, c3 = -gamma*S1/(N*s),
+ *                          s = sqrt(var + eps): the batch-statistics terms and the -N/2 log(var+eps) log-det term)
+ *                          y <- xhat*s + mu           (the bijector undone with the statistics saved by the forward) */
+int gnf_bn_backward_sums(const float* y, const float* g, int64_t n_nodes, int32_t h, const float* beta,
+                         const float* inv_gamma, double* sums, void* workspace, size_t workspace_bytes, void* stream);
+int gnf_bn_backward_apply(float* y, float* g, int64_t n_nodes, int32_t h, const float* coef, void* stream);
 
 /* One message-passing GNN of the flow on its own: NodeBlockGNN._build (gnn.py:155-156) =
  * node_block(edge_block(graph)); x, out [N, D/2] f32.  which: 0 = s, 1 = t.  fp32 arithmetic.
@@ -242,6 +259,17 @@ int gnf_grevnet_backward(const gnf_flow* flow, const float* z, int64_t n_nodes, 
                          const int32_t* rowptr_by_sender, const int32_t* csr_receivers,
                          double loss_scale, float* grads, float* x_out, int32_t math,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* One reversed HALF step of gnf_grevnet_backward on planar halves [N, HP] (the batch-norm variant interleaves
+ * gnf_bn_backward_* between half steps): xa is read; xb holds the post-update half and is restored in place;
+ * gb holds dLoss/d(post-update xb) and becomes dLoss/d(xb); ga is ACCUMULATED into; grads as above.
+ * workspace: gnf_grevnet_backward_workspace(flow, N, math). */
+int gnf_coupling_half_backward(const gnf_flow* flow, int32_t half, int32_t step, const float* xa, float* xb,
+                               float* ga, float* gb, int64_t n_nodes, int64_t n_edges,
+                               const int32_t* rowptr, const int32_t* csr_senders,
+                               const int32_t* rowptr_by_sender, const int32_t* csr_receivers,
+                               double loss_scale, float* grads, int32_t math,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Weight-gradient GEMM of the tensor-core backward on its own (unit tests, profiling):
  * out[fa, fb] = a^T b for row-major fp32 a [n, fa], b [n, fb]; fa in {128,256}, fb in {16,128,256};

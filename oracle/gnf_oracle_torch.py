@@ -85,17 +85,38 @@ def _st(p, which, half, i):
     return p[which][half] if p["weight_sharing"] else p[which][half][i]
 
 
-def grevnet_f_autograd(nodes, senders, receivers, p):
-    """GRevNet.f (gnn.py:304-341), differentiable (tests: reference gradients by autograd)."""
+BN_EPS = 1e-3      # tf.layers.BatchNormalization default epsilon
+
+
+def _bn_inverse(x, gamma, beta):
+    """tfb.BatchNormalization(training=True).inverse + inverse_log_det_jacobian(x, 2) (gnn.py:310-313), as
+    oracle/gnf_oracle.py::bn_inverse restates it: batch moments (biased variance), scalar ildj tiled over the
+    node axis.  Differentiable through the batch statistics."""
+    mean = x.mean(0)
+    var = ((x - mean) ** 2).mean(0)
+    y = gamma * (x - mean) / torch.sqrt(var + BN_EPS) + beta
+    ildj = x.shape[0] * (torch.log(gamma) - 0.5 * torch.log(var + BN_EPS)).sum()
+    return y, ildj
+
+
+def grevnet_f_autograd(nodes, senders, receivers, p, bn=None):
+    """GRevNet.f (gnn.py:304-341), differentiable (tests: reference gradients by autograd).
+    bn = (gamma[2][T][H], beta[2][T][H]) switches use_batch_norm on."""
     cfg = p["cfg"]
     h = nodes.shape[1] // 2
     x0, x1 = nodes[:, :h].contiguous(), nodes[:, h:].contiguous()
     ldj = torch.zeros((), dtype=nodes.dtype)
     for i in range(p["T"]):
+        if bn is not None:
+            x0, l = _bn_inverse(x0, bn[0][0][i], bn[1][0][i])
+            ldj = ldj + l
         s = _gnn(x0, senders, receivers, _st(p, "s", 0, i), cfg)
         t = _gnn(x0, senders, receivers, _st(p, "t", 0, i), cfg)
         ldj = ldj + s.sum()
         x1 = x1 * torch.exp(s) + t
+        if bn is not None:
+            x1, l = _bn_inverse(x1, bn[0][1][i], bn[1][1][i])
+            ldj = ldj + l
         s = _gnn(x1, senders, receivers, _st(p, "s", 1, i), cfg)
         t = _gnn(x1, senders, receivers, _st(p, "t", 1, i), cfg)
         ldj = ldj + s.sum()
@@ -118,10 +139,14 @@ def log_prob_xs(z, ldj):
     return log_prob_xs_autograd(z, ldj)
 
 
-def loss_and_grads(nodes, senders, receivers, params, scale=1.0, dtype=torch.float64):
+def loss_and_grads(nodes, senders, receivers, params, scale=1.0, dtype=torch.float64, bn=None):
     """loss = -scale * log_prob_xs and its gradient w.r.t. every (W, b), by autograd, flattened in the
-    include/gnf_b200.h parameter order (which -> half -> step; W0 b0 W1 b1 ...)."""
+    include/gnf_b200.h parameter order (which -> half -> step; W0 b0 W1 b1 ...).
+    bn = (gamma, beta) numpy [2, T, H]: use_batch_norm=True; returns (loss, grads, g_gamma, g_beta)."""
     p = params_to_torch(params, dtype)
+    bn_t = None
+    if bn is not None:
+        bn_t = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dtype).requires_grad_(True) for a in bn)
     leaves = []
     for which in ("s", "t"):
         for half in range(2):
@@ -137,7 +162,11 @@ def loss_and_grads(nodes, senders, receivers, params, scale=1.0, dtype=torch.flo
                     b.requires_grad_(True)
                     leaves += [w, b]
     z, ldj = grevnet_f_autograd(torch.as_tensor(nodes).to(dtype), torch.as_tensor(senders).long(),
-                                torch.as_tensor(receivers).long(), p)
+                                torch.as_tensor(receivers).long(), p, bn=bn_t)
     loss = -scale * log_prob_xs_autograd(z, ldj)
+    if bn_t is not None:
+        grads = torch.autograd.grad(loss, leaves + list(bn_t))
+        flat = torch.cat([g.reshape(-1) for g in grads[:-2]]).numpy()
+        return float(loss.detach()), flat, grads[-2].numpy(), grads[-1].numpy()
     grads = torch.autograd.grad(loss, leaves)
     return float(loss.detach()), torch.cat([g.reshape(-1) for g in grads]).numpy()

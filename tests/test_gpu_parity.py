@@ -311,6 +311,44 @@ def test_f2_reversible_backward_matches_autograd(block, agg, ws, act, bmath):
     assert np.abs(x_rec.cpu().numpy() - g.nodes).max() < 5e-5
 
 
+@pytest.mark.parametrize("bmath", ["fp32", "tc3x"])
+def test_f2_f4_backward_through_batch_norm(bmath):
+    """use_batch_norm=True training step: reversed half steps (gnf_coupling_half_backward) interleaved with the
+    backward of the batch-norm bijector in training mode (gnf_bn_backward_sums / _apply: batch statistics depend
+    on x, the -N/2 log(var+eps) log-det term too) vs torch autograd of the fp64 restatement
+    (oracle/gnf_oracle_torch.py::_bn_inverse, TFP semantics [upstream, unverifiable]).  Flow parameters, gamma and
+    beta gradients; the input is reconstructed with the saved batch statistics."""
+    from oracle import gnf_oracle_torch as OT
+    rng = np.random.default_rng(27)
+    D, T, L, K = 14, 2, 128, 4
+    g = H.random_batch(rng, 10, 5, 25, D=D)
+    g = g._replace(nodes=(g.nodes * 1.7 + 0.3).astype(np.float32))
+    params = O.make_params(6, T, D, L, K, last_layer_scale=0.1)
+    gm = (1.0 + 0.2 * rng.standard_normal((2, T, D // 2))).astype(np.float32).clip(0.5, 1.5)
+    bt = (0.1 * rng.standard_normal((2, T, D // 2))).astype(np.float32)
+    n = g.nodes.shape[0]
+    tol, ctol = BWD_TOL[bmath]
+    for per_node in (True, False):
+        scale = 1.0 / n if per_node else 1.0
+        loss_ref, grad_ref, gg_ref, gb_ref = OT.loss_and_grads(g.nodes, g.senders, g.receivers, params, scale, bn=(gm, bt))
+        net = H.make_grevnet(params, L, K, device=DEV)
+        net.use_batch_norm = True
+        net.bn_gamma.data.copy_(torch.from_numpy(gm))
+        net.bn_beta.data.copy_(torch.from_numpy(bt))
+        out, grads = net.loss_and_grad(dev_graph(g), per_node=per_node, backward_math=bmath)
+        loss = float(out["loss_per_node"] if per_node else out["total_loss"])
+        assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+        got = grads.double().cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.abs(got - grad_ref).max() <= tol * np.abs(grad_ref).max()
+        assert float(got @ grad_ref) / (np.linalg.norm(got) * np.linalg.norm(grad_ref)) > 1 - ctol
+        gg, gb = net.bn_gamma.grad.double().cpu().numpy(), net.bn_beta.grad.double().cpu().numpy()
+        assert np.abs(gg - gg_ref).max() <= max(tol, 1e-4) * np.abs(gg_ref).max()
+        assert np.abs(gb - gb_ref).max() <= max(tol, 1e-4) * max(np.abs(gb_ref).max(), np.abs(gg_ref).max())
+    _, x_rec = net.backward_from_z(dev_graph(g), out["z"].nodes, 1.0, return_x=True, math=bmath)
+    assert np.abs(x_rec.cpu().numpy() - g.nodes).max() < 5e-5
+
+
 @pytest.mark.parametrize("bmath", ["tc3x", "bf16"])
 def test_f2_tensor_core_backward_many_tiles(bmath):
     """More tiles than SMs (every CTA walks several 128-node tiles; the weight-gradient GEMM splits

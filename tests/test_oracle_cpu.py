@@ -188,6 +188,38 @@ def test_torch_attention_restatement_matches_numpy_oracle():
         assert np.isfinite(grads).all() and grads.shape == (H.flat_from_oracle(p).shape[0],)
 
 
+def test_torch_batch_norm_restatement_matches_numpy_oracle():
+    """a9: the differentiable torch restatement of the TFP batch-norm bijector (reference gradients for the GPU
+    test of the BN backward) reproduces oracle/gnf_oracle.py::grevnet_f_bn; a finite difference on gamma checks the
+    autograd path through the batch statistics and the N-tiled log-det term."""
+    import torch
+    from oracle import gnf_oracle_torch as OT
+    rng = np.random.default_rng(8)
+    g = H.random_batch(rng, 6, 4, 15, D=6)
+    T = 2
+    p = O.make_params(5, T, 6, 32, 3, last_layer_scale=0.1)
+    gm = (1.0 + 0.2 * rng.standard_normal((2, T, 3))).clip(0.5, 1.5)
+    bt = 0.1 * rng.standard_normal((2, T, 3))
+    bns = O.make_bn_state(T, 3, np.float64)
+    for half in range(2):
+        for i in range(T):
+            bns[half][i]["gamma"], bns[half][i]["beta"] = gm[half, i].copy(), bt[half, i].copy()
+    z, ldj = O.grevnet_f_bn(g.nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(p, np.float64), bns)
+    bn_t = (torch.from_numpy(gm), torch.from_numpy(bt))
+    zt, lt = OT.grevnet_f_autograd(torch.from_numpy(g.nodes).double(), torch.from_numpy(g.senders).long(),
+                                   torch.from_numpy(g.receivers).long(), OT.params_to_torch(p, torch.float64), bn=bn_t)
+    assert np.allclose(zt.numpy(), z, rtol=1e-10, atol=1e-10)
+    assert abs(float(lt) - float(ldj)) < 1e-9 * max(1.0, abs(float(ldj)))
+    loss, flat, gg, gb = OT.loss_and_grads(g.nodes, g.senders, g.receivers, p, 1.0, bn=(gm, bt))
+    eps = 1e-6
+    gp, gmn = gm.copy(), gm.copy()
+    gp[1, 0, 2] += eps
+    gmn[1, 0, 2] -= eps
+    lp = OT.loss_and_grads(g.nodes, g.senders, g.receivers, p, 1.0, bn=(gp, bt))[0]
+    lm = OT.loss_and_grads(g.nodes, g.senders, g.receivers, p, 1.0, bn=(gmn, bt))[0]
+    assert abs((lp - lm) / (2 * eps) - gg[1, 0, 2]) < 1e-5 * max(1.0, abs(gg[1, 0, 2]))
+
+
 def test_f4_embedding_pickle_readers(tmp_path):
     """GrevnetDatasetFixed / Variable (train_grevnet_with_data.py:145-234) + transform_example (:237-271)."""
     import pickle

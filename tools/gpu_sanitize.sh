@@ -19,7 +19,9 @@ for math in ("tc3x", "bf16", "fp32"):
     x = net(out["z"], inverse=False)
     print(math, float(out["log_prob_xs"]), float((x.nodes - dg.nodes).abs().max()))
 net = H.make_grevnet(params, 256, 4)
-out, grads = net.loss_and_grad(dg)
+for bm in ("tc3x", "bf16", "fp32"):            # tensor-core backward (k_bwd_chain + k_dw_tc), hi-only dW, FFMA path
+    out, grads = net.loss_and_grad(dg, backward_math=bm)
+    print("backward", bm, float(grads.norm()))
 blocks, off = G.loss.pred_adj(dg)
 torch.cuda.synchronize()
 print("grad norm", float(grads.norm()), "adj", float(blocks.sum()))
