@@ -51,7 +51,6 @@ struct BwdParams {
   uint16_t* h_img;           // [tiles][2][16*128]
   uint16_t* g_img;           // [2][tiles][2][16*128]
   float* gh;                 // [tiles*128][16]
-  float* db_part;            // [grid][4][2][kMaxLayers][256]   (zeroed by the caller)
   int write_lo;              // 0: the weight-gradient GEMM reads only the hi parts, skip the lo images
 };
 
@@ -82,21 +81,6 @@ __device__ __forceinline__ float dact_f(bool positive) {
 // element offset of (feature group fg, node n) inside an image with F features
 __device__ __forceinline__ size_t img_off(int F, int fg, int n) {
   return (size_t)(n >> 3) * (F * 8) + (size_t)fg * 64 + (n & 7) * 8;
-}
-
-// 32 values per lane -> lane j ends with sum over the 32 lanes of value j (fixed order)
-__device__ __forceinline__ float colsum32(float (&d)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool upper = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = upper ? d[i] : d[i + s];
-      const float keep = upper ? d[i + s] : d[i];
-      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return d[0];
 }
 
 template <int LAT, int ACT, bool F16F>
@@ -328,7 +312,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
     uint32_t acc_par = 0;
     int region = 0;
     const int hp4 = p.HP >> 2;
-    float* dbp = p.db_part + ((size_t)blockIdx.x * 4 + q) * 2 * kMaxLayers * 256;
     constexpr int NCH = G::GPH;                     // 32-column chunks per accumulator half per warp
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       float sv[kNOut], tv[kNOut], gh[kNOut];
@@ -356,12 +339,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) mk[g] = mp[g * 8];          // 64 elements = 8 uint4 per feature group
                 const uint32_t* mw = reinterpret_cast<const uint32_t*>(&mk[0]);
-                uint32_t bits = 0;
+                uint32_t bits = 0;          // bit j: element 2j positive, bit 16+j: element 2j+1 positive
+                if (ACT == GNF_ACT_LEAKY_RELU) {
+                  // leaky_relu keeps the sign of the pre-activation: positive <=> sign bit clear (a == 0 is measure zero)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const uint32_t w = mw[j];
-                  bits |= ((int16_t)(w & 0xFFFFu) > 0 ? 1u : 0u) << (2 * j);
-                  bits |= ((int32_t)w >= 0x10000 ? 1u : 0u) << (2 * j + 1);
+                  for (int j = 0; j < 16; ++j) bits |= ((mw[j] >> 15) & 0x10001u) << j;
+                  bits = ~bits;
+                } else {
+                  // relu output is >= 0: positive <=> non-zero
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const uint32_t w = mw[j];
+                    bits |= ((w & 0xFFFFu) ? 1u : 0u) << j;
+                    bits |= ((w >> 16) ? 1u : 0u) << (16 + j);
+                  }
                 }
                 pos[ch] = bits;
               }
@@ -382,7 +373,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
                 for (int j = 0; j < 32; ++j) d[j] = act_f<ACT>(__uint_as_float(v[j]));
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * dact_f<ACT>((pos[ch] >> j) & 1u);
+                for (int j = 0; j < 16; ++j) {
+                  d[2 * j] = __uint_as_float(v[2 * j]) * dact_f<ACT>((pos[ch] >> j) & 1u);
+                  d[2 * j + 1] = __uint_as_float(v[2 * j + 1]) * dact_f<ACT>((pos[ch] >> (16 + j)) & 1u);
+                }
               }
               uint32_t hi[16], lo[16];
               if (bwd) {
@@ -408,10 +402,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
               for (int g = 0; g < 4; ++g) {
                 oh[g * 8] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
                 if (p.write_lo) ol[g * 8] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
-              }
-              if (bwd) {   // bias gradient of layer li: column sums over this warp's 32 rows
-                const float cs = colsum32(d, lane);
-                atomicAdd(dbp + ((size_t)m * kMaxLayers + li) * 256 + col0 + lane, cs);
               }
             }
           }
@@ -498,12 +488,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
           }
           fence_proxy_async();
           mbar_arrive(smem_u32(&bars->g_full));
-          // bias gradient of the last layer: column sums of g_s (lanes 0-15) and g_t (lanes 16-31)
-          float d[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { d[j] = gs[j]; d[16 + j] = gt[j]; }
-          const float cs = colsum32(d, lane);
-          atomicAdd(dbp + ((size_t)(lane >> 4) * kMaxLayers + (K - 1)) * 256 + (lane & 15), cs);
         }
         if (c == 3 && grp == 0 && valid) {
           float* go = p.gh + node * kK0;
@@ -617,6 +601,8 @@ struct DwPair {
   int a_feats, b_feats;
   int first_cta, n_splits;
   int a_bf16, b_bf16;      // element type of each operand's images (0 = fp16)
+  int db_mode;             // bias gradient = column sums over the nodes of: 0 nothing, 1 the B operand, 2 the A operand
+  float* db_part;          // [n_splits][feats of that operand]
 };
 struct DwParams {
   DwPair pair[kDwMaxPairs];
@@ -659,7 +645,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
   if (tid == 0) {
     for (int i = 0; i < kDwStages; ++i) {
       mbar_init(smem_u32(&bars->full[i]), 1);
-      mbar_init(smem_u32(&bars->empty[i]), 1);
+      mbar_init(smem_u32(&bars->empty[i]), pr.db_mode ? 5 : 1);     // MMA commit (+ the 4 column-sum warps)
     }
     mbar_init(smem_u32(&bars->acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -734,6 +720,73 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
     if (elect_one()) tc_commit(smem_u32(&bars->acc_full));
     __syncwarp();
   } else {
+    if (pr.db_mode) {
+      // ---- bias gradient: column sums of one operand over the nodes, straight from the smem stages -----------
+      // MN-major image: per 8-node group, feature group fg is 8 nodes x 16 B; lane i reads node i&7 of feature
+      // group fg0 + (i>>3): a warp-wide LDS.128 covers 4 feature groups x 8 nodes, conflict free.
+      const int cw = warp - 2;
+      const int F = pr.db_mode == 1 ? FB : FA;
+      const uint32_t part_bytes = pr.db_mode == 1 ? b_part : a_part;
+      const uint32_t op_off = pr.db_mode == 1 ? PARTS * a_part : 0u;
+      const int fg_per_warp = F >= 128 ? F / 32 : 2;
+      const int nslots = fg_per_warp > 4 ? fg_per_warp / 4 : 1;
+      const bool active = F >= 128 ? true : (cw == 0 && lane < 16);
+      float acc[2][8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        for (int s = 0; s < 8 / KS; ++s) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase);
+          if (active) {
+            const uint8_t* base = smem + stage * kDwStageBytes + op_off;
+#pragma unroll
+            for (int part = 0; part < PARTS; ++part) {
+              for (int ng = 0; ng < KS * 2; ++ng) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  if (j < nslots) {
+                    const int fg = (F >= 128 ? cw * fg_per_warp + 4 * j : 0) + (lane >> 3);
+                    const uint4 w4 = *reinterpret_cast<const uint4*>(base + part * part_bytes + (size_t)ng * F * 16 +
+                                                                     fg * 128 + (lane & 7) * 16);
+                    const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      acc[j][2 * e] += __uint_as_float(ww[e] << 16);
+                      acc[j][2 * e + 1] += __uint_as_float(ww[e] & 0xFFFF0000u);
+                    }
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->empty[stage]));
+          if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = acc[j][e];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          acc[j][e] = v;
+        }
+      if (active && (lane & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (j < nslots) {
+            const int fg = (F >= 128 ? cw * fg_per_warp + 4 * j : 0) + (lane >> 3);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pr.db_part[(size_t)split * F + fg * 8 + e] = acc[j][e];
+          }
+      }
+    }
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -778,6 +831,9 @@ struct DwReducePair {
   const float* part;
   float* grad;            // W block of this layer inside the flat gradient ([in][out] row-major)
   int n_splits, fa, fb, in_dim, out_dim, transposed;
+  const float* db_part;   // [n_splits][db_feats] column sums (bias gradient), or null
+  float* grad_b;
+  int db_feats;
 };
 struct DwReduceParams {
   DwReducePair pair[kDwMaxPairs];
@@ -785,6 +841,15 @@ struct DwReduceParams {
 __global__ void k_dw_reduce(const DwReduceParams p) {
   const DwReducePair& r = p.pair[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && r.db_part && (int)threadIdx.x < r.out_dim) {     // bias gradient (out_dim <= 256 = blockDim)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int z0 = 0; z0 < r.n_splits; z0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (z0 + u < r.n_splits) acc[u] += r.db_part[(size_t)(z0 + u) * r.db_feats + threadIdx.x];
+    }
+    r.grad_b[threadIdx.x] += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
   if (i >= r.fa * r.fb) return;
   const int a = i / r.fb, b = i - a * r.fb;
   const int in = r.transposed ? b : a, out = r.transposed ? a : b;
@@ -796,29 +861,6 @@ __global__ void k_dw_reduce(const DwReduceParams p) {
       if (z0 + u < r.n_splits) acc[u] += r.part[(size_t)(z0 + u) * r.fa * r.fb + i];
   }
   r.grad[(size_t)in * r.out_dim + out] += (acc[0] + acc[1]) + (acc[2] + acc[3]);
-}
-
-// bias gradients: fixed-order sum over (cta, lane quarter) of the per-CTA column sums
-struct DbReduceParams {
-  const float* part;      // [grid][4][2][kMaxLayers][256]
-  int grid, K;
-  float* grad_b[2][kMaxLayers];
-  int out_dim[kMaxLayers];
-};
-__global__ void k_db_reduce(const DbReduceParams p) {
-  const int m = blockIdx.y / p.K, l = blockIdx.y - m * p.K;
-  const int col = threadIdx.x;
-  if (col >= p.out_dim[l]) return;
-  float acc[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-  const int nz = p.grid * 4;
-  for (int z0 = 0; z0 < nz; z0 += 8) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (z0 + u < nz) acc[u] += p.part[(((size_t)(z0 + u) * 2 + m) * kMaxLayers + l) * 256 + col];
-  }
-  p.grad_b[m][l][col] += ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 // ---- debug / unit-test helper: fp32 [n, F] row-major -> bf16 hi/lo tile images ----------------
@@ -866,7 +908,7 @@ int launch_chain_t(const BwdParams& p, int grid, cudaStream_t stream) {
 }
 
 struct BwdTcWs {
-  float *x0, *x1, *g0, *g1, *gh, *db_part, *dw_part;
+  float *x0, *x1, *g0, *g1, *gh, *dw_part;
   uint16_t *act_img, *dlt_img, *h_img, *g_img;
   size_t dw_part_floats;
   size_t bytes;
@@ -878,6 +920,7 @@ struct DwPlan {
   int splits[kDwMaxPairs], first[kDwMaxPairs];
   int grid;
   size_t part_off[kDwMaxPairs];      // floats
+  size_t db_off[kDwMaxPairs];        // floats: [splits][L] column-sum partials of the pair
   size_t part_floats;
 };
 
@@ -918,6 +961,8 @@ DwPlan plan_dw(const Flow& f, int n_tiles) {
     first += pl.splits[i];
     pl.part_off[i] = off;
     off += (size_t)pl.splits[i] * L * fb;
+    pl.db_off[i] = off;
+    off += (size_t)pl.splits[i] * L;
   }
   pl.grid = first;
   pl.part_floats = off;
@@ -941,7 +986,6 @@ BwdTcWs carve_bwd_tc(const Flow& f, int64_t n, void* base) {
   w.g0 = (float*)take(nn * f.HP * 4);
   w.g1 = (float*)take(nn * f.HP * 4);
   w.gh = (float*)take(tiles * 128 * kK0 * 4);
-  w.db_part = (float*)take((size_t)num_sms() * 4 * 2 * kMaxLayers * 256 * 4);
   const DwPlan pl = plan_dw(f, (int)tiles);
   w.dw_part_floats = pl.part_floats;
   w.dw_part = (float*)take(pl.part_floats * 4);
@@ -981,7 +1025,6 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
   const int K = f.K, L = f.L;
   const int n_tiles = (int)ceil_div(n, kTileM);
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-  GNF_CUDA(cudaMemsetAsync(w.db_part, 0, (size_t)grid * 4 * 2 * kMaxLayers * 256 * 4, stream));
   BwdParams p{};
   p.xa = xa; p.xb = xb; p.gxb = gb;
   p.rowptr = rowptr; p.csr = csr_senders;
@@ -997,7 +1040,7 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
   p.mean = f.d.agg == GNF_AGG_MEAN;
   p.eps = f.d.eps; p.scale = scale;
   p.act_img = w.act_img; p.dlt_img = w.dlt_img; p.h_img = w.h_img; p.g_img = w.g_img;
-  p.gh = w.gh; p.db_part = w.db_part;
+  p.gh = w.gh;
   p.write_lo = dw_parts == 2;
   int rc;
   const bool leaky = f.d.act == GNF_ACT_LEAKY_RELU;
@@ -1040,16 +1083,19 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
         pr.B = w.h_img;
         pr.b_feats = 16;
         pr.a_bf16 = 1; pr.b_bf16 = 1;
+        pr.db_mode = 2;                   // db_0 = column sums of delta_0 (the A operand)
       } else if (l == K - 1) {            // dW_{K-1} = a_{K-2}^T g_top
         pr.A = w.act_img + ((size_t)m * (K - 1) + (K - 2)) * layer_stride;
         pr.B = w.g_img + (size_t)m * n_tiles * 2 * 16 * 128;
         pr.b_feats = 16;
         pr.a_bf16 = 1; pr.b_bf16 = 1;
+        pr.db_mode = 1;                   // db_{K-1} = column sums of the top gradient (the B operand)
       } else {                            // dW_l = a_{l-1}^T delta_l
         pr.A = w.act_img + ((size_t)m * (K - 1) + (l - 1)) * layer_stride;
         pr.B = w.dlt_img + ((size_t)m * (K - 1) + l) * layer_stride;
         pr.b_feats = L;
         pr.a_bf16 = 1; pr.b_bf16 = 1;
+        pr.db_mode = 1;                   // db_l = column sums of delta_l (the B operand)
       }
       rr.part = pr.part;
       rr.grad = gm + f.flat_w_off[l];
@@ -1059,6 +1105,10 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
       rr.in_dim = f.ins[l];
       rr.out_dim = f.outs[l];
       rr.transposed = l == 0;
+      pr.db_part = w.dw_part + pl.db_off[i];
+      rr.db_part = pr.db_part;
+      rr.db_feats = pr.db_mode == 1 ? pr.b_feats : pr.a_feats;
+      rr.grad_b = gm + f.flat_b_off[l];
     }
   }
   rc = launch_dw(dp, pl.grid, dw_parts, stream);
@@ -1066,23 +1116,6 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
   {
     dim3 rg((unsigned)ceil_div((int64_t)L * L, 256), (unsigned)pl.n_pairs);
     k_dw_reduce<<<rg, 256, 0, stream>>>(rp);
-    GNF_LAUNCH_CHECK();
-  }
-  {
-    DbReduceParams bp{};
-    bp.part = w.db_part;
-    bp.grid = grid;
-    bp.K = K;
-    for (int l = 0; l < K; ++l) {
-      bp.out_dim[l] = f.outs[l];
-      bp.grad_b[0][l] = grads + (int64_t)ms * f.params_per_mlp + f.flat_b_off[l];
-      bp.grad_b[1][l] = grads + (int64_t)mt * f.params_per_mlp + f.flat_b_off[l];
-    }
-    if (ms == mt) {   // cannot happen (s and t nets are distinct), keep the two passes independent anyway
-      set_error("bwd_half_tc: s and t MLP alias");
-      return GNF_EINVAL;
-    }
-    k_db_reduce<<<dim3(1, 2 * K), 256, 0, stream>>>(bp);
     GNF_LAUNCH_CHECK();
   }
   return GNF_OK;
@@ -1152,12 +1185,12 @@ int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, i
   DwParams dp{};
   dp.n_pairs = 1;
   dp.n_tiles = n_tiles;
-  dp.pair[0] = DwPair{ai, bi, part, fa, fb, 0, n_splits, 1, 1};
+  dp.pair[0] = DwPair{ai, bi, part, fa, fb, 0, n_splits, 1, 1, 0, nullptr};
   int rc = launch_dw(dp, n_splits, parts, stream);
   if (rc) return rc;
   GNF_CUDA(cudaMemsetAsync(out, 0, (size_t)fa * fb * 4, stream));
   DwReduceParams rp{};
-  rp.pair[0] = DwReducePair{part, out, n_splits, fa, fb, fa, fb, 0};
+  rp.pair[0] = DwReducePair{part, out, n_splits, fa, fb, fa, fb, 0, nullptr, nullptr, 0};
   k_dw_reduce<<<dim3((unsigned)ceil_div((int64_t)fa * fb, 256), 1), 256, 0, stream>>>(rp);
   GNF_LAUNCH_CHECK();
   return GNF_OK;

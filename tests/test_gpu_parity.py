@@ -413,6 +413,27 @@ def test_f2_training_steps_reduce_the_loss():
     assert losses[-1] < losses[0] - 0.05, losses
 
 
+def test_run_grevnet_port_trains_with_reference_defaults(tmp_path, caplog):
+    """The trainer port with the reference's default GNN and bijector (dm_self_attn, use_batch_norm=True,
+    run_grevnet.py:56,83): f1 forward/backward + batch-norm backward + Adam + gamma constraint run end to end and
+    write the checkpoint."""
+    import logging
+    from absl import flags
+    from graph_normalizing_flows_b200 import run_grevnet as RG
+    argv = ["run_grevnet", "--num_train_iters=12", "--train_batch_size=8", "--num_coupling_layers=2",
+            "--gnn_latent_dim=64", "--gnn_num_layers=3", "--log_every_n_steps=4", "--lr=1e-3",
+            f"--logdir={tmp_path}", "--dataset=mog_4", "--last_layer_init_scale=0.1"]
+    flags.FLAGS.unparse_flags()
+    flags.FLAGS(argv)
+    assert flags.FLAGS.make_gnn_fn == "dm_self_attn" and flags.FLAGS.use_batch_norm
+    with caplog.at_level(logging.INFO):
+        assert RG.main([]) == 0
+    assert os.path.exists(os.path.join(str(tmp_path), "grevnet_12.pt"))
+    losses = [float(r.getMessage().split("loss_per_node ")[1].split()[0]) for r in caplog.records
+              if "loss_per_node" in r.getMessage()]
+    assert len(losses) >= 3 and all(np.isfinite(losses)), losses
+
+
 def test_f3_decode_tail_pred_adj():
     """Row f3: pred_adj(graph, scaled_hacky_sigmoid_l2) per graph block vs the dense reference
     formulation (loss.py:154-159,45-53); threshold 0.5 -> networkx graphs as
