@@ -54,8 +54,12 @@ struct BwdParams {
   int write_lo;              // 0: the weight-gradient GEMM reads only the hi parts, skip the lo images
 };
 
+constexpr int kBStages = 3;          // weight ring stages (the forward kernel has 4; 32 KB go to the mask bits)
+constexpr int kMaskLayers = 4;       // hidden activations per MLP whose act' sign bits fit the smem mask store
+constexpr int kMaskWords = 2 * kMaskLayers * kNS * 2;   // per epilogue thread: [mlp][layer][acc half][chunk]
+
 struct __align__(8) BwdBarriers {
-  uint64_t full[kStages], empty[kStages];
+  uint64_t full[kBStages], empty[kBStages];
   uint64_t acc_full[kNS], a_ready[kMaxNA];
   uint64_t h_full[2], h_empty[2];
   uint64_t g_full;
@@ -65,7 +69,8 @@ struct __align__(8) BwdBarriers {
 
 template <int LAT>
 constexpr size_t bwd_smem_bytes() {
-  return 1024 + (size_t)kStages * kStageBytes + 2 * 8192 /*h tiles*/ + 2 * 8192 /*g tiles*/ +
+  return 1024 + (size_t)kBStages * kStageBytes + (size_t)kMaskWords * kEpiThreads * 4 /*mask bits*/ +
+         2 * 8192 /*h tiles*/ + 2 * 8192 /*g tiles*/ +
          (kMaxLayers - 1) * 4096 + 2 * LAT * 32 + 2 * kNOut * 4 + kGatherThreads * 17 * 4 + sizeof(BwdBarriers) + 128;
 }
 
@@ -90,7 +95,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
-  uint8_t* hbuf = ring + kStages * kStageBytes;                 // [buf][hi|lo][4096]
+  uint32_t* mask_s = (uint32_t*)(ring + kBStages * kStageBytes);     // [kMaskWords][kEpiThreads] act' sign bits
+  uint8_t* hbuf = (uint8_t*)(mask_s + kMaskWords * kEpiThreads);  // [buf][hi|lo][4096]
   uint8_t* gbuf = hbuf + 2 * 8192;                              // [m][hi|lo][4096]
   uint8_t* sel = gbuf + 2 * 8192;
   uint8_t* btile = sel + (kMaxLayers - 1) * 4096;
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
   const size_t layer_stride = (size_t)p.n_tiles * 2 * img_elems;
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kBStages; ++i) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
         const uint32_t fb = smem_u32(&bars->full[stage]);
         mbar_expect_tx(fb, bytes);
         bulk_g2s(smem_u32(ring + stage * kStageBytes), src, bytes, fb);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == kBStages) { stage = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < 4; ++c) {
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
             if (c == 1) tc_commit(bar_hempty + 8 * buf);
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
           region ^= 1;
         }
         // ---- hidden chain layers: A from TMEM ----------------------------------------------------
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
                 if (kc == G::NKC - 1) tc_commit(bar_acc + 8 * ph);
               }
               __syncwarp();
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (++stage == kBStages) { stage = 0; phase ^= 1; }
             }
           }
           region ^= 1;
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
             tc_commit(bar_acc_last);
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
           region ^= 1;
         }
       }
@@ -313,6 +319,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
     int region = 0;
     const int hp4 = p.HP >> 2;
     constexpr int NCH = G::GPH;                     // 32-column chunks per accumulator half per warp
+    // act' masks: written by the forward chains' epilogue, read back by the SAME thread in the backward chains.
+    // Up to kMaskLayers hidden layers they live in shared memory (one word per 32-column chunk); deeper MLPs
+    // re-read the sign bits from the activation image in HBM.
+    const bool smem_mask = (K - 1) <= kMaskLayers;
+    uint32_t* my_mask = mask_s + (tid - 64);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       float sv[kNOut], tv[kNOut], gh[kNOut];
       const int64_t node = (int64_t)tile * kTileM + row;
@@ -329,8 +340,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
           const uint16_t* mask_img = p.act_img + ((size_t)m * (K - 1) + li) * layer_stride + (size_t)tile * 2 * img_elems;
 #pragma unroll
           for (int ph = 0; ph < kNS; ++ph) {
-            uint32_t pos[NCH];                       // bit j: a_li[row][col0 + j] > 0
-            if (bwd) {
+            uint32_t pos[NCH];                       // bit j: element 2j positive, bit 16+j: element 2j+1 positive
+            if (bwd && smem_mask) {
+#pragma unroll
+              for (int ch = 0; ch < NCH; ++ch) pos[ch] = my_mask[(((m * kMaskLayers + li) * kNS + ph) * 2 + ch) * kEpiThreads];
+            } else if (bwd) {
 #pragma unroll
               for (int ch = 0; ch < NCH; ++ch) {
                 const int col0 = ph * G::NH + grp * 32 + ch * 64;
@@ -391,6 +405,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(smem_u32(&bars->a_ready[NCH == 2 ? ph * 2 + ch : ph]));
+              if (!bwd && smem_mask) {       // sign bits of a_l for the backward chains (fp16 and bf16 share bit 15)
+                uint32_t bits = 0;
+                if (ACT == GNF_ACT_LEAKY_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) bits |= ((hi[j] >> 15) & 0x10001u) << j;
+                  bits = ~bits;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    bits |= ((hi[j] & 0xFFFFu) ? 1u : 0u) << j;
+                    bits |= ((hi[j] >> 16) ? 1u : 0u) << (16 + j);
+                  }
+                }
+                my_mask[(((m * kMaskLayers + li) * kNS + ph) * 2 + ch) * kEpiThreads] = bits;
+              }
               // image for the weight-gradient GEMM: always bf16 (tcgen05 kind::f16 needs one operand format)
               if (F16F && !bwd) {
 #pragma unroll

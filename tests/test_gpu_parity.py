@@ -349,6 +349,23 @@ def test_f2_f4_backward_through_batch_norm(bmath):
     assert np.abs(x_rec.cpu().numpy() - g.nodes).max() < 5e-5
 
 
+def test_f2_tensor_core_backward_deep_mlp():
+    """K = 7 layers: more hidden activations than the shared-memory act' mask store holds (4), so the backward
+    chains re-read the sign bits from the activation images; tensor-core vs fp32 FFMA backward."""
+    rng = np.random.default_rng(29)
+    g = H.random_batch(rng, 30, 5, 25, D=14)
+    params = O.make_params(4, 1, 14, 128, 7, last_layer_scale=0.1)
+    net = H.make_grevnet(params, 128, 7, device=DEV)
+    dg = dev_graph(g)
+    n = g.nodes.shape[0]
+    z, _ = net.f64(dg)
+    ref = net.backward_from_z(dg, z.nodes, 1.0 / n, math="fp32").double().cpu().numpy()
+    got = net.backward_from_z(dg, z.nodes, 1.0 / n, math="tc3x").double().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= BWD_TOL["tc3x"][0] * np.abs(ref).max()
+    assert float(got @ ref) / (np.linalg.norm(got) * np.linalg.norm(ref)) > 1 - 1e-6
+
+
 @pytest.mark.parametrize("bmath", ["tc3x", "bf16"])
 def test_f2_tensor_core_backward_many_tiles(bmath):
     """More tiles than SMs (every CTA walks several 128-node tiles; the weight-gradient GEMM splits
