@@ -206,8 +206,11 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"                         # keep stdout to the one JSON line
+    # stdout carries exactly ONE JSON line: whatever libraries write to fd 1 (NCCL prints its version banner there)
+    # is sent to stderr; the line itself goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -431,7 +434,7 @@ def main():
                 "gpu_launches": launches, "roofline": roof, "roofline_segment_sum": seg, "cpu_baseline": cpu, "train_step": train,
                 "effective_tflops": value * FLOPS_PER_NODE_UPDATE / 1e12}
         sys.stdout.flush()
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
