@@ -26,7 +26,6 @@
 // Reference semantics: NodeBlockGNN (gnn.py:143-156), ConcatThenMLPBlock / AggThenMLPBlock
 // (gnn.py:100-126), make_mlp_model (gnn.py:159-180), coupling update (gnn.py:320-323,335-338,
 // 353-359,366-372).
-#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -47,7 +46,6 @@ struct TcParams {
   float eps;
   double* partials;
   unsigned long long* trace;   // optional timeline of CTA 0 (gnf_debug_set_trace); null in production
-  int debug;                   // GNF_DEBUG_TC env (experiments only; results are garbage): 1 = no weight re-streaming
 };
 
 // timeline entry: [63:56] event, [55:48] m*16+l, [47:40] ph*4+kc, [39:0] clock
@@ -170,17 +168,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int issued = 0;
       auto issue = [&](const uint8_t* src, uint32_t bytes) {
         mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&bars->full[stage]);
-        if (p.debug == 1 && issued >= kStages) {
-          mbar_arrive(fb);                       // experiment: MMAs re-read whatever the stage holds
-        } else {
-          mbar_expect_tx(fb, bytes);
-          bulk_g2s(smem_u32(ring + stage * kStageBytes), src, bytes, fb);
-        }
-        ++issued;
+        mbar_expect_tx(fb, bytes);
+        bulk_g2s(smem_u32(ring + stage * kStageBytes), src, bytes, fb);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -707,11 +699,6 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   p.eps = f.d.eps;
   p.partials = ldj_partials;
   p.trace = g_trace;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("GNF_DEBUG_TC"); dbg = e ? atoi(e) : 0; }
-    p.debug = dbg;
-  }
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   *n_partials = grid;
   const bool timed = g_timer.on && g_timer.n < kMaxTimed;
