@@ -67,6 +67,8 @@ SIGNATURES = {
     "gnf_bn_moments_workspace": (_sz, [_i32]),
     "gnf_bn_moments": (C.c_int, [_p, _i64, _i32, _p, _p, _sz, _p]),
     "gnf_affine_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "gnf_bn_finalize": (C.c_int, [_p, _i32, _p, _p, C.c_double, C.c_double, _p, _p, _p, _p, _p, C.c_float, _p]),
+    "gnf_bn_backward_coef": (C.c_int, [_p, _p, _i32, _p, _p, C.c_double, C.c_double, _p, _p, _p, _p, _p]),
     "gnf_bn_backward_sums": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "gnf_bn_backward_apply": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
     "gnf_coupling_half_backward": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, C.c_double, _p,

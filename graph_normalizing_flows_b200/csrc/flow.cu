@@ -350,8 +350,10 @@ __global__ void k_bn_partial(const float* __restrict__ x, int64_t total, int hp,
   }
 }
 
-__global__ void k_bn_final(const double* __restrict__ partials, int nblocks, int h, int hp, double* __restrict__ out) {
+__global__ void k_bn_final(const double* __restrict__ partials, int nblocks, int h, int hp, double* __restrict__ out,
+                           double count) {
   const int f = threadIdx.x;
+  if (f == 0 && count >= 0.0) out[2 * h] = count;          // sums[2H] = N (ranks all-reduce it with the sums)
   if (f >= h) return;
   double a = 0.0, b = 0.0;
   for (int k = 0; k < nblocks; ++k) {
@@ -408,6 +410,68 @@ __global__ void k_bn_bwd_apply(float* __restrict__ y, float* __restrict__ g, int
   const float xh = (y[i] - coef[f]) * coef[h + f];
   g[i] = fmaf(coef[2 * h + f], g[i], fmaf(coef[3 * h + f], xh, coef[4 * h + f]));
   y[i] = fmaf(xh, coef[5 * h + f], coef[6 * h + f]);
+}
+
+// [H]-sized bookkeeping of the bijector, density direction: batch moments -> scale/shift of the normalisation, the
+// N-tiled log-det term, the moving averages, and the statistics the backward needs.  One block.
+__global__ void k_bn_finalize(const double* __restrict__ sums, int h, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, double eps, double n_local, double* __restrict__ ldj,
+                              float* __restrict__ scale_shift, double* __restrict__ stats, float* __restrict__ moving_mean,
+                              float* __restrict__ moving_var, float momentum) {
+  __shared__ double red[256];
+  const int f = threadIdx.x;
+  double term = 0.0;
+  if (f < h) {
+    const double n = sums[2 * h];
+    const double mean = sums[f] / n;
+    double var = sums[h + f] / n - mean * mean;          // biased, as tf.nn.moments
+    if (var < 0.0) var = 0.0;
+    const double g = (double)gamma[f], b = (double)beta[f];
+    const double inv = 1.0 / sqrt(var + eps);
+    const double sc = g * inv;
+    scale_shift[f] = (float)sc;
+    scale_shift[h + f] = (float)(b - mean * sc);
+    stats[f] = mean;
+    stats[h + f] = var;
+    if (f == 0) stats[2 * h] = n;
+    term = log(g) - 0.5 * log(var + eps);
+    if (momentum >= 0.f) {
+      moving_mean[f] = moving_mean[f] * momentum + (1.f - momentum) * (float)mean;
+      moving_var[f] = moving_var[f] * momentum + (1.f - momentum) * (float)var;
+    }
+  }
+  red[f] = term;
+  __syncthreads();
+  if (f == 0 && ldj) {
+    double s = 0.0;
+    for (int k = 0; k < h; ++k) s += red[k];
+    ldj[0] += n_local * s;       // scalar ildj tiled over the node axis (event_ndims=2): x N (this rank's share)
+  }
+}
+
+// backward bookkeeping: coefficient rows of gnf_bn_backward_apply and the gamma / beta gradients
+__global__ void k_bn_bwd_coef(const double* __restrict__ sums, const double* __restrict__ stats, int h,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, double eps,
+                              double loss_scale, float* __restrict__ coef, float* __restrict__ inv_gamma_out,
+                              double* __restrict__ g_gamma, double* __restrict__ g_beta) {
+  const int f = threadIdx.x;
+  if (f >= h) return;
+  const double g = (double)gamma[f], b = (double)beta[f];
+  if (!sums) {                      // phase 0: only 1/gamma (input of gnf_bn_backward_sums)
+    inv_gamma_out[f] = (float)(1.0 / g);
+    return;
+  }
+  const double n = stats[2 * h], mean = stats[f], var = stats[h + f];
+  const double s = sqrt(var + eps), s1 = sums[f], s2 = sums[h + f];
+  coef[f] = (float)b;
+  coef[h + f] = (float)(1.0 / g);
+  coef[2 * h + f] = (float)(g / s);
+  coef[3 * h + f] = (float)((loss_scale - g * s2 / n) / s);
+  coef[4 * h + f] = (float)(-g * s1 / (n * s));
+  coef[5 * h + f] = (float)s;
+  coef[6 * h + f] = (float)mean;
+  g_beta[f] += s1;
+  g_gamma[f] += s2 - loss_scale * n / g;
 }
 
 // ---- a8: log-prob ------------------------------------------------------------------------------
@@ -1065,7 +1129,32 @@ extern "C" int gnf_bn_moments(const float* x, int64_t n, int32_t hh, double* sum
   if (blocks < 1) blocks = 1;
   k_bn_partial<<<blocks, tpb, 2 * tpb * sizeof(double), stream>>>(x, total, hp, (double*)ws);
   GNF_LAUNCH_CHECK();
-  k_bn_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, hh, hp, sums);
+  k_bn_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, hh, hp, sums, (double)n);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_bn_finalize(const double* sums, int32_t hh, const float* gamma, const float* beta, double eps,
+                               double n_local, double* ldj_accum, float* scale_shift, double* stats,
+                               float* moving_mean, float* moving_var, float momentum, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(sums && gamma && beta && scale_shift && stats && hh >= 1 && hh <= 256, GNF_EINVAL,
+              "gnf_bn_finalize: bad argument (H <= 256)");
+  GNF_REQUIRE(momentum < 0.f || (moving_mean && moving_var), GNF_EINVAL, "gnf_bn_finalize: null moving statistics");
+  k_bn_finalize<<<1, 256, 0, stream>>>(sums, hh, gamma, beta, eps, n_local, ldj_accum, scale_shift, stats, moving_mean,
+                                       moving_var, momentum);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_bn_backward_coef(const double* sums, const double* stats, int32_t hh, const float* gamma,
+                                    const float* beta, double eps, double loss_scale, float* coef, float* inv_gamma,
+                                    double* g_gamma, double* g_beta, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(gamma && beta && hh >= 1 && hh <= 256, GNF_EINVAL, "gnf_bn_backward_coef: bad argument (H <= 256)");
+  GNF_REQUIRE(sums ? (stats && coef && g_gamma && g_beta) : (inv_gamma != nullptr), GNF_EINVAL,
+              "gnf_bn_backward_coef: null pointer");
+  k_bn_bwd_coef<<<1, 256, 0, stream>>>(sums, stats, hh, gamma, beta, eps, loss_scale, coef, inv_gamma, g_gamma, g_beta);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }
@@ -1084,7 +1173,7 @@ extern "C" int gnf_bn_backward_sums(const float* y, const float* g, int64_t n, i
   if (blocks < 1) blocks = 1;
   k_bn_bwd_partial<<<blocks, tpb, 2 * tpb * sizeof(double), stream>>>(y, g, beta, inv_gamma, total, hh, hp, (double*)ws);
   GNF_LAUNCH_CHECK();
-  k_bn_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, hh, hp, sums);
+  k_bn_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, hh, hp, sums, -1.0);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }

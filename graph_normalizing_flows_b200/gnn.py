@@ -559,35 +559,28 @@ class GRevNet(nn.Module):
     # -- a9: the batch-norm variant, half step by half step ---------------------------------------
     def _bn_inverse_(self, xp, n_local, half, i, ldj):
         """bn.inverse + bn.inverse_log_det_jacobian(x, 2) on a planar half, in place (gnn.py:310-313):
-        batch statistics over ALL nodes of the batch (all ranks when sharded)."""
+        batch statistics over ALL nodes of the batch (all ranks when sharded).  Three launches on the device
+        (moments, [H]-sized bookkeeping, affine) and, when sharded, one all-reduce of the [2H+1] sums."""
         lib, H, dev = self._flow.lib, self.node_embedding_dim // 2, xp.device
+        stream = _lib.stream_ptr(dev)
         sums = torch.empty(2 * H + 1, dtype=torch.float64, device=dev)
         wsb = lib.gnf_bn_moments_workspace(H)
         ws = _lib.workspace(wsb, dev)
-        _lib.check(lib.gnf_bn_moments(_lib.ptr(xp), n_local, H, _lib.ptr(sums), _lib.ptr(ws), wsb,
-                                      _lib.stream_ptr(dev)), "gnf_bn_moments")
-        sums[2 * H] = float(n_local)
+        _lib.check(lib.gnf_bn_moments(_lib.ptr(xp), n_local, H, _lib.ptr(sums), _lib.ptr(ws), wsb, stream), "gnf_bn_moments")
         dist = torch.distributed
         if self.bn_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.bn_group) > 1:
             dist.all_reduce(sums, group=self.bn_group)                   # the extra [2H+1] all-reduce of row a9
-        n = sums[2 * H]
-        mean = sums[:H] / n
-        var = (sums[H:2 * H] / n - mean * mean).clamp_(min=0.0)         # biased, as tf.nn.moments
-        gamma = self.bn_gamma.detach()[half, i].double()
-        beta = self.bn_beta.detach()[half, i].double()
-        inv = torch.rsqrt(var + self.bn_epsilon)
-        scale = gamma * inv
-        shift = beta - mean * scale
-        # scalar ildj tiled over the node axis (event_ndims=2 vs forward_min_event_ndims=1): x N (local share)
-        ldj += float(n_local) * (torch.log(gamma) - 0.5 * torch.log(var + self.bn_epsilon)).sum()
-        self._bn_saved[(half, i)] = (mean, var, n)        # the backward undoes the bijector with these
-        sc, sh = scale.float().contiguous(), shift.float().contiguous()
-        _lib.check(lib.gnf_affine_rows(_lib.ptr(xp), n_local, H, _lib.ptr(sc), _lib.ptr(sh), _lib.stream_ptr(dev)),
+        scale_shift = torch.empty(2 * H, dtype=torch.float32, device=dev)
+        stats = torch.empty(2 * H + 1, dtype=torch.float64, device=dev)  # mean, var, N: the backward undoes the bijector with these
+        gamma, beta = self.bn_gamma.detach()[half, i], self.bn_beta.detach()[half, i]
+        mm, mv = self.bn_moving_mean[half, i], self.bn_moving_var[half, i]
+        _lib.check(lib.gnf_bn_finalize(_lib.ptr(sums), H, _lib.ptr(gamma), _lib.ptr(beta), float(self.bn_epsilon),
+                                       float(n_local), _lib.ptr(ldj), _lib.ptr(scale_shift), _lib.ptr(stats),
+                                       _lib.ptr(mm), _lib.ptr(mv),
+                                       float(self.bn_momentum) if self.bn_update_moving else -1.0, stream), "gnf_bn_finalize")
+        self._bn_saved[(half, i)] = stats
+        _lib.check(lib.gnf_affine_rows(_lib.ptr(xp), n_local, H, _lib.ptr(scale_shift), _lib.ptr(scale_shift[H:]), stream),
                    "gnf_affine_rows")
-        if self.bn_update_moving:
-            m = self.bn_momentum
-            self.bn_moving_mean[half, i].mul_(m).add_((1 - m) * mean.float())
-            self.bn_moving_var[half, i].mul_(m).add_((1 - m) * var.float())
 
     def _bn_forward_(self, zp, n_local, half, i):
         """bn.forward = de-normalise with the MOVING statistics (gnn.py:356-358,369-371)."""
@@ -721,21 +714,24 @@ class GRevNet(nn.Module):
         dist = torch.distributed
         sync = self.bn_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.bn_group) > 1
 
+        coef = torch.empty(7 * H, dtype=torch.float32, device=dev)
+        inv_gamma = torch.empty(H, dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * H, dtype=torch.float64, device=dev)
+
         def bn_backward(half, i):
-            mean, var, n_glob = self._bn_saved[(half, i)]
-            gamma, beta = self.bn_gamma.detach()[half, i].double(), self.bn_beta.detach()[half, i].double()
-            s = torch.sqrt(var + self.bn_epsilon)
-            sums = torch.empty(2 * H, dtype=torch.float64, device=dev)
-            bt, ig = beta.float().contiguous(), (1.0 / gamma).float().contiguous()
-            _lib.check(lib.gnf_bn_backward_sums(_lib.ptr(x[half]), _lib.ptr(g[half]), n, H, _lib.ptr(bt), _lib.ptr(ig),
+            stats = self._bn_saved[(half, i)]
+            gamma, beta = self.bn_gamma.detach()[half, i], self.bn_beta.detach()[half, i]
+            _lib.check(lib.gnf_bn_backward_coef(None, None, H, _lib.ptr(gamma), _lib.ptr(beta), float(self.bn_epsilon),
+                                                float(loss_scale), None, _lib.ptr(inv_gamma), None, None, stream),
+                       "gnf_bn_backward_coef")
+            _lib.check(lib.gnf_bn_backward_sums(_lib.ptr(x[half]), _lib.ptr(g[half]), n, H, _lib.ptr(beta), _lib.ptr(inv_gamma),
                                                 _lib.ptr(sums), _lib.ptr(bws), bwsb, stream), "gnf_bn_backward_sums")
             if sync:
                 dist.all_reduce(sums, group=self.bn_group)
-            s1, s2 = sums[:H], sums[H:]
-            g_beta[half, i] += s1
-            g_gamma[half, i] += s2 - float(loss_scale) * n_glob / gamma
-            coef = torch.stack([beta, 1.0 / gamma, gamma / s, (float(loss_scale) - gamma * s2 / n_glob) / s,
-                                -gamma * s1 / (n_glob * s), s, mean]).float().contiguous()
+            _lib.check(lib.gnf_bn_backward_coef(_lib.ptr(sums), _lib.ptr(stats), H, _lib.ptr(gamma), _lib.ptr(beta),
+                                                float(self.bn_epsilon), float(loss_scale), _lib.ptr(coef), None,
+                                                _lib.ptr(g_gamma[half, i]), _lib.ptr(g_beta[half, i]), stream),
+                       "gnf_bn_backward_coef")
             _lib.check(lib.gnf_bn_backward_apply(_lib.ptr(x[half]), _lib.ptr(g[half]), n, H, _lib.ptr(coef), stream),
                        "gnf_bn_backward_apply")
 

@@ -198,12 +198,20 @@ int gnf_merge_halves(const float* x0, const float* x1, int64_t n_nodes, int32_t 
 
 /* a9  pieces of tfb.BatchNormalization (gnn.py:260-263,310-313,325-328,356-358,369-371) on a
  * planar half x [N, HP]:
- *   gnf_bn_moments : sums[0:H] = sum_n x[n,f], sums[H:2H] = sum_n x[n,f]^2  (device double[2H];
- *                    sums, not moments, so that ranks can all-reduce them before dividing)
+ *   gnf_bn_moments : sums[0:H] = sum_n x[n,f], sums[H:2H] = sum_n x[n,f]^2, sums[2H] = n_nodes  (device
+ *                    double[2H+1]; sums, not moments, so that ranks can all-reduce them before dividing)
+ *   gnf_bn_finalize: the [H]-sized bookkeeping in one launch: scale_shift[0:H] = gamma/sqrt(var+eps),
+ *                    scale_shift[H:2H] = beta - mean*scale (inputs of gnf_affine_rows); *ldj_accum +=
+ *                    n_local * sum_f(log gamma - 1/2 log(var+eps)) (the N-tiled ildj, this rank's share);
+ *                    stats = {mean[H], var[H], N} (double, kept for the backward); moving statistics updated
+ *                    with `momentum` (< 0: left alone)
  *   gnf_affine_rows: x[n,f] <- x[n,f] * scale[f] + shift[f]  (normalise / de-normalise) */
 size_t gnf_bn_moments_workspace(int32_t h);
 int gnf_bn_moments(const float* x, int64_t n_nodes, int32_t h, double* sums,
                    void* workspace, size_t workspace_bytes, void* stream);
+int gnf_bn_finalize(const double* sums, int32_t h, const float* gamma, const float* beta, double eps,
+                    double n_local, double* ldj_accum, float* scale_shift, double* stats,
+                    float* moving_mean, float* moving_var, float momentum, void* stream);
 int gnf_affine_rows(float* x, int64_t n_nodes, int32_t h, const float* scale, const float* shift, void* stream);
 /* Backward of the bijector in training mode (batch statistics depend on x), for loss = -loss_scale * log_prob_xs:
  *   gnf_bn_backward_sums : sums[0:H] = sum_n G_y[n,f], sums[H:2H] = sum_n G_y[n,f] * xhat[n,f],
@@ -213,6 +221,12 @@ int gnf_affine_rows(float* x, int64_t n_nodes, int32_t h, const float* scale, co
  *                          g <- c1*g + c2*xhat + c3   (c1 = gamma/s, c2 = (loss_scale - gamma*S2/N)/s, c3 = -gamma*S1/(N*s),
  *                          s = sqrt(var + eps): the batch-statistics terms and the -N/2 log(var+eps) log-det term)
  *                          y <- xhat*s + mu           (the bijector undone with the statistics saved by the forward) */
+/* gnf_bn_backward_coef: with sums == NULL writes inv_gamma[H] = 1/gamma (input of gnf_bn_backward_sums); with the
+ * (all-reduced) sums it writes the 7 coefficient rows of gnf_bn_backward_apply from stats = {mean, var, N} and
+ * accumulates dL/dgamma = S2 - loss_scale*N/gamma, dL/dbeta = S1 into g_gamma / g_beta (device double[H]). */
+int gnf_bn_backward_coef(const double* sums, const double* stats, int32_t h, const float* gamma, const float* beta,
+                         double eps, double loss_scale, float* coef, float* inv_gamma, double* g_gamma,
+                         double* g_beta, void* stream);
 int gnf_bn_backward_sums(const float* y, const float* g, int64_t n_nodes, int32_t h, const float* beta,
                          const float* inv_gamma, double* sums, void* workspace, size_t workspace_bytes, void* stream);
 int gnf_bn_backward_apply(float* y, float* g, int64_t n_nodes, int32_t h, const float* coef, void* stream);
