@@ -18,7 +18,7 @@ GNF_OK = 0
 GNF_EINVAL, GNF_ECUDA, GNF_EUNSUPPORTED, GNF_EWORKSPACE = -1, -2, -3, -4
 AGG = {"sum": 0, "mean": 1}
 BLOCK = {"concat": 0, "agg_then": 1, "dm_attn": 2}
-ATTN_CONCAT, ATTN_RESIDUAL, ATTN_KQ_DIV = 1, 2, 4
+ATTN_CONCAT, ATTN_RESIDUAL, ATTN_KQ_DIV, ATTN_LAYER_NORM = 1, 2, 4, 8
 ACT = {"leaky_relu": 0, "relu": 1}
 MATH = {"fp32": 0, "tc3x": 1, "bf16": 2, "tc3x_bf16": 3, "tc2x": 4}
 

@@ -393,6 +393,38 @@ __global__ void k_attn_gxa(float* __restrict__ gxa, int h, int hp, const float* 
   gxa[node * hp + f] += v;
 }
 
+// backward of snt.LayerNorm (gnn.py:554-556) per node row: gy (in: dL/d LN output) becomes dL/d(pre-LN input);
+// t = gy * xhat is left for the gamma gradient (column sums), beta's gradient is the column sum of gy (taken before).
+__global__ void k_layer_norm_bwd(const float* __restrict__ pre, float* __restrict__ gy, float* __restrict__ t, int64_t n,
+                                 int h, int hp, int gp, const float* __restrict__ gb) {
+  int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= n) return;
+  const float* r = pre + node * hp;
+  float* g = gy + node * gp;
+  float* tr = t + node * gp;
+  float mean = 0.f;
+  for (int f = 0; f < h; ++f) mean += r[f];
+  mean /= (float)h;
+  float var = 0.f;
+  for (int f = 0; f < h; ++f) var += (r[f] - mean) * (r[f] - mean);
+  var /= (float)h;
+  const float inv = 1.f / sqrtf(var + 1e-5f);
+  float m1 = 0.f, m2 = 0.f;
+  for (int f = 0; f < h; ++f) {
+    const float xh = (r[f] - mean) * inv, a = g[f] * gb[f];
+    m1 += a;
+    m2 += a * xh;
+  }
+  m1 /= (float)h;
+  m2 /= (float)h;
+  for (int f = 0; f < h; ++f) {
+    const float xh = (r[f] - mean) * inv, gyf = g[f];
+    tr[f] = gyf * xh;
+    g[f] = inv * (gyf * gb[f] - m1 - xh * m2);
+  }
+  for (int f = h; f < gp; ++f) tr[f] = 0.f;
+}
+
 __global__ void k_add_rows_p(float* __restrict__ out, const float* __restrict__ x, int h, int hp, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * h) return;
@@ -407,6 +439,7 @@ struct BwdWs {
   // f1 attention block: per-GNN forward intermediates, shared gradient temporaries
   AttnBufs ab[2];
   float *hbuf2, *gproj, *gatt, *gkeys, *gqueries, *gvh, *gv, *gxq, *stats;
+  float *preln[2], *lnt;       // GNF_ATTN_LAYER_NORM: pre-LayerNorm GNN outputs, gy * xhat
   size_t bytes;
 };
 
@@ -456,6 +489,9 @@ BwdWs carve_bwd(const Flow& f, int64_t n, void* base) {
     w.gv = take(nn * f.v_pad * 4);
     w.gxq = take(nn * f.hp8 * 4);
     w.stats = take(nn * f.heads * 3 * 4);
+    w.preln[0] = take(nn * f.HP * 4);
+    w.preln[1] = take(nn * f.HP * 4);
+    w.lnt = take(nn * gp * 4);
     const size_t a1 = (size_t)f.hp8 * f.qk_pad, a2 = (size_t)f.hv_pad * f.cho_pad;
     if (a1 > part_elems) part_elems = a1;
     if (a2 > part_elems) part_elems = a2;
@@ -664,11 +700,30 @@ static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const f
         k_add_rows_p<<<eb, 256, 0, stream>>>(outs[m], xa, H, HP, n);
         GNF_LAUNCH_CHECK();
       }
+      if (f.attn_flags & GNF_ATTN_LAYER_NORM) {                                   // gnn.py:554-556
+        GNF_CUDA(cudaMemcpyAsync(w.preln[m], outs[m], (size_t)n * HP * 4, cudaMemcpyDeviceToDevice, stream));
+        rc = fwd_layer_norm(f, mm[m], outs[m], n, stream);
+        if (rc) return rc;
+      }
     }
     k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
     GNF_LAUNCH_CHECK();
     float* gtop[2] = {w.gs, w.gt};
     for (int m = 0; m < 2; ++m) {
+      if (f.attn_flags & GNF_ATTN_LAYER_NORM) {
+        float* gln = grads + (int64_t)mm[m] * f.params_per_mlp + f.ln_off;      // gamma[H] then beta[H]
+        k_db<<<kSplit, 256, 0, stream>>>(gtop[m], gp, n, gp, w.part);                                  // d beta
+        GNF_LAUNCH_CHECK();
+        k_reduce_split<<<1, 256, 0, stream>>>(w.part, kSplit, 1, gp, 1, H, gln + H);
+        GNF_LAUNCH_CHECK();
+        k_layer_norm_bwd<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(w.preln[m], gtop[m], w.lnt, n, H, HP, gp,
+                                                                        f.wln + (int64_t)mm[m] * 2 * HP);
+        GNF_LAUNCH_CHECK();
+        k_db<<<kSplit, 256, 0, stream>>>(w.lnt, gp, n, gp, w.part);                                    // d gamma
+        GNF_LAUNCH_CHECK();
+        k_reduce_split<<<1, 256, 0, stream>>>(w.part, kSplit, 1, gp, 1, H, gln);
+        GNF_LAUNCH_CHECK();
+      }
       rc = mlp_backward(f, mm[m], w, m, hin[m], gtop[m], gp, n, 0, grads, stream);
       if (rc) return rc;
       rc = attn_backward(f, mm[m], w, m, gtop[m], gp, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, ga,

@@ -85,6 +85,8 @@ struct Flow {
   float* wattn = nullptr;
   int64_t wattn_per_mlp = 0, wq_off = 0, wk_off = 0, wv_off = 0, wo_off = 0;
   float* zeros = nullptr;                 // zero bias for the bias-free projections
+  float* wln = nullptr;                   // LayerNorm gamma|beta per GNN: [n_mlps][2*HP] (GNF_ATTN_LAYER_NORM)
+  int64_t ln_off = 0;                     // offset of gamma inside one GNN's flat parameters
   float* wattnT = nullptr;                // transposed projections for the backward dX GEMMs: W^T [out_pad, in_pad]
   int64_t wattnT_per_mlp = 0, wqT_off = 0, wkT_off = 0, wvT_off = 0, woT_off = 0;
   // tensor-core packed weights (two images: fp16 and bf16 element type), per MLP a stream of
@@ -110,6 +112,7 @@ struct AttnBufs {      // per-GNN intermediates of the f1 attention block (all [
 };
 int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
                    const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream);
+int fwd_layer_norm(const Flow& f, int mlp, float* x, int64_t n, cudaStream_t stream);
 int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                   float* hbuf, cudaStream_t stream);
 

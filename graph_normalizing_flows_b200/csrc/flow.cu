@@ -192,6 +192,29 @@ __global__ void k_add_rows(float* __restrict__ out, const float* __restrict__ x,
   out[node * hp + f] = __fadd_rn(out[node * hp + f], x[node * hp + f]);
 }
 
+// snt.LayerNorm over the H features of every node row, in place (gnn.py:554-556): eps 1e-5 [upstream]
+__global__ void k_layer_norm(float* __restrict__ x, int64_t n, int h, int hp, const float* __restrict__ gb) {
+  int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (node >= n) return;
+  float* r = x + node * hp;
+  float mean = 0.f;
+  for (int f = 0; f < h; ++f) mean += r[f];
+  mean /= (float)h;
+  float var = 0.f;
+  for (int f = 0; f < h; ++f) var += (r[f] - mean) * (r[f] - mean);
+  var /= (float)h;
+  const float inv = 1.f / sqrtf(var + 1e-5f);
+  for (int f = 0; f < h; ++f) r[f] = (r[f] - mean) * inv * gb[f] + gb[hp + f];
+}
+
+__global__ void k_pack_ln(const float* __restrict__ src, int h, int hp, float* __restrict__ dst) {
+  int i = threadIdx.x;
+  if (i < 2 * hp) {
+    const int which = i / hp, f = i - which * hp;
+    dst[i] = f < h ? src[which * h + f] : 0.f;
+  }
+}
+
 __global__ void k_pack_mat(const float* __restrict__ src, int in, int out, int in_pad, int out_pad,
                            float* __restrict__ w) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -623,6 +646,7 @@ int gnn_forward32(const Flow& f, int mlp, bool build_agg, const float* xa, int64
     k_add_rows<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(out, xa, f.H, f.HP, n);
     GNF_LAUNCH_CHECK();
   }
+  if (f.attn && (f.attn_flags & GNF_ATTN_LAYER_NORM)) return fwd_layer_norm(f, mlp, out, n, stream);   // gnn.py:554-556
   return GNF_OK;
 }
 
@@ -713,6 +737,12 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   return GNF_OK;
 }
 
+int fwd_layer_norm(const Flow& f, int mlp, float* x, int64_t n, cudaStream_t stream) {
+  k_layer_norm<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(x, n, f.H, f.HP, f.wln + (int64_t)mlp * 2 * f.HP);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
 int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                   float* hbuf, cudaStream_t stream) {
   k_agg_input<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(
@@ -781,7 +811,8 @@ static int64_t params_per_mlp(const gnf_flow_desc* d) {
     in = (d->attn_flags & GNF_ATTN_CONCAT) ? H + d->attn_out_dim : d->attn_out_dim;
   }
   const int64_t L = d->latent_dim, K = d->num_layers;
-  return attn + in * L + L + (K - 2) * (L * L + L) + L * H + H;
+  const int64_t ln = (d->block == GNF_BLOCK_DM_ATTN && (d->attn_flags & GNF_ATTN_LAYER_NORM)) ? 2 * H : 0;
+  return attn + in * L + L + (K - 2) * (L * L + L) + L * H + H + ln;
 }
 
 extern "C" int64_t gnf_flow_param_count(const gnf_flow_desc* d) {
@@ -820,6 +851,7 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
     f.mlp_off = 2ll * f.H * f.heads * f.kq + (int64_t)f.H * f.vd + (int64_t)f.heads * f.vd * f.cho;
   }
   f.in_pad = pad_to(f.in_dim, 8);
+  if (f.attn && (f.attn_flags & GNF_ATTN_LAYER_NORM)) f.ln_off = params_per_mlp(d) - 2 * f.H;
   f.L = d->latent_dim;
   f.K = d->num_layers;
   f.n_mlps = 4 * (d->weight_sharing ? 1 : d->num_timesteps);
@@ -859,6 +891,7 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
   if (e == cudaSuccess) e = cudaMemset(f.zeros, 0, 8192 * 4);
   if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wattn, (size_t)f.n_mlps * f.wattn_per_mlp * 4);
   if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wattnT, (size_t)f.n_mlps * f.wattnT_per_mlp * 4);
+  if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wln, (size_t)f.n_mlps * 2 * f.HP * 4);
   if (e != cudaSuccess) {
     delete h;
     set_error("gnf_flow_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -888,6 +921,7 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.zeros);
   cudaFree(h->f.wattn);
   cudaFree(h->f.wattnT);
+  cudaFree(h->f.wln);
   cudaFree(h->f.wtc[0]);
   cudaFree(h->f.wtc[1]);
   cudaFree(h->f.btc);
@@ -934,6 +968,10 @@ extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* strea
       GNF_LAUNCH_CHECK();
       packT(src + 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, f.hv_pad, f.cho_pad, wt + f.woT_off);
       GNF_LAUNCH_CHECK();
+      if (f.attn_flags & GNF_ATTN_LAYER_NORM) {
+        k_pack_ln<<<1, 64, 0, stream>>>(src + f.ln_off, f.H, f.HP, f.wln + (int64_t)m * 2 * f.HP);
+        GNF_LAUNCH_CHECK();
+      }
       src += f.mlp_off;
     }
     float* dst = f.w32 + (int64_t)m * f.w32_per_mlp;

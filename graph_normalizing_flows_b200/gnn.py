@@ -337,23 +337,22 @@ class DMSelfAttentionMLP(NodeBlockGNN):
     (run_grevnet.py:56, train_grevnet_with_data.py:42): bias-free q/k/v projections, multi-head
     edge-softmax attention over each receiver's in-edges (DMSelfAttention, gnn.py:385-477; the value
     projection is shared by all heads, gnn.py:528), head-concat projection to
-    `concat_heads_output_dim`, concat with the input, MLP.  fp32 kernels (SURVEY §8 row f1);
-    layer_norm=True is not supported."""
+    `concat_heads_output_dim`, concat with the input, MLP, optional residual and snt.LayerNorm
+    (gamma = 1, beta = 0 at init, eps 1e-5 [upstream]).  fp32 kernels."""
 
     def __init__(self, kq_dim, v_dim, make_mlp_fn, num_heads=8, concat_heads_output_dim=20, concat=True,
                  residual=False, layer_norm=False, kq_dim_division=False, name="dm_self_attention"):
         nn.Module.__init__(self)
-        if layer_norm:
-            raise NotImplementedError("dm_self_attn_gnn(layer_norm=True) (snt.LayerNorm, gnn.py:554-556) is not built")
         self.name = name
         self.kq_dim, self.v_dim, self.num_heads = int(kq_dim), int(v_dim), int(num_heads)
         self.concat_heads_output_dim = int(concat_heads_output_dim)
-        self.concat, self.residual, self.layer_norm = bool(concat), bool(residual), False
+        self.concat, self.residual, self.layer_norm = bool(concat), bool(residual), bool(layer_norm)
         self.kq_dim_division = bool(kq_dim_division)
         self._mlp = make_mlp_fn()
         self._flow = None
         self.params = None
         self.wq = self.wk = self.wv = self.wo = None
+        self.ln_gamma = self.ln_beta = None
 
     @property
     def mlp(self) -> MLP:
@@ -361,11 +360,11 @@ class DMSelfAttentionMLP(NodeBlockGNN):
 
     def config(self):
         return ("dm_attn", self.kq_dim, self.v_dim, self.num_heads, self.concat_heads_output_dim, self.concat,
-                self.residual, self.kq_dim_division) + self.mlp.signature()
+                self.residual, self.kq_dim_division, self.layer_norm) + self.mlp.signature()
 
     def flow_kwargs(self):
         flags = (_lib.ATTN_CONCAT if self.concat else 0) | (_lib.ATTN_RESIDUAL if self.residual else 0) | \
-                (_lib.ATTN_KQ_DIV if self.kq_dim_division else 0)
+                (_lib.ATTN_KQ_DIV if self.kq_dim_division else 0) | (_lib.ATTN_LAYER_NORM if self.layer_norm else 0)
         return dict(block="dm_attn", agg="sum", eps=1.0,
                     attn=dict(num_heads=self.num_heads, kq_dim=self.kq_dim, v_dim=self.v_dim,
                               out_dim=self.concat_heads_output_dim, flags=flags))
@@ -378,7 +377,8 @@ class DMSelfAttentionMLP(NodeBlockGNN):
         return [(half_dim, qk), (half_dim, qk), (half_dim, self.v_dim), (hv, self.concat_heads_output_dim)]
 
     def gnn_param_count(self, half_dim):
-        return sum(i * o for i, o in self._attn_shapes(half_dim)) + self.mlp.param_count(self.mlp_input_dim(half_dim))
+        return sum(i * o for i, o in self._attn_shapes(half_dim)) + self.mlp.param_count(self.mlp_input_dim(half_dim)) + \
+            (2 * half_dim if self.layer_norm else 0)
 
     def bind_params(self, half_dim, flat, generator=None, init=True):
         self._bound = flat
@@ -395,7 +395,15 @@ class DMSelfAttentionMLP(NodeBlockGNN):
                         _truncated_normal_(w, 1.0 / math.sqrt(i), generator)
             mats.append(w)
         self.wq, self.wk, self.wv, self.wo = mats
-        return off + self.mlp.bind(self.mlp_input_dim(half_dim), flat[off:], generator=generator, init=init)
+        off += self.mlp.bind(self.mlp_input_dim(half_dim), flat[off:], generator=generator, init=init)
+        if self.layer_norm:                      # snt.LayerNorm variables, created after the MLP's (gnn.py:554-556)
+            self.ln_gamma, self.ln_beta = flat[off:off + half_dim], flat[off + half_dim:off + 2 * half_dim]
+            if init:
+                with torch.no_grad():
+                    self.ln_gamma.fill_(1.0)
+                    self.ln_beta.zero_()
+            off += 2 * half_dim
+        return off
 
 
 def dm_self_attn_gnn(kq_dim, v_dim, make_mlp_fn, num_heads, concat_heads_output_dim, concat=True, residual=False,

@@ -49,7 +49,7 @@ flags.DEFINE_integer("attn_num_heads", 8, "")
 flags.DEFINE_integer("attn_concat_heads_output_dim", 80, "")
 flags.DEFINE_bool("attn_concat", True, "")
 flags.DEFINE_bool("attn_residual", False, "")
-flags.DEFINE_bool("attn_layer_norm", False, "snt.LayerNorm on the GNN output: not built (raises).")
+flags.DEFINE_bool("attn_layer_norm", False, "snt.LayerNorm on the GNN output.")
 # Training params (:82-109)
 flags.DEFINE_bool("use_batch_norm", True, "TFP batch-norm bijector between half steps (reference default).")
 flags.DEFINE_string("dataset", "mog_4", "Which dataset to use.")

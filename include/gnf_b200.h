@@ -51,6 +51,8 @@ extern "C" {
 #define GNF_ATTN_CONCAT    1   /* concat=True   gnn.py:547-548 */
 #define GNF_ATTN_RESIDUAL  2   /* residual=True gnn.py:551-552 */
 #define GNF_ATTN_KQ_DIV    4   /* kq_dim_division=True gnn.py:462-464 */
+#define GNF_ATTN_LAYER_NORM 8  /* layer_norm=True: snt.LayerNorm on the GNN output (gnn.py:554-556), eps 1e-5, per-GNN
+                                  gamma[H], beta[H] appended to the GNN's parameters after the MLP */
 /* MLP activations: tf.nn.leaky_relu alpha=0.2 (run_grevnet.py:158) / tf.nn.relu (gnn.py:162) */
 #define GNF_ACT_LEAKY_RELU 0
 #define GNF_ACT_RELU       1
@@ -122,7 +124,8 @@ int gnf_gather_segment_sum(const float* x, int32_t h, const int32_t* rowptr,
  * each MLP as  W0[in,L] b0[L]  W1[L,L] b1[L] ... W_{K-1}[L,H] b_{K-1}[H],  row-major,
  * Sonnet Linear convention y = x @ W + b;  in = D (concat) or D/2 (agg_then), H = D/2.
  * GNF_BLOCK_DM_ATTN: every GNN is  Wq[H, heads*kq]  Wk[H, heads*kq]  Wv[H, v]  Wo[heads*v, out]
- * (all without bias, gnn.py:509-545) followed by its MLP with in = H + out (concat) or out.
+ * (all without bias, gnn.py:509-545) followed by its MLP with in = H + out (concat) or out, and, with
+ * GNF_ATTN_LAYER_NORM, the LayerNorm gamma[H] beta[H].
  * ------------------------------------------------------------------------------------------ */
 typedef struct gnf_flow_desc {
   int32_t num_timesteps;       /* T   GRevNet(num_timesteps)       gnn.py:276 */

@@ -168,6 +168,10 @@ def dm_self_attention_mlp(nodes, senders, receivers, gnn, cfg):
     new_nodes = mlp_forward(new_nodes, gnn["mlp"], cfg["act"])
     if cfg["residual"]:
         new_nodes = new_nodes + nodes                                # gnn.py:551-552
+    if cfg.get("layer_norm"):                                        # snt.LayerNorm, gnn.py:554-556 [upstream: eps 1e-5,
+        mean = new_nodes.mean(axis=1, keepdims=True)                 #  moments over the last axis, gamma * xhat + beta]
+        var = ((new_nodes - mean) ** 2).mean(axis=1, keepdims=True)
+        new_nodes = (new_nodes - mean) / np.sqrt(var + dt.type(1e-5)) * gnn["ln_gamma"] + gnn["ln_beta"]
     return new_nodes
 
 
@@ -375,6 +379,9 @@ def make_params(seed, T, D, latent_dim=256, num_layers=5, agg="sum", block="conc
             g = {"wq": xavier(h, qk), "wk": xavier(h, qk), "wv": xavier(h, attn["v_dim"]),
                  "wo": truncated_normal(rng, (hv, attn["out_dim"]), 1.0 / math.sqrt(hv), dtype)}
             g["mlp"] = init_mlp(rng, in_dim, latent_dim, h, num_layers, bias_init_stddev, last_layer_scale, dtype)
+            if attn.get("layer_norm"):           # init is gamma = 1, beta = 0; perturbed so that tests see them
+                g["ln_gamma"] = (1.0 + 0.1 * rng.standard_normal(h)).astype(dtype)
+                g["ln_beta"] = (0.1 * rng.standard_normal(h)).astype(dtype)
             return g
         return init_mlp(rng, in_dim, latent_dim, h, num_layers, bias_init_stddev,
                         last_layer_scale, dtype)
@@ -394,7 +401,7 @@ def make_params(seed, T, D, latent_dim=256, num_layers=5, agg="sum", block="conc
 def cast_params(params, dtype):
     def c(m):
         if isinstance(m, dict):
-            out = {k: m[k].astype(dtype) for k in ("wq", "wk", "wv", "wo")}
+            out = {k: m[k].astype(dtype) for k in ("wq", "wk", "wv", "wo", "ln_gamma", "ln_beta") if k in m}
             out["mlp"] = [(w.astype(dtype), b.astype(dtype)) for (w, b) in m["mlp"]]
             return out
         return [(w.astype(dtype), b.astype(dtype)) for (w, b) in m]

@@ -21,7 +21,7 @@ def params_to_torch(params, dtype=torch.float32):
 
     def c(m):
         if isinstance(m, dict):                  # dm_self_attn GNN: projections + MLP (oracle/gnf_oracle.py)
-            out = {k: t(m[k]) for k in ("wq", "wk", "wv", "wo")}
+            out = {k: t(m[k]) for k in ("wq", "wk", "wv", "wo", "ln_gamma", "ln_beta") if k in m}
             out["mlp"] = [(t(w), t(b)) for (w, b) in m["mlp"]]
             return out
         return [(t(w), t(b)) for (w, b) in m]
@@ -66,6 +66,10 @@ def _dm_attn(nodes, senders, receivers, gnn, cfg):
     new_nodes = _mlp(new_nodes, gnn["mlp"], cfg["act"])
     if cfg["residual"]:
         new_nodes = new_nodes + nodes
+    if cfg.get("layer_norm"):
+        mean = new_nodes.mean(1, keepdim=True)
+        var = ((new_nodes - mean) ** 2).mean(1, keepdim=True)
+        new_nodes = (new_nodes - mean) / torch.sqrt(var + 1e-5) * gnn["ln_gamma"] + gnn["ln_beta"]
     return new_nodes
 
 
@@ -152,15 +156,20 @@ def loss_and_grads(nodes, senders, receivers, params, scale=1.0, dtype=torch.flo
         for half in range(2):
             mlps = [p[which][half]] if p["weight_sharing"] else p[which][half]
             for mlp in mlps:
+                mlp_all = mlp
                 if isinstance(mlp, dict):
                     for k in ("wq", "wk", "wv", "wo"):
                         mlp[k].requires_grad_(True)
                         leaves.append(mlp[k])
                     mlp = mlp["mlp"]
+                ln = [mlp_all[k] for k in ("ln_gamma", "ln_beta") if isinstance(mlp_all, dict) and k in mlp_all]
                 for i, (w, b) in enumerate(mlp):
                     w.requires_grad_(True)
                     b.requires_grad_(True)
                     leaves += [w, b]
+                for v in ln:                     # LayerNorm variables come after the MLP's in the flat layout
+                    v.requires_grad_(True)
+                    leaves.append(v)
     z, ldj = grevnet_f_autograd(torch.as_tensor(nodes).to(dtype), torch.as_tensor(senders).long(),
                                 torch.as_tensor(receivers).long(), p, bn=bn_t)
     loss = -scale * log_prob_xs_autograd(z, ldj)

@@ -54,13 +54,17 @@ def flat_from_oracle(params):
         for half in range(2):
             mlps = [params[which][half]] if params["weight_sharing"] else params[which][half]
             for mlp in mlps:
-                if isinstance(mlp, dict):      # dm_attn: Wq Wk Wv Wo then the MLP (include/gnf_b200.h)
+                gnn = mlp
+                if isinstance(mlp, dict):      # dm_attn: Wq Wk Wv Wo, the MLP, then LayerNorm gamma beta (include/gnf_b200.h)
                     for k in ("wq", "wk", "wv", "wo"):
                         chunks.append(np.asarray(mlp[k], np.float32).reshape(-1))
                     mlp = mlp["mlp"]
                 for (w, b) in mlp:
                     chunks.append(np.asarray(w, np.float32).reshape(-1))
                     chunks.append(np.asarray(b, np.float32).reshape(-1))
+                if isinstance(gnn, dict) and "ln_gamma" in gnn:
+                    chunks.append(np.asarray(gnn["ln_gamma"], np.float32).reshape(-1))
+                    chunks.append(np.asarray(gnn["ln_beta"], np.float32).reshape(-1))
     return np.concatenate(chunks)
 
 
@@ -74,6 +78,7 @@ def make_grevnet(params, latent_dim, num_layers, device="cuda", math=None):
     if cfg["block"] == "dm_attn":
         mk = lambda: G.dm_self_attn_gnn(cfg["kq_dim"], cfg["v_dim"], mlp_fn, cfg["num_heads"], cfg["out_dim"],
                                         concat=cfg["concat"], residual=cfg["residual"],
+                                        layer_norm=bool(cfg.get("layer_norm", False)),
                                         kq_dim_division=cfg["kq_dim_division"])
     elif cfg["block"] == "concat":
         fac = G.sum_concat_then_mlp_gnn if cfg["agg"] == "sum" else G.avg_concat_then_mlp_gnn

@@ -524,7 +524,7 @@ def test_batch_prefetcher_stages_and_validates():
         pf.submit(G.GraphsTuple(*g._replace(n_node=g.n_node + 1)))
 
 
-@pytest.mark.parametrize("variant", ["default_d2_fc", "d14_sparse_noconcat_residual", "kq_division_shared"])
+@pytest.mark.parametrize("variant", ["default_d2_fc", "d14_sparse_noconcat_residual", "kq_division_shared", "layer_norm"])
 def test_f1_dm_self_attn_gnn(variant):
     """Row f1: DMSelfAttentionMLP (gnn.py:385-573), the default GNN of both scripts, inside the flow.
     fp32 kernels vs the oracle restatement (graph_nets segment softmax [upstream])."""
@@ -541,6 +541,12 @@ def test_f1_dm_self_attn_gnn(variant):
         attn = dict(num_heads=3, kq_dim=5, v_dim=7, out_dim=12, concat=False, residual=True, kq_dim_division=False)
         g = H.random_batch(rng, 9, 4, 30, D=D, isolated=True)      # isolated receivers: attention output 0
         g = g._replace(nodes=(g.nodes * 0.1).astype(np.float32))  # residual adds x to s: keep exp(s) tame
+    elif variant == "layer_norm":            # snt.LayerNorm on the GNN output (gnn.py:554-556), with the residual
+        D, T, L, K, ws = 10, 2, 64, 3, False
+        attn = dict(num_heads=2, kq_dim=6, v_dim=5, out_dim=9, concat=True, residual=True, kq_dim_division=False,
+                    layer_norm=True)
+        g = H.random_batch(rng, 8, 4, 25, D=D)
+        g = g._replace(nodes=(g.nodes * 0.3).astype(np.float32))
     else:
         D, T, L, K, ws = 6, 2, 128, 3, True
         attn = dict(num_heads=4, kq_dim=16, v_dim=8, out_dim=20, concat=True, residual=False, kq_dim_division=True)
@@ -571,7 +577,7 @@ def test_f1_dm_self_attn_gnn(variant):
     assert np.abs(got - ref).max() < 1e-4
 
 
-@pytest.mark.parametrize("variant", ["concat_kqdiv", "noconcat_residual_shared"])
+@pytest.mark.parametrize("variant", ["concat_kqdiv", "noconcat_residual_shared", "layer_norm"])
 def test_f1_dm_self_attn_backward_matches_autograd(variant):
     """Row f1 + f2: reversible backward THROUGH the attention GNN (fp32 kernels: k_attn_bwd_recv / k_attn_bwd_send,
     projection dW/dX GEMMs) vs torch autograd of the fp64 restatement.  Tolerance as the fp32 MLP backward (2e-4
@@ -582,6 +588,12 @@ def test_f1_dm_self_attn_backward_matches_autograd(variant):
         D, T, L, K, ws = 6, 2, 64, 3, False
         attn = dict(num_heads=4, kq_dim=16, v_dim=8, out_dim=20, concat=True, residual=False, kq_dim_division=True)
         g = H.random_batch(rng, 8, 4, 25, D=D, isolated=True)
+    elif variant == "layer_norm":
+        D, T, L, K, ws = 10, 2, 64, 3, False
+        attn = dict(num_heads=2, kq_dim=6, v_dim=5, out_dim=9, concat=True, residual=True, kq_dim_division=False,
+                    layer_norm=True)
+        g = H.random_batch(rng, 8, 4, 25, D=D)
+        g = g._replace(nodes=(g.nodes * 0.3).astype(np.float32))
     else:
         D, T, L, K, ws = 14, 2, 32, 4, True
         attn = dict(num_heads=3, kq_dim=5, v_dim=7, out_dim=12, concat=False, residual=True, kq_dim_division=False)

@@ -177,7 +177,9 @@ def test_torch_attention_restatement_matches_numpy_oracle():
     g = H.random_batch(rng, 5, 4, 12, D=6, isolated=True)
     g = g._replace(nodes=(g.nodes * 0.1).astype(np.float32))       # residual adds x to s: keep exp(s) tame
     for attn in (dict(num_heads=3, kq_dim=5, v_dim=4, out_dim=9, concat=True, residual=False, kq_dim_division=True),
-                 dict(num_heads=2, kq_dim=3, v_dim=6, out_dim=5, concat=False, residual=True, kq_dim_division=False)):
+                 dict(num_heads=2, kq_dim=3, v_dim=6, out_dim=5, concat=False, residual=True, kq_dim_division=False),
+                 dict(num_heads=2, kq_dim=3, v_dim=6, out_dim=5, concat=True, residual=True, kq_dim_division=False,
+                      layer_norm=True)):
         p = O.make_params(5, 2, 6, 32, 3, block="dm_attn", act="relu", attn=attn, last_layer_scale=0.1)
         z, ldj = O.grevnet_f(g.nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(p, np.float64))
         zt, lt = OT.grevnet_f(torch.from_numpy(g.nodes).double(), torch.from_numpy(g.senders).long(),
