@@ -84,6 +84,8 @@ class GraphShardedGRevNet:
     def __init__(self, grevnet, group: Optional[dist.ProcessGroup] = None):
         self.grevnet = grevnet
         self.group = group
+        if hasattr(grevnet, "bn_group"):
+            grevnet.bn_group = group          # batch-norm bijector: batch statistics / gradient sums over the same ranks
         on = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if on else 0
         self.world_size = dist.get_world_size(group) if on else 1
@@ -108,7 +110,9 @@ class GraphShardedGRevNet:
     def loss_and_grad(self, local_graph: GraphsTuple, per_node: bool = True):
         """Sharded training-step evaluation: local density pass, all-reduce of the 4-vector (gives the
         global node count the per-node loss is normalised by), local reversible backward, then the
-        gradient all-reduce(SUM) -- every rank ends with the global-batch gradient."""
+        gradient all-reduce(SUM) -- every rank ends with the global-batch gradient.  With use_batch_norm the
+        bijector's gamma/beta gradients (net.bn_gamma.grad / net.bn_beta.grad) are already global on every rank:
+        they come from sums that _backward_bn all-reduced."""
         from .loss import mvn_log_prob_sum, scalars_from_vector
         net = self.grevnet
         z, ldj64 = net.f64(local_graph)
