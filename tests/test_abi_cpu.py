@@ -108,6 +108,59 @@ def test_error_contract_on_host():
         net(G.GraphsTuple(*g), inverse=True)                               # numpy arrays: not device tensors
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Round-1 additions (training-step entry points): bad arguments are rejected on the host, before any CUDA
+    call, with the documented codes and a message in gnf_last_error."""
+    lib = _lib.load()
+    null = C.c_void_p(0)
+    assert lib.gnf_grevnet_backward(null, null, 0, 0, null, null, null, null, 1.0, null, null, 1, null, 0, null) == _lib.GNF_EINVAL
+    assert b"null flow" in lib.gnf_last_error()
+    assert lib.gnf_coupling_half_backward(null, 0, 0, null, null, null, null, 0, 0, null, null, null, null, 1.0, null, 1,
+                                          null, 0, null) == _lib.GNF_EINVAL
+    assert lib.gnf_grevnet_backward_workspace(null, 10, 1) == 0
+    assert lib.gnf_bn_backward_apply(null, null, -1, 4, null, null) == _lib.GNF_EINVAL
+    assert lib.gnf_bn_finalize(null, 4, null, null, 1e-3, 1.0, null, null, null, null, null, -1.0, null) == _lib.GNF_EINVAL
+    assert lib.gnf_bn_backward_coef(null, null, 4, null, null, 1e-3, 1.0, null, null, null, null, null) == _lib.GNF_EINVAL
+    assert lib.gnf_debug_dw_gemm(null, null, 0, 256, 256, 2, 1, null, null, 0, null) == _lib.GNF_EINVAL
+    assert lib.gnf_debug_bwd_layout(null, 10, null) == _lib.GNF_EINVAL
+    assert lib.gnf_debug_kernel_timing(0) == _lib.GNF_OK        # switching the (unused) event brackets off is a no-op
+
+
+def test_attention_gnn_parameter_layout_and_layer_norm():
+    """dm_self_attn_gnn: Wq Wk Wv Wo, the MLP, then (layer_norm=True) the LayerNorm gamma = 1, beta = 0
+    (snt.LayerNorm variables are created after the MLP's, gnn.py:547-556); the C ABI counts the same."""
+    lib = _lib.load()
+    D, Hh, L, K = 6, 3, 16, 3
+    mlp_fn = partial(G.make_mlp_model, L, D / 2, K, G.gnn.relu, 0.1, 0.1)
+    for ln in (False, True):
+        mk_attn = lambda: G.dm_self_attn_gnn(5, 4, mlp_fn, 2, 7, concat=True, residual=True, layer_norm=ln)
+        net = G.GRevNet(mk_attn, 2, D, seed=3, device="cpu")
+        attn = 2 * Hh * 10 + Hh * 4 + 8 * 7
+        mlp = (Hh + 7) * L + L + L * L + L + L * Hh + Hh
+        per = attn + mlp + (2 * Hh if ln else 0)
+        assert net.params.numel() == per * 8
+        flags = _lib.ATTN_CONCAT | _lib.ATTN_RESIDUAL | (_lib.ATTN_LAYER_NORM if ln else 0)
+        d = _lib.FlowDesc(num_timesteps=2, node_embedding_dim=D, latent_dim=L, num_layers=K, agg=0, block=_lib.BLOCK["dm_attn"],
+                          act=1, weight_sharing=0, eps=1.0, attn_num_heads=2, attn_kq_dim=5, attn_v_dim=4, attn_out_dim=7,
+                          attn_flags=flags)
+        assert lib.gnf_flow_param_count(C.byref(d)) == per * 8
+        g0 = net.s[0][0]
+        if ln:
+            assert g0.ln_gamma.data_ptr() == net.params.data_ptr() + 4 * (attn + mlp)
+            assert torch.equal(g0.ln_gamma, torch.ones(Hh)) and torch.equal(g0.ln_beta, torch.zeros(Hh))
+        else:
+            assert g0.ln_gamma is None
+
+
+def test_batch_norm_parameters_are_trainable_only_with_the_bijector():
+    on = G.GRevNet(mk(L=16, K=3, D=4), 2, 4, use_batch_norm=True, device="cpu")
+    off = G.GRevNet(mk(L=16, K=3, D=4), 2, 4, use_batch_norm=False, device="cpu")
+    assert on.bn_gamma.requires_grad and on.bn_beta.requires_grad
+    assert not off.bn_gamma.requires_grad and not off.bn_beta.requires_grad
+    with pytest.raises(RuntimeError, match="CUDA"):
+        on.backward_from_z(None, torch.zeros(3, 4), 1.0)           # no CPU fallback on the BN training path either
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libgnf_b200.so")
