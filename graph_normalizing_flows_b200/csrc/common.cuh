@@ -149,7 +149,7 @@ int tc_kernel_time(double* total_ms, int64_t* launches);
 int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
                      const float* xa, float* xb, int64_t n_nodes,
                      const int32_t* rowptr, const int32_t* csr_senders,
-                     double* ldj_partials, int* n_partials, void* stream);
+                     double* ldj_partials, double* ldj_accum, unsigned int* counter, void* stream);
 
 }  // namespace gnf
 

@@ -45,6 +45,8 @@ struct TcParams {
   int K, H, HP, concat, mean, act, inverse;
   float eps;
   double* partials;
+  double* ldj_accum;           // forward: the LAST CTA to finish adds the fixed-order sum of the partials here
+  unsigned int* counter;       // arrival counter of that hand-off (zero on entry, reset by the last CTA)
   unsigned long long* trace;   // optional timeline of CTA 0 (gnf_debug_set_trace); null in production
 };
 
@@ -419,8 +421,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     for (int o = 16; o > 0; o >>= 1) ldj_local += __shfl_down_sync(0xffffffffu, ldj_local, o);
     if (lane == 0 && grp == 0) ldj_red[q] = ldj_local;
     asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
-    if (warp == 2 && lane == 0 && p.partials)
+    if (warp == 2 && lane == 0 && p.partials) {
       p.partials[blockIdx.x] = ((ldj_red[0] + ldj_red[1]) + ldj_red[2]) + ldj_red[3];
+      if (p.ldj_accum) {
+        // log-det hand-off without a second launch: the last CTA to arrive sums every CTA's partial in CTA order
+        // (fixed order -> the same bits whatever the arrival order) and resets the counter for the next launch
+        __threadfence();
+        const unsigned prev = atomicAdd(p.counter, 1u);
+        if (prev == gridDim.x - 1) {
+          __threadfence();
+          const volatile double* part = p.partials;
+          double s = 0.0;
+          for (unsigned i = 0; i < gridDim.x; ++i) s += part[i];
+          *p.ldj_accum += s;
+          *p.counter = 0u;
+        }
+      }
+    }
   } else {
     // ===== gather warps: a3 + a4 + a5 =========================================================
     const int row = tid - (kThreads - kGatherThreads);
@@ -675,7 +692,7 @@ int tc_pack_mlp_T(const Flow& f, int mlp, const float* params, void* stream) {
 
 int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse, const float* xa,
                      float* xb, int64_t n_nodes, const int32_t* rowptr, const int32_t* csr_senders,
-                     double* ldj_partials, int* n_partials, void* stream_) {
+                     double* ldj_partials, double* ldj_accum, unsigned int* counter, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TcParams p;
   p.xa = xa;
@@ -698,9 +715,10 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   p.inverse = inverse;
   p.eps = f.d.eps;
   p.partials = ldj_partials;
+  p.ldj_accum = (!inverse && counter) ? ldj_accum : nullptr;
+  p.counter = counter;
   p.trace = g_trace;
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-  *n_partials = grid;
   const bool timed = g_timer.on && g_timer.n < kMaxTimed;
   if (timed) GNF_CUDA(cudaEventRecord(g_timer.a[g_timer.n], stream));
   int rc;

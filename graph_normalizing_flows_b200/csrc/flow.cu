@@ -548,6 +548,7 @@ struct Workspace {
   float *x0, *x1, *hbuf, *act0, *act1, *sbuf, *tbuf;
   float *xq, *qbuf, *kbuf, *vbuf, *att, *proj;     // attention block only
   double* partials;
+  unsigned int* counter;       // arrival counter of the fused kernel's log-det hand-off (zeroed per entry point)
   int n_partials_cap;
   size_t bytes;
 };
@@ -567,6 +568,7 @@ Workspace carve(const Flow& f, int64_t n, int math, void* base) {
   w.n_partials_cap = (int)ceil_div((int64_t)nn * f.H, 256);
   if (w.n_partials_cap < 1024) w.n_partials_cap = 1024;
   w.partials = (double*)take((size_t)w.n_partials_cap * 8);
+  w.counter = (unsigned int*)take(256);
   if (math == GNF_MATH_FP32) {
     const int lp = pad_to(f.L, 8);
     w.hbuf = (float*)take(nn * f.in_pad * 4);
@@ -673,15 +675,9 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
     }
     return GNF_OK;
   }
-  int n_partials = 0;
-  int rc = tc_coupling_half(f, ms, mt, math, inverse, xa, xb, n, rowptr, csr_senders, w.partials,
-                            &n_partials, stream);
-  if (rc) return rc;
-  if (!inverse && ldj_accum) {
-    k_reduce_partials<<<1, 256, 0, stream>>>(w.partials, n_partials, ldj_accum, 1);
-    GNF_LAUNCH_CHECK();
-  }
-  return GNF_OK;
+  // the fused kernel's last CTA adds the log-det partials into ldj_accum itself (no reduce launch)
+  return tc_coupling_half(f, ms, mt, math, inverse, xa, xb, n, rowptr, csr_senders, w.partials, ldj_accum, w.counter,
+                          stream);
 }
 
 int check_math(const Flow& f, int math, const char* who) {
@@ -1027,6 +1023,7 @@ extern "C" int gnf_grevnet_forward(const gnf_flow* h, const float* x, int64_t n,
   GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_forward: null x/z");
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
   const int D = f.d.node_embedding_dim;
   if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
   k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(x, n, D, f.H, f.HP, w.x0, w.x1);
@@ -1052,6 +1049,7 @@ extern "C" int gnf_grevnet_inverse(const gnf_flow* h, const float* z, int64_t n,
   GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_inverse: null x/z");
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
   const int D = f.d.node_embedding_dim;
   if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
   k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(z, n, D, f.H, f.HP, w.x0, w.x1);
@@ -1079,6 +1077,7 @@ extern "C" int gnf_coupling_step(const gnf_flow* h, int32_t step, int32_t invers
   GNF_REQUIRE(x0 && x1, GNF_EINVAL, "gnf_coupling_step: null x0/x1");
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
   if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
   if (!inverse) {
     rc = coupling_half(f, 0, step, 0, x0, x1, n, rowptr, csr, ldj_accum, math, w, stream);
@@ -1124,6 +1123,7 @@ extern "C" int gnf_coupling_half(const gnf_flow* h, int32_t half, int32_t step, 
   GNF_REQUIRE(xa && xb && xa != xb, GNF_EINVAL, "gnf_coupling_half: xa/xb must be distinct non-null buffers");
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
   if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
   return coupling_half(f, half, step, inverse, xa, xb, n, rowptr, csr, inverse ? nullptr : ldj_accum, math, w,
                        stream);
