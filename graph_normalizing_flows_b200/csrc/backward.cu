@@ -149,15 +149,32 @@ k_dw(const float* __restrict__ A, int lda, const float* __restrict__ D, int ldd,
   }
 }
 
-// column sums of D over a node range: part[z][n]
-__global__ void k_db(const float* __restrict__ D, int ldd, int64_t n_nodes, int Ndim, float* __restrict__ part) {
+// column sums of D over a node range: part[z][n].  Block (z, c): 32 columns, 8 warps stride the rows of range z
+// (one coalesced 128-byte read per warp and row); the 8 partial sums are combined in warp order (fixed order).
+__global__ void __launch_bounds__(256)
+k_db(const float* __restrict__ D, int ldd, int64_t n_nodes, int Ndim, float* __restrict__ part) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.y * 32 + lane;
   const int64_t per = (n_nodes + gridDim.x - 1) / gridDim.x;
   const int64_t beg = (int64_t)blockIdx.x * per;
   const int64_t end = beg + per < n_nodes ? beg + per : n_nodes;
-  for (int n = threadIdx.x; n < Ndim; n += blockDim.x) {
+  float s0 = 0.f, s1 = 0.f;
+  if (col < Ndim) {
+    int64_t r = beg + warp;
+    for (; r + 8 < end; r += 16) {
+      s0 += D[r * ldd + col];
+      s1 += D[(r + 8) * ldd + col];
+    }
+    if (r < end) s0 += D[r * ldd + col];
+  }
+  red[warp][lane] = s0 + s1;
+  __syncthreads();
+  if (warp == 0 && col < Ndim) {
     float s = 0.f;
-    for (int64_t r = beg; r < end; ++r) s += D[r * ldd + n];
-    part[(int64_t)blockIdx.x * Ndim + n] = s;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][lane];
+    part[(int64_t)blockIdx.x * Ndim + col] = s;
   }
 }
 
@@ -241,9 +258,9 @@ __global__ void k_merge_p(const float* __restrict__ x0, const float* __restrict_
 
 // ---- f1: backward of DMSelfAttention (gnn.py:419-477) -----------------------------------------
 // keys = project_q (at the sender), queries = project_k (at the receiver), as in k_dm_attn.
-// Pass 1, thread per (receiver r, head): softmax statistics, dot = sum_e w_e g_w_e with
-// g_w_e = <g_att[r,h,:], values[s_e,:]>, and g_queries[r,h,:] = sum_e g_l_e keys[s_e,h,:],
-// g_l_e = w_e (g_w_e - dot) * inv_scale.
+// Pass 1, thread per (receiver r, head): with the segment max / sum the recomputed forward left in `stats`,
+// dot = sum_e w_e g_w_e with g_w_e = <g_att[r,h,:], values[s_e,:]>, and
+// g_queries[r,h,:] = sum_e g_l_e keys[s_e,h,:], g_l_e = w_e (g_w_e - dot) * inv_scale.
 __global__ void __launch_bounds__(128)
 k_attn_bwd_recv(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
                 const float* __restrict__ gatt, int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd,
@@ -259,50 +276,33 @@ k_attn_bwd_recv(const float* __restrict__ keys, const float* __restrict__ querie
   float acc[64];
 #pragma unroll
   for (int d = 0; d < 64; ++d) acc[d] = 0.f;
-  float mx = 0.f, sum = 1.f, dot = 0.f;
-  if (end > beg) {
-    mx = -INFINITY;
-    for (int32_t e = beg; e < end; ++e) {
-      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
-      float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
-      mx = fmaxf(mx, l * inv_scale);
-    }
-    sum = 0.f;
-    for (int32_t e = beg; e < end; ++e) {
-      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
-      float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
-      sum += expf(l * inv_scale - mx);
-    }
-    for (int32_t e = beg; e < end; ++e) {
-      const int32_t s = csr_senders[e];
-      const float* ks = keys + (int64_t)s * qk_pad + h * kq;
-      float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
-      const float w = expf(l * inv_scale - mx) / sum;
-      const float* vs = vals + (int64_t)s * v_pad;
-      float gw = 0.f;
-      for (int c = 0; c < vd; ++c) gw = fmaf(ga[c], vs[c], gw);
-      dot = fmaf(w, gw, dot);
-    }
-    for (int32_t e = beg; e < end; ++e) {
-      const int32_t s = csr_senders[e];
-      const float* ks = keys + (int64_t)s * qk_pad + h * kq;
-      float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
-      const float w = expf(l * inv_scale - mx) / sum;
-      const float* vs = vals + (int64_t)s * v_pad;
-      float gw = 0.f;
-      for (int c = 0; c < vd; ++c) gw = fmaf(ga[c], vs[c], gw);
-      const float gl = w * (gw - dot) * inv_scale;
-#pragma unroll
-      for (int d = 0; d < 64; ++d)
-        if (d < kq) acc[d] = fmaf(gl, ks[d], acc[d]);
-    }
+  const float mx = stats[i * 3], rsum = 1.f / stats[i * 3 + 1];      // segment max / sum from the recomputed forward
+  float dot = 0.f;
+  for (int32_t e = beg; e < end; ++e) {
+    const int32_t s = csr_senders[e];
+    const float* ks = keys + (int64_t)s * qk_pad + h * kq;
+    float l = 0.f;
+    for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+    const float w = expf(l * inv_scale - mx) * rsum;
+    const float* vs = vals + (int64_t)s * v_pad;
+    float gw = 0.f;
+    for (int c = 0; c < vd; ++c) gw = fmaf(ga[c], vs[c], gw);
+    dot = fmaf(w, gw, dot);
   }
-  stats[i * 3] = mx;
-  stats[i * 3 + 1] = sum;
+  for (int32_t e = beg; e < end; ++e) {
+    const int32_t s = csr_senders[e];
+    const float* ks = keys + (int64_t)s * qk_pad + h * kq;
+    float l = 0.f;
+    for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+    const float w = expf(l * inv_scale - mx) * rsum;
+    const float* vs = vals + (int64_t)s * v_pad;
+    float gw = 0.f;
+    for (int c = 0; c < vd; ++c) gw = fmaf(ga[c], vs[c], gw);
+    const float gl = w * (gw - dot) * inv_scale;
+#pragma unroll
+    for (int d = 0; d < 64; ++d)
+      if (d < kq) acc[d] = fmaf(gl, ks[d], acc[d]);
+  }
   stats[i * 3 + 2] = dot;
 #pragma unroll
   for (int d = 0; d < 64; ++d)
@@ -438,7 +438,7 @@ struct BwdWs {
   float* act[2][kMaxLayers];
   // f1 attention block: per-GNN forward intermediates, shared gradient temporaries
   AttnBufs ab[2];
-  float *hbuf2, *gproj, *gatt, *gkeys, *gqueries, *gvh, *gv, *gxq, *stats;
+  float *hbuf2, *gproj, *gatt, *gkeys, *gqueries, *gvh, *gv, *gxq;
   float *preln[2], *lnt;       // GNF_ATTN_LAYER_NORM: pre-LayerNorm GNN outputs, gy * xhat
   size_t bytes;
 };
@@ -479,6 +479,7 @@ BwdWs carve_bwd(const Flow& f, int64_t n, void* base) {
       w.ab[m].vbuf = take(nn * f.v_pad * 4);
       w.ab[m].att = take(nn * f.hv_pad * 4);
       w.ab[m].proj = take(nn * f.cho_pad * 4);
+      w.ab[m].stats = take(nn * f.heads * 3 * 4);
     }
     w.hbuf2 = take(nn * f.in_pad * 4);
     w.gproj = take(nn * f.cho_pad * 4);
@@ -488,7 +489,6 @@ BwdWs carve_bwd(const Flow& f, int64_t n, void* base) {
     w.gvh = take(nn * f.hv_pad * 4);
     w.gv = take(nn * f.v_pad * 4);
     w.gxq = take(nn * f.hp8 * 4);
-    w.stats = take(nn * f.heads * 3 * 4);
     w.preln[0] = take(nn * f.HP * 4);
     w.preln[1] = take(nn * f.HP * 4);
     w.lnt = take(nn * gp * 4);
@@ -529,7 +529,7 @@ int run_dw(const Flow& f, int l, const float* a_in, int lda, const float* delta,
   k_reduce_split<<<(unsigned)ceil_div((int64_t)f.ins[l] * f.outs[l], 256), 256, 0, stream>>>(
       part, kSplit, Mdim, Ndim, f.ins[l], f.outs[l], grad_mlp + f.flat_w_off[l]);
   GNF_LAUNCH_CHECK();
-  k_db<<<kSplit, 256, 0, stream>>>(delta, ldd, n, Ndim, part);
+  k_db<<<dim3(kSplit, (unsigned)ceil_div(Ndim, 32)), 256, 0, stream>>>(delta, ldd, n, Ndim, part);
   GNF_LAUNCH_CHECK();
   k_reduce_split<<<(unsigned)ceil_div(f.outs[l], 256), 256, 0, stream>>>(part, kSplit, 1, Ndim, 1, f.outs[l],
                                                                         grad_mlp + f.flat_b_off[l]);
@@ -617,9 +617,9 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   if (rc) return rc;
   const unsigned blocks = (unsigned)ceil_div(n * f.heads, 128);
   k_attn_bwd_recv<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq,
-                                              f.vd, inv_scale, rowptr, csr_senders, n, w.stats, w.gqueries);
+                                              f.vd, inv_scale, rowptr, csr_senders, n, b.stats, w.gqueries);
   GNF_LAUNCH_CHECK();
-  k_attn_bwd_send<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, w.stats, f.qk_pad, f.v_pad, f.hv_pad,
+  k_attn_bwd_send<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
                                               f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys, w.gvh);
   GNF_LAUNCH_CHECK();
   k_sum_heads<<<(unsigned)ceil_div(n * f.v_pad, 256), 256, 0, stream>>>(w.gvh, f.hv_pad, f.heads, f.vd, f.v_pad, n, w.gv);
@@ -712,14 +712,14 @@ static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const f
     for (int m = 0; m < 2; ++m) {
       if (f.attn_flags & GNF_ATTN_LAYER_NORM) {
         float* gln = grads + (int64_t)mm[m] * f.params_per_mlp + f.ln_off;      // gamma[H] then beta[H]
-        k_db<<<kSplit, 256, 0, stream>>>(gtop[m], gp, n, gp, w.part);                                  // d beta
+        k_db<<<dim3(kSplit, (unsigned)ceil_div(gp, 32)), 256, 0, stream>>>(gtop[m], gp, n, gp, w.part);                                  // d beta
         GNF_LAUNCH_CHECK();
         k_reduce_split<<<1, 256, 0, stream>>>(w.part, kSplit, 1, gp, 1, H, gln + H);
         GNF_LAUNCH_CHECK();
         k_layer_norm_bwd<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(w.preln[m], gtop[m], w.lnt, n, H, HP, gp,
                                                                         f.wln + (int64_t)mm[m] * 2 * HP);
         GNF_LAUNCH_CHECK();
-        k_db<<<kSplit, 256, 0, stream>>>(w.lnt, gp, n, gp, w.part);                                    // d gamma
+        k_db<<<dim3(kSplit, (unsigned)ceil_div(gp, 32)), 256, 0, stream>>>(w.lnt, gp, n, gp, w.part);                                    // d gamma
         GNF_LAUNCH_CHECK();
         k_reduce_split<<<1, 256, 0, stream>>>(w.part, kSplit, 1, gp, 1, H, gln);
         GNF_LAUNCH_CHECK();

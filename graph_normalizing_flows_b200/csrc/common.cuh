@@ -109,6 +109,7 @@ int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t
                cudaStream_t stream);
 struct AttnBufs {      // per-GNN intermediates of the f1 attention block (all [n, *_pad] fp32)
   float *xq, *qbuf, *kbuf, *vbuf, *att, *proj;
+  float* stats;        // optional [n, heads, 3]: segment max, segment sum (written by k_dm_attn), dot (backward)
 };
 int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
                    const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream);

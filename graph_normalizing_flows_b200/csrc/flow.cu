@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128)
 k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
           int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
-          float* __restrict__ att) {
+          float* __restrict__ att, float* __restrict__ stats) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * heads) return;
   const int64_t r = i / heads;
@@ -138,36 +138,41 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-  if (end > beg) {
-    float mx = -INFINITY;
-    for (int32_t e = beg; e < end; ++e) {
-      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
-      float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
-      mx = fmaxf(mx, l * inv_scale);
-    }
-    float sum = 0.f;
-    for (int32_t e = beg; e < end; ++e) {
-      const float* ks = keys + (int64_t)csr_senders[e] * qk_pad + h * kq;
-      float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
-      sum += expf(l * inv_scale - mx);
-    }
-    for (int32_t e = beg; e < end; ++e) {
-      const int32_t s = csr_senders[e];
-      const float* ks = keys + (int64_t)s * qk_pad + h * kq;
-      float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
-      const float w = expf(l * inv_scale - mx) / sum;
-      const float* vs = vals + (int64_t)s * v_pad;
+  // one pass over the in-edges with a running maximum (the segment softmax of graph_nets subtracts the segment
+  // max, exponentiates and divides by the segment sum; rescaling the running sums when the max moves gives the
+  // same value up to rounding)
+  float mx = -INFINITY, sum = 0.f;
+  for (int32_t e = beg; e < end; ++e) {
+    const int32_t s = csr_senders[e];
+    const float* ks = keys + (int64_t)s * qk_pad + h * kq;
+    float l = 0.f;
+    for (int d = 0; d < kq; ++d) l = fmaf(ks[d], qr[d], l);
+    l *= inv_scale;
+    float p = 1.f;
+    if (l > mx) {
+      const float sc = expf(mx - l);            // exp(-inf) = 0 on the first edge
+      sum *= sc;
 #pragma unroll
       for (int c = 0; c < 32; ++c)
-        if (c < vd) acc[c] = __fadd_rn(acc[c], __fmul_rn(vs[c], w));
+        if (c < vd) acc[c] *= sc;
+      mx = l;
+    } else {
+      p = expf(l - mx);
     }
+    sum += p;
+    const float* vs = vals + (int64_t)s * v_pad;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < vd) acc[c] = fmaf(vs[c], p, acc[c]);
   }
+  const float inv = end > beg ? 1.f / sum : 0.f;       // empty segments give 0
 #pragma unroll
   for (int c = 0; c < 32; ++c)
-    if (c < vd) att[r * hv_pad + h * vd + c] = acc[c];
+    if (c < vd) att[r * hv_pad + h * vd + c] = acc[c] * inv;
+  if (stats) {                                         // kept for the backward: segment max and sum
+    stats[i * 3] = end > beg ? mx : 0.f;
+    stats[i * 3 + 1] = end > beg ? sum : 1.f;
+  }
 }
 
 // MLP input of DMSelfAttentionMLP: concat([nodes, proj]) or proj (gnn.py:547-548)
@@ -626,7 +631,7 @@ int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n,
 // MLP input of GNN `mlp` from the half xa: aggregation blocks (shared by s and t) or attention
 int build_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
                      const int32_t* csr_senders, const Workspace& w, cudaStream_t stream) {
-  AttnBufs b{w.xq, w.qbuf, w.kbuf, w.vbuf, w.att, w.proj};
+  AttnBufs b{w.xq, w.qbuf, w.kbuf, w.vbuf, w.att, w.proj, nullptr};
   return fwd_attn_input(f, mlp, xa, n, rowptr, csr_senders, b, w.hbuf, stream);
 }
 
@@ -721,7 +726,7 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
   k_dm_attn<<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
                                                                       f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
-                                                                      csr_senders, n, w.att);
+                                                                      csr_senders, n, w.att, w.stats);
   GNF_LAUNCH_CHECK();
   rc = run_linear(w.att, wa + f.wo_off, f.zeros, w.proj, n, f.cho_pad, f.hv_pad, 2, stream);  // new_node_proj gnn.py:543-545
   if (rc) return rc;
