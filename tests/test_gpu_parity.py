@@ -665,6 +665,17 @@ def test_empty_and_tiny_batches():
     z, ldj = O.grevnet_f(noedge.nodes, noedge.senders, noedge.receivers, params)
     got = G.loss.log_prob(net, dev_graph(noedge))
     assert H.rel_err(got["log_prob_xs"], O.log_prob(z, ldj, noedge.n_node)["log_prob_xs"]) < LOGPROB_RTOL
+    # the training-step entry point on the same edge cases: empty batch -> zero gradient, one node / no edges ->
+    # the tensor-core backward (a single, mostly padded tile) agrees with the fp32 FFMA backward
+    _, g0 = net.loss_and_grad(empty)
+    assert float(g0.abs().max()) == 0.0
+    for tiny in (one, noedge):
+        dg = dev_graph(tiny)
+        zt, _ = net.f64(dg)
+        n = tiny.nodes.shape[0]
+        ref = net.backward_from_z(dg, zt.nodes, 1.0 / n, math="fp32").double().cpu().numpy()
+        got = net.backward_from_z(dg, zt.nodes, 1.0 / n, math="tc3x").double().cpu().numpy()
+        assert np.isfinite(got).all() and np.abs(got - ref).max() <= BWD_TOL["tc3x"][0] * np.abs(ref).max()
 
 
 def test_property_random_batches():
