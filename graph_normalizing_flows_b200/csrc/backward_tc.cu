@@ -1,20 +1,22 @@
 // Reversible backward of one half coupling step on the 5th-gen tensor cores.
 //
-// Two kernels per half step, both tcgen05 + TMEM, bf16 hi/lo split operands, fp32 accumulate:
+// Two kernels per half step, both tcgen05 + TMEM, hi/lo split 16-bit operands (3 MMAs per product), fp32 accumulate:
 //
 //   k_bwd_chain : persistent, one CTA per SM, 128-node tiles.  Per tile FOUR MLP chains run through
 //                 the same TMEM ping-pong as the forward kernel (coupling_tc.cu):
 //                   F_s, F_t : recompute s = S(h), t = T(h) from xa (gather + segment-sum as in the
-//                              forward), every hidden activation a_l also written to HBM as a bf16
-//                              hi/lo image for the weight-gradient GEMM;
+//                              forward; fp16 hi/lo in the tc3x/tc2x modes), every hidden activation a_l also
+//                              written to HBM as a bf16 hi/lo image for the weight-gradient GEMM, its sign
+//                              bits kept in shared memory for act';
 //                   coupling : xb <- (xb' - t) * exp(-s)  (gnn.py:359,372),  g_s = g*xb*exp(s) - scale,
 //                              g_t = g,  g_xb <- g * exp(s);
 //                   B_s, B_t : delta_{l-1} = (delta_l W_l^T) (.) act'(a_{l-1}) with the TRANSPOSED weight
-//                              images; delta_l images to HBM, bias gradients (column sums) reduced
-//                              with warp shuffles, g_h = delta_0 W_0^T out in fp32.
+//                              images (bf16 hi/lo); delta_l images to HBM, g_h = delta_0 W_0^T out in fp32.
 //   k_dw_tc     : dW_l = a_{l-1}^T delta_l over all nodes: M = input features, N = output features,
 //                 K = nodes.  Both operands are MN-major (node index strided), read straight from
 //                 the images with cp.async.bulk; split over node ranges, fixed-order reduction after.
+//                 Its epilogue warps, idle during the main loop, sum the columns of the delta operand
+//                 from the smem stages: the bias gradients.
 //
 // Image layout (one per 128-node tile, per part hi|lo): the UMMA no-swizzle MN-major canonical form,
 //   elem(f, n) = (n>>3)*(F*8) + (f>>3)*64 + (n&7)*8 + (f&7)        F = feature count (LAT or 16)
@@ -41,7 +43,7 @@ struct BwdParams {
   const int32_t* csr;
   int64_t n_nodes;
   int n_tiles;
-  const uint8_t* wf[2];      // forward weight images (bf16 hi/lo) of the s and t MLP
+  const uint8_t* wf[2];      // forward weight images (fp16 or bf16 hi/lo, template flag F16F) of the s and t MLP
   const uint8_t* wb[2];      // transposed-chain weight images
   const float* bias[2];
   int K, H, HP, concat, mean;
