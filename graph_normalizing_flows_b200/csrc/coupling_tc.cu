@@ -26,6 +26,7 @@
 // Reference semantics: NodeBlockGNN (gnn.py:143-156), ConcatThenMLPBlock / AggThenMLPBlock
 // (gnn.py:100-126), make_mlp_model (gnn.py:159-180), coupling update (gnn.py:320-323,335-338,
 // 353-359,366-372).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     }
   } else if (warp < 2 + kEpiWarps) {
     // ===== epilogue warps ======================================================================
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // x_b and the log-det come from the previous launch
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;             // which 32-column chunk of every 64-column group
     const int row = q * 32 + lane;
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     }
   } else {
     // ===== gather warps: a3 + a4 + a5 =========================================================
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // x_a comes from the previous launch
     const int row = tid - (kThreads - kGatherThreads);
     float* my = hstage + row * 17;
     const int hp4 = p.HP >> 2;
@@ -618,7 +621,21 @@ int launch_tc_act(const TcParams& p, int grid, cudaStream_t stream) {
     GNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(p);
+  // Programmatic dependent launch: the CTAs of this launch may start on an SM as soon as the previous kernel's
+  // CTA there has exited, run their prologue (barrier init, TMEM allocation, bias tiles, first weight chunks) and
+  // block in griddepcontrol.wait before the first read of anything the previous kernel wrote (x halves, log-det).
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const bool pdl = getenv("GNF_NO_PDL") == nullptr;     // GNF_NO_PDL=1: plain stream-ordered launches (A/B timing)
+  cfg.numAttrs = pdl ? 1 : 0;
+  GNF_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }
