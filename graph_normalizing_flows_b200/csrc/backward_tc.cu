@@ -16,7 +16,7 @@
 //                 K = nodes.  Both operands are MN-major (node index strided), read straight from
 //                 the images with cp.async.bulk; split over node ranges, fixed-order reduction after.
 //                 Its epilogue warps, idle during the main loop, sum the columns of the delta operand
-//                 from the smem stages: the bias gradients.
+//                 (read from the images through L2, in step with the ring): the bias gradients.
 //
 // Image layout (one per 128-node tile, per part hi|lo): the UMMA no-swizzle MN-major canonical form,
 //   elem(f, n) = (n>>3)*(F*8) + (f>>3)*64 + (n&7)*8 + (f&7)        F = feature count (LAT or 16)
@@ -752,13 +752,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
     __syncwarp();
   } else {
     if (pr.db_mode) {
-      // ---- bias gradient: column sums of one operand over the nodes, straight from the smem stages -----------
+      // ---- bias gradient: column sums of one operand over the nodes -------------------------------------------
+      // The warps follow the ring (wait on full[stage], arrive on empty[stage]) only to stay in step with the
+      // producer: they read the SAME bytes the stage's bulk copy has just pulled through L2, but from the image in
+      // global memory (read-only path), not from shared memory -- no generic-proxy reads of async-proxy writes.
       // MN-major image: per 8-node group, feature group fg is 8 nodes x 16 B; lane i reads node i&7 of feature
-      // group fg0 + (i>>3): a warp-wide LDS.128 covers 4 feature groups x 8 nodes, conflict free.
+      // group fg0 + (i>>3): a warp-wide 16-byte load covers 4 feature groups x 8 nodes = 512 contiguous bytes.
       const int cw = warp - 2;
       const int F = pr.db_mode == 1 ? FB : FA;
       const uint32_t part_bytes = pr.db_mode == 1 ? b_part : a_part;
-      const uint32_t op_off = pr.db_mode == 1 ? PARTS * a_part : 0u;
+      const uint16_t* op_img = pr.db_mode == 1 ? pr.B : pr.A;
       const int fg_per_warp = F >= 128 ? F / 32 : 2;
       const int nslots = fg_per_warp > 4 ? fg_per_warp / 4 : 1;
       const bool active = F >= 128 ? true : (cw == 0 && lane < 16);
@@ -772,7 +775,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
         for (int s = 0; s < 8 / KS; ++s) {
           mbar_wait(smem_u32(&bars->full[stage]), phase);
           if (active) {
-            const uint8_t* base = smem + stage * kDwStageBytes + op_off;
+            const uint8_t* base = (const uint8_t*)(op_img + (size_t)tile * 2 * F * 128) + (size_t)s * part_bytes;
 #pragma unroll
             for (int part = 0; part < PARTS; ++part) {
               for (int ng = 0; ng < KS * 2; ++ng) {
@@ -780,8 +783,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
                 for (int j = 0; j < 2; ++j) {
                   if (j < nslots) {
                     const int fg = (F >= 128 ? cw * fg_per_warp + 4 * j : 0) + (lane >> 3);
-                    const uint4 w4 = *reinterpret_cast<const uint4*>(base + part * part_bytes + (size_t)ng * F * 16 +
-                                                                     fg * 128 + (lane & 7) * 16);
+                    const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)part * F * 256 + (size_t)ng * F * 16 +
+                                                                          fg * 128 + (lane & 7) * 16));
                     const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
