@@ -1,4 +1,4 @@
-"""Training-step timing (row f2): tc3x forward + fp32 reversible backward at the bench workload."""
+"""Training-step timing (row f2): tc3x forward + tensor-core reversible backward + Adam at the bench workload."""
 import json, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
