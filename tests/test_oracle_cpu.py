@@ -222,6 +222,72 @@ def test_torch_batch_norm_restatement_matches_numpy_oracle():
     assert abs((lp - lm) / (2 * eps) - gg[1, 0, 2]) < 1e-5 * max(1.0, abs(gg[1, 0, 2]))
 
 
+def test_batch_norm_backward_formulas_match_autograd():
+    """The closed forms the CUDA path implements for the bijector's backward (include/gnf_b200.h:
+    gnf_bn_backward_sums / _coef / _apply) against torch autograd of the restatement, on the CPU:
+        S1 = sum G_y, S2 = sum G_y xhat;  dL/dbeta = S1;  dL/dgamma = S2 - c N / gamma
+        dL/dx = gamma/s * G_y + (c - gamma S2 / N)/s * xhat - gamma S1 / (N s),   c = loss_scale, s = sqrt(var + eps)
+    for L = sum(G_y_fixed * y) - c * ildj(x)  (a downstream gradient G_y plus the bijector's own log-det term)."""
+    import torch
+    from oracle import gnf_oracle_torch as OT
+    rng = np.random.default_rng(9)
+    n, h, c = 37, 5, 0.3
+    x = torch.from_numpy(rng.standard_normal((n, h)) * 1.5 + 0.4).requires_grad_(True)
+    gamma = torch.from_numpy(1.0 + 0.2 * rng.standard_normal(h)).requires_grad_(True)
+    beta = torch.from_numpy(0.1 * rng.standard_normal(h)).requires_grad_(True)
+    gy = torch.from_numpy(rng.standard_normal((n, h)))
+    y, ildj = OT._bn_inverse(x, gamma, beta)
+    loss = (gy * y).sum() - c * ildj
+    gx_ref, gg_ref, gb_ref = torch.autograd.grad(loss, [x, gamma, beta])
+    with torch.no_grad():
+        mean = x.mean(0)
+        var = ((x - mean) ** 2).mean(0)
+        s = torch.sqrt(var + OT.BN_EPS)
+        xhat = (y - beta) / gamma                                  # what the kernels recover from y
+        s1, s2 = gy.sum(0), (gy * xhat).sum(0)
+        gb, gg = s1, s2 - c * n / gamma
+        gx = gamma / s * gy + (c - gamma * s2 / n) / s * xhat - gamma * s1 / (n * s)
+        x_back = xhat * s + mean
+    assert torch.allclose(gx, gx_ref, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(gg, gg_ref, rtol=1e-10, atol=1e-12) and torch.allclose(gb, gb_ref, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(x_back, x.detach(), rtol=1e-12, atol=1e-12)
+
+
+def test_attention_backward_formulas_match_autograd():
+    """The closed forms of k_attn_bwd_recv / k_attn_bwd_send (backward.cu) against torch autograd of the segment-softmax
+    attention core (DMSelfAttention._build, gnn.py:419-477), on the CPU: with w_e the softmax weight of edge e at its
+    receiver r and head h, g_w_e = <G[r,h,:], v[s_e,:]>, dot[r,h] = sum_e w_e g_w_e, g_l_e = w_e (g_w_e - dot) * inv_scale:
+        dL/dqueries[r,h,:] = sum_{e into r} g_l_e keys[s_e,h,:]     dL/dkeys[s,h,:] = sum_{e out of s} g_l_e queries[r_e,h,:]
+        dL/dv[s,:] = sum_h sum_{e out of s} w_e G[r_e,h,:]          (the value projection is shared by the heads)"""
+    import torch
+    rng = np.random.default_rng(10)
+    g = H.random_batch(rng, 4, 4, 9, D=4, isolated=True)
+    n, heads, kq, vd, inv_scale = g.nodes.shape[0], 3, 4, 5, 1.0 / np.sqrt(4.0)
+    snd, rcv = torch.from_numpy(g.senders).long(), torch.from_numpy(g.receivers).long()
+    keys = torch.from_numpy(rng.standard_normal((n, heads, kq))).requires_grad_(True)
+    queries = torch.from_numpy(rng.standard_normal((n, heads, kq))).requires_grad_(True)
+    vals = torch.from_numpy(rng.standard_normal((n, vd))).requires_grad_(True)
+    G = torch.from_numpy(rng.standard_normal((n, heads, vd)))
+    logits = (keys[snd] * queries[rcv]).sum(-1) * inv_scale
+    idx = rcv[:, None].expand(-1, heads)
+    seg_max = torch.full((n, heads), -float("inf"), dtype=torch.float64).scatter_reduce(0, idx, logits.detach(), "amax")
+    ex = torch.exp(logits - seg_max[rcv])
+    seg_sum = torch.zeros((n, heads), dtype=torch.float64).index_add_(0, rcv, ex)
+    w = ex / seg_sum[rcv]
+    att = torch.zeros((n, heads, vd), dtype=torch.float64).index_add_(0, rcv, vals[snd][:, None, :] * w[..., None])
+    gk_ref, gq_ref, gv_ref = torch.autograd.grad((att * G).sum(), [keys, queries, vals])
+    with torch.no_grad():
+        gw = (G[rcv] * vals[snd][:, None, :]).sum(-1)                                   # [E, heads]
+        dot = torch.zeros((n, heads), dtype=torch.float64).index_add_(0, rcv, w * gw)
+        gl = w * (gw - dot[rcv]) * inv_scale
+        g_queries = torch.zeros_like(queries).index_add_(0, rcv, gl[..., None] * keys[snd])
+        g_keys = torch.zeros_like(keys).index_add_(0, snd, gl[..., None] * queries[rcv])
+        g_v = torch.zeros_like(vals).index_add_(0, snd, (w[..., None] * G[rcv]).sum(1))
+    assert torch.allclose(g_queries, gq_ref, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(g_keys, gk_ref, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(g_v, gv_ref, rtol=1e-10, atol=1e-12)
+
+
 def test_f4_embedding_pickle_readers(tmp_path):
     """GrevnetDatasetFixed / Variable (train_grevnet_with_data.py:145-234) + transform_example (:237-271)."""
     import pickle
