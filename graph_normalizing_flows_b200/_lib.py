@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgnf_b200.so")
 
 GNF_OK = 0
+ABI_VERSION = 4
 GNF_EINVAL, GNF_ECUDA, GNF_EUNSUPPORTED, GNF_EWORKSPACE = -1, -2, -3, -4
 AGG = {"sum": 0, "mean": 1}
 BLOCK = {"concat": 0, "agg_then": 1, "dm_attn": 2}
@@ -54,6 +55,7 @@ SIGNATURES = {
     "gnf_flow_param_count": (_i64, [C.POINTER(FlowDesc)]),
     "gnf_flow_create": (C.c_int, [C.POINTER(_p), C.POINTER(FlowDesc)]),
     "gnf_flow_set_params": (C.c_int, [_p, _p, _p]),
+    "gnf_flow_range_flag": (C.c_int, [_p, _p, _i32, _p]),
     "gnf_flow_destroy": (C.c_int, [_p]),
     "gnf_flow_supports": (C.c_int, [_p, _i32]),
     "gnf_grevnet_workspace": (_sz, [_p, _i64, _i32]),
@@ -100,6 +102,9 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if lib.gnf_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} has ABI version {lib.gnf_abi_version()}, this package binds version "
+                               f"{ABI_VERSION}: rebuild it (make -C graph_normalizing_flows_b200/csrc)")
         _lib = lib
     return _lib
 

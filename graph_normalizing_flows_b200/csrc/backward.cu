@@ -312,6 +312,7 @@ k_attn_bwd_recv(const float* __restrict__ keys, const float* __restrict__ querie
 // Pass 2, thread per (sender s, head): walks the out-edges (CSR by sender) and rebuilds each edge's
 // weight from the receiver's statistics:  g_keys[s,h,:] = sum g_l_e queries[r_e,h,:],
 // g_vh[s,h,:] = sum w_e g_att[r_e,h,:]  (the value projection is shared by the heads: summed after).
+template <int VMAX>
 __global__ void __launch_bounds__(128)
 k_attn_bwd_send(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
                 const float* __restrict__ gatt, const float* __restrict__ stats, int qk_pad, int v_pad, int hv_pad,
@@ -324,11 +325,11 @@ k_attn_bwd_send(const float* __restrict__ keys, const float* __restrict__ querie
   const int h = (int)(i - s * heads);
   const float* ks = keys + s * qk_pad + h * kq;
   const float* vs = vals + s * v_pad;
-  float acc[64], accv[32];
+  float acc[64], accv[VMAX];
 #pragma unroll
   for (int d = 0; d < 64; ++d) acc[d] = 0.f;
 #pragma unroll
-  for (int c = 0; c < 32; ++c) accv[c] = 0.f;
+  for (int c = 0; c < VMAX; ++c) accv[c] = 0.f;
   const int32_t end = rowptr_s[s + 1];
   for (int32_t e = rowptr_s[s]; e < end; ++e) {
     const int64_t r = csr_receivers[e];
@@ -345,14 +346,14 @@ k_attn_bwd_send(const float* __restrict__ keys, const float* __restrict__ querie
     for (int d = 0; d < 64; ++d)
       if (d < kq) acc[d] = fmaf(gl, qr[d], acc[d]);
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
+    for (int c = 0; c < VMAX; ++c)
       if (c < vd) accv[c] = fmaf(w, ga[c], accv[c]);
   }
 #pragma unroll
   for (int d = 0; d < 64; ++d)
     if (d < kq) gkeys[s * qk_pad + h * kq + d] = acc[d];
 #pragma unroll
-  for (int c = 0; c < 32; ++c)
+  for (int c = 0; c < VMAX; ++c)
     if (c < vd) gvh[s * hv_pad + h * vd + c] = accv[c];
 }
 
@@ -619,8 +620,14 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   k_attn_bwd_recv<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq,
                                               f.vd, inv_scale, rowptr, csr_senders, n, b.stats, w.gqueries);
   GNF_LAUNCH_CHECK();
-  k_attn_bwd_send<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
-                                              f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys, w.gvh);
+  if (f.vd <= 32)
+    k_attn_bwd_send<32><<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
+                                                    f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys,
+                                                    w.gvh);
+  else
+    k_attn_bwd_send<64><<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
+                                                    f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys,
+                                                    w.gvh);
   GNF_LAUNCH_CHECK();
   k_sum_heads<<<(unsigned)ceil_div(n * f.v_pad, 256), 256, 0, stream>>>(w.gvh, f.hv_pad, f.heads, f.vd, f.v_pad, n, w.gv);
   GNF_LAUNCH_CHECK();

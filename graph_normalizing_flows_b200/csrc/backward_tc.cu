@@ -915,11 +915,10 @@ __global__ void k_make_images(const float* __restrict__ x, int64_t n, int F, int
 
 int launch_dw(const DwParams& p, int grid, int parts, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)kDwStages * kDwStageBytes + sizeof(DwBarriers) + 64;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     GNF_CUDA(cudaFuncSetAttribute(k_dw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GNF_CUDA(cudaFuncSetAttribute(k_dw_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   if (parts == 2) k_dw_tc<2><<<grid, kDwThreads, smem, stream>>>(p);
   else k_dw_tc<1><<<grid, kDwThreads, smem, stream>>>(p);
@@ -930,12 +929,10 @@ int launch_dw(const DwParams& p, int grid, int parts, cudaStream_t stream) {
 template <int LAT, int ACT, bool F16F>
 int launch_chain_t(const BwdParams& p, int grid, cudaStream_t stream) {
   auto kern = k_bwd_chain<LAT, ACT, F16F>;
-  static bool configured = false;
+  static bool configured[kMaxDevices] = {};
   const size_t smem = bwd_smem_bytes<LAT>();
-  if (!configured) {
+  if (first_use_on_device(configured))
     GNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   kern<<<grid, kThreads, smem, stream>>>(p);
   GNF_LAUNCH_CHECK();
   return GNF_OK;

@@ -51,6 +51,17 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int num_sms();
 
+// Per-device one-time setup (cudaFuncSetAttribute belongs to the device's copy of a function): returns true the
+// first time it is called with `done` on the current device.
+constexpr int kMaxDevices = 64;
+static inline bool first_use_on_device(bool (&done)[kMaxDevices]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 // ---- packed flow ---------------------------------------------------------------------------
 constexpr int kMaxLayers = 8;
 
@@ -96,6 +107,9 @@ struct Flow {
   float* btc = nullptr;        // biases for the TC kernel: per MLP K*256 floats
   uint8_t* wtcT = nullptr;     // bf16 hi/lo images of the TRANSPOSED MLP chains (backward dX), same geometry
   bool tc_ok = false;
+  void* pack_jobs = nullptr;   // device job table of the one-launch re-pack (pack.cu)
+  int n_pack_jobs = 0, pack_blocks = 0;
+  int* range_flag = nullptr;   // sticky device flag: an fp16-split operand left the fp16 range (gnf_flow_range_flag)
 
   int mlp_index(int which, int half, int step) const {
     int T = d.weight_sharing ? 1 : d.num_timesteps;
@@ -116,6 +130,10 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
 int fwd_layer_norm(const Flow& f, int mlp, float* x, int64_t n, cudaStream_t stream);
 int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                   float* hbuf, cudaStream_t stream);
+
+// pack.cu
+int pack_build_jobs(Flow& f);
+int pack_all(const Flow& f, const float* params, cudaStream_t stream);
 
 // backward.cu (shared with backward_tc.cu)
 int bwd_agg_transpose(const Flow& f, const float* gh, int gh_stride, const int32_t* rowptr_s,
@@ -140,9 +158,7 @@ int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, i
                     void* ws, size_t ws_bytes, void* stream);
 
 // coupling_tc.cu
-int tc_pack_mlp_T(const Flow& f, int mlp, const float* params, void* stream);
 size_t tc_bytes_per_mlp(int L, int K);
-int tc_pack_mlp(const Flow& f, int mlp, const float* params, void* stream);
 bool tc_shape_supported(const Flow& f);
 void tc_set_trace(void* buf);
 int tc_kernel_timing(int enable);

@@ -48,6 +48,7 @@ struct TcParams {
   double* partials;
   double* ldj_accum;           // forward: the LAST CTA to finish adds the fixed-order sum of the partials here
   unsigned int* counter;       // arrival counter of that hand-off (zero on entry, reset by the last CTA)
+  int* range_flag;             // sticky: set when an fp16-split operand exceeded the fp16 range (fp16 modes only)
   unsigned long long* trace;   // optional timeline of CTA 0 (gnf_debug_set_trace); null in production
 };
 
@@ -89,12 +90,17 @@ __device__ __forceinline__ float act_t(float v) {
 }
 
 // activation + hi/lo split of one 32-column accumulator chunk, written back in place
+// (fp16 modes keep a running max |a| of what they split: above 65504 the hi part is inf where the reference's fp32
+// arithmetic stays finite -- reported through TcParams::range_flag, never silently)
 template <int NPROD, bool BF16, int ACT>
-__device__ __forceinline__ void convert_chunk(uint32_t taddr, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void convert_chunk(uint32_t taddr, const uint32_t (&v)[32], float& amax) {
   uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    split_pair<BF16>(act_t<ACT>(__uint_as_float(v[2 * j])), act_t<ACT>(__uint_as_float(v[2 * j + 1])), hi[j], lo[j]);
+  for (int j = 0; j < 16; ++j) {
+    const float a = act_t<ACT>(__uint_as_float(v[2 * j])), b = act_t<ACT>(__uint_as_float(v[2 * j + 1]));
+    if constexpr (!BF16) amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+    split_pair<BF16>(a, b, hi[j], lo[j]);
+  }
   tmem_st16(taddr, hi);
   if (NPROD == 3) tmem_st16(taddr + 16, lo);
 }
@@ -333,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     uint32_t acc_par = 0;
     int region = 0;
     double ldj_local = 0.0;
+    float amax = 0.f;
     const int hp4 = p.HP >> 2;
     Tracer tr;
     tr.init(p.trace, 1 + (warp - 2), blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6));
@@ -353,11 +360,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
               tmem_ld32(t0, v0);
               tmem_ld32(t0 + 64, v1);
               tmem_wait_ld();
-              convert_chunk<NPROD, BF16, ACT>(t0, v0);
+              convert_chunk<NPROD, BF16, ACT>(t0, v0, amax);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(smem_u32(&bars->a_ready[ph * 2]));
-              convert_chunk<NPROD, BF16, ACT>(t0 + 64, v1);
+              convert_chunk<NPROD, BF16, ACT>(t0 + 64, v1, amax);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(smem_u32(&bars->a_ready[ph * 2 + 1]));
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
               uint32_t v0[32];
               tmem_ld32(t0, v0);
               tmem_wait_ld();
-              convert_chunk<NPROD, BF16, ACT>(t0, v0);
+              convert_chunk<NPROD, BF16, ACT>(t0, v0, amax);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(smem_u32(&bars->a_ready[ph]));
@@ -418,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       }
     }
     tr.ev(23, 0, 0);
+    if (!BF16 && amax > 65504.f && p.range_flag) *p.range_flag = 1;
     // fixed-order reduction of the log-det partial: lanes, then the 4 lane-quarter warps
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ldj_local += __shfl_down_sync(0xffffffffu, ldj_local, o);
@@ -447,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     float* my = hstage + row * 17;
     const int hp4 = p.HP >> 2;
     int it = 0;
+    float amax = 0.f;
     Tracer tr;
     tr.init(p.trace, 9, blockIdx.x == 0 && row == 0);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -500,7 +509,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       __syncwarp();
       uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_pair<BF16>(my[2 * j], my[2 * j + 1], hi[j], lo[j]);
+      for (int j = 0; j < 8; ++j) {
+        if constexpr (!BF16) amax = fmaxf(amax, fmaxf(fabsf(my[2 * j]), fabsf(my[2 * j + 1])));
+        split_pair<BF16>(my[2 * j], my[2 * j + 1], hi[j], lo[j]);
+      }
       tr.ev(31, 0, 0);
       mbar_wait(smem_u32(&bars->h_empty[buf]), ((it >> 1) & 1) ^ 1);
       tr.ev(32, 0, 0);
@@ -514,6 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->h_full[buf]));
     }
+    if (!BF16 && amax > 65504.f && p.range_flag) *p.range_flag = 1;
   }
 
   // ---- teardown ---------------------------------------------------------------------------
@@ -525,102 +538,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
   }
 }
 
-// ---- weight image packing ------------------------------------------------------------------
-// One logical layer W[in,out] -> chunked UMMA B images (B[n][k] = W[k][n]); see header comment.
-// transposed: the logical layer is W^T, i.e. W is stored [out, in] row-major (in/out are those of the logical layer)
-__global__ void k_pack_tc(const float* __restrict__ W, int in, int out, int kpad, int npad, int nhc,
-                          int kcc, uint8_t* __restrict__ img_f16, uint8_t* __restrict__ img_bf16, int transposed) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kpad * npad) return;
-  const int n = i / kpad, k = i - n * kpad;
-  const float w = (k < in && n < out) ? (transposed ? W[n * in + k] : W[k * out + n]) : 0.f;
-  const int ph = n / nhc, nl = n - ph * nhc, kc = k / kcc, kl = k - kc * kcc;
-  const int mat_bytes = nhc * kcc * 2;
-  const size_t chunk = (size_t)(ph * (kpad / kcc) + kc) * (2 * mat_bytes);
-  const size_t off = chunk + (size_t)(kl >> 3) * (nhc * 16) + (nl >> 3) * 128 + (nl & 7) * 16 + (kl & 7) * 2;
-  if (img_f16) {
-    __half h = __float2half_rn(w);
-    __half l = __float2half_rn(w - __half2float(h));
-    *reinterpret_cast<__half*>(img_f16 + off) = h;
-    *reinterpret_cast<__half*>(img_f16 + off + mat_bytes) = l;
-  }
-  {
-    __nv_bfloat16 h = __float2bfloat16_rn(w);
-    __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
-    *reinterpret_cast<__nv_bfloat16*>(img_bf16 + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(img_bf16 + off + mat_bytes) = l;
-  }
-}
-
-__global__ void k_pack_bias(const float* __restrict__ b, int out, float* __restrict__ dst) {
-  int i = threadIdx.x;
-  if (i < 256) dst[i] = i < out ? b[i] : 0.f;
-}
-
+// (the weight images are written by pack.cu: one launch for every format)
 template <int LAT>
 size_t bytes_per_mlp_t(int K) {
   using G = Geo<LAT>;
   return (size_t)G::L0_BYTES + (size_t)(K - 2) * kNS * G::NKC * G::CHUNK_BYTES + G::LAST_BYTES;
 }
 
-template <int LAT>
-int pack_mlp_t(const Flow& f, int mlp, const float* params, cudaStream_t stream) {
-  using G = Geo<LAT>;
-  uint8_t* i16 = f.wtc[0] + (size_t)mlp * f.wtc_per_mlp;
-  uint8_t* ibf = f.wtc[1] + (size_t)mlp * f.wtc_per_mlp;
-  float* bias = f.btc + (size_t)mlp * f.K * 256;
-  const float* src = params;
-  size_t off = 0;
-  for (int l = 0; l < f.K; ++l) {
-    const int in = f.ins[l], out = f.outs[l];
-    int kpad, npad, nhc, kcc;
-    size_t bytes;
-    if (l == 0) { kpad = kK0; npad = LAT; nhc = LAT; kcc = kK0; bytes = G::L0_BYTES; }
-    else if (l == f.K - 1) { kpad = LAT; npad = kNOut; nhc = kNOut; kcc = LAT; bytes = G::LAST_BYTES; }
-    else { kpad = LAT; npad = LAT; nhc = G::NH; kcc = G::KC; bytes = (size_t)kNS * G::NKC * G::CHUNK_BYTES; }
-    k_pack_tc<<<(unsigned)ceil_div((int64_t)kpad * npad, 256), 256, 0, stream>>>(src, in, out, kpad, npad, nhc,
-                                                                                 kcc, i16 + off, ibf + off, 0);
-    GNF_LAUNCH_CHECK();
-    k_pack_bias<<<1, 256, 0, stream>>>(src + (size_t)in * out, out, bias + l * 256);
-    GNF_LAUNCH_CHECK();
-    off += bytes;
-    src += (size_t)in * out + out;
-  }
-  return GNF_OK;
-}
-
-// the backward dX chain as an MLP: chain layer j applies W_{K-1-j}^T (no bias); same chunk geometry
-template <int LAT>
-int pack_mlp_T_t(const Flow& f, int mlp, const float* params, cudaStream_t stream) {
-  using G = Geo<LAT>;
-  uint8_t* ibf = f.wtcT + (size_t)mlp * f.wtc_per_mlp;
-  size_t off = 0;
-  for (int j = 0; j < f.K; ++j) {
-    const int l = f.K - 1 - j;                              // forward layer whose transpose this is
-    const float* src = params + (f.flat_w_off[l] - f.mlp_off);
-    const int in = f.outs[l], out = f.ins[l];               // logical dims of W_l^T
-    int kpad, npad, nhc, kcc;
-    size_t bytes;
-    if (j == 0) { kpad = kK0; npad = LAT; nhc = LAT; kcc = kK0; bytes = G::L0_BYTES; }
-    else if (j == f.K - 1) { kpad = LAT; npad = kNOut; nhc = kNOut; kcc = LAT; bytes = G::LAST_BYTES; }
-    else { kpad = LAT; npad = LAT; nhc = G::NH; kcc = G::KC; bytes = (size_t)kNS * G::NKC * G::CHUNK_BYTES; }
-    k_pack_tc<<<(unsigned)ceil_div((int64_t)kpad * npad, 256), 256, 0, stream>>>(src, in, out, kpad, npad, nhc, kcc,
-                                                                                 nullptr, ibf + off, 1);
-    GNF_LAUNCH_CHECK();
-    off += bytes;
-  }
-  return GNF_OK;
-}
-
 template <int LAT, int NPROD, bool BF16, int ACT>
 int launch_tc_act(const TcParams& p, int grid, cudaStream_t stream) {
   auto kern = k_coupling_tc<LAT, NPROD, BF16, ACT>;
-  static bool configured = false;
+  static bool configured[kMaxDevices] = {};
   const size_t smem = smem_bytes<LAT>();
-  if (!configured) {
+  if (first_use_on_device(configured))
     GNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   // Programmatic dependent launch: the CTAs of this launch may start on an SM as soon as the previous kernel's
   // CTA there has exited, run their prologue (barrier init, TMEM allocation, bias tiles, first weight chunks) and
   // block in griddepcontrol.wait before the first read of anything the previous kernel wrote (x halves, log-det).
@@ -696,17 +627,6 @@ bool tc_shape_supported(const Flow& f) {
 
 size_t tc_bytes_per_mlp(int L, int K) { return L == 256 ? bytes_per_mlp_t<256>(K) : bytes_per_mlp_t<128>(K); }
 
-int tc_pack_mlp(const Flow& f, int mlp, const float* params, void* stream) {
-  return f.L == 256 ? pack_mlp_t<256>(f, mlp, params, (cudaStream_t)stream)
-                    : pack_mlp_t<128>(f, mlp, params, (cudaStream_t)stream);
-}
-
-int tc_pack_mlp_T(const Flow& f, int mlp, const float* params, void* stream) {
-  if (!f.wtcT) return GNF_OK;
-  return f.L == 256 ? pack_mlp_T_t<256>(f, mlp, params, (cudaStream_t)stream)
-                    : pack_mlp_T_t<128>(f, mlp, params, (cudaStream_t)stream);
-}
-
 int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse, const float* xa,
                      float* xb, int64_t n_nodes, const int32_t* rowptr, const int32_t* csr_senders,
                      double* ldj_partials, double* ldj_accum, unsigned int* counter, void* stream_) {
@@ -734,6 +654,7 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   p.partials = ldj_partials;
   p.ldj_accum = (!inverse && counter) ? ldj_accum : nullptr;
   p.counter = counter;
+  p.range_flag = f.range_flag;
   p.trace = g_trace;
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   const bool timed = g_timer.on && g_timer.n < kMaxTimed;

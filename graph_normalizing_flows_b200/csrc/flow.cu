@@ -20,31 +20,21 @@ int64_t& launch_counter() {
   return c;
 }
 int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  static int cached[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool slot = dev >= 0 && dev < kMaxDevices;
+  if (slot && cached[dev]) return cached[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (slot) cached[dev] = n;
   return n;
 }
 
 namespace {
 
 static inline int pad_to(int x, int a) { return (x + a - 1) / a * a; }
-
-// ---- weight packing (fp32 path) ------------------------------------------------------------
-__global__ void k_pack32(const float* __restrict__ src, int in, int out, int in_pad, int out_pad,
-                         float* __restrict__ w, float* __restrict__ b) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int total = in_pad * out_pad;
-  if (i < total) {
-    int r = i / out_pad, c = i - r * out_pad;
-    w[i] = (r < in && c < out) ? src[r * out + c] : 0.f;
-  }
-  if (i < out_pad) b[i] = (i < out) ? src[in * out + i] : 0.f;
-}
 
 // ---- planar split / merge ------------------------------------------------------------------
 __global__ void k_split(const float* __restrict__ x, int64_t n, int d, int h, int hp,
@@ -124,6 +114,7 @@ k_agg_input(const float* __restrict__ xa, int h, int hp, const int32_t* __restri
 // logits_e = <keys[s_e], queries[r]> (/ sqrt(kq)); softmax over the receiver's in-edges as
 // gn.modules._unsorted_segment_softmax (subtract segment max, exp, divide by segment sum);
 // attended = sum_e values[s_e] * w_e in ascending edge order.  Empty segments give 0.
+template <int VMAX>
 __global__ void __launch_bounds__(128)
 k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
           int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
@@ -135,9 +126,9 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
   const int h = (int)(i - r * heads);
   const int32_t beg = rowptr[r], end = rowptr[r + 1];
   const float* qr = queries + r * qk_pad + h * kq;
-  float acc[32];
+  float acc[VMAX];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int c = 0; c < VMAX; ++c) acc[c] = 0.f;
   // one pass over the in-edges with a running maximum (the segment softmax of graph_nets subtracts the segment
   // max, exponentiates and divides by the segment sum; rescaling the running sums when the max moves gives the
   // same value up to rounding)
@@ -153,7 +144,7 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
       const float sc = expf(mx - l);            // exp(-inf) = 0 on the first edge
       sum *= sc;
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
+      for (int c = 0; c < VMAX; ++c)
         if (c < vd) acc[c] *= sc;
       mx = l;
     } else {
@@ -162,12 +153,12 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
     sum += p;
     const float* vs = vals + (int64_t)s * v_pad;
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
+    for (int c = 0; c < VMAX; ++c)
       if (c < vd) acc[c] = fmaf(vs[c], p, acc[c]);
   }
   const float inv = end > beg ? 1.f / sum : 0.f;       // empty segments give 0
 #pragma unroll
-  for (int c = 0; c < 32; ++c)
+  for (int c = 0; c < VMAX; ++c)
     if (c < vd) att[r * hv_pad + h * vd + c] = acc[c] * inv;
   if (stats) {                                         // kept for the backward: segment max and sum
     stats[i * 3] = end > beg ? mx : 0.f;
@@ -210,23 +201,6 @@ __global__ void k_layer_norm(float* __restrict__ x, int64_t n, int h, int hp, co
   var /= (float)h;
   const float inv = 1.f / sqrtf(var + 1e-5f);
   for (int f = 0; f < h; ++f) r[f] = (r[f] - mean) * inv * gb[f] + gb[hp + f];
-}
-
-__global__ void k_pack_ln(const float* __restrict__ src, int h, int hp, float* __restrict__ dst) {
-  int i = threadIdx.x;
-  if (i < 2 * hp) {
-    const int which = i / hp, f = i - which * hp;
-    dst[i] = f < h ? src[which * h + f] : 0.f;
-  }
-}
-
-__global__ void k_pack_mat(const float* __restrict__ src, int in, int out, int in_pad, int out_pad,
-                           float* __restrict__ w) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < in_pad * out_pad) {
-    int r = i / out_pad, c = i - r * out_pad;
-    w[i] = (r < in && c < out) ? src[r * out + c] : 0.f;
-  }
 }
 
 // ---- a6: one Sonnet Linear (+ activation), fp32 FFMA -----------------------------------------
@@ -695,15 +669,6 @@ int check_math(const Flow& f, int math, const char* who) {
   return GNF_OK;
 }
 
-__global__ void k_pack32T(const float* __restrict__ src, int in, int out, int in_pad, int out_pad8,
-                          float* __restrict__ wt) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < in_pad * out_pad8) {
-    int r = i / in_pad, c = i - r * in_pad;          // wt[r = out index][c = in index]
-    wt[i] = (r < out && c < in) ? src[c * out + r] : 0.f;
-  }
-}
-
 }  // namespace
 
 int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K, int act,
@@ -724,9 +689,14 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
   if (rc) return rc;
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
-  k_dm_attn<<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
-                                                                      f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
-                                                                      csr_senders, n, w.att, w.stats);
+  if (f.vd <= 32)
+    k_dm_attn<32><<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
+                                                                            f.hv_pad, f.heads, f.kq, f.vd, inv_scale,
+                                                                            rowptr, csr_senders, n, w.att, w.stats);
+  else
+    k_dm_attn<64><<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
+                                                                            f.hv_pad, f.heads, f.kq, f.vd, inv_scale,
+                                                                            rowptr, csr_senders, n, w.att, w.stats);
   GNF_LAUNCH_CHECK();
   rc = run_linear(w.att, wa + f.wo_off, f.zeros, w.proj, n, f.cho_pad, f.hv_pad, 2, stream);  // new_node_proj gnn.py:543-545
   if (rc) return rc;
@@ -750,17 +720,6 @@ int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowp
       xa, f.H, f.HP, rowptr, csr_senders, n, f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps,
       f.in_pad, hbuf);
   GNF_LAUNCH_CHECK();
-  return GNF_OK;
-}
-
-int pack_w32T(const Flow& f, int mlp, const float* src, cudaStream_t stream) {
-  float* dst = f.w32T + (int64_t)mlp * f.w32T_per_mlp;
-  for (int l = 0; l < f.K; ++l) {
-    int total = f.in_pads[l] * f.out_pad8[l];
-    k_pack32T<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src + f.flat_w_off[l], f.ins[l], f.outs[l],
-                                                                 f.in_pads[l], f.out_pad8[l], dst + f.w32T_layer_off[l]);
-    GNF_LAUNCH_CHECK();
-  }
   return GNF_OK;
 }
 
@@ -795,9 +754,11 @@ static int validate_desc(const gnf_flow_desc* d) {
   GNF_REQUIRE(d->block == GNF_BLOCK_CONCAT || d->block == GNF_BLOCK_AGG_THEN || d->block == GNF_BLOCK_DM_ATTN,
               GNF_EINVAL, "bad block");
   if (d->block == GNF_BLOCK_DM_ATTN)
-    GNF_REQUIRE(d->attn_num_heads >= 1 && d->attn_kq_dim >= 1 && d->attn_kq_dim <= 64 && d->attn_v_dim >= 1 &&
-                    d->attn_v_dim <= 32 && d->attn_out_dim >= 1,
-                GNF_EINVAL, "dm_self_attn: need heads >= 1, 1 <= kq_dim <= 64, 1 <= v_dim <= 32, out_dim >= 1");
+    GNF_REQUIRE(d->attn_num_heads >= 1 && d->attn_num_heads <= 64 && d->attn_kq_dim >= 1 && d->attn_kq_dim <= 64 &&
+                    d->attn_v_dim >= 1 && d->attn_v_dim <= 64 && d->attn_out_dim >= 1 && d->attn_out_dim <= 4096,
+                GNF_EINVAL, "dm_self_attn: need 1 <= heads <= 64, 1 <= kq_dim <= 64, 1 <= v_dim <= 64, 1 <= out_dim <= 4096");
+  GNF_REQUIRE(d->node_embedding_dim <= 8192 && d->latent_dim <= 8192, GNF_EINVAL,
+              "node_embedding_dim and latent_dim must be <= 8192");
   GNF_REQUIRE(d->act == GNF_ACT_LEAKY_RELU || d->act == GNF_ACT_RELU, GNF_EINVAL, "bad act");
   return GNF_OK;
 }
@@ -888,8 +849,12 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
   }
   cudaError_t e = cudaMalloc(&f.w32, (size_t)f.n_mlps * f.w32_per_mlp * 4);
   if (e == cudaSuccess) e = cudaMalloc(&f.w32T, (size_t)f.n_mlps * f.w32T_per_mlp * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&f.zeros, 8192 * 4);
-  if (e == cudaSuccess) e = cudaMemset(f.zeros, 0, 8192 * 4);
+  size_t n_zeros = 8192;                  // zero bias of the bias-free projections: as wide as the widest of them
+  for (int v : {f.qk_pad, f.v_pad, f.hv_pad, f.cho_pad}) n_zeros = (size_t)v > n_zeros ? (size_t)v : n_zeros;
+  if (e == cudaSuccess) e = cudaMalloc(&f.zeros, n_zeros * 4);
+  if (e == cudaSuccess) e = cudaMemset(f.zeros, 0, n_zeros * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&f.range_flag, 256);
+  if (e == cudaSuccess) e = cudaMemset(f.range_flag, 0, 256);
   if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wattn, (size_t)f.n_mlps * f.wattn_per_mlp * 4);
   if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wattnT, (size_t)f.n_mlps * f.wattnT_per_mlp * 4);
   if (e == cudaSuccess && f.attn) e = cudaMalloc(&f.wln, (size_t)f.n_mlps * 2 * f.HP * 4);
@@ -911,7 +876,19 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
       return GNF_ECUDA;
     }
   }
+  if (pack_build_jobs(f) != GNF_OK) {
+    gnf_flow_destroy(h);
+    return GNF_ECUDA;
+  }
   *out = h;
+  return GNF_OK;
+}
+
+extern "C" int gnf_flow_range_flag(const gnf_flow* h, int32_t* host_flag, int32_t reset, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(h, GNF_EINVAL, "gnf_flow_range_flag: null flow");
+  if (host_flag) GNF_CUDA(cudaMemcpyAsync(host_flag, h->f.range_flag, 4, cudaMemcpyDeviceToHost, stream));
+  if (reset) GNF_CUDA(cudaMemsetAsync(h->f.range_flag, 0, 4, stream));
   return GNF_OK;
 }
 
@@ -927,6 +904,8 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.wtc[1]);
   cudaFree(h->f.btc);
   cudaFree(h->f.wtcT);
+  cudaFree(h->f.pack_jobs);
+  cudaFree(h->f.range_flag);
   delete h;
   return GNF_OK;
 }
@@ -940,62 +919,7 @@ extern "C" int gnf_flow_supports(const gnf_flow* h, int32_t math) {
 extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GNF_REQUIRE(h && params, GNF_EINVAL, "gnf_flow_set_params: null pointer");
-  Flow& f = h->f;
-  for (int m = 0; m < f.n_mlps; ++m) {
-    const float* src = params + (int64_t)m * f.params_per_mlp;
-    if (f.attn) {
-      float* wa = f.wattn + (int64_t)m * f.wattn_per_mlp;
-      const int qk = f.heads * f.kq, hv = f.heads * f.vd;
-      auto pack = [&](const float* s_, int in, int out, int in_pad, int out_pad, float* d_) {
-        k_pack_mat<<<(unsigned)ceil_div((int64_t)in_pad * out_pad, 256), 256, 0, stream>>>(s_, in, out, in_pad, out_pad, d_);
-      };
-      pack(src, f.H, qk, f.hp8, f.qk_pad, wa + f.wq_off);
-      GNF_LAUNCH_CHECK();
-      pack(src + (int64_t)f.H * qk, f.H, qk, f.hp8, f.qk_pad, wa + f.wk_off);
-      GNF_LAUNCH_CHECK();
-      pack(src + 2ll * f.H * qk, f.H, f.vd, f.hp8, f.v_pad, wa + f.wv_off);
-      GNF_LAUNCH_CHECK();
-      pack(src + 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, f.hv_pad, f.cho_pad, wa + f.wo_off);
-      GNF_LAUNCH_CHECK();
-      float* wt = f.wattnT + (int64_t)m * f.wattnT_per_mlp;
-      auto packT = [&](const float* s_, int in, int out, int in_pad, int out_pad, float* d_) {   // d_[out_pad][in_pad]
-        k_pack32T<<<(unsigned)ceil_div((int64_t)in_pad * out_pad, 256), 256, 0, stream>>>(s_, in, out, in_pad, out_pad, d_);
-      };
-      packT(src, f.H, qk, f.hp8, f.qk_pad, wt + f.wqT_off);
-      GNF_LAUNCH_CHECK();
-      packT(src + (int64_t)f.H * qk, f.H, qk, f.hp8, f.qk_pad, wt + f.wkT_off);
-      GNF_LAUNCH_CHECK();
-      packT(src + 2ll * f.H * qk, f.H, f.vd, f.hp8, f.v_pad, wt + f.wvT_off);
-      GNF_LAUNCH_CHECK();
-      packT(src + 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, f.hv_pad, f.cho_pad, wt + f.woT_off);
-      GNF_LAUNCH_CHECK();
-      if (f.attn_flags & GNF_ATTN_LAYER_NORM) {
-        k_pack_ln<<<1, 64, 0, stream>>>(src + f.ln_off, f.H, f.HP, f.wln + (int64_t)m * 2 * f.HP);
-        GNF_LAUNCH_CHECK();
-      }
-      src += f.mlp_off;
-    }
-    float* dst = f.w32 + (int64_t)m * f.w32_per_mlp;
-    for (int l = 0; l < f.K; ++l) {
-      int total = f.in_pads[l] * f.out_pads[l];
-      k_pack32<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
-          src, f.ins[l], f.outs[l], f.in_pads[l], f.out_pads[l], dst + f.w32_layer_off[l],
-          dst + f.b32_layer_off[l]);
-      GNF_LAUNCH_CHECK();
-      src += (int64_t)f.ins[l] * f.outs[l] + f.outs[l];
-    }
-    {
-      int rc = pack_w32T(f, m, params + (int64_t)m * f.params_per_mlp, stream);
-      if (rc) return rc;
-    }
-    if (f.tc_ok) {
-      int rc = tc_pack_mlp(f, m, params + (int64_t)m * f.params_per_mlp + f.mlp_off, stream_);
-      if (rc) return rc;
-      rc = tc_pack_mlp_T(f, m, params + (int64_t)m * f.params_per_mlp + f.mlp_off, stream_);
-      if (rc) return rc;
-    }
-  }
-  return GNF_OK;
+  return pack_all(h->f, params, stream);
 }
 
 extern "C" size_t gnf_grevnet_workspace(const gnf_flow* h, int64_t n_nodes, int32_t math) {

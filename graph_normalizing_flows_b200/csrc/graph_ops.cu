@@ -25,10 +25,16 @@ __global__ void k_validate(const int32_t* __restrict__ senders, const int32_t* _
   if (local) atomicAdd(bad, local);
 }
 
-__global__ void k_degree(const int32_t* __restrict__ receivers, int64_t n_edges,
+// ids outside [0, n_nodes) are skipped here and in k_fill (they are counted by k_validate and reported as a
+// ValueError by the host; with deferred validation the CSR build runs before that count is read, so it must
+// stay inside its buffers whatever the ids are)
+__global__ void k_degree(const int32_t* __restrict__ receivers, int64_t n_edges, int64_t n_nodes,
                          int32_t* __restrict__ deg) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e < n_edges) atomicAdd(&deg[receivers[e]], 1);
+  if (e < n_edges) {
+    const int32_t r = receivers[e];
+    if (r >= 0 && r < n_nodes) atomicAdd(&deg[r], 1);
+  }
 }
 
 // exclusive scan, pass 1: per-tile exclusive scan + tile totals
@@ -110,21 +116,21 @@ __global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ sums, 
   }
 }
 
-// pass 3: add tile offsets; also writes rowptr[n] = total
-__global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* __restrict__ tile_sums,
-                           int64_t n_edges) {
+// pass 3: add tile offsets over all n + 1 entries: rowptr[n] = number of edges with a valid receiver
+// (= n_edges for validated input; never the raw n_edges, so the last segment cannot cover unfilled slots)
+__global__ void k_scan_add(int32_t* __restrict__ out, int64_t n, const int32_t* __restrict__ tile_sums) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) out[i] += tile_sums[i / kScanTile];
-  if (i == 0) out[n] = (int32_t)n_edges;
+  if (i <= n) out[i] += tile_sums[i / kScanTile];
 }
 
 // unordered placement into segments
-__global__ void k_fill(const int32_t* __restrict__ receivers, int64_t n_edges,
+__global__ void k_fill(const int32_t* __restrict__ receivers, int64_t n_edges, int64_t n_nodes,
                        const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
                        int32_t* __restrict__ tmp) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e < n_edges) {
     int32_t r = receivers[e];
+    if (r < 0 || r >= n_nodes) return;
     int32_t pos = atomicAdd(&cursor[r], 1);
     tmp[rowptr[r] + pos] = (int32_t)e;
   }
@@ -276,7 +282,7 @@ extern "C" int gnf_build_csr(const int32_t* receivers, const int32_t* senders, i
   const int64_t n1 = n_nodes + 1;
   GNF_CUDA(cudaMemsetAsync(deg, 0, (size_t)n1 * 4, stream));
   if (n_edges > 0) {
-    k_degree<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(receivers, n_edges, deg);
+    k_degree<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(receivers, n_edges, n_nodes, deg);
     GNF_LAUNCH_CHECK();
   }
   const int tiles = (int)ceil_div(n1, kScanTile);
@@ -284,11 +290,11 @@ extern "C" int gnf_build_csr(const int32_t* receivers, const int32_t* senders, i
   GNF_LAUNCH_CHECK();
   k_scan_sums<<<1, 1024, 0, stream>>>(tile_sums, tiles);
   GNF_LAUNCH_CHECK();
-  k_scan_add<<<(unsigned)ceil_div(n1, 256), 256, 0, stream>>>(rowptr, n_nodes, tile_sums, n_edges);
+  k_scan_add<<<(unsigned)ceil_div(n1, 256), 256, 0, stream>>>(rowptr, n_nodes, tile_sums);
   GNF_LAUNCH_CHECK();
   if (n_edges > 0) {
     GNF_CUDA(cudaMemsetAsync(deg, 0, (size_t)n1 * 4, stream));  // reuse as cursor
-    k_fill<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(receivers, n_edges, rowptr, deg, tmp);
+    k_fill<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(receivers, n_edges, n_nodes, rowptr, deg, tmp);
     GNF_LAUNCH_CHECK();
     k_sort_segments<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, stream>>>(
         rowptr, tmp, senders, n_nodes, perm, csr_senders);

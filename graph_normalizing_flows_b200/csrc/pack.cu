@@ -1,0 +1,228 @@
+// Weight re-pack in ONE launch (gnf_flow_set_params runs after every optimiser step).
+//
+// The flat parameter vector (include/gnf_b200.h: which -> half -> step, per MLP W0 b0 W1 b1 ...) is repacked into
+// every image a kernel family consumes: zero-padded fp32 W/b (k_linear), transposed fp32 (backward dX GEMMs), the
+// fp16 and bf16 hi/lo UMMA chunk images of the fused tcgen05 kernels, their transposed bf16 images (backward dX
+// chain), the bias rows, and the f1 attention projections / LayerNorm rows.  A job table is built once per flow
+// (shapes are fixed); one kernel walks it, a block belongs to exactly one job.
+#include <vector>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gnf {
+namespace {
+
+enum PackKind : int { kPack32 = 0, kPack32T = 1, kPackTc = 2, kPackBias = 3, kPackMat = 4, kPackLn = 5 };
+
+struct PackJob {
+  int kind, transposed;
+  int in, out;            // logical layer dims (rows of W = in, columns = out; Sonnet y = x @ W + b)
+  int p0, p1, p2, p3;     // kind specific padding / chunk geometry
+  int64_t src_off;        // floats into the flat parameter vector
+  void *d0, *d1;          // destinations
+  int first_block, n_blocks;
+};
+
+constexpr int kPackThreads = 256;
+
+__global__ void __launch_bounds__(kPackThreads) k_pack_all(const PackJob* __restrict__ jobs, int n_jobs,
+                                                           const float* __restrict__ params) {
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {                                   // last job whose first_block <= blockIdx.x (block uniform)
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const int i = ((int)blockIdx.x - j.first_block) * kPackThreads + (int)threadIdx.x;
+  const float* __restrict__ src = params + j.src_off;
+  switch (j.kind) {
+    case kPack32: {        // p0 = in_pad, p1 = out_pad; d0 = W [in_pad, out_pad], d1 = b [out_pad]
+      const int in_pad = j.p0, out_pad = j.p1;
+      float* w = (float*)j.d0;
+      float* b = (float*)j.d1;
+      if (i < in_pad * out_pad) {
+        const int r = i / out_pad, c = i - r * out_pad;
+        w[i] = (r < j.in && c < j.out) ? src[r * j.out + c] : 0.f;
+      }
+      if (i < out_pad) b[i] = (i < j.out) ? src[j.in * j.out + i] : 0.f;
+      break;
+    }
+    case kPack32T: {       // p0 = in_pad, p1 = out_pad8; d0 = W^T [out_pad8, in_pad]
+      const int in_pad = j.p0;
+      if (i < in_pad * j.p1) {
+        const int r = i / in_pad, c = i - r * in_pad;
+        ((float*)j.d0)[i] = (r < j.out && c < j.in) ? src[c * j.out + r] : 0.f;
+      }
+      break;
+    }
+    case kPackMat: {       // bias-free projection: p0 = in_pad, p1 = out_pad; d0 = W [in_pad, out_pad]
+      const int out_pad = j.p1;
+      if (i < j.p0 * out_pad) {
+        const int r = i / out_pad, c = i - r * out_pad;
+        ((float*)j.d0)[i] = (r < j.in && c < j.out) ? src[r * j.out + c] : 0.f;
+      }
+      break;
+    }
+    case kPackBias: {      // d0 = 256 floats
+      if (i < 256) ((float*)j.d0)[i] = i < j.out ? src[i] : 0.f;
+      break;
+    }
+    case kPackLn: {        // in = H, p0 = HP; src = gamma[H] beta[H]; d0 = [2][HP]
+      const int hp = j.p0;
+      if (i < 2 * hp) {
+        const int which = i / hp, f = i - which * hp;
+        ((float*)j.d0)[i] = f < j.in ? src[which * j.in + f] : 0.f;
+      }
+      break;
+    }
+    case kPackTc: {
+      // One logical layer W[in, out] -> chunked UMMA B images (B[n][k] = W[k][n]), K-major no-swizzle core matrices
+      // (coupling_tc.cu header).  p0 = kpad, p1 = npad, p2 = nhc (N per accumulator half), p3 = kcc (K per chunk).
+      // transposed: the logical layer is W^T, i.e. src is stored [out, in] row-major.
+      const int kpad = j.p0, npad = j.p1, nhc = j.p2, kcc = j.p3;
+      if (i >= kpad * npad) break;
+      const int n = i / kpad, k = i - n * kpad;
+      const float w = (k < j.in && n < j.out) ? (j.transposed ? src[n * j.in + k] : src[k * j.out + n]) : 0.f;
+      const int ph = n / nhc, nl = n - ph * nhc, kc = k / kcc, kl = k - kc * kcc;
+      const int mat_bytes = nhc * kcc * 2;
+      const size_t chunk = (size_t)(ph * (kpad / kcc) + kc) * (2 * mat_bytes);
+      const size_t off = chunk + (size_t)(kl >> 3) * (nhc * 16) + (nl >> 3) * 128 + (nl & 7) * 16 + (kl & 7) * 2;
+      if (j.d0) {
+        uint8_t* img = (uint8_t*)j.d0;
+        const __half h = __float2half_rn(w);
+        const __half l = __float2half_rn(w - __half2float(h));
+        *reinterpret_cast<__half*>(img + off) = h;
+        *reinterpret_cast<__half*>(img + off + mat_bytes) = l;
+      }
+      {
+        uint8_t* img = (uint8_t*)j.d1;
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(img + off + mat_bytes) = l;
+      }
+      break;
+    }
+  }
+}
+
+template <int LAT>
+void tc_layer_geometry(int pos, int K, int& kpad, int& npad, int& nhc, int& kcc, size_t& bytes) {
+  using G = tcx::Geo<LAT>;
+  if (pos == 0) { kpad = tcx::kK0; npad = LAT; nhc = LAT; kcc = tcx::kK0; bytes = G::L0_BYTES; }
+  else if (pos == K - 1) { kpad = LAT; npad = tcx::kNOut; nhc = tcx::kNOut; kcc = LAT; bytes = G::LAST_BYTES; }
+  else { kpad = LAT; npad = LAT; nhc = G::NH; kcc = G::KC; bytes = (size_t)tcx::kNS * G::NKC * G::CHUNK_BYTES; }
+}
+
+}  // namespace
+
+// Builds the job table of a freshly created flow (all device buffers already allocated) and uploads it.
+int pack_build_jobs(Flow& f) {
+  std::vector<PackJob> jobs;
+  int blocks = 0;
+  auto add = [&](PackJob j, int64_t elems) {
+    j.first_block = blocks;
+    j.n_blocks = (int)ceil_div(elems, kPackThreads);
+    blocks += j.n_blocks;
+    jobs.push_back(j);
+  };
+  for (int m = 0; m < f.n_mlps; ++m) {
+    const int64_t base = (int64_t)m * f.params_per_mlp;
+    if (f.attn) {
+      const int qk = f.heads * f.kq, hv = f.heads * f.vd;
+      float* wa = f.wattn + (int64_t)m * f.wattn_per_mlp;
+      float* wt = f.wattnT + (int64_t)m * f.wattnT_per_mlp;
+      struct Proj { int64_t src; int in, out, in_pad, out_pad; int64_t off, offT; };
+      const Proj pr[4] = {
+          {0, f.H, qk, f.hp8, f.qk_pad, f.wq_off, f.wqT_off},
+          {(int64_t)f.H * qk, f.H, qk, f.hp8, f.qk_pad, f.wk_off, f.wkT_off},
+          {2ll * f.H * qk, f.H, f.vd, f.hp8, f.v_pad, f.wv_off, f.wvT_off},
+          {2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, f.hv_pad, f.cho_pad, f.wo_off, f.woT_off}};
+      for (const Proj& q : pr) {
+        PackJob j{};
+        j.kind = kPackMat; j.in = q.in; j.out = q.out; j.p0 = q.in_pad; j.p1 = q.out_pad;
+        j.src_off = base + q.src; j.d0 = wa + q.off;
+        add(j, (int64_t)q.in_pad * q.out_pad);
+        PackJob t{};
+        t.kind = kPack32T; t.in = q.in; t.out = q.out; t.p0 = q.in_pad; t.p1 = q.out_pad;
+        t.src_off = base + q.src; t.d0 = wt + q.offT;
+        add(t, (int64_t)q.in_pad * q.out_pad);
+      }
+      if (f.attn_flags & GNF_ATTN_LAYER_NORM) {
+        PackJob j{};
+        j.kind = kPackLn; j.in = f.H; j.p0 = f.HP; j.src_off = base + f.ln_off;
+        j.d0 = f.wln + (int64_t)m * 2 * f.HP;
+        add(j, 2 * f.HP);
+      }
+    }
+    size_t tc_off[kMaxLayers + 1] = {0};
+    if (f.tc_ok)
+      for (int pos = 0; pos < f.K; ++pos) {
+        int a, b, c, d; size_t bytes;
+        if (f.L == 256) tc_layer_geometry<256>(pos, f.K, a, b, c, d, bytes);
+        else tc_layer_geometry<128>(pos, f.K, a, b, c, d, bytes);
+        tc_off[pos + 1] = tc_off[pos] + bytes;
+      }
+    for (int l = 0; l < f.K; ++l) {
+      const int64_t wsrc = base + f.flat_w_off[l];
+      {
+        PackJob j{};
+        j.kind = kPack32; j.in = f.ins[l]; j.out = f.outs[l]; j.p0 = f.in_pads[l]; j.p1 = f.out_pads[l];
+        j.src_off = wsrc;
+        j.d0 = f.w32 + (int64_t)m * f.w32_per_mlp + f.w32_layer_off[l];
+        j.d1 = f.w32 + (int64_t)m * f.w32_per_mlp + f.b32_layer_off[l];
+        add(j, (int64_t)f.in_pads[l] * f.out_pads[l] > f.out_pads[l] ? (int64_t)f.in_pads[l] * f.out_pads[l] : f.out_pads[l]);
+      }
+      {
+        PackJob j{};
+        j.kind = kPack32T; j.in = f.ins[l]; j.out = f.outs[l]; j.p0 = f.in_pads[l]; j.p1 = f.out_pad8[l];
+        j.src_off = wsrc;
+        j.d0 = f.w32T + (int64_t)m * f.w32T_per_mlp + f.w32T_layer_off[l];
+        add(j, (int64_t)f.in_pads[l] * f.out_pad8[l]);
+      }
+      if (!f.tc_ok) continue;
+      {   // forward chain position l
+        int kpad, npad, nhc, kcc; size_t bytes;
+        if (f.L == 256) tc_layer_geometry<256>(l, f.K, kpad, npad, nhc, kcc, bytes);
+        else tc_layer_geometry<128>(l, f.K, kpad, npad, nhc, kcc, bytes);
+        PackJob j{};
+        j.kind = kPackTc; j.transposed = 0; j.in = f.ins[l]; j.out = f.outs[l];
+        j.p0 = kpad; j.p1 = npad; j.p2 = nhc; j.p3 = kcc; j.src_off = wsrc;
+        j.d0 = f.wtc[0] + (size_t)m * f.wtc_per_mlp + tc_off[l];
+        j.d1 = f.wtc[1] + (size_t)m * f.wtc_per_mlp + tc_off[l];
+        add(j, (int64_t)kpad * npad);
+        PackJob b{};
+        b.kind = kPackBias; b.out = f.outs[l]; b.src_off = base + f.flat_b_off[l];
+        b.d0 = f.btc + ((size_t)m * f.K + l) * 256;
+        add(b, 256);
+      }
+      if (f.wtcT) {   // backward dX chain: position K-1-l applies W_l^T (no bias), same chunk geometry
+        const int pos = f.K - 1 - l;
+        int kpad, npad, nhc, kcc; size_t bytes;
+        if (f.L == 256) tc_layer_geometry<256>(pos, f.K, kpad, npad, nhc, kcc, bytes);
+        else tc_layer_geometry<128>(pos, f.K, kpad, npad, nhc, kcc, bytes);
+        PackJob j{};
+        j.kind = kPackTc; j.transposed = 1; j.in = f.outs[l]; j.out = f.ins[l];
+        j.p0 = kpad; j.p1 = npad; j.p2 = nhc; j.p3 = kcc; j.src_off = wsrc;
+        j.d0 = nullptr;
+        j.d1 = f.wtcT + (size_t)m * f.wtc_per_mlp + tc_off[pos];
+        add(j, (int64_t)kpad * npad);
+      }
+    }
+  }
+  f.n_pack_jobs = (int)jobs.size();
+  f.pack_blocks = blocks;
+  GNF_CUDA(cudaMalloc(&f.pack_jobs, jobs.size() * sizeof(PackJob)));
+  GNF_CUDA(cudaMemcpy(f.pack_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  return GNF_OK;
+}
+
+int pack_all(const Flow& f, const float* params, cudaStream_t stream) {
+  if (f.pack_blocks == 0) return GNF_OK;
+  k_pack_all<<<(unsigned)f.pack_blocks, kPackThreads, 0, stream>>>((const PackJob*)f.pack_jobs, f.n_pack_jobs, params);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+}  // namespace gnf

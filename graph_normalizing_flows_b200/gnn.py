@@ -431,7 +431,15 @@ class GRevNet(nn.Module):
 
     `math` selects the arithmetic of the MLP contraction: "tc3x" (tcgen05, fp16 hi/lo split,
     fp32 accumulate; the default when the shape is supported), "fp32" (FFMA, any shape),
-    "bf16" (tcgen05 single pass), "tc3x_bf16".
+    "bf16" (tcgen05 single pass), "tc3x_bf16", "tc2x".
+
+    fp16 range guard: the reference computes in fp32 and never clamps exp(s) (gnn.py:323), so node
+    features / hidden activations beyond the fp16 range (|v| > 65504) are legal inputs, but the fp16
+    hi/lo split of "tc3x"/"tc2x" turns them into inf/NaN.  The kernels raise a sticky device flag when
+    that happens; it is copied back asynchronously after every call and `check_numerics()` (called
+    without blocking at the start of every later call, or by the user with block=True) raises
+    FloatingPointError.  With math=None (auto) the module then switches to "tc3x_bf16" (same 3-MMA
+    scheme, fp32 exponent range, 2^-17 instead of 2^-22 operand error) for all later calls.
     """
 
     def __init__(self, make_gnn_fn: Callable[[], NodeBlockGNN], num_timesteps, node_embedding_dim,
@@ -484,6 +492,9 @@ class GRevNet(nn.Module):
         self._in_dim = in_dim
         self._rebind()
         self._math = math
+        self._range_host = None               # pinned int32[1]: last copy of the flow's fp16 range flag
+        self._range_event = None              # recorded after that copy
+        self._range_tripped = False           # auto mode: an overflow was seen -> tc3x_bf16 from then on
         # bns[2][T] = make_batch_norm() (gnn.py:260-263,301-302): tf.layers.BatchNormalization(axis=-1)
         # defaults gamma=1, beta=0, moving_mean=0, moving_variance=1, epsilon=1e-3, momentum=0.99,
         # wrapped in tfb.BatchNormalization(training=True).  Always constructed, as in the reference.
@@ -527,7 +538,9 @@ class GRevNet(nn.Module):
         if self._math is not None:
             return self._math
         self._flow.ensure(self.params.detach())
-        return "tc3x" if self._flow.supports("tc3x") else "fp32"
+        if not self._flow.supports("tc3x"):
+            return "fp32"
+        return "tc3x_bf16" if self._range_tripped else "tc3x"
 
     @math.setter
     def math(self, value):
@@ -535,8 +548,44 @@ class GRevNet(nn.Module):
             raise ValueError(f"math must be one of {sorted(_lib.MATH)}")
         self._math = value
 
+    # -- fp16 range guard -------------------------------------------------------------------------
+    def _arm_range_guard(self, handle, math_name: str, device):
+        """After a tc3x / tc2x call: queue an async copy of the sticky device flag + an event."""
+        if math_name not in ("tc3x", "tc2x") or torch.cuda.is_current_stream_capturing():
+            return
+        if self._range_host is None:
+            self._range_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _lib.check(self._flow.lib.gnf_flow_range_flag(handle, C.c_void_p(self._range_host.data_ptr()), 0,
+                                                      _lib.stream_ptr(device)), "gnf_flow_range_flag")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._range_event = ev
+
+    def check_numerics(self, block: bool = True):
+        """Raise FloatingPointError if an earlier "tc3x"/"tc2x" call left the fp16 range.  block=False only
+        looks at copies that have already landed (no host sync)."""
+        ev = self._range_event
+        if ev is None:
+            return
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._range_event = None
+        if int(self._range_host[0]) == 0:
+            return
+        self._range_host[0] = 0
+        if self._flow.handle is not None:       # clear the sticky flag (stream ordered)
+            self._flow.lib.gnf_flow_range_flag(self._flow.handle, None, 1, _lib.stream_ptr(self.params.device))
+        self._range_tripped = True
+        raise FloatingPointError(
+            "GRevNet: an MLP input or hidden activation exceeded the fp16 range (|v| > 65504) in an earlier "
+            "'tc3x'/'tc2x' call; its outputs contain inf/NaN where the reference's fp32 arithmetic stays finite. "
+            "Re-run that batch: math=None (auto) has switched to 'tc3x_bf16', or set math='tc3x_bf16' / 'fp32'.")
+
     # -- the hot path ---------------------------------------------------------------------------
     def _run(self, x: GraphsTuple, inverse_kernel: bool):
+        self.check_numerics(block=False)
         if self.use_batch_norm:
             return self._run_bn(x, inverse_kernel)
         nodes = _lib.require_cuda(x.nodes, "graph.nodes", torch.float32)
@@ -547,7 +596,8 @@ class GRevNet(nn.Module):
         st = structure_of(x)
         handle = self._flow.ensure(self.params.detach())
         lib = self._flow.lib
-        m = _lib.MATH[self.math]
+        math_name = self.math
+        m = _lib.MATH[math_name]
         n = nodes.shape[0]
         wsb = lib.gnf_grevnet_workspace(handle, n, m)
         ws = _lib.workspace(wsb, nodes.device)
@@ -558,10 +608,12 @@ class GRevNet(nn.Module):
             _lib.check(lib.gnf_grevnet_forward(handle, _lib.ptr(nodes), n, st.n_edges, _lib.ptr(st.rowptr),
                                                _lib.ptr(st.csr_senders), _lib.ptr(out), _lib.ptr(ldj), m,
                                                _lib.ptr(ws), wsb, stream), "gnf_grevnet_forward")
+            self._arm_range_guard(handle, math_name, nodes.device)
             return out, ldj
         _lib.check(lib.gnf_grevnet_inverse(handle, _lib.ptr(nodes), n, st.n_edges, _lib.ptr(st.rowptr),
                                            _lib.ptr(st.csr_senders), _lib.ptr(out), m, _lib.ptr(ws), wsb,
                                            stream), "gnf_grevnet_inverse")
+        self._arm_range_guard(handle, math_name, nodes.device)
         return out, None
 
     # -- a9: the batch-norm variant, half step by half step ---------------------------------------
@@ -607,7 +659,8 @@ class GRevNet(nn.Module):
         st = structure_of(x)
         handle = self._flow.ensure(self.params.detach())
         lib, dev = self._flow.lib, nodes.device
-        m = _lib.MATH[self.math]
+        math_name = self.math
+        m = _lib.MATH[math_name]
         n = nodes.shape[0]
         hp = lib.gnf_padded_half(D // 2)
         wsb = lib.gnf_grevnet_workspace(handle, n, m)
@@ -640,6 +693,7 @@ class GRevNet(nn.Module):
                 self._bn_forward_(x0, n, 0, i)
         out = torch.empty_like(nodes)
         _lib.check(lib.gnf_merge_halves(_lib.ptr(x0), _lib.ptr(x1), n, D, _lib.ptr(out), stream), "gnf_merge_halves")
+        self._arm_range_guard(handle, math_name, dev)
         return out, ldj
 
     def f(self, x: GraphsTuple):

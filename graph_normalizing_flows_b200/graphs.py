@@ -152,18 +152,26 @@ class BatchPrefetcher:
             st = BatchStructure(g.senders, g.receivers, n, validate="deferred")
             s, r = g.senders, g.receivers
             s._gnf_structure = ((id(r), r._version, s._version, n), weakref.ref(r), st)
+            bad_host = torch.empty(1, dtype=torch.int32).pin_memory()
+            bad_host.copy_(st._bad, non_blocking=True)       # lands with the staging work, on the side stream
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return g, st, ev
+        return g, st, ev, bad_host
 
     def wait(self, ticket) -> GraphsTuple:
-        g, st, ev = ticket
+        g, st, ev, bad_host = ticket
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
         for t in list(g) + [st.rowptr, st.perm, st.csr_senders]:
             if isinstance(t, torch.Tensor) and t.is_cuda:
                 t.record_stream(cur)
-        st.check()
+        # the host waits for the STAGING stream's event only (copies + CSR build of a batch submitted a step ago),
+        # never for the compute stream: no pipeline stall, and the ids are checked before any kernel consumes them
+        ev.synchronize()
+        st._bad = None
+        nbad = int(bad_host[0])
+        if nbad:
+            raise ValueError(f"{nbad} sender/receiver indices outside [0, {st.n_nodes})")
         return g
 
 
@@ -181,15 +189,26 @@ def structure_of(graph: GraphsTuple) -> BatchStructure:
     hit = getattr(s, "_gnf_structure", None)
     if hit is not None and hit[0] == key and hit[1]() is r:
         return hit[2]
-    if graph.n_node is not None:
-        tot = int(torch.as_tensor(graph.n_node).sum().item())
-        if tot != n:
-            raise ValueError(f"sum(n_node)={tot} does not match nodes.shape[0]={n}")
-    if graph.n_edge is not None:
-        tot = int(torch.as_tensor(graph.n_edge).sum().item())
-        if tot != int(s.numel()):
-            raise ValueError(f"sum(n_edge)={tot} does not match len(senders)={int(s.numel())}")
-    st = BatchStructure(s, r, n)
+    # validation + CSR build are enqueued first; the bad-id count and the two size sums come back in ONE host read
+    st = BatchStructure(s, r, n, validate="deferred")
+    dev_vals, names, host_checks = [st._bad.to(torch.int64).reshape(1)], ["bad"], []
+    for name, v, want in (("n_node", graph.n_node, n), ("n_edge", graph.n_edge, int(s.numel()))):
+        if v is None:
+            continue
+        v = torch.as_tensor(v)
+        if v.is_cuda:
+            dev_vals.append(v.sum(dtype=torch.int64).reshape(1))
+            names.append((name, want))
+        else:
+            host_checks.append((name, int(v.sum()), want))
+    got = torch.cat(dev_vals).tolist()
+    st._bad = None
+    for name, tot, want in host_checks + [(nm[0], got[i], nm[1]) for i, nm in enumerate(names) if i > 0]:
+        if tot != want:
+            what = "nodes.shape[0]" if name == "n_node" else "len(senders)"
+            raise ValueError(f"sum({name})={tot} does not match {what}={want}")
+    if got[0]:
+        raise ValueError(f"{got[0]} sender/receiver indices outside [0, {n})")
     s._gnf_structure = (key, weakref.ref(r), st)
     return st
 

@@ -114,9 +114,9 @@ def main(argv):
                            eps=FLAGS.adam_epsilon)                                   # run_grevnet.py:357-361
     t0 = time.time()
     for step in range(1, FLAGS.num_train_iters + 1):
-        if FLAGS.use_lr_decay:                                                       # staircase exponential decay :347-353
+        if FLAGS.use_lr_decay:                                                       # tf.train.exponential_decay(staircase=False) :346-352
             for grp in opt.param_groups:
-                grp["lr"] = FLAGS.lr * FLAGS.lr_decay_rate ** (step // FLAGS.lr_decay_steps)
+                grp["lr"] = FLAGS.lr * FLAGS.lr_decay_rate ** ((step - 1) / FLAGS.lr_decay_steps)   # global_step = step - 1
         graph = dataset.get_next_batch(FLAGS.train_batch_size).to("cuda")
         scalars, grads = grevnet.loss_and_grad(graph, per_node=False)               # total_loss, :296,362-364
         if FLAGS.clip_gradient_by_value:                                             # :365-370

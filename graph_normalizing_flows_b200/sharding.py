@@ -95,8 +95,14 @@ class GraphShardedGRevNet:
         return shard_graphs_tuple(host_batch, parts[self.rank])
 
     def broadcast_parameters(self, src: int = 0):
+        """Replicate rank `src`'s flow parameters, batch-norm gamma/beta and moving statistics on every rank,
+        and force the packed weight images to be rebuilt from them."""
         if self.world_size > 1:
-            dist.broadcast(self.grevnet.params.data, src=src, group=self.group)
+            net = self.grevnet
+            with torch.no_grad():
+                for t in (net.params, net.bn_gamma, net.bn_beta, net.bn_moving_mean, net.bn_moving_var):
+                    dist.broadcast(t.detach(), src=src, group=self.group)
+            net._flow._packed_version = None
 
     def log_prob(self, local_graph: GraphsTuple, return_z: bool = False) -> dict:
         from .loss import mvn_log_prob_sum, scalars_from_vector

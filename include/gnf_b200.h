@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GNF_ABI_VERSION 3
+#define GNF_ABI_VERSION 4
 
 /* status codes */
 #define GNF_OK            0
@@ -140,7 +140,7 @@ typedef struct gnf_flow_desc {
   /* GNF_BLOCK_DM_ATTN only (dm_self_attn_gnn arguments, gnn.py:555-573); zero otherwise */
   int32_t attn_num_heads;      /* num_heads               */
   int32_t attn_kq_dim;         /* kq_dim   (<= 64)        */
-  int32_t attn_v_dim;          /* v_dim    (<= 32)        */
+  int32_t attn_v_dim;          /* v_dim    (<= 64)        */
   int32_t attn_out_dim;        /* concat_heads_output_dim */
   int32_t attn_flags;          /* GNF_ATTN_* */
 } gnf_flow_desc;
@@ -149,8 +149,16 @@ typedef struct gnf_flow gnf_flow;   /* opaque: packed device-side weights */
 
 int64_t gnf_flow_param_count(const gnf_flow_desc* desc);
 int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* desc);
-/* (re)pack weights from the flat buffer; call after every optimiser step */
+/* (re)pack weights from the flat buffer into every image the kernels consume (padded fp32, transposed fp32, fp16 and
+ * bf16 hi/lo tensor-core chunk images, their transposes, biases): ONE kernel launch; call after every optimiser step */
 int gnf_flow_set_params(gnf_flow* flow, const float* params, void* stream);
+/* fp16 range guard of GNF_MATH_TC3X / GNF_MATH_TC2X.  The reference computes in fp32 and never clamps exp(s)
+ * (gnn.py:323), so MLP inputs / hidden activations beyond the fp16 range (|v| > 65504) are legal; the fp16 hi/lo split
+ * turns them into inf/NaN.  The fused kernels therefore set a STICKY device flag whenever an operand they split exceeds
+ * that range.  gnf_flow_range_flag enqueues on `stream` an asynchronous copy of the flag into *host_flag (pinned host
+ * memory; may be NULL) and, if reset != 0, clears the device flag after the copy.  The host mirror raises
+ * FloatingPointError and re-runs in GNF_MATH_TC3X_BF16 (same 3-MMA scheme, bf16 range = fp32 range). */
+int gnf_flow_range_flag(const gnf_flow* flow, int32_t* host_flag, int32_t reset, void* stream);
 int gnf_flow_destroy(gnf_flow* flow);
 /* 1 if (flow shape, math) is served by the fused tcgen05 kernel, 0 if only GNF_MATH_FP32 is */
 int gnf_flow_supports(const gnf_flow* flow, int32_t math);
