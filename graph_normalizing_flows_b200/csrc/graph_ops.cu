@@ -179,33 +179,74 @@ __global__ void k_gather_rows(const float* __restrict__ x, int h, const int32_t*
   }
 }
 
-// thread per (node, feature); serial in-order accumulation, 4 loads in flight
-template <bool kIndirectRows>
-__global__ void __launch_bounds__(256)
-k_segment_reduce(const float* __restrict__ src, int h, const int32_t* __restrict__ rowptr,
-                 const int32_t* __restrict__ idx, int64_t total, int mean, float* __restrict__ out) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int64_t node = i / h;
-  const int f = (int)(i - node * h);
-  int32_t e = rowptr[node];
-  const int32_t end = rowptr[node + 1];
-  const int32_t cnt = end - e;
-  float acc = 0.f;
-  for (; e + 4 <= end; e += 4) {
-    int32_t i0 = idx[e], i1 = idx[e + 1], i2 = idx[e + 2], i3 = idx[e + 3];
-    float v0 = src[(int64_t)i0 * h + f];
-    float v1 = src[(int64_t)i1 * h + f];
-    float v2 = src[(int64_t)i2 * h + f];
-    float v3 = src[(int64_t)i3 * h + f];
-    acc = __fadd_rn(acc, v0);
-    acc = __fadd_rn(acc, v1);
-    acc = __fadd_rn(acc, v2);
-    acc = __fadd_rn(acc, v3);
+// a3 + a4 standalone: out[r, :] = reduce over the CSR segment of r of src[idx[e], :], SERIAL in ascending e per
+// (receiver, feature) -- the bits of TF-CPU UnsortedSegmentSum.  HBM-bound sub-op, so the kernel is
+// organised around memory-level parallelism, not arithmetic:
+//   * a CTA owns kSegNodes consecutive receivers, i.e. ONE contiguous range of the CSR; rowptr and that index range are
+//     staged in shared memory with coalesced loads (every index is read from DRAM exactly once, and the dependent
+//     "load index -> load row" chain of a thread-per-feature loop disappears);
+//   * a thread owns one (receiver, feature), keeps 8 row loads in flight and adds them in edge order;
+//   * sender rows of a graph are contiguous and reused ~deg times by the CTA: they come from L1/L2 after first touch;
+//   * the h lanes of a receiver write h consecutive floats: output stores are fully coalesced.
+// Index ranges larger than the staging buffer (very high in-degree) read their indices from global memory instead.
+constexpr int kSegNodes = 128;
+constexpr int kSegCap = 4096;
+constexpr int kSegThreads = 256;
+
+__global__ void __launch_bounds__(kSegThreads)
+k_gather_segment(const float* __restrict__ src, int h, const int32_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ idx, int64_t n_nodes, int mean, float* __restrict__ out) {
+  __shared__ int32_t s_row[kSegNodes + 1];
+  __shared__ int32_t s_idx[kSegCap];
+  const int tid = threadIdx.x;
+  const int64_t n0 = (int64_t)blockIdx.x * kSegNodes;
+  const int nn = (int)((n_nodes - n0) < kSegNodes ? (n_nodes - n0) : kSegNodes);
+  for (int i = tid; i <= nn; i += kSegThreads) s_row[i] = rowptr[n0 + i];
+  __syncthreads();
+  const int32_t e0 = s_row[0];
+  const int32_t ne = s_row[nn] - e0;
+  const bool staged = ne <= kSegCap;
+  if (staged)
+    for (int i = tid; i < ne; i += kSegThreads) s_idx[i] = idx[e0 + i];
+  __syncthreads();
+  const int items = nn * h;
+  for (int item = tid; item < items; item += kSegThreads) {
+    const int node = item / h;
+    const int f = item - node * h;
+    const int32_t beg = s_row[node] - e0, end = s_row[node + 1] - e0;
+    const float* __restrict__ col = src + f;
+    float acc = 0.f;
+    int32_t e = beg;
+    if (staged) {
+      for (; e + 8 <= end; e += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = col[(int64_t)s_idx[e + j] * h];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, v[j]);
+      }
+      if (e + 4 <= end) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = col[(int64_t)s_idx[e + j] * h];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = __fadd_rn(acc, v[j]);
+        e += 4;
+      }
+      for (; e < end; ++e) acc = __fadd_rn(acc, col[(int64_t)s_idx[e] * h]);
+    } else {
+      const int32_t* __restrict__ gi = idx + e0;
+      for (; e + 4 <= end; e += 4) {
+        const int32_t i0 = gi[e], i1 = gi[e + 1], i2 = gi[e + 2], i3 = gi[e + 3];
+        const float v0 = col[(int64_t)i0 * h], v1 = col[(int64_t)i1 * h], v2 = col[(int64_t)i2 * h],
+                    v3 = col[(int64_t)i3 * h];
+        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v0), v1), v2), v3);
+      }
+      for (; e < end; ++e) acc = __fadd_rn(acc, col[(int64_t)gi[e] * h]);
+    }
+    if (mean) acc = __fdiv_rn(acc, fmaxf((float)(end - beg), 1.f));
+    out[(n0 + node) * h + f] = acc;
   }
-  for (; e < end; ++e) acc = __fadd_rn(acc, src[(int64_t)idx[e] * h + f]);
-  if (mean) acc = __fdiv_rn(acc, fmaxf((float)cnt, 1.f));
-  out[i] = acc;
 }
 
 // f3  pred_adj(graph, scaled_hacky_sigmoid_l2) (loss.py:154-159,45-53,131-151,83-85), block-diagonal:
@@ -337,9 +378,8 @@ static int segment_common(const float* src, int32_t h, const int32_t* rowptr, co
   GNF_REQUIRE(agg == GNF_AGG_SUM || agg == GNF_AGG_MEAN, GNF_EINVAL, "%s: bad agg %d", who, agg);
   if (n_nodes == 0) return GNF_OK;
   GNF_REQUIRE(rowptr && out, GNF_EINVAL, "%s: null pointer", who);
-  int64_t total = n_nodes * h;
-  k_segment_reduce<true><<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
-      src, h, rowptr, idx, total, agg == GNF_AGG_MEAN, out);
+  k_gather_segment<<<(unsigned)ceil_div(n_nodes, kSegNodes), kSegThreads, 0, stream>>>(
+      src, h, rowptr, idx, n_nodes, agg == GNF_AGG_MEAN, out);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }

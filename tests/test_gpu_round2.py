@@ -1,0 +1,201 @@
+"""GPU tests added in round 2 (-m gpu): fp16 range guard, the embedding-flow default shape of
+train_grevnet_with_data.py, NCCL world_size 2 through GraphShardedGRevNet, deferred index validation."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import helpers as H
+from oracle import gnf_oracle as O
+import graph_normalizing_flows_b200 as G
+from graph_normalizing_flows_b200 import sharding
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LOGPROB_RTOL = 1e-5
+
+
+def dev_graph(g):
+    return H.to_device_graph(g, DEV)
+
+
+# ------------------------------------------------------------------------------- fp16 range guard ---
+def _big_hidden_params():
+    """Weights that drive a hidden PRE-activation past 65504 with O(1) inputs: first layer scaled up, later layers
+    scaled down so that s, t (and exp(s)) stay ordinary numbers in fp32 arithmetic."""
+    params = O.make_params(3, 2, 14, 128, 4, last_layer_scale=0.05)
+    for which in ("s", "t"):
+        for half in range(2):
+            for i in range(2):
+                layers = params[which][half][i]
+                w0, b0 = layers[0]
+                layers[0] = ((w0 * 3e5).astype(np.float32), b0)
+                w1, b1 = layers[1]
+                layers[1] = ((w1 / 3e5).astype(np.float32), b1)
+    return params
+
+
+@pytest.mark.parametrize("case", ["inputs_x1e3", "hidden_preactivation"])
+def test_fp16_range_guard_raises_and_auto_mode_falls_back(case):
+    """The reference computes in fp32 (unclamped exp, gnn.py:323): inputs or hidden activations beyond the fp16
+    range are legal.  tc3x (fp16 hi/lo split) must not return inf/NaN silently: the device flag raises
+    FloatingPointError at check_numerics(); math=None then re-runs in tc3x_bf16 and meets the fp64 oracle."""
+    rng = np.random.default_rng(31)
+    g = H.random_batch(rng, 10, 5, 30, D=14)
+    if case == "inputs_x1e3":
+        # node features x 1e3 and a sum aggregation over ~10 neighbours; the first layer is scaled down to keep s small
+        g = g._replace(nodes=(g.nodes * 3e4).astype(np.float32))
+        params = O.make_params(3, 2, 14, 128, 4, last_layer_scale=0.05)
+        for which in ("s", "t"):
+            for half in range(2):
+                for i in range(2):
+                    w0, b0 = params[which][half][i][0]
+                    params[which][half][i][0] = ((w0 / 3e4).astype(np.float32), b0)
+    else:
+        params = _big_hidden_params()
+    z64, ldj64 = O.grevnet_f(g.nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(params, np.float64))
+    want = O.log_prob(z64, ldj64, g.n_node)["log_prob_xs"]
+    assert np.isfinite(z64).all() and np.isfinite(want)
+    dg = dev_graph(g)
+    # explicit tc3x: loud failure
+    net = H.make_grevnet(params, 128, 4, device=DEV, math="tc3x")
+    G.loss.log_prob(net, dg)
+    with pytest.raises(FloatingPointError, match="fp16 range"):
+        net.check_numerics()
+    net.check_numerics()                         # the flag was consumed and reset
+    # auto mode: first call trips the guard, later calls run in tc3x_bf16 and are right
+    auto = H.make_grevnet(params, 128, 4, device=DEV, math=None)
+    assert auto.math == "tc3x"
+    G.loss.log_prob(auto, dg)
+    with pytest.raises(FloatingPointError):
+        auto.check_numerics()
+    assert auto.math == "tc3x_bf16"
+    out = G.loss.log_prob(auto, dg, return_z=True)
+    auto.check_numerics()
+    assert H.rel_err(out["log_prob_xs"], want) < LOGPROB_RTOL
+    scale = max(1.0, float(np.abs(z64).max()))
+    assert np.abs(out["z"].nodes.cpu().numpy() - z64).max() < 1e-4 * scale
+    # the fp32 kernels agree as well (independent arithmetic)
+    o32 = G.loss.log_prob(H.make_grevnet(params, 128, 4, device=DEV, math="fp32"), dg)
+    assert H.rel_err(o32["log_prob_xs"], want) < LOGPROB_RTOL
+
+
+def test_fp16_range_guard_is_quiet_on_ordinary_batches():
+    rng = np.random.default_rng(32)
+    g = H.random_batch(rng, 10, 5, 30, D=14)
+    params = O.make_params(3, 2, 14, 256, 5, last_layer_scale=0.05)
+    net = H.make_grevnet(params, 256, 5, device=DEV, math=None)
+    for _ in range(3):
+        out = G.loss.log_prob(net, dev_graph(g), return_z=True)
+        net(out["z"], inverse=False)
+    net.check_numerics()
+    assert net.math == "tc3x"
+
+
+# ------------------------------------------------- train_grevnet_with_data.py default shape (f1/f4) ---
+def test_embedding_flow_default_shape_runs_and_matches_oracle():
+    """train_grevnet_with_data.py:41-47,104-117 defaults: node_embedding_dim=200, gnn_latent_dim=2048,
+    gnn_num_layers=3, dm_self_attn with attn_kq_dim=64, attn_v_dim=64, 1 head, concat_heads_output_dim=64, on fully
+    connected graphs (round 1 rejected v_dim > 32).  Two coupling steps instead of ten keep the oracle in seconds."""
+    from graph_normalizing_flows_b200 import utils as U
+    rng = np.random.default_rng(33)
+    n_node = np.array([5, 9, 7], np.int32)
+    senders, receivers = U.senders_receivers(n_node)
+    n = int(n_node.sum())
+    nodes = (0.5 * rng.standard_normal((n, 200))).astype(np.float32)
+    g = O.GraphsTuple(nodes, None, np.asarray(receivers, np.int32), np.asarray(senders, np.int32), None, n_node,
+                      (n_node.astype(np.int64) ** 2).astype(np.int32))
+    params = O.make_params(12345, 2, 200, 2048, 3, block="dm_attn", act="relu", last_layer_scale=0.02,
+                           attn=dict(num_heads=1, kq_dim=64, v_dim=64, out_dim=64, concat=True, residual=False,
+                                     kq_dim_division=True, layer_norm=False))
+    z64, ldj64 = O.grevnet_f(nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(params, np.float64))
+    want = O.log_prob(z64, ldj64, n_node)["log_prob_xs"]
+    net = H.make_grevnet(params, 2048, 3, device=DEV)
+    dg = dev_graph(g)
+    out = G.loss.log_prob(net, dg, return_z=True)
+    assert H.rel_err(out["log_prob_xs"], want) < LOGPROB_RTOL
+    assert np.abs(out["z"].nodes.cpu().numpy() - z64).max() < 2e-4
+    x_back = net(out["z"], inverse=False).nodes
+    assert float((x_back - dg.nodes).abs().max()) < 1e-3
+    # and it trains: reversible backward vs autograd of the fp64 restatement
+    from oracle import gnf_oracle_torch as OT
+    loss_ref, grad_ref = OT.loss_and_grads(nodes, g.senders, g.receivers, params, 1.0 / n)
+    scal, grads = net.loss_and_grad(dg, per_node=True)
+    got = grads.double().cpu().numpy()
+    assert abs(float(scal["loss_per_node"]) - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert np.abs(got - grad_ref).max() <= 5e-4 * np.abs(grad_ref).max()
+
+
+# ------------------------------------------------------------------------- deferred validation safety ---
+def test_deferred_validation_never_writes_out_of_bounds():
+    """BatchPrefetcher builds the CSR before the bad-id count is read: out-of-range receivers must be skipped by the
+    CSR kernels (no illegal address, no corruption of neighbouring allocations) and reported as ValueError."""
+    rng = np.random.default_rng(34)
+    g = H.random_batch(rng, 20, 5, 30, D=14)
+    canary = torch.full((1 << 16,), 7, dtype=torch.int32, device=DEV)
+    bad = g._replace(receivers=g.receivers.copy(), senders=g.senders.copy())
+    n = g.nodes.shape[0]
+    bad.receivers[::7] = n + 100000
+    bad.receivers[3] = -5
+    bad.senders[11] = 2 ** 30
+    host = G.GraphsTuple(*[torch.from_numpy(np.ascontiguousarray(v)).pin_memory() if v is not None else None for v in bad])
+    pf = G.graphs.BatchPrefetcher(DEV)
+    with pytest.raises(ValueError, match="outside"):
+        pf.wait(pf.submit(host))
+    with pytest.raises(ValueError, match="outside"):
+        G.graphs.structure_of(G.GraphsTuple(*bad).to(DEV))
+    torch.cuda.synchronize()                      # a sticky illegal-address error would surface here
+    assert bool((canary == 7).all())
+    ok = G.loss.log_prob(H.make_grevnet(O.make_params(1, 1, 14, 128, 3, last_layer_scale=0.05), 128, 3, device=DEV),
+                         dev_graph(g))
+    assert np.isfinite(float(ok["log_prob_xs"]))
+
+
+# --------------------------------------------------------------------------------- NCCL, world size 2 ---
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 CUDA devices (gpurun --gpus 2)")
+def test_nccl_two_ranks_sharded_wrapper_matches_unsharded():
+    """GraphShardedGRevNet on real NCCL (one process per GPU): local_shard + log_prob / log_prob_async (4-vector
+    all-reduce), loss_and_grad (gradient all-reduce), use_batch_norm (the [2H+1] moment and [2H] gradient-sum
+    all-reduces inside every half step), broadcast_parameters -- against the unsharded single-GPU result."""
+    import dist_worker as W
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=W.run, args=(r, 2, port, "nccl", q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g, params, gm, bt = W.make_case()
+    dg = dev_graph(g)
+    n = g.nodes.shape[0]
+    for key, use_bn in (("plain", False), ("bn", True)):
+        net = W.build_net(params, DEV, use_bn, gm, bt)
+        ref = G.loss.log_prob(net, dg)
+        G.loss.log_prob(net, dg)
+        scal, grads = net.loss_and_grad(dg, per_node=True)
+        want = [float(ref[k]) for k in ("log_prob_zs", "log_det_jacobian", "log_prob_xs", "num_nodes")]
+        gref = grads.double().cpu().numpy()
+        assert res[0][key]["n_local"] + res[1][key]["n_local"] == n
+        for r in range(2):
+            got = res[r][key]
+            for a, b in zip(got["vec"], want):
+                assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (key, r, a, b)
+            assert got["vec"] == res[0][key]["vec"]                       # every rank holds the same global scalars
+            for a, b in zip(got["vec_async"], want):
+                assert abs(a - b) <= 1e-6 * max(1.0, abs(b))
+            assert abs(got["loss_per_node"] - float(scal["loss_per_node"])) <= 1e-6 * abs(float(scal["loss_per_node"]))
+            assert np.abs(got["grads"] - gref).max() <= 2e-4 * np.abs(gref).max(), (key, r)
+            assert np.array_equal(got["grads"], res[0][key]["grads"])      # all-reduced: identical on both ranks
+            if use_bn:
+                gg, gb = net.bn_gamma.grad.double().cpu().numpy(), net.bn_beta.grad.double().cpu().numpy()
+                assert np.abs(got["g_gamma"] - gg).max() <= 2e-4 * np.abs(gg).max()
+                assert np.abs(got["g_beta"] - gb).max() <= 2e-4 * max(np.abs(gb).max(), np.abs(gg).max())
+                assert np.allclose(got["moving_mean"], net.bn_moving_mean.double().cpu().numpy(), atol=1e-6)
