@@ -180,58 +180,124 @@ __global__ void k_gather_rows(const float* __restrict__ x, int h, const int32_t*
 }
 
 // a3 + a4 standalone: out[r, :] = reduce over the CSR segment of r of src[idx[e], :], SERIAL in ascending e per
-// (receiver, feature) -- the bits of TF-CPU UnsortedSegmentSum.  HBM-bound sub-op, so the kernel is
-// organised around memory-level parallelism, not arithmetic:
-//   * a CTA owns kSegNodes consecutive receivers, i.e. ONE contiguous range of the CSR; rowptr and that index range are
-//     staged in shared memory with coalesced loads (every index is read from DRAM exactly once, and the dependent
-//     "load index -> load row" chain of a thread-per-feature loop disappears);
-//   * a thread owns one (receiver, feature), keeps 8 row loads in flight and adds them in edge order;
-//   * sender rows of a graph are contiguous and reused ~deg times by the CTA: they come from L1/L2 after first touch;
-//   * the h lanes of a receiver write h consecutive floats: output stores are fully coalesced.
-// Index ranges larger than the staging buffer (very high in-degree) read their indices from global memory instead.
+// (receiver, feature) -- the bits of TF-CPU UnsortedSegmentSum.  HBM-bound sub-op.
+//
+// A CTA owns kSegNodes consecutive receivers = ONE contiguous CSR range.  What it needs is staged in shared memory
+// with coalesced loads: rowptr, its index range (each index leaves DRAM once) and -- when h <= 8 and the senders of
+// that range span at most kSegRows rows (graphs are contiguous node blocks, so they do) -- those rows, re-laid as
+// 8-float padded rows.  Then ONE thread per receiver walks its segment: per edge one index read and two 128-bit
+// shared-memory loads feed h serial adds, 7x fewer instructions and L1 wavefronts than a thread per (receiver,
+// feature).  Results leave through a staging row: the CTA's h * 128 output floats are one contiguous, coalesced store.
+// (ncu of the thread-per-feature kernel this replaces: issue slots 79 % busy, L1 data pipe 50 %, DRAM 13 % --
+// instruction bound, not bandwidth bound.)
+// CTAs that cannot stage (h > 8, materialised edge tensors whose rows are spread out, very high in-degree) fall back
+// to a thread per (receiver, feature) with 4 loads in flight -- same order, same bits.
 constexpr int kSegNodes = 128;
-constexpr int kSegCap = 4096;
-constexpr int kSegThreads = 256;
+constexpr int kSegCap = 4096;      // staged indices per CTA
+constexpr int kSegRows = 512;      // staged sender rows per CTA (8 floats each)
 
-__global__ void __launch_bounds__(kSegThreads)
+__global__ void __launch_bounds__(kSegNodes)
 k_gather_segment(const float* __restrict__ src, int h, const int32_t* __restrict__ rowptr,
                  const int32_t* __restrict__ idx, int64_t n_nodes, int mean, float* __restrict__ out) {
   __shared__ int32_t s_row[kSegNodes + 1];
   __shared__ int32_t s_idx[kSegCap];
-  const int tid = threadIdx.x;
+  __shared__ __align__(16) float s_rows[kSegRows * 8];
+  __shared__ float s_out[kSegNodes * 8];
+  __shared__ int32_t s_red[2 * (kSegNodes / 32)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n0 = (int64_t)blockIdx.x * kSegNodes;
   const int nn = (int)((n_nodes - n0) < kSegNodes ? (n_nodes - n0) : kSegNodes);
-  for (int i = tid; i <= nn; i += kSegThreads) s_row[i] = rowptr[n0 + i];
+  for (int i = tid; i <= nn; i += kSegNodes) s_row[i] = rowptr[n0 + i];
   __syncthreads();
   const int32_t e0 = s_row[0];
   const int32_t ne = s_row[nn] - e0;
-  const bool staged = ne <= kSegCap;
-  if (staged)
-    for (int i = tid; i < ne; i += kSegThreads) s_idx[i] = idx[e0 + i];
+  const bool idx_staged = ne <= kSegCap;
+  int32_t lo = 0x7fffffff, hi = -1;
+  if (idx_staged)
+    for (int i = tid; i < ne; i += kSegNodes) {
+      const int32_t v = idx[e0 + i];
+      s_idx[i] = v;
+      lo = min(lo, v);
+      hi = max(hi, v);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { s_red[warp] = lo; s_red[kSegNodes / 32 + warp] = hi; }
   __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kSegNodes / 32; ++w) { lo = min(lo, s_red[w]); hi = max(hi, s_red[kSegNodes / 32 + w]); }
+  const int nrows = ne > 0 ? hi - lo + 1 : 0;
+
+  if (idx_staged && h <= 8 && nrows <= kSegRows) {
+    // ---- staged rows: lane r reads h words at stride h, so a warp covers 32 consecutive rows of src ----------
+    for (int r = tid; r < nrows; r += kSegNodes) {
+      const float* __restrict__ g = src + (int64_t)(lo + r) * h;
+      float v[8];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) v[f] = f < h ? g[f] : 0.f;
+      *reinterpret_cast<float4*>(&s_rows[r * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&s_rows[r * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    if (tid < nn) {
+      float acc[8];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+      const int32_t beg = s_row[tid] - e0, end = s_row[tid + 1] - e0;
+      int32_t e = beg;
+      for (; e + 2 <= end; e += 2) {                      // two rows in flight, added in edge order
+        const int r0 = s_idx[e] - lo, r1 = s_idx[e + 1] - lo;
+        const float4 a0 = *reinterpret_cast<const float4*>(&s_rows[r0 * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&s_rows[r0 * 8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&s_rows[r1 * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&s_rows[r1 * 8 + 4]);
+        acc[0] = __fadd_rn(__fadd_rn(acc[0], a0.x), b0.x); acc[1] = __fadd_rn(__fadd_rn(acc[1], a0.y), b0.y);
+        acc[2] = __fadd_rn(__fadd_rn(acc[2], a0.z), b0.z); acc[3] = __fadd_rn(__fadd_rn(acc[3], a0.w), b0.w);
+        acc[4] = __fadd_rn(__fadd_rn(acc[4], a1.x), b1.x); acc[5] = __fadd_rn(__fadd_rn(acc[5], a1.y), b1.y);
+        acc[6] = __fadd_rn(__fadd_rn(acc[6], a1.z), b1.z); acc[7] = __fadd_rn(__fadd_rn(acc[7], a1.w), b1.w);
+      }
+      if (e < end) {
+        const int r0 = s_idx[e] - lo;
+        const float4 a0 = *reinterpret_cast<const float4*>(&s_rows[r0 * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&s_rows[r0 * 8 + 4]);
+        acc[0] = __fadd_rn(acc[0], a0.x); acc[1] = __fadd_rn(acc[1], a0.y); acc[2] = __fadd_rn(acc[2], a0.z);
+        acc[3] = __fadd_rn(acc[3], a0.w); acc[4] = __fadd_rn(acc[4], a1.x); acc[5] = __fadd_rn(acc[5], a1.y);
+        acc[6] = __fadd_rn(acc[6], a1.z); acc[7] = __fadd_rn(acc[7], a1.w);
+      }
+      if (mean) {
+        const float dv = fmaxf((float)(end - beg), 1.f);
+#pragma unroll
+        for (int f = 0; f < 8; ++f) acc[f] = __fdiv_rn(acc[f], dv);
+      }
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+        if (f < h) s_out[tid * h + f] = acc[f];
+    }
+    __syncthreads();
+    float* __restrict__ o = out + n0 * h;
+    for (int i = tid; i < nn * h; i += kSegNodes) o[i] = s_out[i];
+    return;
+  }
+
+  // ---- generic: thread per (receiver, feature) ---------------------------------------------------------------
   const int items = nn * h;
-  for (int item = tid; item < items; item += kSegThreads) {
+  for (int item = tid; item < items; item += kSegNodes) {
     const int node = item / h;
     const int f = item - node * h;
     const int32_t beg = s_row[node] - e0, end = s_row[node + 1] - e0;
     const float* __restrict__ col = src + f;
     float acc = 0.f;
     int32_t e = beg;
-    if (staged) {
-      for (; e + 8 <= end; e += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = col[(int64_t)s_idx[e + j] * h];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, v[j]);
-      }
-      if (e + 4 <= end) {
+    if (idx_staged) {
+      for (; e + 4 <= end; e += 4) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = col[(int64_t)s_idx[e + j] * h];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc = __fadd_rn(acc, v[j]);
-        e += 4;
       }
       for (; e < end; ++e) acc = __fadd_rn(acc, col[(int64_t)s_idx[e] * h]);
     } else {
@@ -378,7 +444,7 @@ static int segment_common(const float* src, int32_t h, const int32_t* rowptr, co
   GNF_REQUIRE(agg == GNF_AGG_SUM || agg == GNF_AGG_MEAN, GNF_EINVAL, "%s: bad agg %d", who, agg);
   if (n_nodes == 0) return GNF_OK;
   GNF_REQUIRE(rowptr && out, GNF_EINVAL, "%s: null pointer", who);
-  k_gather_segment<<<(unsigned)ceil_div(n_nodes, kSegNodes), kSegThreads, 0, stream>>>(
+  k_gather_segment<<<(unsigned)ceil_div(n_nodes, kSegNodes), kSegNodes, 0, stream>>>(
       src, h, rowptr, idx, n_nodes, agg == GNF_AGG_MEAN, out);
   GNF_LAUNCH_CHECK();
   return GNF_OK;

@@ -585,7 +585,8 @@ class GRevNet(nn.Module):
 
     # -- the hot path ---------------------------------------------------------------------------
     def _run(self, x: GraphsTuple, inverse_kernel: bool):
-        self.check_numerics(block=False)
+        if self._range_event is not None and not torch.cuda.is_current_stream_capturing():
+            self.check_numerics(block=False)                  # (cudaEventQuery would invalidate a capture)
         if self.use_batch_norm:
             return self._run_bn(x, inverse_kernel)
         nodes = _lib.require_cuda(x.nodes, "graph.nodes", torch.float32)

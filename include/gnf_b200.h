@@ -72,10 +72,11 @@ int64_t     gnf_launch_count(int reset);
 /* Developer aid: when device_buf (>= 10*2048 uint64, zeroed) is non-NULL, CTA 0 of every fused
  * coupling kernel records a clock64 timeline of its warp roles into it; NULL switches it off. */
 int         gnf_debug_set_trace(void* device_buf);
-/* CUDA-event bracket around every fused coupling launch (k_coupling_tc): enable = 1 resets the counters and
- * starts recording (up to 4096 launches), 0 stops.  gnf_debug_kernel_time synchronises the recorded events and
- * returns their summed duration and count, so a benchmark can report the kernel's average duration inside its
- * own timed steps.  Host-side state, not thread safe. */
+/* Device-side duration of every fused coupling launch (k_coupling_tc): enable = 1 resets the slots and starts recording
+ * (up to 8192 launches), 0 stops.  Each launch writes {first CTA past its dependency wait, last CTA done} from
+ * %globaltimer into its own slot -- no host events between launches, so a benchmark can keep this on inside its timed
+ * steps.  gnf_debug_kernel_time synchronises the device and returns the summed duration and the launch count.
+ * Host-side state, not thread safe. */
 int         gnf_debug_kernel_timing(int32_t enable);
 int         gnf_debug_kernel_time(double* total_ms, int64_t* launches);
 

@@ -103,9 +103,11 @@ def _bn_inverse(x, gamma, beta):
     return y, ildj
 
 
-def grevnet_f_autograd(nodes, senders, receivers, p, bn=None):
+def grevnet_f_autograd(nodes, senders, receivers, p, bn=None, ldj64_out=None):
     """GRevNet.f (gnn.py:304-341), differentiable (tests: reference gradients by autograd).
-    bn = (gamma[2][T][H], beta[2][T][H]) switches use_batch_norm on."""
+    bn = (gamma[2][T][H], beta[2][T][H]) switches use_batch_norm on.
+    ldj64_out: optional list; receives the same log-det with every reduce_sum(s) accumulated in float64 (separates the
+    reference's fp32 summation error from the error of s itself when a parity report compares log-dets)."""
     cfg = p["cfg"]
     h = nodes.shape[1] // 2
     x0, x1 = nodes[:, :h].contiguous(), nodes[:, h:].contiguous()
@@ -117,6 +119,8 @@ def grevnet_f_autograd(nodes, senders, receivers, p, bn=None):
         s = _gnn(x0, senders, receivers, _st(p, "s", 0, i), cfg)
         t = _gnn(x0, senders, receivers, _st(p, "t", 0, i), cfg)
         ldj = ldj + s.sum()
+        if ldj64_out is not None:
+            ldj64_out.append(float(s.detach().double().sum()))
         x1 = x1 * torch.exp(s) + t
         if bn is not None:
             x1, l = _bn_inverse(x1, bn[0][1][i], bn[1][1][i])
@@ -124,13 +128,15 @@ def grevnet_f_autograd(nodes, senders, receivers, p, bn=None):
         s = _gnn(x1, senders, receivers, _st(p, "s", 1, i), cfg)
         t = _gnn(x1, senders, receivers, _st(p, "t", 1, i), cfg)
         ldj = ldj + s.sum()
+        if ldj64_out is not None:
+            ldj64_out.append(float(s.detach().double().sum()))
         x0 = x0 * torch.exp(s) + t
     return torch.cat([x0, x1], 1), ldj
 
 
 @torch.no_grad()
-def grevnet_f(nodes, senders, receivers, p):
-    return grevnet_f_autograd(nodes, senders, receivers, p)
+def grevnet_f(nodes, senders, receivers, p, ldj64_out=None):
+    return grevnet_f_autograd(nodes, senders, receivers, p, ldj64_out=ldj64_out)
 
 
 def log_prob_xs_autograd(z, ldj):              # run_grevnet.py:292-295
