@@ -109,6 +109,7 @@ struct Flow {
   bool tc_ok = false;
   void* pack_jobs = nullptr;   // device job table of the one-launch re-pack (pack.cu)
   int n_pack_jobs = 0, pack_blocks = 0;
+  void* half_tables = nullptr; // device HalfDesc[2 images][2 directions][2T] of the persistent launch (coupling_tc.cu)
   int* range_flag = nullptr;   // sticky device flag: an fp16-split operand left the fp16 range (gnf_flow_range_flag)
 
   int mlp_index(int which, int half, int step) const {
@@ -163,6 +164,11 @@ bool tc_shape_supported(const Flow& f);
 void tc_set_trace(void* buf);
 int tc_kernel_timing(int enable);
 int tc_kernel_time(double* total_ms, int64_t* launches);
+int tc_build_half_tables(Flow& f);
+bool tc_persistent_wanted(int64_t n_nodes);
+int tc_flow_persistent(const Flow& f, int math, int inverse, float* x0, float* x1, int64_t n_nodes,
+                       const int32_t* rowptr, const int32_t* csr_senders, double* ldj_partials, double* ldj_accum,
+                       unsigned int* counter, void* stream);
 int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
                      const float* xa, float* xb, int64_t n_nodes,
                      const int32_t* rowptr, const int32_t* csr_senders,

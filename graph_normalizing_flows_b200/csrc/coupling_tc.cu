@@ -27,6 +27,7 @@
 // (gnn.py:100-126), make_mlp_model (gnn.py:159-180), coupling update (gnn.py:320-323,335-338,
 // 353-359,366-372).
 #include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -34,15 +35,24 @@ namespace gnf {
 namespace {
 
 using namespace tcx;
+// One half coupling step: which planar half is read (xa) / updated (xb) and the two MLP images.
+struct HalfDesc {
+  const uint8_t* w[2];     // weight images of the s and t MLP
+  const float* bias[2];    // [K][256]
+  int32_t swap;            // 0: xa = x[0], xb = x[1] (gnn.py:320-323);  1: xa = x[1], xb = x[0] (gnn.py:335-338)
+  int32_t pad;
+};
+
 struct TcParams {
-  const float* xa;
-  float* xb;
+  float* x[2];                 // planar halves [N, HP]
   const int32_t* rowptr;
   const int32_t* csr;
   int64_t n_nodes;
   int n_tiles;
-  const uint8_t* w[2];     // weight images of the s and t MLP
-  const float* bias[2];    // [K][256]
+  HalfDesc one;                // per-half-step launch: this launch's half step
+  const HalfDesc* halves;      // persistent launch: device table of the n_halves half steps, in execution order
+  int n_halves;
+  unsigned int* grid_bar;      // persistent launch: {arrival count, generation} of the grid barrier between half steps
   int K, H, HP, concat, mean, act, inverse;
   float eps;
   double* partials;
@@ -112,7 +122,54 @@ __device__ __forceinline__ void convert_chunk(uint32_t taddr, const uint32_t (&v
   if (NPROD == 3) tmem_st16(taddr + 16, lo);
 }
 
-template <int LAT, int NPROD, bool BF16, int ACT>
+// Grid-wide barrier of the persistent launch (one CTA per SM, all co-resident: cooperative launch).  Executed by ONE
+// thread per CTA after a CTA-level barrier; generation counter, so the same two words serve every half step.  The
+// spin gives up after ~2 s of %globaltimer (a lost CTA must not hang the device; results are then garbage and the
+// range flag is set to 2 so the host raises).
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n_ctas, int* fail_flag) {
+  __threadfence();                                            // release: this CTA's x_b rows, before it arrives
+  const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(bar + 1);
+  if (atomicAdd(bar, 1u) == n_ctas - 1) {
+    *reinterpret_cast<volatile unsigned int*>(bar) = 0u;
+    __threadfence();
+    atomicAdd(bar + 1, 1u);
+  } else {
+    const unsigned long long t0 = globaltimer_ns();
+    while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen) {
+      __nanosleep(32);
+      if (globaltimer_ns() - t0 > 2000000000ull) {
+        if (fail_flag) *fail_flag = 2;
+        break;
+      }
+    }
+  }
+  __threadfence();                                            // acquire: the other CTAs' rows, before anyone reads them
+}
+
+// Biases ride on the tensor pipe: layer l (< K-1) adds  Sel_l[128x16] * BiasTile[N x 16]^T  where Sel_l has ones in
+// K-columns 2l, 2l+1 and BiasTile holds (hi, lo) of b_l in those columns.  (Re)built per half step by `nthr` threads.
+template <int LAT, bool BF16>
+__device__ __forceinline__ void build_bias_tiles(uint8_t* btile, float* blast, const float* bias_s, const float* bias_t,
+                                                 int K, int t, int nthr) {
+  for (int i = t; i < 2 * LAT * 8; i += nthr) {                // (mlp, n, layer slot j): k = 2j, 2j+1
+    const int m = i / (LAT * 8), r = i - m * (LAT * 8), n = r >> 3, j = r & 7;
+    const float b = (j < K - 1) ? (m ? bias_t : bias_s)[j * 256 + n] : 0.f;
+    uint32_t hi, lo;
+    split_pair<BF16>(b, 0.f, hi, lo);
+    const uint32_t packed = (hi & 0xFFFFu) | (lo << 16);       // k = 2j -> hi(b), k = 2j+1 -> lo(b)
+    const int k = 2 * j;
+    *reinterpret_cast<uint32_t*>(btile + m * (LAT * 32) + (k >> 3) * (LAT * 16) + (n >> 3) * 128 + (n & 7) * 16 +
+                                 (k & 7) * 2) = packed;
+  }
+  if (t >= 0 && t < 2 * kNOut) blast[t] = ((t >> 4) ? bias_t : bias_s)[(K - 1) * 256 + (t & 15)];
+}
+
+// PERSIST = false: one half coupling step per launch (2T launches per flow, chained by programmatic dependent launch).
+// PERSIST = true : the WHOLE flow in one cooperative launch -- every CTA keeps its tiles (same static round robin) for
+//                  all 2T half steps, a grid barrier stands where the launch boundary was, the weight ring streams
+//                  straight on into the next half step's images, x halves are read with ld.global.cg (another SM
+//                  rewrote them since this SM last cached them).
+template <int LAT, int NPROD, bool BF16, int ACT, bool PERSIST>
 __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
   using G = Geo<LAT>;
   extern __shared__ uint8_t smem_raw[];
@@ -146,8 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     mbar_init(smem_u32(&bars->acc_last), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // Biases ride on the tensor pipe: layer l (< K-1) adds  Sel_l[128x16] * BiasTile[N x 16]^T  where
-  // Sel_l has ones in K-columns 2l, 2l+1 and BiasTile holds (hi, lo) of b_l in those columns.
+  const int n_halves = PERSIST ? p.n_halves : 1;
   {
     const uint16_t one = BF16 ? 0x3F80 : 0x3C00;
     for (int i = tid; i < (K - 1) * 128 * 16; i += kThreads) {
@@ -155,17 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       *reinterpret_cast<uint16_t*>(sel + l * 4096 + (k >> 3) * 2048 + m * 16 + (k & 7) * 2) =
           (k == 2 * l || k == 2 * l + 1) ? one : (uint16_t)0;
     }
-    for (int i = tid; i < 2 * LAT * 8; i += kThreads) {          // (mlp, n, layer slot j): k = 2j, 2j+1
-      const int m = i / (LAT * 8), r = i - m * (LAT * 8), n = r >> 3, j = r & 7;
-      const float b = (j < K - 1) ? p.bias[m][j * 256 + n] : 0.f;
-      uint32_t hi, lo;
-      split_pair<BF16>(b, 0.f, hi, lo);
-      const uint32_t packed = (hi & 0xFFFFu) | (lo << 16);       // k = 2j -> hi(b), k = 2j+1 -> lo(b)
-      const int k = 2 * j;
-      *reinterpret_cast<uint32_t*>(btile + m * (LAT * 32) + (k >> 3) * (LAT * 16) + (n >> 3) * 128 + (n & 7) * 16 +
-                                   (k & 7) * 2) = packed;
-    }
-    if (tid < 2 * kNOut) blast[tid] = p.bias[tid >> 4][(K - 1) * 256 + (tid & 15)];
+    const float* const bs0 = PERSIST ? p.halves[0].bias[0] : p.one.bias[0];
+    const float* const bt0 = PERSIST ? p.halves[0].bias[1] : p.one.bias[1];
+    build_bias_tiles<LAT, BF16>(btile, blast, bs0, bt0, K, tid, kThreads);
     fence_proxy_async();
   }
   if (warp == 1) {
@@ -191,9 +239,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
         bulk_g2s(smem_u32(ring + stage * kStageBytes), src, bytes, fb);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       };
+      for (int hs = 0; hs < n_halves; ++hs) {
+      // (runs ahead into the next half step's images)
+      const uint8_t* const w_s = PERSIST ? p.halves[hs].w[0] : p.one.w[0];
+      const uint8_t* const w_t = PERSIST ? p.halves[hs].w[1] : p.one.w[1];
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int m = 0; m < 2; ++m) {
-          const uint8_t* src = p.w[m];
+          const uint8_t* src = m ? w_t : w_s;
           issue(src, NPROD >= 2 ? G::L0_BYTES : G::L0_MAT_BYTES);
           src += G::L0_BYTES;
           for (int l = 1; l < K - 1; ++l)
@@ -203,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
             }
           issue(src, NPROD >= 2 ? G::LAST_BYTES : G::LAST_MAT_BYTES);
         }
+      }
       }
     }
   } else if (warp == 1) {
@@ -232,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
             waited |= 1u << q;
           }
       };
+      for (int hs = 0; hs < n_halves; ++hs)
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(bar_hfull + 8 * buf, (it >> 1) & 1);
@@ -353,6 +407,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     const int hp4 = p.HP >> 2;
     Tracer tr;
     tr.init(p.trace, 1 + (warp - 2), blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6));
+    for (int hs = 0; hs < n_halves; ++hs) {
+    const int swap = PERSIST ? p.halves[hs].swap : 0;
+    float* const xb_base = swap ? p.x[0] : p.x[1];
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       float st[2][kNOut];
 #pragma unroll
@@ -410,11 +467,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       // ---- affine coupling update + log-det partial (gnn.py:322-323 / :359) ------------------
       const int64_t node = (int64_t)tile * kTileM + row;
       if (grp == 0 && node < p.n_nodes) {
-        float* xrow = p.xb + node * p.HP;
+        float* xrow = xb_base + node * p.HP;
 #pragma unroll
         for (int g4 = 0; g4 < kNOut / 4; ++g4) {
           if (g4 < hp4) {
-            float4 x = *reinterpret_cast<const float4*>(xrow + g4 * 4);
+            float4 x = PERSIST ? __ldcg(reinterpret_cast<const float4*>(xrow + g4 * 4))
+                               : *reinterpret_cast<const float4*>(xrow + g4 * 4);
             float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -434,6 +492,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
         }
       }
     }
+    if (PERSIST && hs + 1 < n_halves) {
+      // where the launch boundary was: every x_b row of this half step written (CTA barrier, then the grid barrier
+      // with its fences), the next half step's bias tiles rebuilt; the gather warps stand at the same two barriers
+      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+      if (tid == 64) grid_barrier(p.grid_bar, gridDim.x, p.range_flag);
+      build_bias_tiles<LAT, BF16>(btile, blast, p.halves[hs + 1].bias[0], p.halves[hs + 1].bias[1], K, tid - 64,
+                                  kEpiThreads + kGatherThreads);
+      fence_proxy_async();
+      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+    }
+    }
     tr.ev(23, 0, 0);
     if (p.tstamp && tid == 64) atomicMax(p.tstamp + 1, globaltimer_ns());
     if (!BF16 && amax > 65504.f && p.range_flag) *p.range_flag = 1;
@@ -442,19 +511,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     for (int o = 16; o > 0; o >>= 1) ldj_local += __shfl_down_sync(0xffffffffu, ldj_local, o);
     if (lane == 0 && grp == 0) ldj_red[q] = ldj_local;
     asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
-    if (warp == 2 && lane == 0 && p.partials) {
-      p.partials[blockIdx.x] = ((ldj_red[0] + ldj_red[1]) + ldj_red[2]) + ldj_red[3];
-      if (p.ldj_accum) {
-        // log-det hand-off without a second launch: the last CTA to arrive sums every CTA's partial in CTA order
-        // (fixed order -> the same bits whatever the arrival order) and resets the counter for the next launch
-        __threadfence();
-        const unsigned prev = atomicAdd(p.counter, 1u);
-        if (prev == gridDim.x - 1) {
+    if (warp == 2 && p.partials) {
+      // log-det hand-off without a second launch: the last CTA to arrive folds every CTA's partial in a FIXED order
+      // (lane-strided sums, then a fixed shuffle tree: the same bits whatever the arrival order), 32 loads in flight
+      // instead of one thread walking the array, and resets the counter for the next launch
+      unsigned prev = 0;
+      if (lane == 0) {
+        p.partials[blockIdx.x] = ((ldj_red[0] + ldj_red[1]) + ldj_red[2]) + ldj_red[3];
+        if (p.ldj_accum) {
           __threadfence();
-          const volatile double* part = p.partials;
-          double s = 0.0;
-          for (unsigned i = 0; i < gridDim.x; ++i) s += part[i];
-          *p.ldj_accum += s;
+          prev = atomicAdd(p.counter, 1u);
+        }
+      }
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (p.ldj_accum && prev == gridDim.x - 1) {
+        __threadfence();
+        const volatile double* part = p.partials;
+        double acc = 0.0;
+        for (unsigned i = lane; i < gridDim.x; i += 32) acc += part[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+          *p.ldj_accum += acc;
           *p.counter = 0u;
         }
       }
@@ -469,6 +547,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     float amax = 0.f;
     Tracer tr;
     tr.init(p.trace, 9, blockIdx.x == 0 && row == 0);
+    for (int hs = 0; hs < n_halves; ++hs) {
+    const int swap = PERSIST ? p.halves[hs].swap : 0;
+    const float* const xa_base = swap ? p.x[1] : p.x[0];
+    // persistent launch: rows of xa were rewritten by other SMs one half step ago -> bypass this SM's L1
+    auto ldx = [](const float* q) -> float4 {
+      return PERSIST ? __ldcg(reinterpret_cast<const float4*>(q)) : *reinterpret_cast<const float4*>(q);
+    };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       tr.ev(30, 0, 0);
@@ -477,22 +562,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
 #pragma unroll
       for (int j = 0; j < kNOut; ++j) { self[j] = 0.f; agg[j] = 0.f; }
       if (node < p.n_nodes) {
-        const float* xr = p.xa + node * p.HP;
+        const float* xr = xa_base + node * p.HP;
 #pragma unroll
         for (int g4 = 0; g4 < kNOut / 4; ++g4)
           if (g4 < hp4) {
-            float4 x = *reinterpret_cast<const float4*>(xr + g4 * 4);
+            float4 x = ldx(xr + g4 * 4);
             self[g4 * 4] = x.x; self[g4 * 4 + 1] = x.y; self[g4 * 4 + 2] = x.z; self[g4 * 4 + 3] = x.w;
           }
         int32_t e = p.rowptr[node];
         const int32_t end = p.rowptr[node + 1];
         const int32_t cnt = end - e;
         for (; e < end; ++e) {       // ascending edge index inside the segment: TF-CPU order
-          const float* sr = p.xa + (int64_t)p.csr[e] * p.HP;
+          const float* sr = xa_base + (int64_t)p.csr[e] * p.HP;
 #pragma unroll
           for (int g4 = 0; g4 < kNOut / 4; ++g4)
             if (g4 < hp4) {
-              float4 x = *reinterpret_cast<const float4*>(sr + g4 * 4);
+              float4 x = ldx(sr + g4 * 4);
               agg[g4 * 4] = __fadd_rn(agg[g4 * 4], x.x);
               agg[g4 * 4 + 1] = __fadd_rn(agg[g4 * 4 + 1], x.y);
               agg[g4 * 4 + 2] = __fadd_rn(agg[g4 * 4 + 2], x.z);
@@ -537,6 +622,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->h_full[buf]));
     }
+    if (PERSIST && hs + 1 < n_halves) {
+      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+      build_bias_tiles<LAT, BF16>(btile, blast, p.halves[hs + 1].bias[0], p.halves[hs + 1].bias[1], K, tid - 64,
+                                  kEpiThreads + kGatherThreads);
+      fence_proxy_async();
+      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+    }
+    }
     if (!BF16 && amax > 65504.f && p.range_flag) *p.range_flag = 1;
   }
 
@@ -556,36 +649,59 @@ size_t bytes_per_mlp_t(int K) {
   return (size_t)G::L0_BYTES + (size_t)(K - 2) * kNS * G::NKC * G::CHUNK_BYTES + G::LAST_BYTES;
 }
 
-template <int LAT, int NPROD, bool BF16, int ACT>
+template <int LAT, int NPROD, bool BF16, int ACT, bool PERSIST>
 int launch_tc_act(const TcParams& p, int grid, cudaStream_t stream) {
-  auto kern = k_coupling_tc<LAT, NPROD, BF16, ACT>;
+  auto kern = k_coupling_tc<LAT, NPROD, BF16, ACT, PERSIST>;
   static bool configured[kMaxDevices] = {};
   const size_t smem = smem_bytes<LAT>();
   if (first_use_on_device(configured))
     GNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // Programmatic dependent launch: the CTAs of this launch may start on an SM as soon as the previous kernel's
-  // CTA there has exited, run their prologue (barrier init, TMEM allocation, bias tiles, first weight chunks) and
-  // block in griddepcontrol.wait before the first read of anything the previous kernel wrote (x halves, log-det).
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  static const bool pdl = getenv("GNF_NO_PDL") == nullptr;     // GNF_NO_PDL=1: plain stream-ordered launches (A/B timing)
-  cfg.numAttrs = pdl ? 1 : 0;
+  if (PERSIST) {
+    // whole flow in one launch: the CTAs meet at a grid barrier between half steps, so all of them must be resident
+    // (grid <= number of SMs, one CTA per SM): cooperative launch makes the runtime check exactly that
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    // Programmatic dependent launch: the CTAs of this launch may start on an SM as soon as the previous kernel's
+    // CTA there has exited, run their prologue (barrier init, TMEM allocation, bias tiles, first weight chunks) and
+    // block in griddepcontrol.wait before the first read of anything the previous kernel wrote (x halves, log-det).
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool pdl = getenv("GNF_NO_PDL") == nullptr;   // GNF_NO_PDL=1: plain stream-ordered launches (A/B timing)
+    cfg.numAttrs = pdl ? 1 : 0;
+  }
   GNF_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }
 
-template <int LAT, int NPROD, bool BF16>
+template <int LAT, int NPROD, bool BF16, bool PERSIST>
 int launch_tc(const TcParams& p, int grid, cudaStream_t stream) {
-  return p.act == GNF_ACT_LEAKY_RELU ? launch_tc_act<LAT, NPROD, BF16, GNF_ACT_LEAKY_RELU>(p, grid, stream)
-                                     : launch_tc_act<LAT, NPROD, BF16, GNF_ACT_RELU>(p, grid, stream);
+  return p.act == GNF_ACT_LEAKY_RELU ? launch_tc_act<LAT, NPROD, BF16, GNF_ACT_LEAKY_RELU, PERSIST>(p, grid, stream)
+                                     : launch_tc_act<LAT, NPROD, BF16, GNF_ACT_RELU, PERSIST>(p, grid, stream);
+}
+
+template <bool PERSIST>
+int launch_tc_math(const TcParams& p, int L, int math, int grid, cudaStream_t stream) {
+  if (L == 256) {
+    if (math == GNF_MATH_TC2X) return launch_tc<256, 2, false, PERSIST>(p, grid, stream);
+    if (math == GNF_MATH_TC3X) return launch_tc<256, 3, false, PERSIST>(p, grid, stream);
+    if (math == GNF_MATH_TC3X_BF16) return launch_tc<256, 3, true, PERSIST>(p, grid, stream);
+    return launch_tc<256, 1, true, PERSIST>(p, grid, stream);
+  }
+  if (math == GNF_MATH_TC2X) return launch_tc<128, 2, false, PERSIST>(p, grid, stream);
+  if (math == GNF_MATH_TC3X) return launch_tc<128, 3, false, PERSIST>(p, grid, stream);
+  if (math == GNF_MATH_TC3X_BF16) return launch_tc<128, 3, true, PERSIST>(p, grid, stream);
+  return launch_tc<128, 1, true, PERSIST>(p, grid, stream);
 }
 
 }  // namespace
@@ -646,18 +762,20 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
                      float* xb, int64_t n_nodes, const int32_t* rowptr, const int32_t* csr_senders,
                      double* ldj_partials, double* ldj_accum, unsigned int* counter, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  TcParams p;
-  p.xa = xa;
-  p.xb = xb;
+  TcParams p = {};
+  p.x[0] = const_cast<float*>(xa);
+  p.x[1] = xb;
   p.rowptr = rowptr;
   p.csr = csr_senders;
   p.n_nodes = n_nodes;
   p.n_tiles = (int)ceil_div(n_nodes, kTileM);
   const int img = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 0 : 1;
-  p.w[0] = f.wtc[img] + (size_t)mlp_s * f.wtc_per_mlp;
-  p.w[1] = f.wtc[img] + (size_t)mlp_t * f.wtc_per_mlp;
-  p.bias[0] = f.btc + (size_t)mlp_s * f.K * 256;
-  p.bias[1] = f.btc + (size_t)mlp_t * f.K * 256;
+  p.one.w[0] = f.wtc[img] + (size_t)mlp_s * f.wtc_per_mlp;
+  p.one.w[1] = f.wtc[img] + (size_t)mlp_t * f.wtc_per_mlp;
+  p.one.bias[0] = f.btc + (size_t)mlp_s * f.K * 256;
+  p.one.bias[1] = f.btc + (size_t)mlp_t * f.K * 256;
+  p.one.swap = 0;
+  p.n_halves = 1;
   p.K = f.K;
   p.H = f.H;
   p.HP = f.HP;
@@ -673,19 +791,78 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   p.trace = g_trace;
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   p.tstamp = (g_timer.on && g_timer.n < kMaxTimed) ? g_timer.slots + 2 * (size_t)g_timer.n++ : nullptr;
-  int rc;
-  if (f.L == 256) {
-    if (math == GNF_MATH_TC2X) rc = launch_tc<256, 2, false>(p, grid, stream);
-    else if (math == GNF_MATH_TC3X) rc = launch_tc<256, 3, false>(p, grid, stream);
-    else if (math == GNF_MATH_TC3X_BF16) rc = launch_tc<256, 3, true>(p, grid, stream);
-    else rc = launch_tc<256, 1, true>(p, grid, stream);
-  } else {
-    if (math == GNF_MATH_TC2X) rc = launch_tc<128, 2, false>(p, grid, stream);
-    else if (math == GNF_MATH_TC3X) rc = launch_tc<128, 3, false>(p, grid, stream);
-    else if (math == GNF_MATH_TC3X_BF16) rc = launch_tc<128, 3, true>(p, grid, stream);
-    else rc = launch_tc<128, 1, true>(p, grid, stream);
-  }
-  return rc;
+  return launch_tc_math<false>(p, f.L, math, grid, stream);
+}
+
+// Half-step tables of the persistent launch, per weight image (fp16 / bf16) and direction (f: step-major, half 0 then
+// half 1, gnn.py:309-338; g: reversed steps, half 1 then half 0, gnn.py:347-372).  Built once per flow.
+int tc_build_half_tables(Flow& f) {
+  if (!f.tc_ok) return GNF_OK;
+  const int T = f.d.num_timesteps, n = 2 * T;
+  std::vector<HalfDesc> tab((size_t)4 * n);
+  for (int img = 0; img < 2; ++img)
+    for (int inv = 0; inv < 2; ++inv)
+      for (int k = 0; k < n; ++k) {
+        int step, half;
+        if (!inv) { step = k >> 1; half = k & 1; }
+        else { step = T - 1 - (k >> 1); half = 1 - (k & 1); }
+        const int ms = f.mlp_index(0, half, step), mt = f.mlp_index(1, half, step);
+        HalfDesc& d = tab[((size_t)img * 2 + inv) * n + k];
+        d.w[0] = f.wtc[img] + (size_t)ms * f.wtc_per_mlp;
+        d.w[1] = f.wtc[img] + (size_t)mt * f.wtc_per_mlp;
+        d.bias[0] = f.btc + (size_t)ms * f.K * 256;
+        d.bias[1] = f.btc + (size_t)mt * f.K * 256;
+        d.swap = half;
+        d.pad = 0;
+      }
+  GNF_CUDA(cudaMalloc(&f.half_tables, tab.size() * sizeof(HalfDesc)));
+  GNF_CUDA(cudaMemcpy(f.half_tables, tab.data(), tab.size() * sizeof(HalfDesc), cudaMemcpyHostToDevice));
+  return GNF_OK;
+}
+
+bool tc_persistent_wanted(int64_t n_nodes) {
+  // GNF_PERSIST=0: one launch per half step always; =1: whole flow in one cooperative launch always;
+  // default: the cooperative launch up to kPersistAutoTiles tiles per SM (small and medium batches, where the
+  // launch boundaries are a visible share of the step)
+  const char* env = getenv("GNF_PERSIST");          // read per call: tests and A/B timings flip it at run time
+  if (env && env[0] == '0') return false;
+  if (env && env[0] == '1') return true;
+  const char* lim = getenv("GNF_PERSIST_TILES_PER_SM");
+  const int64_t per_sm = lim ? atoll(lim) : 4;
+  return ceil_div(n_nodes, kTileM) <= per_sm * num_sms();
+}
+
+int tc_flow_persistent(const Flow& f, int math, int inverse, float* x0, float* x1, int64_t n_nodes,
+                       const int32_t* rowptr, const int32_t* csr_senders, double* ldj_partials, double* ldj_accum,
+                       unsigned int* counter, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TcParams p = {};
+  p.x[0] = x0;
+  p.x[1] = x1;
+  p.rowptr = rowptr;
+  p.csr = csr_senders;
+  p.n_nodes = n_nodes;
+  p.n_tiles = (int)ceil_div(n_nodes, kTileM);
+  const int img = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 0 : 1;
+  p.n_halves = 2 * f.d.num_timesteps;
+  p.halves = (const HalfDesc*)f.half_tables + ((size_t)img * 2 + (inverse ? 1 : 0)) * p.n_halves;
+  p.grid_bar = counter + 16;                 // counter block is 256 bytes, zeroed by the caller
+  p.K = f.K;
+  p.H = f.H;
+  p.HP = f.HP;
+  p.concat = f.d.block == GNF_BLOCK_CONCAT;
+  p.mean = f.d.agg == GNF_AGG_MEAN;
+  p.act = f.d.act;
+  p.inverse = inverse;
+  p.eps = f.d.eps;
+  p.partials = ldj_partials;
+  p.ldj_accum = inverse ? nullptr : ldj_accum;
+  p.counter = counter;
+  p.range_flag = f.range_flag;
+  p.trace = g_trace;
+  p.tstamp = (g_timer.on && g_timer.n < kMaxTimed) ? g_timer.slots + 2 * (size_t)g_timer.n++ : nullptr;
+  const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  return launch_tc_math<true>(p, f.L, math, grid, stream);
 }
 
 }  // namespace gnf

@@ -876,7 +876,7 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
       return GNF_ECUDA;
     }
   }
-  if (pack_build_jobs(f) != GNF_OK) {
+  if (pack_build_jobs(f) != GNF_OK || tc_build_half_tables(f) != GNF_OK) {
     gnf_flow_destroy(h);
     return GNF_ECUDA;
   }
@@ -905,6 +905,7 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.btc);
   cudaFree(h->f.wtcT);
   cudaFree(h->f.pack_jobs);
+  cudaFree(h->f.half_tables);
   cudaFree(h->f.range_flag);
   delete h;
   return GNF_OK;
@@ -952,12 +953,17 @@ extern "C" int gnf_grevnet_forward(const gnf_flow* h, const float* x, int64_t n,
   GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_forward: null x/z");
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
-  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 256, stream));
   const int D = f.d.node_embedding_dim;
   if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
   k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(x, n, D, f.H, f.HP, w.x0, w.x1);
   GNF_LAUNCH_CHECK();
-  for (int i = 0; i < f.d.num_timesteps; ++i) {   // gnn.py:309
+  const bool persistent = math != GNF_MATH_FP32 && tc_persistent_wanted(n);
+  if (persistent) {   // all 2T half steps in ONE cooperative launch (grid barrier where the launch boundaries were)
+    rc = tc_flow_persistent(f, math, 0, w.x0, w.x1, n, rowptr, csr, w.partials, ldj, w.counter, stream);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < f.d.num_timesteps && !persistent; ++i) {   // gnn.py:309
     rc = coupling_half(f, 0, i, 0, w.x0, w.x1, n, rowptr, csr, ldj, math, w, stream);   // gnn.py:320-323
     if (rc) return rc;
     rc = coupling_half(f, 1, i, 0, w.x1, w.x0, n, rowptr, csr, ldj, math, w, stream);   // gnn.py:335-338
@@ -978,12 +984,17 @@ extern "C" int gnf_grevnet_inverse(const gnf_flow* h, const float* z, int64_t n,
   GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_inverse: null x/z");
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
-  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 256, stream));
   const int D = f.d.node_embedding_dim;
   if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
   k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(z, n, D, f.H, f.HP, w.x0, w.x1);
   GNF_LAUNCH_CHECK();
-  for (int i = f.d.num_timesteps - 1; i >= 0; --i) {   // gnn.py:347
+  const bool persistent = math != GNF_MATH_FP32 && tc_persistent_wanted(n);
+  if (persistent) {
+    rc = tc_flow_persistent(f, math, 1, w.x0, w.x1, n, rowptr, csr, w.partials, nullptr, w.counter, stream);
+    if (rc) return rc;
+  }
+  for (int i = f.d.num_timesteps - 1; i >= 0 && !persistent; --i) {   // gnn.py:347
     rc = coupling_half(f, 1, i, 1, w.x1, w.x0, n, rowptr, csr, nullptr, math, w, stream);  // gnn.py:353-359
     if (rc) return rc;
     rc = coupling_half(f, 0, i, 1, w.x0, w.x1, n, rowptr, csr, nullptr, math, w, stream);  // gnn.py:366-372

@@ -199,3 +199,57 @@ def test_nccl_two_ranks_sharded_wrapper_matches_unsharded():
                 assert np.abs(got["g_gamma"] - gg).max() <= 2e-4 * np.abs(gg).max()
                 assert np.abs(got["g_beta"] - gb).max() <= 2e-4 * max(np.abs(gb).max(), np.abs(gg).max())
                 assert np.allclose(got["moving_mean"], net.bn_moving_mean.double().cpu().numpy(), atol=1e-6)
+
+
+# ----------------------------------------------------- whole flow in one cooperative launch (persistent) ---
+def _with_persist(value, fn):
+    old = os.environ.get("GNF_PERSIST")
+    os.environ["GNF_PERSIST"] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("GNF_PERSIST", None)
+        else:
+            os.environ["GNF_PERSIST"] = old
+
+
+@pytest.mark.parametrize("math", ["tc3x", "bf16", "tc3x_bf16"])
+@pytest.mark.parametrize("shape", ["small", "many_tiles", "agg_then_mean_l128"])
+def test_persistent_launch_matches_per_half_step_launches(shape, math):
+    """gnf_grevnet_forward / _inverse run the whole flow either as 2T launches (one fused kernel per half step) or
+    as ONE cooperative launch with a grid barrier between half steps (GNF_PERSIST=1).  Same tiles, same arithmetic:
+    z and x must be bit-identical, the log-det equal up to the order of its fp64 partial sums; and the persistent
+    path meets the oracle on its own."""
+    rng = np.random.default_rng(51)
+    if shape == "small":
+        g = H.random_batch(rng, 6, 5, 40, D=14)                      # 1-2 tiles: fewer CTAs than SMs
+        params, L, K = O.make_params(2, 3, 14, 256, 5, last_layer_scale=0.05), 256, 5
+    elif shape == "many_tiles":
+        g = H.random_batch(rng, 900, 20, 60, p_edge=0.15, D=14)      # ~36 k nodes, ~280 tiles: 2 tiles on most CTAs
+        params, L, K = O.make_params(2, 2, 14, 256, 5, last_layer_scale=0.05), 256, 5
+    else:
+        g = H.random_batch(rng, 40, 5, 40, D=6, isolated=True)
+        params, L, K = O.make_params(2, 4, 6, 128, 3, agg="mean", block="agg_then", eps=0.7, act="relu",
+                                     last_layer_scale=0.1), 128, 3
+    dg = dev_graph(g)
+    net = H.make_grevnet(params, L, K, device=DEV, math=math)
+
+    def run():
+        out = G.loss.log_prob(net, dg, return_z=True)
+        x = net(out["z"], inverse=False).nodes
+        torch.cuda.synchronize()
+        return out["z"].nodes.clone(), float(out["log_det_jacobian"]), float(out["log_prob_xs"]), x.clone()
+
+    z0, ldj0, lp0, x0 = _with_persist("0", run)
+    z1, ldj1, lp1, x1 = _with_persist("1", run)
+    z1b, ldj1b, _, _ = _with_persist("1", run)
+    assert torch.equal(z0, z1) and torch.equal(x0, x1)
+    assert torch.equal(z1, z1b) and ldj1 == ldj1b                      # deterministic run to run
+    assert abs(ldj0 - ldj1) <= 1e-12 * max(1.0, abs(ldj0))
+    if shape != "many_tiles" and math != "bf16":
+        z64, ldj64 = O.grevnet_f(g.nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(params, np.float64))
+        want = O.log_prob(z64, ldj64, g.n_node)["log_prob_xs"]
+        assert H.rel_err(lp1, want) < LOGPROB_RTOL
+        assert float((x1 - dg.nodes).abs().max()) < 1e-3
+    net.check_numerics()
