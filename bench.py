@@ -152,6 +152,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.power, self.reasons, self.max_mhz = index, [], [], set(), None
         self._halt = threading.Event()
+        self.armed = False            # NVML's first queries are slow and can hold up launches: the thread starts before
+                                      # the warm-up and only RECORDS between arm() and stop()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -174,15 +176,21 @@ class ClockSampler(threading.Thread):
         }
         while not self._halt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, nm in names.items():
-                    if mask & bit:
-                        self.reasons.add(nm)
+                if self.armed:
+                    self.samples.append(clk)
+                    self.power.append(pw)
+                    for bit, nm in names.items():
+                        if mask & bit:
+                            self.reasons.add(nm)
             except Exception:
                 pass
             time.sleep(0.02)
+
+    def arm(self):
+        self.armed = True
 
     def stop(self):
         self._halt.set()
@@ -194,6 +202,19 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+def cpu_fp64_truth(wl, host):
+    """One float64 pass of the same restatement on the same batch: the yardstick both fp32 arms are measured against
+    in the parity object (untimed)."""
+    import torch
+    from oracle import gnf_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = OT.params_to_torch(make_oracle_params(wl), torch.float64)
+    nodes = torch.from_numpy(host.nodes).double()
+    s, r = torch.from_numpy(host.senders).long(), torch.from_numpy(host.receivers).long()
+    z, ldj = OT.grevnet_f(nodes, s, r, p)
+    return {"z": z.numpy(), "ldj": float(ldj), "log_prob_xs": float(OT.log_prob_xs(z, ldj))}
+
+
 def cpu_reference_run(wl, host, steps, warmup, keep_outputs=False):
     """The reference's CPU path (torch-CPU restatement, all host threads) on `host` (a GraphsTuple of numpy arrays)."""
     import torch
@@ -340,21 +361,22 @@ def main():
                 events[1][i].record()
         return handles
 
+    import ctypes
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.gnf_debug_kernel_timing(1)                                # device timestamps per fused launch (no host events)
     run_steps(warmup)
     torch.cuda.synchronize()
     net.check_numerics()
-    if world > 1:
-        dist.barrier()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = ([torch.cuda.Event(enable_timing=True) for _ in range(args.steps)],
           [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)])
+    k_total, k_count = ctypes.c_double(0.0), ctypes.c_int64(0)
+    lib.gnf_debug_kernel_timing(1)                                # reset the slots: only the timed launches are kept
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     lib.gnf_launch_count(1)
-    import ctypes
-    k_total, k_count = ctypes.c_double(0.0), ctypes.c_int64(0)
-    lib.gnf_debug_kernel_timing(1)                                # device timestamps per fused launch (no host events)
+    sampler.arm()
     if args.profile:
         torch.cuda.profiler.start()
     handles = run_steps(args.steps, events=ev)
@@ -368,6 +390,8 @@ def main():
         dist.barrier()
     ms = [s.elapsed_time(e) for s, e in zip(*ev)]
     my_ms = float(sum(ms)) / args.steps
+    ms_sorted = sorted(ms)
+    step_stats = {"min": ms_sorted[0], "median": ms_sorted[len(ms) // 2], "max": ms_sorted[-1], "first": ms[0]}
     ar_ms = float(np.mean([h.all_reduce_ms() for h in handles]))
     stats = torch.tensor([my_ms, float(n_nodes), float(n_edges), ar_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -389,8 +413,9 @@ def main():
         # CTA done} from the device's %globaltimer into its own slot (gnf_debug_kernel_timing) -- no host events between
         # launches, programmatic dependent launch overlaps as in production, so 2T x ms_per_launch <= ms_per_step
         k_ms = k_total.value / k_count.value
-        share = (2 * T * k_ms) / my_ms
-        flops = n_nodes * F
+        per_step = k_count.value / args.steps                      # 2T launches per step, or 1 (persistent launch)
+        share = (per_step * k_ms) / my_ms
+        flops = n_nodes * F * (2 * T / per_step)                   # a persistent launch runs all 2T half steps
         ach = flops / (k_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         ncu_file = os.path.join(ROOT, "profiles", "r2_ncu_full_k_coupling_tc.csv")
@@ -405,7 +430,8 @@ def main():
                 "ms_per_launch": k_ms,
                 "ms_per_launch_how": "mean over the launches of the HEADLINE loop of (last CTA done - first CTA past "
                                      "griddepcontrol.wait), device %globaltimer written by the kernel itself",
-                "launches_timed": int(k_count.value), "algorithmic_flops_per_launch": flops,
+                "launches_timed": int(k_count.value), "launches_per_step": per_step,
+                "algorithmic_flops_per_launch": flops,
                 "executed_mma_flops_per_algorithmic_flop": {"tc3x": 3, "tc3x_bf16": 3, "tc2x": 2}.get(math, 1),
                 "share_of_step": share}
 
@@ -564,9 +590,18 @@ def main():
                   "ldj_note": "against the CPU arm's own s with its reduce_sums accumulated in float64; the CPU arm's fp32 "
                               "reduce_sum (what TF does) is itself off by ldj_cpu_fp32_sum_rel",
                   "ldj_cpu_fp32_sum_rel": abs(r["ldj"] - r["ldj_f64_sums"]) / abs(r["ldj_f64_sums"]),
+                  "vs_fp64": None,
                   "tolerance": "1e-5 relative on log-prob (north star)" if math != "bf16" else
                                "bf16 single pass: 1e-3 relative on log-prob (stated in tests/test_gpu_parity.py::test_config2_grid_12_step_bf16)"}
 
+    if parity is not None and args.workload in ("community_medium", "protein_b256"):
+        t64 = cpu_fp64_truth(wl, host)                               # ~10 s at B=4096; untimed
+        rel = lambda a, b: abs(a - b) / abs(b)
+        parity["vs_fp64"] = {
+            "what": "both fp32 arms against ONE float64 pass of the restatement on the same batch (the common yardstick)",
+            "log_prob_rel_b200": rel(log_prob_xs, t64["log_prob_xs"]), "log_prob_rel_cpu_fp32": rel(r["log_prob_xs"], t64["log_prob_xs"]),
+            "ldj_rel_b200": rel(float(ldj_dev.item()), t64["ldj"]), "ldj_rel_cpu_fp32": rel(r["ldj"], t64["ldj"]),
+            "z_max_abs_b200": float(np.abs(zg - t64["z"]).max()), "z_max_abs_cpu_fp32": float(np.abs(r["z"] - t64["z"]).max())}
     if rank == 0:
         config = base_config(wl, args.workload, world, gpg, int(allst[0, 1]), int(allst[0, 2]))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -579,7 +614,7 @@ def main():
                         "returns": "the 4 log-prob scalars (fp64) per step; z stays on the device (sharded), as the "
                                    "reference's sess.run fetches scalars"},
                 "gpu_launches": launches, "roofline": roof, "roofline_segment_sum": seg, "cpu_baseline": cpu,
-                "parity": parity, "train_step": train, "log_prob_xs": log_prob_xs,
+                "parity": parity, "train_step": train, "log_prob_xs": log_prob_xs, "ms_per_step_stats_rank0": step_stats,
                 "per_rank": {"ms_per_step": [float(v) for v in allst[:, 0]], "n_nodes": [int(v) for v in allst[:, 1]],
                              "n_edges": [int(v) for v in allst[:, 2]], "all_reduce_ms": [float(v) for v in allst[:, 3]],
                              "n_nodes_global": n_global,

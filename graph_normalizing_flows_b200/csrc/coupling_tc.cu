@@ -822,13 +822,14 @@ int tc_build_half_tables(Flow& f) {
 
 bool tc_persistent_wanted(int64_t n_nodes) {
   // GNF_PERSIST=0: one launch per half step always; =1: whole flow in one cooperative launch always;
-  // default: the cooperative launch up to kPersistAutoTiles tiles per SM (small and medium batches, where the
-  // launch boundaries are a visible share of the step)
+  // default: the cooperative launch up to 2 tiles per SM (GNF_PERSIST_TILES_PER_SM), i.e. small batches, where the
+  // launch boundaries are a visible share of the step (protein B=256: 0.627 -> 0.574 ms); at 8.8 tiles per SM the 2T
+  // launches chained by programmatic dependent launch are as fast (A/B in profiles/r2_ab_launch_schemes.jsonl)
   const char* env = getenv("GNF_PERSIST");          // read per call: tests and A/B timings flip it at run time
   if (env && env[0] == '0') return false;
   if (env && env[0] == '1') return true;
   const char* lim = getenv("GNF_PERSIST_TILES_PER_SM");
-  const int64_t per_sm = lim ? atoll(lim) : 4;
+  const int64_t per_sm = lim ? atoll(lim) : 2;
   return ceil_div(n_nodes, kTileM) <= per_sm * num_sms();
 }
 
