@@ -58,6 +58,7 @@ SIGNATURES = {
     "gnf_flow_range_flag": (C.c_int, [_p, _p, _i32, _p]),
     "gnf_flow_destroy": (C.c_int, [_p]),
     "gnf_flow_supports": (C.c_int, [_p, _i32]),
+    "gnf_flow_supports_backward": (C.c_int, [_p, _i32]),
     "gnf_grevnet_workspace": (_sz, [_p, _i64, _i32]),
     "gnf_grevnet_forward": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i32, _p, _sz, _p]),
     "gnf_grevnet_inverse": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _i32, _p, _sz, _p]),

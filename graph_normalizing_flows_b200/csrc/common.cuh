@@ -106,7 +106,8 @@ struct Flow {
   int64_t wtc_per_mlp = 0;
   float* btc = nullptr;        // biases for the TC kernel: per MLP K*256 floats
   uint8_t* wtcT = nullptr;     // bf16 hi/lo images of the TRANSPOSED MLP chains (backward dX), same geometry
-  bool tc_ok = false;
+  bool tc_ok = false;          // fully fused tcgen05 kernel (MLP input <= 16)
+  bool tc_inject = false;      // layer 0 in the fp32 kernels, layers 1..K-1 + coupling in the tcgen05 kernel (MODE inject)
   void* pack_jobs = nullptr;   // device job table of the one-launch re-pack (pack.cu)
   int n_pack_jobs = 0, pack_blocks = 0;
   void* half_tables = nullptr; // device HalfDesc[2 images][2 directions][2T] of the persistent launch (coupling_tc.cu)
@@ -164,6 +165,10 @@ bool tc_shape_supported(const Flow& f);
 void tc_set_trace(void* buf);
 int tc_kernel_timing(int enable);
 int tc_kernel_time(double* total_ms, int64_t* launches);
+bool tc_inject_supported(const Flow& f);
+int tc_coupling_inject(const Flow& f, int mlp_s, int mlp_t, int math, int inverse, const float* pre0_s,
+                       const float* pre0_t, float* xb, int64_t n_nodes, double* ldj_partials, double* ldj_accum,
+                       unsigned int* counter, void* stream);
 int tc_build_half_tables(Flow& f);
 bool tc_persistent_wanted(int64_t n_nodes);
 int tc_flow_persistent(const Flow& f, int math, int inverse, float* x0, float* x1, int64_t n_nodes,

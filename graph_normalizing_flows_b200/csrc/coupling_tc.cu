@@ -59,6 +59,7 @@ struct TcParams {
   double* ldj_accum;           // forward: the LAST CTA to finish adds the fixed-order sum of the partials here
   unsigned int* counter;       // arrival counter of that hand-off (zero on entry, reset by the last CTA)
   int* range_flag;             // sticky: set when an fp16-split operand exceeded the fp16 range (fp16 modes only)
+  const float* pre0[2];        // INJECT: layer-0 pre-activations (bias included) of the s and t MLP, [N, LAT] fp32
   unsigned long long* trace;   // optional timeline of CTA 0 (gnf_debug_set_trace); null in production
   unsigned long long* tstamp;  // optional {min start, max end} globaltimer of this launch (gnf_debug_kernel_timing)
 };
@@ -169,8 +170,16 @@ __device__ __forceinline__ void build_bias_tiles(uint8_t* btile, float* blast, c
 //                  all 2T half steps, a grid barrier stands where the launch boundary was, the weight ring streams
 //                  straight on into the next half step's images, x halves are read with ld.global.cg (another SM
 //                  rewrote them since this SM last cached them).
-template <int LAT, int NPROD, bool BF16, int ACT, bool PERSIST>
+// MODE 2 (INJECT): per-half-step launch whose layer 0 was computed by the layered fp32 kernels (MLP inputs wider
+//                  than 16: the dm_self_attn GNN's [x, attention] rows, node widths above 8): the epilogue warps read
+//                  the layer-0 pre-activations from global memory where they would read the layer-0 accumulator from
+//                  TMEM; layers 1..K-1, the coupling update and the log-det run here exactly as in MODE 0.
+constexpr int kModeStep = 0, kModePersist = 1, kModeInject = 2;
+
+template <int LAT, int NPROD, bool BF16, int ACT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
+  constexpr bool PERSIST = MODE == kModePersist;
+  constexpr bool INJECT = MODE == kModeInject;
   using G = Geo<LAT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int m = 0; m < 2; ++m) {
           const uint8_t* src = m ? w_t : w_s;
-          issue(src, NPROD >= 2 ? G::L0_BYTES : G::L0_MAT_BYTES);
+          if constexpr (!INJECT) issue(src, NPROD >= 2 ? G::L0_BYTES : G::L0_MAT_BYTES);
           src += G::L0_BYTES;
           for (int l = 1; l < K - 1; ++l)
             for (int c = 0; c < kNS * G::NKC; ++c) {
@@ -288,14 +297,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       for (int hs = 0; hs < n_halves; ++hs)
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
-        mbar_wait(bar_hfull + 8 * buf, (it >> 1) & 1);
+        if constexpr (!INJECT) mbar_wait(bar_hfull + 8 * buf, (it >> 1) & 1);
         tr.ev(10, 0, 0);
         const uint32_t h_hi = hbuf_u + buf * 8192;
         const uint32_t h_lo = h_hi + 4096;
         for (int m = 0; m < 2; ++m) {
           const uint32_t bt = btile_u + m * (LAT * 32);
           // ---- layer 0: bias, then A = h (smem), B = W0 chunk, N = LAT, K = 16 ----------------
-          {
+          if constexpr (INJECT) {
+            region ^= 1;       // the epilogue warps write layer 0's activations into this region from global memory
+          } else {
             const uint32_t d = tmem_base + region * LAT;
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
@@ -415,18 +426,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
         for (int l = 0; l < K - 1; ++l) {
+          const bool from_global = INJECT && l == 0;
 #pragma unroll
           for (int ph = 0; ph < kNS; ++ph) {
-            mbar_wait(smem_u32(&bars->acc_full[ph]), (acc_par >> ph) & 1u);
-            acc_par ^= 1u << ph;
-            tc_fence_after();
+            if (!from_global) {
+              mbar_wait(smem_u32(&bars->acc_full[ph]), (acc_par >> ph) & 1u);
+              acc_par ^= 1u << ph;
+              tc_fence_after();
+            }
             tr.ev(20, m * 16 + l, ph * 4);
             const uint32_t t0 = lane_base + region * LAT + ph * G::NH + grp * 32;
+            // INJECT, layer 0: this thread's row of the pre-activation matrix, the same 32-column chunks
+            const int64_t inj_node = (int64_t)tile * kTileM + row;
+            const float* inj = (INJECT && inj_node < p.n_nodes)
+                                   ? p.pre0[m] + inj_node * LAT + ph * G::NH + grp * 32 : nullptr;
+            auto load_chunk = [&](const float* src, uint32_t (&v)[32]) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 q = src ? __ldg(reinterpret_cast<const float4*>(src) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 * j] = __float_as_uint(q.x); v[4 * j + 1] = __float_as_uint(q.y);
+                v[4 * j + 2] = __float_as_uint(q.z); v[4 * j + 3] = __float_as_uint(q.w);
+              }
+            };
             if constexpr (G::GPH == 2) {
               uint32_t v0[32], v1[32];
-              tmem_ld32(t0, v0);
-              tmem_ld32(t0 + 64, v1);
-              tmem_wait_ld();
+              if (from_global) {
+                load_chunk(inj, v0);
+                load_chunk(inj ? inj + 64 : nullptr, v1);
+              } else {
+                tmem_ld32(t0, v0);
+                tmem_ld32(t0 + 64, v1);
+                tmem_wait_ld();
+              }
               convert_chunk<NPROD, BF16, ACT>(t0, v0, amax);
               tmem_wait_st();
               tc_fence_before();
@@ -438,8 +469,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
               tr.ev(21, m * 16 + l, ph * 4);
             } else {
               uint32_t v0[32];
-              tmem_ld32(t0, v0);
-              tmem_wait_ld();
+              if (from_global) {
+                load_chunk(inj, v0);
+              } else {
+                tmem_ld32(t0, v0);
+                tmem_wait_ld();
+              }
               convert_chunk<NPROD, BF16, ACT>(t0, v0, amax);
               tmem_wait_st();
               tc_fence_before();
@@ -547,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     float amax = 0.f;
     Tracer tr;
     tr.init(p.trace, 9, blockIdx.x == 0 && row == 0);
-    for (int hs = 0; hs < n_halves; ++hs) {
+    for (int hs = 0; hs < (INJECT ? 0 : n_halves); ++hs) {      // INJECT: the MLP input never enters this kernel
     const int swap = PERSIST ? p.halves[hs].swap : 0;
     const float* const xa_base = swap ? p.x[1] : p.x[0];
     // persistent launch: rows of xa were rewritten by other SMs one half step ago -> bypass this SM's L1
@@ -649,9 +684,10 @@ size_t bytes_per_mlp_t(int K) {
   return (size_t)G::L0_BYTES + (size_t)(K - 2) * kNS * G::NKC * G::CHUNK_BYTES + G::LAST_BYTES;
 }
 
-template <int LAT, int NPROD, bool BF16, int ACT, bool PERSIST>
+template <int LAT, int NPROD, bool BF16, int ACT, int MODE>
 int launch_tc_act(const TcParams& p, int grid, cudaStream_t stream) {
-  auto kern = k_coupling_tc<LAT, NPROD, BF16, ACT, PERSIST>;
+  constexpr bool PERSIST = MODE == kModePersist;
+  auto kern = k_coupling_tc<LAT, NPROD, BF16, ACT, MODE>;
   static bool configured[kMaxDevices] = {};
   const size_t smem = smem_bytes<LAT>();
   if (first_use_on_device(configured))
@@ -684,24 +720,24 @@ int launch_tc_act(const TcParams& p, int grid, cudaStream_t stream) {
   return GNF_OK;
 }
 
-template <int LAT, int NPROD, bool BF16, bool PERSIST>
+template <int LAT, int NPROD, bool BF16, int MODE>
 int launch_tc(const TcParams& p, int grid, cudaStream_t stream) {
-  return p.act == GNF_ACT_LEAKY_RELU ? launch_tc_act<LAT, NPROD, BF16, GNF_ACT_LEAKY_RELU, PERSIST>(p, grid, stream)
-                                     : launch_tc_act<LAT, NPROD, BF16, GNF_ACT_RELU, PERSIST>(p, grid, stream);
+  return p.act == GNF_ACT_LEAKY_RELU ? launch_tc_act<LAT, NPROD, BF16, GNF_ACT_LEAKY_RELU, MODE>(p, grid, stream)
+                                     : launch_tc_act<LAT, NPROD, BF16, GNF_ACT_RELU, MODE>(p, grid, stream);
 }
 
-template <bool PERSIST>
+template <int MODE>
 int launch_tc_math(const TcParams& p, int L, int math, int grid, cudaStream_t stream) {
   if (L == 256) {
-    if (math == GNF_MATH_TC2X) return launch_tc<256, 2, false, PERSIST>(p, grid, stream);
-    if (math == GNF_MATH_TC3X) return launch_tc<256, 3, false, PERSIST>(p, grid, stream);
-    if (math == GNF_MATH_TC3X_BF16) return launch_tc<256, 3, true, PERSIST>(p, grid, stream);
-    return launch_tc<256, 1, true, PERSIST>(p, grid, stream);
+    if (math == GNF_MATH_TC2X) return launch_tc<256, 2, false, MODE>(p, grid, stream);
+    if (math == GNF_MATH_TC3X) return launch_tc<256, 3, false, MODE>(p, grid, stream);
+    if (math == GNF_MATH_TC3X_BF16) return launch_tc<256, 3, true, MODE>(p, grid, stream);
+    return launch_tc<256, 1, true, MODE>(p, grid, stream);
   }
-  if (math == GNF_MATH_TC2X) return launch_tc<128, 2, false, PERSIST>(p, grid, stream);
-  if (math == GNF_MATH_TC3X) return launch_tc<128, 3, false, PERSIST>(p, grid, stream);
-  if (math == GNF_MATH_TC3X_BF16) return launch_tc<128, 3, true, PERSIST>(p, grid, stream);
-  return launch_tc<128, 1, true, PERSIST>(p, grid, stream);
+  if (math == GNF_MATH_TC2X) return launch_tc<128, 2, false, MODE>(p, grid, stream);
+  if (math == GNF_MATH_TC3X) return launch_tc<128, 3, false, MODE>(p, grid, stream);
+  if (math == GNF_MATH_TC3X_BF16) return launch_tc<128, 3, true, MODE>(p, grid, stream);
+  return launch_tc<128, 1, true, MODE>(p, grid, stream);
 }
 
 }  // namespace
@@ -791,13 +827,54 @@ int tc_coupling_half(const Flow& f, int mlp_s, int mlp_t, int math, int inverse,
   p.trace = g_trace;
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   p.tstamp = (g_timer.on && g_timer.n < kMaxTimed) ? g_timer.slots + 2 * (size_t)g_timer.n++ : nullptr;
-  return launch_tc_math<false>(p, f.L, math, grid, stream);
+  return launch_tc_math<kModeStep>(p, f.L, math, grid, stream);
+}
+
+// Flows whose MLP input is wider than the fused kernel's 16-column layer-0 tile (dm_self_attn: [x, attention] rows;
+// message passing with node_embedding_dim > 16): layer 0 runs in the layered fp32 kernels, everything after it here.
+bool tc_inject_supported(const Flow& f) {
+  const bool plain_attn = f.attn && !(f.attn_flags & (GNF_ATTN_RESIDUAL | GNF_ATTN_LAYER_NORM));
+  return (f.L == 128 || f.L == 256) && f.H <= kNOut && f.K >= 2 && f.K <= kMaxLayers &&
+         (plain_attn || (!f.attn && f.in_dim > kK0));
+}
+
+int tc_coupling_inject(const Flow& f, int mlp_s, int mlp_t, int math, int inverse, const float* pre0_s,
+                       const float* pre0_t, float* xb, int64_t n_nodes, double* ldj_partials, double* ldj_accum,
+                       unsigned int* counter, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TcParams p = {};
+  p.x[0] = nullptr;
+  p.x[1] = xb;
+  p.pre0[0] = pre0_s;
+  p.pre0[1] = pre0_t;
+  p.n_nodes = n_nodes;
+  p.n_tiles = (int)ceil_div(n_nodes, kTileM);
+  const int img = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 0 : 1;
+  p.one.w[0] = f.wtc[img] + (size_t)mlp_s * f.wtc_per_mlp;
+  p.one.w[1] = f.wtc[img] + (size_t)mlp_t * f.wtc_per_mlp;
+  p.one.bias[0] = f.btc + (size_t)mlp_s * f.K * 256;
+  p.one.bias[1] = f.btc + (size_t)mlp_t * f.K * 256;
+  p.one.swap = 0;
+  p.n_halves = 1;
+  p.K = f.K;
+  p.H = f.H;
+  p.HP = f.HP;
+  p.act = f.d.act;
+  p.inverse = inverse;
+  p.partials = ldj_partials;
+  p.ldj_accum = (!inverse && counter) ? ldj_accum : nullptr;
+  p.counter = counter;
+  p.range_flag = f.range_flag;
+  p.trace = g_trace;
+  const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  p.tstamp = (g_timer.on && g_timer.n < kMaxTimed) ? g_timer.slots + 2 * (size_t)g_timer.n++ : nullptr;
+  return launch_tc_math<kModeInject>(p, f.L, math, grid, stream);
 }
 
 // Half-step tables of the persistent launch, per weight image (fp16 / bf16) and direction (f: step-major, half 0 then
 // half 1, gnn.py:309-338; g: reversed steps, half 1 then half 0, gnn.py:347-372).  Built once per flow.
 int tc_build_half_tables(Flow& f) {
-  if (!f.tc_ok) return GNF_OK;
+  if (!f.tc_ok) return GNF_OK;          // (the persistent launch serves the fully fused shapes only)
   const int T = f.d.num_timesteps, n = 2 * T;
   std::vector<HalfDesc> tab((size_t)4 * n);
   for (int img = 0; img < 2; ++img)
@@ -863,7 +940,7 @@ int tc_flow_persistent(const Flow& f, int math, int inverse, float* x0, float* x
   p.trace = g_trace;
   p.tstamp = (g_timer.on && g_timer.n < kMaxTimed) ? g_timer.slots + 2 * (size_t)g_timer.n++ : nullptr;
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-  return launch_tc_math<true>(p, f.L, math, grid, stream);
+  return launch_tc_math<kModePersist>(p, f.L, math, grid, stream);
 }
 
 }  // namespace gnf

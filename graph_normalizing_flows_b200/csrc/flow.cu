@@ -166,6 +166,93 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
   }
 }
 
+// Warp per receiver (round 2): the in-edges of r are spread over the lanes, 32 at a time.
+//   logits   : lane e computes <keys[s_e, h, :], queries[r, h, :]> for every head (the query row sits in shared memory)
+//   softmax  : per head a running (max, sum) over the chunks, reduced across the lanes by shuffles
+//   values   : p[e][h] and v[s_e][:] are staged in shared memory and the heads*vd outputs are dealt out to the lanes,
+//              so the weighted sum needs no cross-lane reduction (lane j owns outputs j, j + 32, ...)
+// Same mathematics as k_dm_attn (segment softmax = subtract the segment max, exponentiate, divide by the segment sum);
+// the summation order over a segment differs, as any parallel reduction's does (fp32 tolerance, not a bit-exact op).
+constexpr int kAttnWarps = 4;
+constexpr int kAttnMaxOut = 8;           // outputs per lane: heads * vd <= 256
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+               int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
+               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
+               float* __restrict__ att, float* __restrict__ stats) {
+  extern __shared__ float sm_attn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * kAttnWarps + warp;
+  if (r >= n) return;
+  const int qk = heads * kq, hv = heads * vd;
+  float* q_s = sm_attn + (size_t)warp * (qk + 32 * (heads + vd) + 3 * heads);   // [qk]
+  float* p_s = q_s + qk;                                                          // [32][heads]
+  float* v_s = p_s + 32 * heads;                                                  // [32][vd]
+  float* mx_s = v_s + 32 * vd;                                                    // [heads] running max
+  float* sum_s = mx_s + heads;                                                    // [heads] running sum
+  float* sc_s = sum_s + heads;                                                    // [heads] rescale of this chunk
+  for (int i = lane; i < qk; i += 32) q_s[i] = queries[r * qk_pad + i];
+  for (int h = lane; h < heads; h += 32) { mx_s[h] = -INFINITY; sum_s[h] = 0.f; }
+  float acc[kAttnMaxOut];
+#pragma unroll
+  for (int k = 0; k < kAttnMaxOut; ++k) acc[k] = 0.f;
+  __syncwarp();
+  const int32_t beg = rowptr[r], end = rowptr[r + 1];
+  for (int32_t c0 = beg; c0 < end; c0 += 32) {
+    const int32_t e = c0 + lane;
+    const bool valid = e < end;
+    const int64_t s = valid ? csr_senders[e] : 0;
+    const float* __restrict__ ks = keys + s * qk_pad;
+    for (int h = 0; h < heads; ++h) {
+      float l = 0.f;
+      for (int d = 0; d < kq; ++d) l = fmaf(ks[h * kq + d], q_s[h * kq + d], l);
+      l = valid ? l * inv_scale : -INFINITY;
+      float m = l;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float m_old = mx_s[h];
+      const float m_new = fmaxf(m_old, m);                 // finite: every chunk holds at least one valid edge
+      const float pe = valid ? expf(l - m_new) : 0.f;
+      float ps = pe;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      p_s[lane * heads + h] = pe;
+      __syncwarp();
+      if (lane == 0) {
+        const float sc = expf(m_old - m_new);              // exp(-inf) = 0 on the first chunk
+        sc_s[h] = sc;
+        sum_s[h] = sum_s[h] * sc + ps;
+        mx_s[h] = m_new;
+      }
+    }
+    const float* __restrict__ vs = vals + s * v_pad;
+    for (int c = 0; c < vd; ++c) v_s[lane * vd + c] = valid ? vs[c] : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kAttnMaxOut; ++k) {
+      const int o = lane + 32 * k;
+      if (o < hv) {
+        const int h = o / vd, c = o - h * vd;
+        float a = acc[k] * sc_s[h];
+        for (int j = 0; j < 32; ++j) a = fmaf(p_s[j * heads + h], v_s[j * vd + c], a);
+        acc[k] = a;
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int k = 0; k < kAttnMaxOut; ++k) {
+    const int o = lane + 32 * k;
+    if (o < hv) att[r * hv_pad + o] = end > beg ? acc[k] / sum_s[o / vd] : 0.f;      // empty segments give 0
+  }
+  if (stats)
+    for (int h = lane; h < heads; h += 32) {
+      stats[(r * heads + h) * 3] = end > beg ? mx_s[h] : 0.f;
+      stats[(r * heads + h) * 3 + 1] = end > beg ? sum_s[h] : 1.f;
+    }
+}
+
 // MLP input of DMSelfAttentionMLP: concat([nodes, proj]) or proj (gnn.py:547-548)
 __global__ void k_attn_input(const float* __restrict__ xa, int h, int hp, const float* __restrict__ proj, int cho,
                              int cho_pad, int concat, int in_pad, int64_t n, float* __restrict__ hbuf) {
@@ -548,13 +635,16 @@ Workspace carve(const Flow& f, int64_t n, int math, void* base) {
   if (w.n_partials_cap < 1024) w.n_partials_cap = 1024;
   w.partials = (double*)take((size_t)w.n_partials_cap * 8);
   w.counter = (unsigned int*)take(256);
-  if (math == GNF_MATH_FP32) {
+  const bool inject = math != GNF_MATH_FP32 && f.tc_inject;
+  if (math == GNF_MATH_FP32 || inject) {
     const int lp = pad_to(f.L, 8);
     w.hbuf = (float*)take(nn * f.in_pad * 4);
-    w.act0 = (float*)take(nn * lp * 4);
-    w.act1 = (float*)take(nn * lp * 4);
-    w.sbuf = (float*)take(nn * f.HP * 4);
-    w.tbuf = (float*)take(nn * f.HP * 4);
+    w.act0 = (float*)take(nn * lp * 4);        // inject: layer-0 pre-activations of the s MLP
+    w.act1 = (float*)take(nn * lp * 4);        //         ... and of the t MLP
+    if (!inject) {
+      w.sbuf = (float*)take(nn * f.HP * 4);
+      w.tbuf = (float*)take(nn * f.HP * 4);
+    }
     if (f.attn) {
       w.xq = (float*)take(nn * f.hp8 * 4);
       w.qbuf = (float*)take(nn * f.qk_pad * 4);
@@ -654,6 +744,22 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
     }
     return GNF_OK;
   }
+  if (f.tc_inject) {
+    // MLP input wider than the fused kernel's layer-0 tile: input assembly (aggregation or attention) and layer 0
+    // (pre-activation, bias included, no activation) in the fp32 kernels, layers 1..K-1 + coupling update fused
+    for (int which = 0; which < 2; ++which) {
+      const int mlp = which ? mt : ms;
+      int rc = GNF_OK;
+      if (f.attn) rc = build_attn_input(f, mlp, xa, n, rowptr, csr_senders, w, stream);
+      else if (which == 0) rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, w.hbuf, stream);    // shared by s and t
+      if (rc) return rc;
+      const float* base = f.w32 + (int64_t)mlp * f.w32_per_mlp;
+      rc = run_linear(w.hbuf, base + f.w32_layer_off[0], base + f.b32_layer_off[0], which ? w.act1 : w.act0, n,
+                      f.out_pads[0], f.in_pads[0], 2, stream);
+      if (rc) return rc;
+    }
+    return tc_coupling_inject(f, ms, mt, math, inverse, w.act0, w.act1, xb, n, w.partials, ldj_accum, w.counter, stream);
+  }
   // the fused kernel's last CTA adds the log-det partials into ldj_accum itself (no reduce launch)
   return tc_coupling_half(f, ms, mt, math, inverse, xa, xb, n, rowptr, csr_senders, w.partials, ldj_accum, w.counter,
                           stream);
@@ -662,9 +768,9 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
 int check_math(const Flow& f, int math, const char* who) {
   GNF_REQUIRE(math >= GNF_MATH_FP32 && math <= GNF_MATH_TC2X, GNF_EINVAL, "%s: bad math %d", who, math);
   if (math != GNF_MATH_FP32)
-    GNF_REQUIRE(f.tc_ok, GNF_EUNSUPPORTED,
-                "%s: fused tcgen05 kernel needs latent_dim in {128,256}, MLP input dim <= 16, "
-                "D/2 <= 16, 2 <= num_layers <= %d (got L=%d in=%d H=%d K=%d); use GNF_MATH_FP32",
+    GNF_REQUIRE(f.tc_ok || f.tc_inject, GNF_EUNSUPPORTED,
+                "%s: the tcgen05 kernels need latent_dim in {128,256}, D/2 <= 16, 2 <= num_layers <= %d and, for "
+                "dm_self_attn, residual = layer_norm = False (got L=%d in=%d H=%d K=%d); use GNF_MATH_FP32",
                 who, kMaxLayers, f.L, f.in_dim, f.H, f.K);
   return GNF_OK;
 }
@@ -689,7 +795,12 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
   if (rc) return rc;
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
-  if (f.vd <= 32)
+  const size_t attn_smem = (size_t)kAttnWarps * (f.heads * f.kq + 32 * (f.heads + f.vd) + 3 * f.heads) * sizeof(float);
+  if (f.heads * f.vd <= 32 * kAttnMaxOut && attn_smem <= 48 * 1024)
+    k_dm_attn_warp<<<(unsigned)ceil_div(n, kAttnWarps), kAttnWarps * 32, attn_smem, stream>>>(
+        w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr, csr_senders, n,
+        w.att, w.stats);
+  else if (f.vd <= 32)
     k_dm_attn<32><<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
                                                                             f.hv_pad, f.heads, f.kq, f.vd, inv_scale,
                                                                             rowptr, csr_senders, n, w.att, w.stats);
@@ -864,12 +975,13 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
     return GNF_ECUDA;
   }
   f.tc_ok = tc_shape_supported(f);
-  if (f.tc_ok) {
+  f.tc_inject = !f.tc_ok && tc_inject_supported(f);
+  if (f.tc_ok || f.tc_inject) {
     f.wtc_per_mlp = (int64_t)tc_bytes_per_mlp(f.L, f.K);
     cudaError_t e0 = cudaMalloc(&f.wtc[0], (size_t)f.n_mlps * f.wtc_per_mlp);
     cudaError_t e1 = cudaMalloc(&f.wtc[1], (size_t)f.n_mlps * f.wtc_per_mlp);
     cudaError_t e2 = cudaMalloc(&f.btc, (size_t)f.n_mlps * f.K * 256 * 4);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&f.wtcT, (size_t)f.n_mlps * f.wtc_per_mlp);
+    if (e2 == cudaSuccess && f.tc_ok) e2 = cudaMalloc(&f.wtcT, (size_t)f.n_mlps * f.wtc_per_mlp);
     if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
       gnf_flow_destroy(h);
       set_error("gnf_flow_create: cudaMalloc (tc weights) failed");
@@ -914,7 +1026,13 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
 extern "C" int gnf_flow_supports(const gnf_flow* h, int32_t math) {
   if (!h) return 0;
   if (math == GNF_MATH_FP32) return 1;
-  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && h->f.tc_ok) ? 1 : 0;
+  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && (h->f.tc_ok || h->f.tc_inject)) ? 1 : 0;
+}
+
+extern "C" int gnf_flow_supports_backward(const gnf_flow* h, int32_t math) {
+  if (!h) return 0;
+  if (math == GNF_MATH_FP32) return 1;
+  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && tc_bwd_supported(h->f)) ? 1 : 0;
 }
 
 extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* stream_) {
@@ -955,10 +1073,10 @@ extern "C" int gnf_grevnet_forward(const gnf_flow* h, const float* x, int64_t n,
   Workspace w = carve(f, n, math, ws);
   GNF_CUDA(cudaMemsetAsync(w.counter, 0, 256, stream));
   const int D = f.d.node_embedding_dim;
-  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  if (w.hbuf) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));   // pad columns must be 0, not NaN
   k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(x, n, D, f.H, f.HP, w.x0, w.x1);
   GNF_LAUNCH_CHECK();
-  const bool persistent = math != GNF_MATH_FP32 && tc_persistent_wanted(n);
+  const bool persistent = math != GNF_MATH_FP32 && f.tc_ok && tc_persistent_wanted(n);
   if (persistent) {   // all 2T half steps in ONE cooperative launch (grid barrier where the launch boundaries were)
     rc = tc_flow_persistent(f, math, 0, w.x0, w.x1, n, rowptr, csr, w.partials, ldj, w.counter, stream);
     if (rc) return rc;
@@ -986,10 +1104,10 @@ extern "C" int gnf_grevnet_inverse(const gnf_flow* h, const float* z, int64_t n,
   Workspace w = carve(f, n, math, ws);
   GNF_CUDA(cudaMemsetAsync(w.counter, 0, 256, stream));
   const int D = f.d.node_embedding_dim;
-  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  if (w.hbuf) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));   // pad columns must be 0, not NaN
   k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(z, n, D, f.H, f.HP, w.x0, w.x1);
   GNF_LAUNCH_CHECK();
-  const bool persistent = math != GNF_MATH_FP32 && tc_persistent_wanted(n);
+  const bool persistent = math != GNF_MATH_FP32 && f.tc_ok && tc_persistent_wanted(n);
   if (persistent) {
     rc = tc_flow_persistent(f, math, 1, w.x0, w.x1, n, rowptr, csr, w.partials, nullptr, w.counter, stream);
     if (rc) return rc;
@@ -1018,7 +1136,7 @@ extern "C" int gnf_coupling_step(const gnf_flow* h, int32_t step, int32_t invers
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
   GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
-  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  if (w.hbuf) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));   // pad columns must be 0, not NaN
   if (!inverse) {
     rc = coupling_half(f, 0, step, 0, x0, x1, n, rowptr, csr, ldj_accum, math, w, stream);
     if (rc) return rc;
@@ -1064,7 +1182,7 @@ extern "C" int gnf_coupling_half(const gnf_flow* h, int32_t half, int32_t step, 
   const Flow& f = h->f;
   Workspace w = carve(f, n, math, ws);
   GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
-  if (math == GNF_MATH_FP32) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  if (w.hbuf) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));   // pad columns must be 0, not NaN
   return coupling_half(f, half, step, inverse, xa, xb, n, rowptr, csr, inverse ? nullptr : ldj_accum, math, w,
                        stream);
 }

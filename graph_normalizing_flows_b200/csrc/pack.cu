@@ -157,7 +157,7 @@ int pack_build_jobs(Flow& f) {
       }
     }
     size_t tc_off[kMaxLayers + 1] = {0};
-    if (f.tc_ok)
+    if (f.tc_ok || f.tc_inject)
       for (int pos = 0; pos < f.K; ++pos) {
         int a, b, c, d; size_t bytes;
         if (f.L == 256) tc_layer_geometry<256>(pos, f.K, a, b, c, d, bytes);
@@ -181,8 +181,8 @@ int pack_build_jobs(Flow& f) {
         j.d0 = f.w32T + (int64_t)m * f.w32T_per_mlp + f.w32T_layer_off[l];
         add(j, (int64_t)f.in_pads[l] * f.out_pad8[l]);
       }
-      if (!f.tc_ok) continue;
-      {   // forward chain position l
+      if (!f.tc_ok && !f.tc_inject) continue;
+      {   // forward chain position l (the layer-0 image is not used by inject flows: their layer 0 is wider than kK0)
         int kpad, npad, nhc, kcc; size_t bytes;
         if (f.L == 256) tc_layer_geometry<256>(l, f.K, kpad, npad, nhc, kcc, bytes);
         else tc_layer_geometry<128>(l, f.K, kpad, npad, nhc, kcc, bytes);
@@ -191,7 +191,7 @@ int pack_build_jobs(Flow& f) {
         j.p0 = kpad; j.p1 = npad; j.p2 = nhc; j.p3 = kcc; j.src_off = wsrc;
         j.d0 = f.wtc[0] + (size_t)m * f.wtc_per_mlp + tc_off[l];
         j.d1 = f.wtc[1] + (size_t)m * f.wtc_per_mlp + tc_off[l];
-        add(j, (int64_t)kpad * npad);
+        if (!(l == 0 && f.tc_inject)) add(j, (int64_t)kpad * npad);
         PackJob b{};
         b.kind = kPackBias; b.out = f.outs[l]; b.src_off = base + f.flat_b_off[l];
         b.d0 = f.btc + ((size_t)m * f.K + l) * 256;

@@ -243,6 +243,10 @@ class _Flow:
     def supports(self, math_name: str) -> bool:
         return bool(self.handle is not None and self.lib.gnf_flow_supports(self.handle, _lib.MATH[math_name]))
 
+    def supports_backward(self, math_name: str) -> bool:
+        return bool(self.handle is not None and
+                    self.lib.gnf_flow_supports_backward(self.handle, _lib.MATH[math_name]))
+
     def __del__(self):
         try:
             if self.handle is not None:
@@ -730,7 +734,7 @@ class GRevNet(nn.Module):
             grads = torch.zeros_like(self.params.detach())
         _lib.require_cuda(grads, "grads", torch.float32)
         x_out = torch.empty_like(z_nodes) if return_x else None
-        m = _lib.MATH[math if math is not None else self.math]
+        m = _lib.MATH[self._backward_math(math)]
         wsb = lib.gnf_grevnet_backward_workspace(handle, n, m)
         ws = _lib.workspace(wsb, dev)
         _lib.check(lib.gnf_grevnet_backward(handle, _lib.ptr(z_nodes), n, st.n_edges, _lib.ptr(st.rowptr),
@@ -739,6 +743,14 @@ class GRevNet(nn.Module):
                                             _lib.stream_ptr(dev)), "gnf_grevnet_backward")
         self._last_backward_workspace = ws if getattr(self, "_keep_backward_workspace", False) else None
         return (grads, x_out) if return_x else grads
+
+    def _backward_math(self, math: Optional[str]) -> str:
+        """Arithmetic of the backward: an explicit `math` is taken as is (and rejected by the library if the shape
+        does not support it); otherwise the forward's mode when the tensor-core backward serves this flow, else fp32."""
+        if math is not None:
+            return math
+        name = self.math
+        return name if self._flow.supports_backward(name) else "fp32"
 
     def _backward_bn(self, graph, z_nodes, loss_scale, grads, return_x, math):
         """backward_from_z with use_batch_norm=True: the reversed half steps (gnf_coupling_half_backward)
@@ -762,7 +774,7 @@ class GRevNet(nn.Module):
         if grads is None:
             grads = torch.zeros_like(self.params.detach())
         _lib.require_cuda(grads, "grads", torch.float32)
-        m = _lib.MATH[math if math is not None else self.math]
+        m = _lib.MATH[self._backward_math(math)]
         stream = _lib.stream_ptr(dev)
         hp = lib.gnf_padded_half(H)
         wsb = lib.gnf_grevnet_backward_workspace(handle, n, m)

@@ -161,8 +161,14 @@ int gnf_flow_set_params(gnf_flow* flow, const float* params, void* stream);
  * FloatingPointError and re-runs in GNF_MATH_TC3X_BF16 (same 3-MMA scheme, bf16 range = fp32 range). */
 int gnf_flow_range_flag(const gnf_flow* flow, int32_t* host_flag, int32_t reset, void* stream);
 int gnf_flow_destroy(gnf_flow* flow);
-/* 1 if (flow shape, math) is served by the fused tcgen05 kernel, 0 if only GNF_MATH_FP32 is */
+/* 1 if (flow shape, math) is served by the tcgen05 kernels in the density / sampling direction, 0 if only
+ * GNF_MATH_FP32 is.  Two shapes qualify: MLP input <= 16 (message-passing blocks up to D = 16: everything fused), and
+ * wider MLP inputs (dm_self_attn without residual / layer_norm; message passing with 16 < D <= 32), where the input
+ * assembly and layer 0 run in the fp32 kernels and layers 1..K-1 + the coupling update in the fused kernel. */
 int gnf_flow_supports(const gnf_flow* flow, int32_t math);
+/* same question for gnf_grevnet_backward / gnf_coupling_half_backward (the tensor-core backward needs the fully fused
+ * shape; everything else trains through GNF_MATH_FP32) */
+int gnf_flow_supports_backward(const gnf_flow* flow, int32_t math);
 
 /* ------------------------------------------------------------------------------------------
  * a7  GRevNet.f (gnn.py:304-341) / GRevNet.g (gnn.py:343-373) / _build(inverse) (gnn.py:379-381),

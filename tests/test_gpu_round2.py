@@ -253,3 +253,54 @@ def test_persistent_launch_matches_per_half_step_launches(shape, math):
         assert H.rel_err(lp1, want) < LOGPROB_RTOL
         assert float((x1 - dg.nodes).abs().max()) < 1e-3
     net.check_numerics()
+
+
+# ------------------------------------------------- wide MLP inputs: layer 0 in fp32, the rest on tensor cores ---
+@pytest.mark.parametrize("case", ["mp_d24_concat", "mp_d32_mean", "attn_many_tiles"])
+def test_inject_mode_wide_mlp_inputs(case):
+    """MLP inputs wider than the fused kernel's 16-column layer-0 tile (message passing with D > 16; dm_self_attn):
+    input assembly + layer 0 in the fp32 kernels, layers 1..K-1 + coupling update in the tcgen05 kernel (k_coupling_tc
+    MODE inject).  Against the fp64 oracle, the all-fp32 kernels, and the round trip through the inverse."""
+    rng = np.random.default_rng(61)
+    if case == "mp_d24_concat":
+        D, T, L, K = 24, 2, 256, 4
+        g = H.random_batch(rng, 12, 5, 40, D=D)
+        params = O.make_params(5, T, D, L, K, last_layer_scale=0.05)
+    elif case == "mp_d32_mean":
+        D, T, L, K = 32, 2, 128, 3
+        g = H.random_batch(rng, 12, 5, 40, D=D, isolated=True)
+        params = O.make_params(5, T, D, L, K, agg="mean", block="concat", act="relu", last_layer_scale=0.05)
+    else:
+        D, T, L, K = 2, 2, 256, 5
+        n_node = rng.integers(10, 40, size=40)                       # ~1000 nodes: several tiles per launch
+        s, r = G.utils.senders_receivers(n_node)
+        nodes = rng.standard_normal((int(n_node.sum()), D)).astype(np.float32)
+        g = O.GraphsTuple(nodes, None, r, s, None, n_node.astype(np.int32), (n_node ** 2).astype(np.int32))
+        params = O.make_params(13, T, D, L, K, block="dm_attn", act="relu", last_layer_scale=0.1,
+                               attn=dict(num_heads=8, kq_dim=10, v_dim=10, out_dim=80, concat=True, residual=False,
+                                         kq_dim_division=False))
+    z64, ldj64 = O.grevnet_f(g.nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(params, np.float64))
+    want = O.log_prob(z64, ldj64, g.n_node)["log_prob_xs"]
+    dg = dev_graph(g)
+    net = H.make_grevnet(params, L, K, device=DEV)
+    assert net.math == "tc3x"
+    res = {}
+    for math in ("tc3x", "tc3x_bf16", "tc2x", "fp32"):
+        net.math = math
+        out = G.loss.log_prob(net, dg, return_z=True)
+        res[math] = out["z"].nodes.clone()
+        assert H.rel_err(out["log_prob_xs"], want) < LOGPROB_RTOL, math
+        tol = 1e-3 if math == "tc2x" else 1e-4
+        assert np.abs(res[math].cpu().numpy() - z64).max() < tol * max(1.0, np.abs(z64).max()), math
+        x_back = net(out["z"], inverse=False).nodes
+        assert float((x_back - dg.nodes).abs().max()) < 10 * tol, math
+    net.check_numerics()
+    # training still works for these shapes: the backward falls back to the fp32 kernels
+    net.math = None
+    from oracle import gnf_oracle_torch as OT
+    n = g.nodes.shape[0]
+    loss_ref, grad_ref = OT.loss_and_grads(g.nodes, g.senders, g.receivers, params, 1.0 / n)
+    scal, grads = net.loss_and_grad(dg, per_node=True)
+    got = grads.double().cpu().numpy()
+    assert abs(float(scal["loss_per_node"]) - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert np.abs(got - grad_ref).max() <= 5e-4 * np.abs(grad_ref).max()

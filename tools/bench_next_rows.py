@@ -58,14 +58,15 @@ def f1(n_graphs=2048, T=12, math=None):
 
 
 def f3_and_bn():
-    host = bench.make_batch(4096, 12345)
+    wl = bench.WORKLOADS["community_medium"]
+    host = bench.make_global_batch(wl, 1, 4096)
     dg = host.to("cuda")
     n = dg.nodes.shape[0]
     t = timeit(lambda: G.loss.pred_adj(dg))
     n2 = int((host.n_node.astype(np.int64) ** 2).sum())
     print(json.dumps({"row": "f3", "what": "pred_adj(scaled_hacky_sigmoid_l2), per-graph blocks", "nodes": n, "adj_entries": n2,
                       "ms": t, "GB_per_s_written": n2 * 4 / (t * 1e-3) / 1e9}))
-    net = H.make_grevnet(bench.make_oracle_params(), 256, 5, device="cuda", math="tc3x")
+    net = H.make_grevnet(bench.make_oracle_params(wl), 256, 5, device="cuda", math="tc3x")
     net.use_batch_norm = True
     fwd = timeit(lambda: G.loss.log_prob(net, dg))
     step = timeit(lambda: net.loss_and_grad(dg), reps=5, warm=3)
@@ -75,4 +76,5 @@ def f3_and_bn():
 
 if __name__ == "__main__":
     f1(math=sys.argv[1] if len(sys.argv) > 1 else None)
-    f3_and_bn()
+    if len(sys.argv) <= 2:
+        f3_and_bn()
