@@ -328,7 +328,7 @@ def main():
     peaks = load_peaks()
 
     net = H.make_grevnet(make_oracle_params(wl), L, K, device=dev, math=math)
-    sharded = SH.GraphShardedGRevNet(net)
+    sharded = SH.GraphShardedGRevNet(net, peer_memory=False if os.environ.get("GNF_NO_PEER") else "auto")
     assert sharded.world_size == world and sharded.rank == rank
     sharded.broadcast_parameters(0)
     host = sharded.local_shard(global_host)                       # this rank's whole graphs (same LPT on every rank)
@@ -618,6 +618,8 @@ def main():
                 "per_rank": {"ms_per_step": [float(v) for v in allst[:, 0]], "n_nodes": [int(v) for v in allst[:, 1]],
                              "n_edges": [int(v) for v in allst[:, 2]], "all_reduce_ms": [float(v) for v in allst[:, 3]],
                              "n_nodes_global": n_global,
+                             "collective": ("nvlink peer memory (own one-warp kernel, cudaIpc)" if sharded.peer is not None
+                                            else "nccl" if world > 1 else "none"),
                              "note": "all_reduce_ms = device time from reaching the all-reduce on the side stream to its "
                                      "completion (includes waiting for the slowest rank)"},
                 "effective_tflops": value * F / 1e12}

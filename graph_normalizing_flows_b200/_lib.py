@@ -84,6 +84,11 @@ SIGNATURES = {
     "gnf_pred_adj": (C.c_int, [_p, _i32, _p, _p, _i64, C.c_float, C.c_float, _p, _p]),
     "gnf_log_prob_workspace": (_sz, [_i64, _i32]),
     "gnf_log_prob": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "gnf_peer_create": (C.c_int, [C.POINTER(_p), _i32, _i32, _p]),
+    "gnf_peer_connect": (C.c_int, [_p, _p]),
+    "gnf_peer_destroy": (C.c_int, [_p]),
+    "gnf_peer_allreduce4": (C.c_int, [_p, _p, _p]),
+    "gnf_log_prob_allreduce": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p, _p]),
 }
 
 _lib = None

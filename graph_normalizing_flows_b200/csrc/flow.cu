@@ -166,15 +166,24 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
   }
 }
 
-// Warp per receiver (round 2): the in-edges of r are spread over the lanes, 32 at a time.
-//   logits   : lane e computes <keys[s_e, h, :], queries[r, h, :]> for every head (the query row sits in shared memory)
+// Warp per receiver (round 2): the in-edges of r are taken 32 at a time.
+//   staging  : the chunk's 32 sender key rows are copied to shared memory ROW BY ROW (the 32 lanes read one row's
+//              heads*kq contiguous floats: coalesced), padded to an odd stride so that the per-lane reads below are
+//              bank-conflict free; likewise the value rows
+//   logits   : lane e computes <keys[s_e, h, :], queries[r, h, :]> for every head out of shared memory
 //   softmax  : per head a running (max, sum) over the chunks, reduced across the lanes by shuffles
-//   values   : p[e][h] and v[s_e][:] are staged in shared memory and the heads*vd outputs are dealt out to the lanes,
-//              so the weighted sum needs no cross-lane reduction (lane j owns outputs j, j + 32, ...)
+//   values   : p[e][h] is staged too and the heads*vd outputs are dealt out to the lanes, so the weighted sum needs
+//              no cross-lane reduction (lane j owns outputs j, j + 32, ...)
 // Same mathematics as k_dm_attn (segment softmax = subtract the segment max, exponentiate, divide by the segment sum);
 // the summation order over a segment differs, as any parallel reduction's does (fp32 tolerance, not a bit-exact op).
 constexpr int kAttnWarps = 4;
 constexpr int kAttnMaxOut = 8;           // outputs per lane: heads * vd <= 256
+
+__host__ __device__ inline int attn_odd(int x) { return x | 1; }
+__host__ __device__ inline size_t attn_warp_floats(int heads, int kq, int vd) {
+  return (size_t)heads * kq + 32 * (size_t)attn_odd(heads * kq) + 32 * (size_t)attn_odd(heads) + 32 * (size_t)attn_odd(vd) +
+         3 * (size_t)heads;
+}
 
 __global__ void __launch_bounds__(kAttnWarps * 32)
 k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
@@ -186,12 +195,14 @@ k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries
   const int64_t r = (int64_t)blockIdx.x * kAttnWarps + warp;
   if (r >= n) return;
   const int qk = heads * kq, hv = heads * vd;
-  float* q_s = sm_attn + (size_t)warp * (qk + 32 * (heads + vd) + 3 * heads);   // [qk]
-  float* p_s = q_s + qk;                                                          // [32][heads]
-  float* v_s = p_s + 32 * heads;                                                  // [32][vd]
-  float* mx_s = v_s + 32 * vd;                                                    // [heads] running max
-  float* sum_s = mx_s + heads;                                                    // [heads] running sum
-  float* sc_s = sum_s + heads;                                                    // [heads] rescale of this chunk
+  const int ks_ld = attn_odd(qk), p_ld = attn_odd(heads), v_ld = attn_odd(vd);
+  float* q_s = sm_attn + (size_t)warp * attn_warp_floats(heads, kq, vd);   // [qk]
+  float* k_s = q_s + qk;                                                     // [32][ks_ld] sender key rows
+  float* p_s = k_s + 32 * ks_ld;                                             // [32][p_ld]
+  float* v_s = p_s + 32 * p_ld;                                              // [32][v_ld]
+  float* mx_s = v_s + 32 * v_ld;                                             // [heads] running max
+  float* sum_s = mx_s + heads;                                               // [heads] running sum
+  float* sc_s = sum_s + heads;                                               // [heads] rescale of this chunk
   for (int i = lane; i < qk; i += 32) q_s[i] = queries[r * qk_pad + i];
   for (int h = lane; h < heads; h += 32) { mx_s[h] = -INFINITY; sum_s[h] = 0.f; }
   float acc[kAttnMaxOut];
@@ -202,11 +213,23 @@ k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries
   for (int32_t c0 = beg; c0 < end; c0 += 32) {
     const int32_t e = c0 + lane;
     const bool valid = e < end;
-    const int64_t s = valid ? csr_senders[e] : 0;
-    const float* __restrict__ ks = keys + s * qk_pad;
+    const int32_t s_mine = valid ? csr_senders[e] : 0;
+    const int cnt = min(32, end - c0);
+    for (int j = 0; j < cnt; ++j) {                         // row j of the chunk: one coalesced read per 32 floats
+      const int64_t sj = __shfl_sync(0xffffffffu, s_mine, j);
+      const float* __restrict__ kr = keys + sj * qk_pad;
+      for (int i = lane; i < qk; i += 32) k_s[j * ks_ld + i] = kr[i];
+      if (lane < vd) v_s[j * v_ld + lane] = vals[sj * v_pad + lane];
+      for (int c = 32 + lane; c < vd; c += 32) v_s[j * v_ld + c] = vals[sj * v_pad + c];
+    }
+    if (!valid)
+      for (int c = 0; c < vd; ++c) v_s[lane * v_ld + c] = 0.f;
+    __syncwarp();
+    const float* mine = k_s + lane * ks_ld;
     for (int h = 0; h < heads; ++h) {
       float l = 0.f;
-      for (int d = 0; d < kq; ++d) l = fmaf(ks[h * kq + d], q_s[h * kq + d], l);
+      if (valid)
+        for (int d = 0; d < kq; ++d) l = fmaf(mine[h * kq + d], q_s[h * kq + d], l);
       l = valid ? l * inv_scale : -INFINITY;
       float m = l;
 #pragma unroll
@@ -217,7 +240,7 @@ k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries
       float ps = pe;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-      p_s[lane * heads + h] = pe;
+      p_s[lane * p_ld + h] = pe;
       __syncwarp();
       if (lane == 0) {
         const float sc = expf(m_old - m_new);              // exp(-inf) = 0 on the first chunk
@@ -226,8 +249,6 @@ k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries
         mx_s[h] = m_new;
       }
     }
-    const float* __restrict__ vs = vals + s * v_pad;
-    for (int c = 0; c < vd; ++c) v_s[lane * vd + c] = valid ? vs[c] : 0.f;
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < kAttnMaxOut; ++k) {
@@ -235,7 +256,7 @@ k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries
       if (o < hv) {
         const int h = o / vd, c = o - h * vd;
         float a = acc[k] * sc_s[h];
-        for (int j = 0; j < 32; ++j) a = fmaf(p_s[j * heads + h], v_s[j * vd + c], a);
+        for (int j = 0; j < 32; ++j) a = fmaf(p_s[j * p_ld + h], v_s[j * v_ld + c], a);
         acc[k] = a;
       }
     }
@@ -795,8 +816,11 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
   if (rc) return rc;
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
-  const size_t attn_smem = (size_t)kAttnWarps * (f.heads * f.kq + 32 * (f.heads + f.vd) + 3 * f.heads) * sizeof(float);
-  if (f.heads * f.vd <= 32 * kAttnMaxOut && attn_smem <= 48 * 1024)
+  const size_t attn_smem = (size_t)kAttnWarps * attn_warp_floats(f.heads, f.kq, f.vd) * sizeof(float);
+  static bool attn_configured[kMaxDevices] = {};
+  if (first_use_on_device(attn_configured))
+    GNF_CUDA(cudaFuncSetAttribute(k_dm_attn_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  if (f.heads * f.vd <= 32 * kAttnMaxOut && attn_smem <= 160 * 1024)
     k_dm_attn_warp<<<(unsigned)ceil_div(n, kAttnWarps), kAttnWarps * 32, attn_smem, stream>>>(
         w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr, csr_senders, n,
         w.att, w.stats);
@@ -1299,19 +1323,30 @@ extern "C" int gnf_affine_rows(float* x, int64_t n, int32_t hh, const float* sca
 
 extern "C" size_t gnf_log_prob_workspace(int64_t, int32_t) { return (size_t)kLogProbBlocks * 8; }
 
-extern "C" int gnf_log_prob(const float* z, int64_t n, int32_t d, const double* ldj, double* out,
-                            void* ws, size_t ws_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  GNF_REQUIRE(out && n >= 0 && d > 0, GNF_EINVAL, "gnf_log_prob: bad argument");
+namespace gnf {
+// |z|^2 partials of the log-prob assembly (fp64, fixed order) into the workspace; shared with peer.cu
+int log_prob_partials(const float* z, int64_t n, int32_t d, void* ws, size_t ws_bytes, cudaStream_t stream, int* n_blocks) {
+  GNF_REQUIRE(n >= 0 && d > 0, GNF_EINVAL, "gnf_log_prob: bad argument");
   GNF_REQUIRE(ws && ws_bytes >= (size_t)kLogProbBlocks * 8, GNF_EWORKSPACE, "gnf_log_prob: workspace too small");
   GNF_REQUIRE(n == 0 || z, GNF_EINVAL, "gnf_log_prob: null z");
-  double* partials = (double*)ws;
   const int64_t total = n * d;
   int blocks = (int)(ceil_div(total, 256) < kLogProbBlocks ? ceil_div(total, 256) : kLogProbBlocks);
   if (blocks < 1) blocks = 1;
-  k_sumsq<<<blocks, 256, 0, stream>>>(z, total, partials);
+  k_sumsq<<<blocks, 256, 0, stream>>>(z, total, (double*)ws);
   GNF_LAUNCH_CHECK();
-  k_log_prob_final<<<1, 256, 0, stream>>>(partials, blocks, ldj, (double)n, d, out);
+  *n_blocks = blocks;
+  return GNF_OK;
+}
+}  // namespace gnf
+
+extern "C" int gnf_log_prob(const float* z, int64_t n, int32_t d, const double* ldj, double* out,
+                            void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNF_REQUIRE(out, GNF_EINVAL, "gnf_log_prob: null out");
+  int blocks = 0;
+  int rc = log_prob_partials(z, n, d, ws, ws_bytes, stream, &blocks);
+  if (rc) return rc;
+  k_log_prob_final<<<1, 256, 0, stream>>>((const double*)ws, blocks, ldj, (double)n, d, out);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }

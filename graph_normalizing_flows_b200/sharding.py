@@ -73,6 +73,82 @@ def all_reduce_log_prob(vec4: torch.Tensor, group: Optional[dist.ProcessGroup] =
     return vec4
 
 
+class PeerComm:
+    """The path's one collective over NVLink peer memory (include/gnf_b200.h section e): every rank exports a small
+    slot buffer with cudaIpc, peers store their 4-vector into it, the sum is taken in rank order.  One node, world <= 8.
+
+        comm = PeerComm(group)                 # collective: every rank of the group must construct it
+        comm.all_reduce_(vec4)                 # device float64 [4], in place, one one-warp kernel on the current stream
+
+    Construction raises (RuntimeError) where peer access is not available; GraphShardedGRevNet then keeps NCCL."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, device=None):
+        import ctypes as C
+        import socket
+        from . import _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        handle = (C.c_uint8 * 64)()
+        peer = C.c_void_p()
+        err = None
+        with torch.cuda.device(self.device):
+            rc = self.lib.gnf_peer_create(C.byref(peer), self.rank, self.world, handle) if self.world <= 8 else -1
+        if rc != 0:
+            err = _lib.last_error() if self.world <= 8 else "more than 8 ranks"
+        mine = (socket.gethostname(), bytes(handle) if rc == 0 else None)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)              # the exchange IS the host-side all-gather
+        self._peer = peer if rc == 0 else None
+        if err is None and any(h is None for _, h in everyone):
+            err = "a peer could not export its buffer"
+        if err is None and len({host for host, _ in everyone}) != 1:
+            err = "ranks span several hosts"
+        if err is None:
+            blob = b"".join(h for _, h in everyone)
+            with torch.cuda.device(self.device):
+                if self.lib.gnf_peer_connect(self._peer, blob) != 0:
+                    err = _lib.last_error()
+        ok = torch.tensor([0 if err else 1], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)          # all or nothing: every rank takes the same path
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer-memory all-reduce unavailable: {err or 'a peer failed'}")
+
+    def all_reduce_(self, vec4: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+        if vec4.dtype != torch.float64 or vec4.numel() != 4 or not vec4.is_cuda:
+            raise ValueError("expected a CUDA float64 4-vector")
+        _lib.check(self.lib.gnf_peer_allreduce4(self._peer, _lib.ptr(vec4), _lib.stream_ptr(vec4.device)),
+                   "gnf_peer_allreduce4")
+        return vec4
+
+    def log_prob_all_reduce(self, z_nodes: torch.Tensor, ldj64: Optional[torch.Tensor]) -> torch.Tensor:
+        """gnf_log_prob and the all-reduce of its 4-vector in ONE kernel: the global scalars on every rank."""
+        from . import _lib
+        _lib.require_cuda(z_nodes, "z.nodes", torch.float32)
+        n, d = z_nodes.shape
+        out = torch.empty(4, dtype=torch.float64, device=z_nodes.device)
+        wsb = self.lib.gnf_log_prob_workspace(n, d)
+        ws = _lib.workspace(wsb, z_nodes.device)
+        _lib.check(self.lib.gnf_log_prob_allreduce(_lib.ptr(z_nodes), n, d, _lib.ptr(ldj64), _lib.ptr(out), _lib.ptr(ws),
+                                                   wsb, self._peer, _lib.stream_ptr(z_nodes.device)),
+                   "gnf_log_prob_allreduce")
+        return out
+
+    def close(self):
+        if getattr(self, "_peer", None) is not None:
+            self.lib.gnf_peer_destroy(self._peer)
+            self._peer = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PendingLogProb:
     """Result of GraphShardedGRevNet.log_prob_async: the local latent and the (in flight) all-reduced 4-vector."""
 
@@ -100,7 +176,9 @@ class GraphShardedGRevNet:
         scalars = sharded.log_prob(local)                          # global batch scalars on every rank
     """
 
-    def __init__(self, grevnet, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, grevnet, group: Optional[dist.ProcessGroup] = None, peer_memory="auto"):
+        """peer_memory: "auto" = the 4-vector all-reduce goes over NVLink peer memory (PeerComm) when every rank sits
+        on one node with CUDA peer access and the backend is NCCL, else NCCL; True = require it; False = NCCL."""
         self.grevnet = grevnet
         self.group = group
         if hasattr(grevnet, "bn_group"):
@@ -109,6 +187,13 @@ class GraphShardedGRevNet:
         self.rank = dist.get_rank(group) if on else 0
         self.world_size = dist.get_world_size(group) if on else 1
         self._comm_stream = None              # side stream of log_prob_async
+        self.peer = None
+        if peer_memory and self.world_size > 1 and dist.get_backend(group) == "nccl":
+            try:
+                self.peer = PeerComm(group, device=grevnet.params.device)
+            except RuntimeError:
+                if peer_memory is True:
+                    raise
 
     def local_shard(self, host_batch: GraphsTuple) -> GraphsTuple:
         parts = partition_graphs(host_batch.n_node, host_batch.n_edge, self.world_size)
@@ -127,7 +212,10 @@ class GraphShardedGRevNet:
     def log_prob(self, local_graph: GraphsTuple, return_z: bool = False) -> dict:
         from .loss import mvn_log_prob_sum, scalars_from_vector
         z, ldj64 = self.grevnet.f64(local_graph)
-        vec = all_reduce_log_prob(mvn_log_prob_sum(z.nodes, ldj64), self.group)
+        if self.peer is not None:             # log-prob assembly + all-reduce in ONE kernel over NVLink peer memory
+            vec = self.peer.log_prob_all_reduce(z.nodes, ldj64)
+        else:
+            vec = all_reduce_log_prob(mvn_log_prob_sum(z.nodes, ldj64), self.group)
         out = scalars_from_vector(vec)
         if return_z:
             out["z"] = z
@@ -150,7 +238,10 @@ class GraphShardedGRevNet:
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(cs):
             t0.record(cs)
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=self.group)
+            if self.peer is not None:         # one-warp kernel: co-resides with the next batch's fused CTAs
+                self.peer.all_reduce_(vec)
+            else:
+                dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=self.group)
             t1.record(cs)
         vec.record_stream(cs)
         return PendingLogProb(vec, z, cs, t0, t1)
@@ -164,7 +255,10 @@ class GraphShardedGRevNet:
         from .loss import mvn_log_prob_sum, scalars_from_vector
         net = self.grevnet
         z, ldj64 = net.f64(local_graph)
-        vec = all_reduce_log_prob(mvn_log_prob_sum(z.nodes, ldj64), self.group)
+        if self.peer is not None:
+            vec = self.peer.log_prob_all_reduce(z.nodes, ldj64)
+        else:
+            vec = all_reduce_log_prob(mvn_log_prob_sum(z.nodes, ldj64), self.group)
         out = scalars_from_vector(vec)
         n_global = max(float(vec[3].item()), 1.0)
         grads = net.backward_from_z(local_graph, z.nodes, 1.0 / n_global if per_node else 1.0)

@@ -336,6 +336,29 @@ size_t gnf_log_prob_workspace(int64_t n_nodes, int32_t d);
 int gnf_log_prob(const float* z, int64_t n_nodes, int32_t d, const double* ldj, double* out,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * e  The one collective of the path over NVLink peer memory (the reference has no distributed code):
+ * all-reduce(SUM) of the fp64 4-vector of gnf_log_prob across the ranks of ONE node (world <= 8), one process per
+ * GPU.  Every rank owns a small slot buffer, exported with cudaIpc; peers write into it with plain stores through
+ * the NVLink mapping, a release/acquire flag word orders them, the sum is taken in rank order (bit-identical on all
+ * ranks).  The kernels are one warp wide and co-reside with the fused coupling kernel, which an NCCL kernel cannot.
+ *   gnf_peer_create   allocates this rank's slots, returns the 64-byte cudaIpcMemHandle_t in handle_out (HOST)
+ *   gnf_peer_connect  handles_host = the `world` handles in rank order (exchange them with any host-side all-gather)
+ *   gnf_peer_allreduce4      vec (device double[4]) all-reduced in place, one tiny kernel on `stream`
+ *   gnf_log_prob_allreduce   gnf_log_prob AND the all-reduce of its result in ONE kernel: out holds the global
+ *                            (log_prob_zs, log_det_jacobian, log_prob_xs, num_nodes) on every rank
+ * Every rank must issue the same sequence of peer calls.  A peer that never arrives turns the result into NaN after
+ * ~2 s instead of hanging the device.
+ * ------------------------------------------------------------------------------------------ */
+#define GNF_PEER_HANDLE_BYTES 64
+typedef struct gnf_peer gnf_peer;
+int gnf_peer_create(gnf_peer** out, int32_t rank, int32_t world, uint8_t* handle_out);
+int gnf_peer_connect(gnf_peer* peer, const uint8_t* handles_host);
+int gnf_peer_destroy(gnf_peer* peer);
+int gnf_peer_allreduce4(gnf_peer* peer, double* vec, void* stream);
+int gnf_log_prob_allreduce(const float* z, int64_t n_nodes, int32_t d, const double* ldj, double* out,
+                           void* workspace, size_t workspace_bytes, gnf_peer* peer, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,9 +58,13 @@ def run(rank, world, port, backend, q):
             net.bn_update_moving = False
             _ = G.loss.log_prob(net, S.shard_graphs_tuple(host, np.arange(2)).to(dev))   # packs the PERTURBED weights first
             net.bn_update_moving = True
-            sharded = S.GraphShardedGRevNet(net)
+            sharded = S.GraphShardedGRevNet(net)                       # peer-memory all-reduce when the GPUs allow it
             sharded.broadcast_parameters(0)
             local = sharded.local_shard(host).to(dev)
+            nccl_only = S.GraphShardedGRevNet(net, peer_memory=False)
+            net.bn_update_moving = False
+            out_nccl = nccl_only.log_prob(local)
+            net.bn_update_moving = True
             out = sharded.log_prob(local)
             pend = sharded.log_prob_async(local)
             out_async = pend.wait()
@@ -69,6 +73,8 @@ def run(rank, world, port, backend, q):
             key = "bn" if use_bn else "plain"
             res[key] = {
                 "vec": [float(out[k]) for k in ("log_prob_zs", "log_det_jacobian", "log_prob_xs", "num_nodes")],
+                "vec_nccl": [float(out_nccl[k]) for k in ("log_prob_zs", "log_det_jacobian", "log_prob_xs", "num_nodes")],
+                "peer_used": sharded.peer is not None,
                 "vec_async": [float(out_async[k]) for k in ("log_prob_zs", "log_det_jacobian", "log_prob_xs", "num_nodes")],
                 "loss_per_node": float(scal["loss_per_node"]),
                 "grads": grads.double().cpu().numpy(),
