@@ -164,7 +164,7 @@ class ClockSampler(threading.Thread):
             self.nv = None
 
     def run(self):
-        if self.nv is None:
+        if self.nv is None or os.environ.get("GNF_BENCH_NO_SAMPLER"):
             return
         nv = self.nv
         names = {
@@ -391,7 +391,8 @@ def main():
     ms = [s.elapsed_time(e) for s, e in zip(*ev)]
     my_ms = float(sum(ms)) / args.steps
     ms_sorted = sorted(ms)
-    step_stats = {"min": ms_sorted[0], "median": ms_sorted[len(ms) // 2], "max": ms_sorted[-1], "first": ms[0]}
+    step_stats = {"min": ms_sorted[0], "median": ms_sorted[len(ms) // 2], "max": ms_sorted[-1], "first": ms[0],
+                  "slowest_steps": sorted(range(len(ms)), key=lambda i: -ms[i])[:3]}
     ar_ms = float(np.mean([h.all_reduce_ms() for h in handles]))
     stats = torch.tensor([my_ms, float(n_nodes), float(n_edges), ar_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -215,12 +215,37 @@ k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries
     const bool valid = e < end;
     const int32_t s_mine = valid ? csr_senders[e] : 0;
     const int cnt = min(32, end - c0);
-    for (int j = 0; j < cnt; ++j) {                         // row j of the chunk: one coalesced read per 32 floats
-      const int64_t sj = __shfl_sync(0xffffffffu, s_mine, j);
-      const float* __restrict__ kr = keys + sj * qk_pad;
-      for (int i = lane; i < qk; i += 32) k_s[j * ks_ld + i] = kr[i];
-      if (lane < vd) v_s[j * v_ld + lane] = vals[sj * v_pad + lane];
-      for (int c = 32 + lane; c < vd; c += 32) v_s[j * v_ld + c] = vals[sj * v_pad + c];
+    // rows of the chunk, 16 at a time: lane = column, so every load instruction reads 32 consecutive floats of one
+    // sender row (coalesced) and 16 independent loads are in flight before the first store
+    for (int t = 0; t < qk; t += 32) {
+      const int col = t + lane;
+      const bool cok = col < qk;
+      for (int j0 = 0; j0 < cnt; j0 += 16) {
+        float tmp[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int64_t sj = __shfl_sync(0xffffffffu, s_mine, (j0 + jj) & 31);
+          tmp[jj] = (cok && j0 + jj < cnt) ? keys[sj * qk_pad + col] : 0.f;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+          if (cok && j0 + jj < cnt) k_s[(j0 + jj) * ks_ld + col] = tmp[jj];
+      }
+    }
+    for (int t = 0; t < vd; t += 32) {
+      const int col = t + lane;
+      const bool cok = col < vd;
+      for (int j0 = 0; j0 < cnt; j0 += 16) {
+        float tmp[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int64_t sj = __shfl_sync(0xffffffffu, s_mine, (j0 + jj) & 31);
+          tmp[jj] = (cok && j0 + jj < cnt) ? vals[sj * v_pad + col] : 0.f;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+          if (cok && j0 + jj < cnt) v_s[(j0 + jj) * v_ld + col] = tmp[jj];
+      }
     }
     if (!valid)
       for (int c = 0; c < vd; ++c) v_s[lane * v_ld + c] = 0.f;
