@@ -481,6 +481,7 @@ BwdWs carve_bwd(const Flow& f, int64_t n, void* base) {
       w.ab[m].att = take(nn * f.hv_pad * 4);
       w.ab[m].proj = take(nn * f.cho_pad * 4);
       w.ab[m].stats = take(nn * f.heads * 3 * 4);
+      w.ab[m].fallback = (int32_t*)take((nn / 32 + 2) * 4);
     }
     w.hbuf2 = take(nn * f.in_pad * 4);
     w.gproj = take(nn * f.cho_pad * 4);

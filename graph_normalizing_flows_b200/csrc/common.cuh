@@ -126,6 +126,7 @@ int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t
 struct AttnBufs {      // per-GNN intermediates of the f1 attention block (all [n, *_pad] fp32)
   float *xq, *qbuf, *kbuf, *vbuf, *att, *proj;
   float* stats;        // optional [n, heads, 3]: segment max, segment sum (written by k_dm_attn), dot (backward)
+  int32_t* fallback;   // optional [n / 32 + 1] scratch of the staged attention kernel (null: thread-per-head kernel only)
 };
 int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
                    const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream);

@@ -119,10 +119,11 @@ __global__ void __launch_bounds__(128)
 k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
           int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
-          float* __restrict__ att, float* __restrict__ stats) {
+          float* __restrict__ att, float* __restrict__ stats, const int32_t* __restrict__ only, int only_shift) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * heads) return;
   const int64_t r = i / heads;
+  if (only && !only[r >> only_shift]) return;      // second pass: only the receiver groups k_dm_attn_block handed back
   const int h = (int)(i - r * heads);
   const int32_t beg = rowptr[r], end = rowptr[r + 1];
   const float* qr = queries + r * qk_pad + h * kq;
@@ -166,137 +167,167 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
   }
 }
 
-// Warp per receiver (round 2): the in-edges of r are taken 32 at a time.
-//   staging  : the chunk's 32 sender key rows are copied to shared memory ROW BY ROW (the 32 lanes read one row's
-//              heads*kq contiguous floats: coalesced), padded to an odd stride so that the per-lane reads below are
-//              bank-conflict free; likewise the value rows
-//   logits   : lane e computes <keys[s_e, h, :], queries[r, h, :]> for every head out of shared memory
-//   softmax  : per head a running (max, sum) over the chunks, reduced across the lanes by shuffles
-//   values   : p[e][h] is staged too and the heads*vd outputs are dealt out to the lanes, so the weighted sum needs
-//              no cross-lane reduction (lane j owns outputs j, j + 32, ...)
+// Block-staged attention (round 2).  A CTA owns kAttnRecv consecutive receivers; like k_gather_segment it stages what
+// they need ONCE in shared memory with coalesced loads: their CSR index range and -- graphs being contiguous node
+// blocks -- the sender rows [lo, hi] of the key and value matrices, plus their own query rows.  Every warp then takes
+// receivers in turn, 32 in-edges at a time:
+//   logits   : lane = edge; <keys[s_e, h, :], queries[r, h, :]> for up to 8 heads at once out of shared memory (rows
+//              padded to an odd stride: conflict free)
+//   softmax  : running (max, sum) per head, kept in registers on every lane; the 8 heads' shuffle reductions are
+//              interleaved, so their latencies overlap
+//   values   : lane = (value column, edge residue): acc[h] += p[e][h] * v[s_e][c]; one 3-way shuffle fold per chunk
 // Same mathematics as k_dm_attn (segment softmax = subtract the segment max, exponentiate, divide by the segment sum);
 // the summation order over a segment differs, as any parallel reduction's does (fp32 tolerance, not a bit-exact op).
-constexpr int kAttnWarps = 4;
-constexpr int kAttnMaxOut = 8;           // outputs per lane: heads * vd <= 256
+// CTAs whose senders are too spread out, and shapes beyond heads <= 8 / vd <= 10 per pass, use k_dm_attn.
+constexpr int kAttnRecv = 32;            // receivers per CTA (= 1 << 5: k_dm_attn's only_shift)
+constexpr int kAttnWarps = 8;
+constexpr int kAttnRows = 128;           // staged sender rows per CTA
+constexpr int kAttnIdx = 2048;           // staged CSR indices per CTA
+constexpr int kAttnH = 8;                // heads per register pass
 
 __host__ __device__ inline int attn_odd(int x) { return x | 1; }
-__host__ __device__ inline size_t attn_warp_floats(int heads, int kq, int vd) {
-  return (size_t)heads * kq + 32 * (size_t)attn_odd(heads * kq) + 32 * (size_t)attn_odd(heads) + 32 * (size_t)attn_odd(vd) +
-         3 * (size_t)heads;
+__host__ __device__ inline size_t attn_block_bytes(int heads, int kq, int vd) {
+  const int qk = heads * kq;
+  return ((size_t)kAttnRows * attn_odd(qk) + (size_t)kAttnRows * attn_odd(vd) + (size_t)kAttnRecv * qk +
+          (size_t)kAttnWarps * 32 * kAttnH) * sizeof(float) +
+         ((size_t)kAttnIdx + kAttnRecv + 1 + 2 * kAttnWarps + 2) * sizeof(int32_t);
 }
 
 __global__ void __launch_bounds__(kAttnWarps * 32)
-k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
-               int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
-               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
-               float* __restrict__ att, float* __restrict__ stats) {
+k_dm_attn_block(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+                int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
+                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
+                float* __restrict__ att, float* __restrict__ stats, int32_t* __restrict__ fallback) {
   extern __shared__ float sm_attn[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * kAttnWarps + warp;
-  if (r >= n) return;
-  const int qk = heads * kq, hv = heads * vd;
-  const int ks_ld = attn_odd(qk), p_ld = attn_odd(heads), v_ld = attn_odd(vd);
-  float* q_s = sm_attn + (size_t)warp * attn_warp_floats(heads, kq, vd);   // [qk]
-  float* k_s = q_s + qk;                                                     // [32][ks_ld] sender key rows
-  float* p_s = k_s + 32 * ks_ld;                                             // [32][p_ld]
-  float* v_s = p_s + 32 * p_ld;                                              // [32][v_ld]
-  float* mx_s = v_s + 32 * v_ld;                                             // [heads] running max
-  float* sum_s = mx_s + heads;                                               // [heads] running sum
-  float* sc_s = sum_s + heads;                                               // [heads] rescale of this chunk
-  for (int i = lane; i < qk; i += 32) q_s[i] = queries[r * qk_pad + i];
-  for (int h = lane; h < heads; h += 32) { mx_s[h] = -INFINITY; sum_s[h] = 0.f; }
-  float acc[kAttnMaxOut];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qk = heads * kq;
+  const int ks_ld = attn_odd(qk), v_ld = attn_odd(vd);
+  float* k_s = sm_attn;                                   // [kAttnRows][ks_ld]
+  float* v_s = k_s + kAttnRows * ks_ld;                   // [kAttnRows][v_ld]
+  float* q_s = v_s + kAttnRows * v_ld;                    // [kAttnRecv][qk]
+  float* p_s = q_s + kAttnRecv * qk;                      // [warps][32][kAttnH]
+  int32_t* idx_s = reinterpret_cast<int32_t*>(p_s + kAttnWarps * 32 * kAttnH);   // [kAttnIdx]
+  int32_t* row_s = idx_s + kAttnIdx;                      // [kAttnRecv + 1]
+  int32_t* red_s = row_s + kAttnRecv + 1;                 // [2 * warps + 2]
+  const int64_t r0 = (int64_t)blockIdx.x * kAttnRecv;
+  const int nr = (int)((n - r0) < kAttnRecv ? (n - r0) : kAttnRecv);
+  for (int i = tid; i <= nr; i += kAttnWarps * 32) row_s[i] = rowptr[r0 + i];
+  __syncthreads();
+  const int32_t e0 = row_s[0], ne = row_s[nr] - e0;
+  int32_t lo = 0x7fffffff, hi = -1;
+  if (ne <= kAttnIdx)
+    for (int i = tid; i < ne; i += kAttnWarps * 32) {
+      const int32_t v = csr_senders[e0 + i];
+      idx_s[i] = v;
+      lo = min(lo, v);
+      hi = max(hi, v);
+    }
 #pragma unroll
-  for (int k = 0; k < kAttnMaxOut; ++k) acc[k] = 0.f;
-  __syncwarp();
-  const int32_t beg = rowptr[r], end = rowptr[r + 1];
-  for (int32_t c0 = beg; c0 < end; c0 += 32) {
-    const int32_t e = c0 + lane;
-    const bool valid = e < end;
-    const int32_t s_mine = valid ? csr_senders[e] : 0;
-    const int cnt = min(32, end - c0);
-    // rows of the chunk, 16 at a time: lane = column, so every load instruction reads 32 consecutive floats of one
-    // sender row (coalesced) and 16 independent loads are in flight before the first store
-    for (int t = 0; t < qk; t += 32) {
-      const int col = t + lane;
-      const bool cok = col < qk;
-      for (int j0 = 0; j0 < cnt; j0 += 16) {
-        float tmp[16];
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { red_s[warp] = lo; red_s[kAttnWarps + warp] = hi; }
+  __syncthreads();
+  for (int w = 0; w < kAttnWarps; ++w) { lo = min(lo, red_s[w]); hi = max(hi, red_s[kAttnWarps + w]); }
+  const int nrows = ne > 0 ? hi - lo + 1 : 0;
+  if (ne > kAttnIdx || nrows > kAttnRows) {               // uniform: hand the CTA's receivers to k_dm_attn
+    if (tid == 0) fallback[blockIdx.x] = 1;
+    return;
+  }
+  // ---- stage: contiguous global rows [lo, hi] of keys / values, rows [r0, r0 + nr) of queries ------------------
+  for (int i = tid; i < nrows * qk; i += kAttnWarps * 32) {
+    const int row = i / qk, col = i - row * qk;
+    k_s[row * ks_ld + col] = keys[(int64_t)(lo + row) * qk_pad + col];
+  }
+  for (int i = tid; i < nrows * vd; i += kAttnWarps * 32) {
+    const int row = i / vd, col = i - row * vd;
+    v_s[row * v_ld + col] = vals[(int64_t)(lo + row) * v_pad + col];
+  }
+  for (int i = tid; i < nr * qk; i += kAttnWarps * 32) {
+    const int row = i / qk, col = i - row * qk;
+    q_s[i] = queries[(r0 + row) * qk_pad + col];
+  }
+  __syncthreads();
+  float* pw = p_s + warp * 32 * kAttnH;
+  const int vc = lane % 10, vg = lane / 10;               // value phase: column vc (< vd <= 10), edge residue vg (0..2)
+  for (int rl = warp; rl < nr; rl += kAttnWarps) {
+    const int32_t beg = row_s[rl] - e0, end = row_s[rl + 1] - e0;
+    const float* qr = q_s + rl * qk;
+    for (int h0 = 0; h0 < heads; h0 += kAttnH) {          // up to 8 heads per register pass
+      const int nh = min(kAttnH, heads - h0);
+      float mx[kAttnH], sum[kAttnH], acc[kAttnH];
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int64_t sj = __shfl_sync(0xffffffffu, s_mine, (j0 + jj) & 31);
-          tmp[jj] = (cok && j0 + jj < cnt) ? keys[sj * qk_pad + col] : 0.f;
+      for (int h = 0; h < kAttnH; ++h) { mx[h] = -INFINITY; sum[h] = 0.f; acc[h] = 0.f; }
+      for (int32_t c0 = beg; c0 < end; c0 += 32) {
+        const int32_t e = c0 + lane;
+        const bool valid = e < end;
+        const int row = valid ? idx_s[e] - lo : 0;
+        const float* kr = k_s + row * ks_ld + h0 * kq;
+        float l[kAttnH];
+#pragma unroll
+        for (int h = 0; h < kAttnH; ++h) {
+          float a = 0.f;
+          if (h < nh)
+            for (int d = 0; d < kq; ++d) a = fmaf(kr[h * kq + d], qr[(h0 + h) * kq + d], a);
+          l[h] = (valid && h < nh) ? a * inv_scale : -INFINITY;
+        }
+        float m[kAttnH];
+#pragma unroll
+        for (int h = 0; h < kAttnH; ++h) m[h] = l[h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int h = 0; h < kAttnH; ++h) m[h] = fmaxf(m[h], __shfl_xor_sync(0xffffffffu, m[h], o));
+        float pe[kAttnH], ps[kAttnH], sc[kAttnH];
+#pragma unroll
+        for (int h = 0; h < kAttnH; ++h) {
+          const float m_new = fmaxf(mx[h], m[h]);
+          sc[h] = h < nh ? expf(mx[h] - m_new) : 0.f;      // exp(-inf) = 0 on the first chunk
+          pe[h] = (valid && h < nh) ? expf(l[h] - m_new) : 0.f;
+          ps[h] = pe[h];
+          mx[h] = m_new;
         }
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
-          if (cok && j0 + jj < cnt) k_s[(j0 + jj) * ks_ld + col] = tmp[jj];
-      }
-    }
-    for (int t = 0; t < vd; t += 32) {
-      const int col = t + lane;
-      const bool cok = col < vd;
-      for (int j0 = 0; j0 < cnt; j0 += 16) {
-        float tmp[16];
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int64_t sj = __shfl_sync(0xffffffffu, s_mine, (j0 + jj) & 31);
-          tmp[jj] = (cok && j0 + jj < cnt) ? vals[sj * v_pad + col] : 0.f;
+          for (int h = 0; h < kAttnH; ++h) ps[h] += __shfl_xor_sync(0xffffffffu, ps[h], o);
+#pragma unroll
+        for (int h = 0; h < kAttnH; ++h) {
+          sum[h] = sum[h] * sc[h] + ps[h];
+          acc[h] *= sc[h];
         }
+        *reinterpret_cast<float4*>(pw + lane * kAttnH) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+        *reinterpret_cast<float4*>(pw + lane * kAttnH + 4) = make_float4(pe[4], pe[5], pe[6], pe[7]);
+        __syncwarp();
+        // values: lane (vc, vg) adds the edges j = vg, vg + 3, ... of this chunk for its column
+        if (vg < 3 && vc < vd) {
+          const int cnt = min(32, end - c0);
+          for (int j = vg; j < cnt; j += 3) {
+            const float v = v_s[(idx_s[c0 + j] - lo) * v_ld + vc];
+            const float4 p0 = *reinterpret_cast<const float4*>(pw + j * kAttnH);
+            const float4 p1 = *reinterpret_cast<const float4*>(pw + j * kAttnH + 4);
+            acc[0] = fmaf(p0.x, v, acc[0]); acc[1] = fmaf(p0.y, v, acc[1]); acc[2] = fmaf(p0.z, v, acc[2]);
+            acc[3] = fmaf(p0.w, v, acc[3]); acc[4] = fmaf(p1.x, v, acc[4]); acc[5] = fmaf(p1.y, v, acc[5]);
+            acc[6] = fmaf(p1.z, v, acc[6]); acc[7] = fmaf(p1.w, v, acc[7]);
+          }
+        }
+        __syncwarp();
+      }
+      // fold the three edge residues (lanes vc, vc + 10, vc + 20) and write head h0 + h, column vc
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
-          if (cok && j0 + jj < cnt) v_s[(j0 + jj) * v_ld + col] = tmp[jj];
+      for (int h = 0; h < kAttnH; ++h) {
+        const float a1 = __shfl_sync(0xffffffffu, acc[h], (lane + 10) & 31);
+        const float a2 = __shfl_sync(0xffffffffu, acc[h], (lane + 20) & 31);
+        if (lane < 10 && lane < vd && h < nh)
+          att[(r0 + rl) * hv_pad + (h0 + h) * vd + lane] = end > beg ? ((acc[h] + a1) + a2) / sum[h] : 0.f;
+        if (stats && lane == 0 && h < nh) {
+          stats[((r0 + rl) * heads + h0 + h) * 3] = end > beg ? mx[h] : 0.f;
+          stats[((r0 + rl) * heads + h0 + h) * 3 + 1] = end > beg ? sum[h] : 1.f;
+        }
       }
     }
-    if (!valid)
-      for (int c = 0; c < vd; ++c) v_s[lane * v_ld + c] = 0.f;
-    __syncwarp();
-    const float* mine = k_s + lane * ks_ld;
-    for (int h = 0; h < heads; ++h) {
-      float l = 0.f;
-      if (valid)
-        for (int d = 0; d < kq; ++d) l = fmaf(mine[h * kq + d], q_s[h * kq + d], l);
-      l = valid ? l * inv_scale : -INFINITY;
-      float m = l;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const float m_old = mx_s[h];
-      const float m_new = fmaxf(m_old, m);                 // finite: every chunk holds at least one valid edge
-      const float pe = valid ? expf(l - m_new) : 0.f;
-      float ps = pe;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-      p_s[lane * p_ld + h] = pe;
-      __syncwarp();
-      if (lane == 0) {
-        const float sc = expf(m_old - m_new);              // exp(-inf) = 0 on the first chunk
-        sc_s[h] = sc;
-        sum_s[h] = sum_s[h] * sc + ps;
-        mx_s[h] = m_new;
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < kAttnMaxOut; ++k) {
-      const int o = lane + 32 * k;
-      if (o < hv) {
-        const int h = o / vd, c = o - h * vd;
-        float a = acc[k] * sc_s[h];
-        for (int j = 0; j < 32; ++j) a = fmaf(p_s[j * p_ld + h], v_s[j * v_ld + c], a);
-        acc[k] = a;
-      }
-    }
-    __syncwarp();
   }
-#pragma unroll
-  for (int k = 0; k < kAttnMaxOut; ++k) {
-    const int o = lane + 32 * k;
-    if (o < hv) att[r * hv_pad + o] = end > beg ? acc[k] / sum_s[o / vd] : 0.f;      // empty segments give 0
-  }
-  if (stats)
-    for (int h = lane; h < heads; h += 32) {
-      stats[(r * heads + h) * 3] = end > beg ? mx_s[h] : 0.f;
-      stats[(r * heads + h) * 3 + 1] = end > beg ? sum_s[h] : 1.f;
-    }
 }
 
 // MLP input of DMSelfAttentionMLP: concat([nodes, proj]) or proj (gnn.py:547-548)
@@ -659,6 +690,7 @@ constexpr int kLogProbBlocks = 1184;  // 148 SMs x 8
 struct Workspace {
   float *x0, *x1, *hbuf, *act0, *act1, *sbuf, *tbuf;
   float *xq, *qbuf, *kbuf, *vbuf, *att, *proj;     // attention block only
+  int32_t* attn_fallback;                          // per 32-receiver group: staged attention kernel handed it back
   double* partials;
   unsigned int* counter;       // arrival counter of the fused kernel's log-det hand-off (zeroed per entry point)
   int n_partials_cap;
@@ -698,6 +730,7 @@ Workspace carve(const Flow& f, int64_t n, int math, void* base) {
       w.vbuf = (float*)take(nn * f.v_pad * 4);
       w.att = (float*)take(nn * f.hv_pad * 4);
       w.proj = (float*)take(nn * f.cho_pad * 4);
+      w.attn_fallback = (int32_t*)take((nn / 32 + 2) * 4);
     }
   }
   w.bytes = off;
@@ -741,7 +774,7 @@ int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n,
 // MLP input of GNN `mlp` from the half xa: aggregation blocks (shared by s and t) or attention
 int build_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
                      const int32_t* csr_senders, const Workspace& w, cudaStream_t stream) {
-  AttnBufs b{w.xq, w.qbuf, w.kbuf, w.vbuf, w.att, w.proj, nullptr};
+  AttnBufs b{w.xq, w.qbuf, w.kbuf, w.vbuf, w.att, w.proj, nullptr, w.attn_fallback};
   return fwd_attn_input(f, mlp, xa, n, rowptr, csr_senders, b, w.hbuf, stream);
 }
 
@@ -841,22 +874,29 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
   if (rc) return rc;
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
-  const size_t attn_smem = (size_t)kAttnWarps * attn_warp_floats(f.heads, f.kq, f.vd) * sizeof(float);
-  static bool attn_configured[kMaxDevices] = {};
-  if (first_use_on_device(attn_configured))
-    GNF_CUDA(cudaFuncSetAttribute(k_dm_attn_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  if (f.heads * f.vd <= 32 * kAttnMaxOut && attn_smem <= 160 * 1024)
-    k_dm_attn_warp<<<(unsigned)ceil_div(n, kAttnWarps), kAttnWarps * 32, attn_smem, stream>>>(
-        w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr, csr_senders, n,
-        w.att, w.stats);
-  else if (f.vd <= 32)
+  const size_t attn_smem = attn_block_bytes(f.heads, f.kq, f.vd);
+  const bool staged = w.fallback && f.vd <= 10 && attn_smem <= 200 * 1024;
+  const int32_t* only = nullptr;
+  if (staged) {
+    static bool attn_configured[kMaxDevices] = {};
+    if (first_use_on_device(attn_configured))
+      GNF_CUDA(cudaFuncSetAttribute(k_dm_attn_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const unsigned nblk = (unsigned)ceil_div(n, kAttnRecv);
+    GNF_CUDA(cudaMemsetAsync(w.fallback, 0, (size_t)nblk * 4, stream));
+    k_dm_attn_block<<<nblk, kAttnWarps * 32, attn_smem, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad, f.hv_pad,
+                                                                 f.heads, f.kq, f.vd, inv_scale, rowptr, csr_senders, n,
+                                                                 w.att, w.stats, w.fallback);
+    GNF_LAUNCH_CHECK();
+    only = w.fallback;                  // receiver groups whose senders are not one compact row range
+  }
+  if (f.vd <= 32)
     k_dm_attn<32><<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
                                                                             f.hv_pad, f.heads, f.kq, f.vd, inv_scale,
-                                                                            rowptr, csr_senders, n, w.att, w.stats);
+                                                                            rowptr, csr_senders, n, w.att, w.stats, only, 5);
   else
     k_dm_attn<64><<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
                                                                             f.hv_pad, f.heads, f.kq, f.vd, inv_scale,
-                                                                            rowptr, csr_senders, n, w.att, w.stats);
+                                                                            rowptr, csr_senders, n, w.att, w.stats, only, 5);
   GNF_LAUNCH_CHECK();
   rc = run_linear(w.att, wa + f.wo_off, f.zeros, w.proj, n, f.cho_pad, f.hv_pad, 2, stream);  // new_node_proj gnn.py:543-545
   if (rc) return rc;
