@@ -47,6 +47,7 @@ int64_t& launch_counter();
   } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int pad16(int x) { return (x + 15) / 16 * 16; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int num_sms();
@@ -110,6 +111,10 @@ struct Flow {
   bool tc_inject = false;      // layer 0 in the fp32 kernels, layers 1..K-1 + coupling in the tcgen05 kernel (MODE inject)
   void* pack_jobs = nullptr;   // device job table of the one-launch re-pack (pack.cu)
   int n_pack_jobs = 0, pack_blocks = 0;
+  // stand-alone tensor-core linears (linear_tc.cu): fp16 / bf16 hi-lo images per GNN of Wq, Wk, Wv, Wo (attention) and
+  // of layer 0 (inject flows); offset < 0: that matrix stays on the fp32 kernels
+  uint8_t* wlin[2] = {nullptr, nullptr};
+  int64_t wlin_per_mlp = 0, lin_off[5] = {-1, -1, -1, -1, -1};     // q, k, v, o, layer 0
   void* half_tables = nullptr; // device HalfDesc[2 images][2 directions][2T] of the persistent launch (coupling_tc.cu)
   int* range_flag = nullptr;   // sticky device flag: an fp16-split operand left the fp16 range (gnf_flow_range_flag)
 
@@ -129,7 +134,8 @@ struct AttnBufs {      // per-GNN intermediates of the f1 attention block (all [
   int32_t* fallback;   // optional [n / 32 + 1] scratch of the staged attention kernel (null: thread-per-head kernel only)
 };
 int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
-                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream);
+                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream,
+                   int math = GNF_MATH_FP32);
 int fwd_layer_norm(const Flow& f, int mlp, float* x, int64_t n, cudaStream_t stream);
 int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
                   float* hbuf, cudaStream_t stream);
@@ -145,6 +151,12 @@ int bwd_agg_transpose(const Flow& f, const float* gh, int gh_stride, const int32
 int bwd_split_scale(const float* z, int64_t n, int d, int h, int hp, float scale, float* x0, float* x1, float* g0,
                     float* g1, cudaStream_t stream);
 int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp, float* x, cudaStream_t stream);
+
+// linear_tc.cu
+bool tc_linear_shape_ok(int k, int n);
+size_t tc_linear_image_bytes(int k, int n);
+int tc_linear(const Flow& f, int math, const float* A, int lda, int kvalid, const uint8_t* img_f16, const uint8_t* img_bf16,
+              int k, int n, const float* bias, int act, float* C, int ldc, int nvalid, int64_t M, cudaStream_t stream);
 
 // backward_tc.cu
 bool tc_bwd_supported(const Flow& f);

@@ -740,8 +740,8 @@ Workspace carve(const Flow& f, int64_t n, int math, void* base) {
 int run_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K,
                int act, cudaStream_t stream);
 }  // namespace
-int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
-                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream);
+static int linear_any(const Flow& f, int mlp, int math, int slot, const float* A, int lda, int k, const float* w32,
+                      const float* bias, float* C, int ldc, int n, int64_t M, cudaStream_t stream);
 namespace {
 int run_linear(const float* A, const float* W, const float* b, float* C, int64_t M, int N, int K,
                int act, cudaStream_t stream) {
@@ -773,9 +773,9 @@ int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n,
 
 // MLP input of GNN `mlp` from the half xa: aggregation blocks (shared by s and t) or attention
 int build_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
-                     const int32_t* csr_senders, const Workspace& w, cudaStream_t stream) {
+                     const int32_t* csr_senders, const Workspace& w, cudaStream_t stream, int math = GNF_MATH_FP32) {
   AttnBufs b{w.xq, w.qbuf, w.kbuf, w.vbuf, w.att, w.proj, nullptr, w.attn_fallback};
-  return fwd_attn_input(f, mlp, xa, n, rowptr, csr_senders, b, w.hbuf, stream);
+  return fwd_attn_input(f, mlp, xa, n, rowptr, csr_senders, b, w.hbuf, stream, math);
 }
 
 int gnn_forward32(const Flow& f, int mlp, bool build_agg, const float* xa, int64_t n, const int32_t* rowptr,
@@ -829,12 +829,12 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
     for (int which = 0; which < 2; ++which) {
       const int mlp = which ? mt : ms;
       int rc = GNF_OK;
-      if (f.attn) rc = build_attn_input(f, mlp, xa, n, rowptr, csr_senders, w, stream);
+      if (f.attn) rc = build_attn_input(f, mlp, xa, n, rowptr, csr_senders, w, stream, math);
       else if (which == 0) rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, w.hbuf, stream);    // shared by s and t
       if (rc) return rc;
       const float* base = f.w32 + (int64_t)mlp * f.w32_per_mlp;
-      rc = run_linear(w.hbuf, base + f.w32_layer_off[0], base + f.b32_layer_off[0], which ? w.act1 : w.act0, n,
-                      f.out_pads[0], f.in_pads[0], 2, stream);
+      rc = linear_any(f, mlp, math, 4, w.hbuf, f.in_pads[0], f.in_dim, base + f.w32_layer_off[0],
+                      base + f.b32_layer_off[0], which ? w.act1 : w.act0, f.out_pads[0], f.L, n, stream);
       if (rc) return rc;
     }
     return tc_coupling_inject(f, ms, mt, math, inverse, w.act0, w.act1, xb, n, w.partials, ldj_accum, w.counter, stream);
@@ -861,17 +861,29 @@ int fwd_linear(const float* A, const float* W, const float* b, float* C, int64_t
   return run_linear(A, W, b, C, M, N, K, act, stream);
 }
 
+// One bias-free projection / layer: on the tensor cores (linear_tc.cu) when `math` asks for them and the matrix has an
+// image (slot of Flow::lin_off), else the fp32 FFMA kernel.
+static int linear_any(const Flow& f, int mlp, int math, int slot, const float* A, int lda, int k, const float* w32,
+                      const float* bias, float* C, int ldc, int n, int64_t M, cudaStream_t stream) {
+  if (math != GNF_MATH_FP32 && f.lin_off[slot] >= 0) {
+    const size_t off = (size_t)mlp * f.wlin_per_mlp + f.lin_off[slot];
+    return tc_linear(f, math, A, lda, lda, f.wlin[0] + off, f.wlin[1] + off, k, n, bias, 2, C, ldc, ldc, M, stream);
+  }
+  return run_linear(A, w32, bias, C, M, ldc, lda, 2, stream);
+}
+
 int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int32_t* rowptr,
-                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream) {
+                   const int32_t* csr_senders, const AttnBufs& w, float* hbuf, cudaStream_t stream, int math) {
   const float* wa = f.wattn + (int64_t)mlp * f.wattn_per_mlp;
   k_pad_rows<<<(unsigned)ceil_div(n * f.hp8, 256), 256, 0, stream>>>(xa, n, f.HP < f.hp8 ? f.HP : f.hp8, f.hp8, w.xq);
   GNF_LAUNCH_CHECK();
   // xa rows are [HP] wide with zero padding, so reading min(HP, hp8) columns and zero-filling is exact
-  int rc = run_linear(w.xq, wa + f.wq_off, f.zeros, w.qbuf, n, f.qk_pad, f.hp8, 2, stream);   // project_q  gnn.py:509-512
+  const int qk = f.heads * f.kq;
+  int rc = linear_any(f, mlp, math, 0, w.xq, f.hp8, f.H, wa + f.wq_off, f.zeros, w.qbuf, f.qk_pad, qk, n, stream);   // project_q  gnn.py:509-512
   if (rc) return rc;
-  rc = run_linear(w.xq, wa + f.wk_off, f.zeros, w.kbuf, n, f.qk_pad, f.hp8, 2, stream);       // project_k  gnn.py:513-516
+  rc = linear_any(f, mlp, math, 1, w.xq, f.hp8, f.H, wa + f.wk_off, f.zeros, w.kbuf, f.qk_pad, qk, n, stream);       // project_k  gnn.py:513-516
   if (rc) return rc;
-  rc = run_linear(w.xq, wa + f.wv_off, f.zeros, w.vbuf, n, f.v_pad, f.hp8, 2, stream);        // project_v  gnn.py:525-528
+  rc = linear_any(f, mlp, math, 2, w.xq, f.hp8, f.H, wa + f.wv_off, f.zeros, w.vbuf, f.v_pad, f.vd, n, stream);      // project_v  gnn.py:525-528
   if (rc) return rc;
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
   const size_t attn_smem = attn_block_bytes(f.heads, f.kq, f.vd);
@@ -898,7 +910,8 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
                                                                             f.hv_pad, f.heads, f.kq, f.vd, inv_scale,
                                                                             rowptr, csr_senders, n, w.att, w.stats, only, 5);
   GNF_LAUNCH_CHECK();
-  rc = run_linear(w.att, wa + f.wo_off, f.zeros, w.proj, n, f.cho_pad, f.hv_pad, 2, stream);  // new_node_proj gnn.py:543-545
+  rc = linear_any(f, mlp, math, 3, w.att, f.hv_pad, f.heads * f.vd, wa + f.wo_off, f.zeros, w.proj, f.cho_pad, f.cho, n,
+                  stream);                                                                  // new_node_proj gnn.py:543-545
   if (rc) return rc;
   const int concat = (f.attn_flags & GNF_ATTN_CONCAT) ? 1 : 0;
   const int width = concat ? f.H + f.cho : f.cho;
@@ -1077,6 +1090,33 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
       return GNF_ECUDA;
     }
   }
+  if (f.tc_inject) {
+    // stand-alone tensor-core linears of the inject path: layer 0 and, for dm_self_attn, the four projections
+    int64_t off = 0;
+    auto want = [&](int slot, int k, int n) {
+      if (tc_linear_shape_ok(k, n)) {
+        f.lin_off[slot] = off;
+        off += (int64_t)align_up(tc_linear_image_bytes(k, n), 256);
+      }
+    };
+    if (f.attn) {
+      want(0, f.H, f.heads * f.kq);
+      want(1, f.H, f.heads * f.kq);
+      want(2, f.H, f.vd);
+      want(3, f.heads * f.vd, f.cho);
+    }
+    want(4, f.in_dim, f.L);
+    f.wlin_per_mlp = off;
+    if (off > 0) {
+      cudaError_t e0 = cudaMalloc(&f.wlin[0], (size_t)f.n_mlps * off);
+      cudaError_t e1 = cudaMalloc(&f.wlin[1], (size_t)f.n_mlps * off);
+      if (e0 != cudaSuccess || e1 != cudaSuccess) {
+        gnf_flow_destroy(h);
+        set_error("gnf_flow_create: cudaMalloc (linear images) failed");
+        return GNF_ECUDA;
+      }
+    }
+  }
   if (pack_build_jobs(f) != GNF_OK || tc_build_half_tables(f) != GNF_OK) {
     gnf_flow_destroy(h);
     return GNF_ECUDA;
@@ -1106,6 +1146,8 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.btc);
   cudaFree(h->f.wtcT);
   cudaFree(h->f.pack_jobs);
+  cudaFree(h->f.wlin[0]);
+  cudaFree(h->f.wlin[1]);
   cudaFree(h->f.half_tables);
   cudaFree(h->f.range_flag);
   delete h;

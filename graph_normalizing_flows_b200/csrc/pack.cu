@@ -156,6 +156,25 @@ int pack_build_jobs(Flow& f) {
         add(j, 2 * f.HP);
       }
     }
+    if (f.wlin[0]) {      // images of the stand-alone tensor-core linears (linear_tc.cu): chunk geometry kcc = 16, one N block
+      const int qk = f.heads * f.kq, hv = f.heads * f.vd;
+      struct Lin { int slot; int64_t src; int k, n; };
+      const Lin lins[5] = {{0, 0, f.H, qk},
+                           {1, (int64_t)f.H * qk, f.H, qk},
+                           {2, 2ll * f.H * qk, f.H, f.vd},
+                           {3, 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho},
+                           {4, f.flat_w_off[0], f.in_dim, f.L}};
+      for (const Lin& q : lins) {
+        if (f.lin_off[q.slot] < 0) continue;
+        PackJob j{};
+        j.kind = kPackTc; j.transposed = 0; j.in = q.k; j.out = q.n;
+        j.p0 = pad16(q.k); j.p1 = pad16(q.n); j.p2 = pad16(q.n); j.p3 = 16;
+        j.src_off = base + q.src;
+        j.d0 = f.wlin[0] + (size_t)m * f.wlin_per_mlp + f.lin_off[q.slot];
+        j.d1 = f.wlin[1] + (size_t)m * f.wlin_per_mlp + f.lin_off[q.slot];
+        add(j, (int64_t)j.p0 * j.p1);
+      }
+    }
     size_t tc_off[kMaxLayers + 1] = {0};
     if (f.tc_ok || f.tc_inject)
       for (int pos = 0; pos < f.K; ++pos) {
