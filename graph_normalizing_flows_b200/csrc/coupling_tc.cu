@@ -374,26 +374,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
             const uint32_t in_col = tmem_base + (region ^ 1) * LAT;
             const uint32_t d = tmem_base + region * LAT;
             uint32_t waited = 0;
-            wait_groups(waited, 0, G::NA - 1);
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t sb = ring_u + stage * kStageBytes;
             tr.ev(13, m * 16 + K - 1, 0);
-            if (elect_one()) {
-              const uint64_t b_hi0 = smem_desc(sb, kNOut * 16, 128);
-              const uint64_t b_lo0 = smem_desc(sb + G::LAST_MAT_BYTES, kNOut * 16, 128);
+            // one 64-feature group of the previous layer at a time: the k-steps of the groups converted while that
+            // layer's second accumulator half was still being multiplied run under the epilogue of that half
+#pragma unroll 1
+            for (int qg = 0; qg < G::NA; ++qg) {
+              wait_groups(waited, qg, qg);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t b_hi0 = smem_desc(sb, kNOut * 16, 128);
+                const uint64_t b_lo0 = smem_desc(sb + G::LAST_MAT_BYTES, kNOut * 16, 128);
 #pragma unroll
-              for (int ks = 0; ks < LAT / 16; ++ks) {
-                const uint64_t koff = (uint64_t)((ks * 2 * (kNOut * 16)) >> 4);
-                const uint32_t a_hi = in_col + a_col(ks * 16);
-                mma_ts(d, a_hi, b_hi0 + koff, idesc_last, ks ? 1u : 0u);
-                if (NPROD == 3) mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_last, 1);
-                if (NPROD >= 2) mma_ts(d, a_hi, b_lo0 + koff, idesc_last, 1);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const int ks = qg * 4 + k4;
+                  const uint64_t koff = (uint64_t)((ks * 2 * (kNOut * 16)) >> 4);
+                  const uint32_t a_hi = in_col + a_col(ks * 16);
+                  mma_ts(d, a_hi, b_hi0 + koff, idesc_last, ks ? 1u : 0u);
+                  if (NPROD == 3) mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_last, 1);
+                  if (NPROD >= 2) mma_ts(d, a_hi, b_lo0 + koff, idesc_last, 1);
+                }
+                if (qg == G::NA - 1) {
+                  tc_commit(bar_empty + 8 * stage);
+                  tc_commit(smem_u32(&bars->acc_last));
+                }
               }
-              tc_commit(bar_empty + 8 * stage);
-              tc_commit(smem_u32(&bars->acc_last));
+              __syncwarp();
             }
-            __syncwarp();
             tr.ev(14, m * 16 + K - 1, 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             region ^= 1;
@@ -530,11 +539,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     if (PERSIST && hs + 1 < n_halves) {
       // where the launch boundary was: every x_b row of this half step written (CTA barrier, then the grid barrier
       // with its fences), the next half step's bias tiles rebuilt; the gather warps stand at the same two barriers
+      // (bar.sync is warp-aligned: reconverge first -- rows past n_nodes skipped the update above, and the bias
+      //  rebuild below has per-thread trip counts)
+      __syncwarp();
       asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
       if (tid == 64) grid_barrier(p.grid_bar, gridDim.x, p.range_flag);
       build_bias_tiles<LAT, BF16>(btile, blast, p.halves[hs + 1].bias[0], p.halves[hs + 1].bias[1], K, tid - 64,
                                   kEpiThreads + kGatherThreads);
       fence_proxy_async();
+      __syncwarp();
       asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
     }
     }
@@ -658,10 +671,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       mbar_arrive(smem_u32(&bars->h_full[buf]));
     }
     if (PERSIST && hs + 1 < n_halves) {
+      __syncwarp();
       asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
       build_bias_tiles<LAT, BF16>(btile, blast, p.halves[hs + 1].bias[0], p.halves[hs + 1].bias[1], K, tid - 64,
                                   kEpiThreads + kGatherThreads);
       fence_proxy_async();
+      __syncwarp();
       asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
     }
     }
