@@ -89,8 +89,10 @@ struct Tracer {
 
 struct __align__(8) Barriers {
   uint64_t full[kStages], empty[kStages];
-  uint64_t acc_full[kNS], a_ready[kMaxNA];
+  uint64_t acc_full[kNS], a_ready[kMaxNA];      // (the forward kernel uses acc_full[0 .. kFwdNS))
   uint64_t h_full[2], h_empty[2];
+  uint64_t role_bar;   // persistent launch: CTA-level barrier of the epilogue + gather warps at a half-step boundary (an
+                       // mbarrier, not bar.sync: arrivals are per thread, no warp convergence required)
   uint64_t acc_last;   // last layer's own barrier: the next MLP's layer 0 commits acc_full without waiting for the
                        // epilogue, so sharing acc_full[0] could advance it two phases past a late waiter
 };
@@ -180,7 +182,7 @@ template <int LAT, int NPROD, bool BF16, int ACT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
   constexpr bool PERSIST = MODE == kModePersist;
   constexpr bool INJECT = MODE == kModeInject;
-  using G = Geo<LAT>;
+  using G = Geo<LAT, kFwdNS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
@@ -203,13 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
-    for (int i = 0; i < kNS; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1);
+    for (int i = 0; i < kNS; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1);   // all of them: harmless
     for (int i = 0; i < kMaxNA; ++i) mbar_init(smem_u32(&bars->a_ready[i]), kEpiThreads);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->h_full[i]), kGatherThreads);
       mbar_init(smem_u32(&bars->h_empty[i]), 1);
     }
     mbar_init(smem_u32(&bars->acc_last), 1);
+    mbar_init(smem_u32(&bars->role_bar), kEpiThreads + kGatherThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int n_halves = PERSIST ? p.n_halves : 1;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
           if constexpr (!INJECT) issue(src, NPROD >= 2 ? G::L0_BYTES : G::L0_MAT_BYTES);
           src += G::L0_BYTES;
           for (int l = 1; l < K - 1; ++l)
-            for (int c = 0; c < kNS * G::NKC; ++c) {
+            for (int c = 0; c < kFwdNS * G::NKC; ++c) {
               issue(src, NPROD >= 2 ? G::CHUNK_BYTES : G::MAT_BYTES);
               src += G::CHUNK_BYTES;
             }
@@ -320,8 +323,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
               if (NPROD == 3) mma_ss(d, a_lo, b_hi, idesc_l0, 1);   // activation residual
               if (NPROD >= 2) mma_ss(d, a_hi, b_lo, idesc_l0, 1);   // weight residual
               tc_commit(bar_empty + 8 * stage);
-              tc_commit(bar_acc);
-              tc_commit(bar_acc + 8);
+#pragma unroll
+              for (int ph = 0; ph < kFwdNS; ++ph) tc_commit(bar_acc + 8 * ph);
               if (m == 1) tc_commit(bar_hempty + 8 * buf);
             }
             __syncwarp();
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
             const uint32_t sel_l = sel_u + l * 4096;
             uint32_t waited = 0;
 #pragma unroll 1
-            for (int ph = 0; ph < kNS; ++ph) {
+            for (int ph = 0; ph < kFwdNS; ++ph) {
               const uint32_t d = out_col + ph * G::NH;
 #pragma unroll 1
               for (int kc = 0; kc < G::NKC; ++kc) {
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     int region = 0;
     double ldj_local = 0.0;
     float amax = 0.f;
+    uint32_t role_par = 0;
     const int hp4 = p.HP >> 2;
     Tracer tr;
     tr.init(p.trace, 1 + (warp - 2), blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6));
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
         for (int l = 0; l < K - 1; ++l) {
           const bool from_global = INJECT && l == 0;
 #pragma unroll
-          for (int ph = 0; ph < kNS; ++ph) {
+          for (int ph = 0; ph < kFwdNS; ++ph) {
             if (!from_global) {
               mbar_wait(smem_u32(&bars->acc_full[ph]), (acc_par >> ph) & 1u);
               acc_par ^= 1u << ph;
@@ -457,38 +461,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
                 v[4 * j + 2] = __float_as_uint(q.z); v[4 * j + 3] = __float_as_uint(q.w);
               }
             };
-            if constexpr (G::GPH == 2) {
-              uint32_t v0[32], v1[32];
-              if (from_global) {
-                load_chunk(inj, v0);
-                load_chunk(inj ? inj + 64 : nullptr, v1);
-              } else {
-                tmem_ld32(t0, v0);
-                tmem_ld32(t0 + 64, v1);
-                tmem_wait_ld();
-              }
-              convert_chunk<NPROD, BF16, ACT>(t0, v0, amax);
+            // this warp's 32-column chunk of every 64-column group, in K order (the next layer starts on group 0
+            // while the later groups are still being converted); two chunks in flight: the next one is loaded before
+            // the current one is converted
+            uint32_t va[32], vb[32];
+            auto fetch = [&](int g, uint32_t (&v)[32]) {
+              if (from_global) load_chunk(inj ? inj + 64 * g : nullptr, v);
+              else tmem_ld32(t0 + 64 * g, v);
+            };
+            fetch(0, va);
+#pragma unroll
+            for (int g = 0; g < G::GPH; ++g) {
+              uint32_t (&cur)[32] = (g & 1) ? vb : va;
+              uint32_t (&nxt)[32] = (g & 1) ? va : vb;
+              if (g + 1 < G::GPH) fetch(g + 1, nxt);
+              if (!from_global) tmem_wait_ld();
+              convert_chunk<NPROD, BF16, ACT>(t0 + 64 * g, cur, amax);
               tmem_wait_st();
               tc_fence_before();
-              mbar_arrive(smem_u32(&bars->a_ready[ph * 2]));
-              convert_chunk<NPROD, BF16, ACT>(t0 + 64, v1, amax);
-              tmem_wait_st();
-              tc_fence_before();
-              mbar_arrive(smem_u32(&bars->a_ready[ph * 2 + 1]));
-              tr.ev(21, m * 16 + l, ph * 4);
-            } else {
-              uint32_t v0[32];
-              if (from_global) {
-                load_chunk(inj, v0);
-              } else {
-                tmem_ld32(t0, v0);
-                tmem_wait_ld();
-              }
-              convert_chunk<NPROD, BF16, ACT>(t0, v0, amax);
-              tmem_wait_st();
-              tc_fence_before();
-              mbar_arrive(smem_u32(&bars->a_ready[ph]));
+              mbar_arrive(smem_u32(&bars->a_ready[ph * G::GPH + g]));
             }
+            tr.ev(21, m * 16 + l, ph * 4);
           }
           region ^= 1;
         }
@@ -538,17 +531,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     }
     if (PERSIST && hs + 1 < n_halves) {
       // where the launch boundary was: every x_b row of this half step written (CTA barrier, then the grid barrier
-      // with its fences), the next half step's bias tiles rebuilt; the gather warps stand at the same two barriers
-      // (bar.sync is warp-aligned: reconverge first -- rows past n_nodes skipped the update above, and the bias
-      //  rebuild below has per-thread trip counts)
-      __syncwarp();
-      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+      // with its fences), the next half step's bias tiles rebuilt; the gather warps stand at the same two CTA barriers
+      mbar_arrive(smem_u32(&bars->role_bar));
+      mbar_wait(smem_u32(&bars->role_bar), role_par);
+      role_par ^= 1u;
       if (tid == 64) grid_barrier(p.grid_bar, gridDim.x, p.range_flag);
       build_bias_tiles<LAT, BF16>(btile, blast, p.halves[hs + 1].bias[0], p.halves[hs + 1].bias[1], K, tid - 64,
                                   kEpiThreads + kGatherThreads);
       fence_proxy_async();
-      __syncwarp();
-      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+      mbar_arrive(smem_u32(&bars->role_bar));
+      mbar_wait(smem_u32(&bars->role_bar), role_par);
+      role_par ^= 1u;
     }
     }
     tr.ev(23, 0, 0);
@@ -593,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     const int hp4 = p.HP >> 2;
     int it = 0;
     float amax = 0.f;
+    uint32_t role_par = 0;
     Tracer tr;
     tr.init(p.trace, 9, blockIdx.x == 0 && row == 0);
     for (int hs = 0; hs < (INJECT ? 0 : n_halves); ++hs) {      // INJECT: the MLP input never enters this kernel
@@ -671,13 +665,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       mbar_arrive(smem_u32(&bars->h_full[buf]));
     }
     if (PERSIST && hs + 1 < n_halves) {
-      __syncwarp();
-      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+      mbar_arrive(smem_u32(&bars->role_bar));
+      mbar_wait(smem_u32(&bars->role_bar), role_par);
+      role_par ^= 1u;
       build_bias_tiles<LAT, BF16>(btile, blast, p.halves[hs + 1].bias[0], p.halves[hs + 1].bias[1], K, tid - 64,
                                   kEpiThreads + kGatherThreads);
       fence_proxy_async();
-      __syncwarp();
-      asm volatile("bar.sync 2, %0;" ::"r"(kEpiThreads + kGatherThreads) : "memory");
+      mbar_arrive(smem_u32(&bars->role_bar));
+      mbar_wait(smem_u32(&bars->role_bar), role_par);
+      role_par ^= 1u;
     }
     }
     if (!BF16 && amax > 65504.f && p.range_flag) *p.range_flag = 1;
@@ -695,8 +691,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
 // (the weight images are written by pack.cu: one launch for every format)
 template <int LAT>
 size_t bytes_per_mlp_t(int K) {
-  using G = Geo<LAT>;
-  return (size_t)G::L0_BYTES + (size_t)(K - 2) * kNS * G::NKC * G::CHUNK_BYTES + G::LAST_BYTES;
+  using G = Geo<LAT, kFwdNS>;
+  return (size_t)G::L0_BYTES + (size_t)(K - 2) * kFwdNS * G::NKC * G::CHUNK_BYTES + G::LAST_BYTES;
 }
 
 template <int LAT, int NPROD, bool BF16, int ACT, int MODE>

@@ -107,12 +107,22 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_all(const PackJob* __rest
   }
 }
 
-template <int LAT>
-void tc_layer_geometry(int pos, int K, int& kpad, int& npad, int& nhc, int& kcc, size_t& bytes) {
-  using G = tcx::Geo<LAT>;
+// NS = accumulator column splits of the consuming kernel: kFwdNS (k_coupling_tc) or kNS (k_bwd_chain)
+template <int LAT, int NS>
+void tc_layer_geometry_t(int pos, int K, int& kpad, int& npad, int& nhc, int& kcc, size_t& bytes) {
+  using G = tcx::Geo<LAT, NS>;
   if (pos == 0) { kpad = tcx::kK0; npad = LAT; nhc = LAT; kcc = tcx::kK0; bytes = G::L0_BYTES; }
   else if (pos == K - 1) { kpad = LAT; npad = tcx::kNOut; nhc = tcx::kNOut; kcc = LAT; bytes = G::LAST_BYTES; }
-  else { kpad = LAT; npad = LAT; nhc = G::NH; kcc = G::KC; bytes = (size_t)tcx::kNS * G::NKC * G::CHUNK_BYTES; }
+  else { kpad = LAT; npad = LAT; nhc = G::NH; kcc = G::KC; bytes = (size_t)NS * G::NKC * G::CHUNK_BYTES; }
+}
+void tc_layer_geometry(int L, bool forward_kernel, int pos, int K, int& kpad, int& npad, int& nhc, int& kcc, size_t& bytes) {
+  if (L == 256) {
+    if (forward_kernel) tc_layer_geometry_t<256, tcx::kFwdNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+    else tc_layer_geometry_t<256, tcx::kNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+  } else {
+    if (forward_kernel) tc_layer_geometry_t<128, tcx::kFwdNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+    else tc_layer_geometry_t<128, tcx::kNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+  }
 }
 
 }  // namespace
@@ -179,8 +189,7 @@ int pack_build_jobs(Flow& f) {
     if (f.tc_ok || f.tc_inject)
       for (int pos = 0; pos < f.K; ++pos) {
         int a, b, c, d; size_t bytes;
-        if (f.L == 256) tc_layer_geometry<256>(pos, f.K, a, b, c, d, bytes);
-        else tc_layer_geometry<128>(pos, f.K, a, b, c, d, bytes);
+        tc_layer_geometry(f.L, true, pos, f.K, a, b, c, d, bytes);       // (byte counts do not depend on the split)
         tc_off[pos + 1] = tc_off[pos] + bytes;
       }
     for (int l = 0; l < f.K; ++l) {
@@ -203,14 +212,21 @@ int pack_build_jobs(Flow& f) {
       if (!f.tc_ok && !f.tc_inject) continue;
       {   // forward chain position l (the layer-0 image is not used by inject flows: their layer 0 is wider than kK0)
         int kpad, npad, nhc, kcc; size_t bytes;
-        if (f.L == 256) tc_layer_geometry<256>(l, f.K, kpad, npad, nhc, kcc, bytes);
-        else tc_layer_geometry<128>(l, f.K, kpad, npad, nhc, kcc, bytes);
+        tc_layer_geometry(f.L, true, l, f.K, kpad, npad, nhc, kcc, bytes);
         PackJob j{};
         j.kind = kPackTc; j.transposed = 0; j.in = f.ins[l]; j.out = f.outs[l];
         j.p0 = kpad; j.p1 = npad; j.p2 = nhc; j.p3 = kcc; j.src_off = wsrc;
         j.d0 = f.wtc[0] + (size_t)m * f.wtc_per_mlp + tc_off[l];
         j.d1 = f.wtc[1] + (size_t)m * f.wtc_per_mlp + tc_off[l];
         if (!(l == 0 && f.tc_inject)) add(j, (int64_t)kpad * npad);
+        if (f.wtcB[0]) {   // the same layer in the backward kernel's chunk geometry (its forward recompute chains)
+          tc_layer_geometry(f.L, false, l, f.K, kpad, npad, nhc, kcc, bytes);
+          PackJob jb = j;
+          jb.p0 = kpad; jb.p1 = npad; jb.p2 = nhc; jb.p3 = kcc;
+          jb.d0 = f.wtcB[0] + (size_t)m * f.wtc_per_mlp + tc_off[l];
+          jb.d1 = f.wtcB[1] + (size_t)m * f.wtc_per_mlp + tc_off[l];
+          add(jb, (int64_t)kpad * npad);
+        }
         PackJob b{};
         b.kind = kPackBias; b.out = f.outs[l]; b.src_off = base + f.flat_b_off[l];
         b.d0 = f.btc + ((size_t)m * f.K + l) * 256;
@@ -219,8 +235,7 @@ int pack_build_jobs(Flow& f) {
       if (f.wtcT) {   // backward dX chain: position K-1-l applies W_l^T (no bias), same chunk geometry
         const int pos = f.K - 1 - l;
         int kpad, npad, nhc, kcc; size_t bytes;
-        if (f.L == 256) tc_layer_geometry<256>(pos, f.K, kpad, npad, nhc, kcc, bytes);
-        else tc_layer_geometry<128>(pos, f.K, kpad, npad, nhc, kcc, bytes);
+        tc_layer_geometry(f.L, false, pos, f.K, kpad, npad, nhc, kcc, bytes);
         PackJob j{};
         j.kind = kPackTc; j.transposed = 1; j.in = f.outs[l]; j.out = f.ins[l];
         j.p0 = kpad; j.p1 = npad; j.p2 = nhc; j.p3 = kcc; j.src_off = wsrc;

@@ -58,7 +58,7 @@ ed = torch.randn(st.n_edges, 7, device="cuda")
 print("segsum edges", float(G.gnn.unsorted_segment_sum(ed, dg.receivers, dg.nodes.shape[0]).sum()))
 torch.cuda.synchronize()
 PY
-for tool in memcheck racecheck synccheck; do
+for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
   tail -6 gpurun_out/sanitizer_$tool.log
 done
