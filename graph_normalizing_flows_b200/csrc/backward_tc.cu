@@ -1030,7 +1030,7 @@ BwdTcWs carve_bwd_tc(const Flow& f, int64_t n, void* base) {
 
 }  // namespace
 
-bool tc_bwd_supported(const Flow& f) { return f.tc_ok && f.wtcT != nullptr && f.K >= 2; }
+bool tc_bwd_supported(const Flow& f) { return f.tc_ok && f.wtcT != nullptr && f.wtcB[0] != nullptr && f.K >= 2; }
 
 size_t tc_bwd_workspace(const Flow& f, int64_t n) { return carve_bwd_tc(f, n, nullptr).bytes; }
 
@@ -1060,8 +1060,8 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
   p.xa = xa; p.xb = xb; p.gxb = gb;
   p.rowptr = rowptr; p.csr = csr_senders;
   p.n_nodes = n; p.n_tiles = n_tiles;
-  p.wf[0] = f.wtc[fwd_f16 ? 0 : 1] + (size_t)ms * f.wtc_per_mlp;
-  p.wf[1] = f.wtc[fwd_f16 ? 0 : 1] + (size_t)mt * f.wtc_per_mlp;
+  p.wf[0] = f.wtcB[fwd_f16 ? 0 : 1] + (size_t)ms * f.wtc_per_mlp;
+  p.wf[1] = f.wtcB[fwd_f16 ? 0 : 1] + (size_t)mt * f.wtc_per_mlp;
   p.wb[0] = f.wtcT + (size_t)ms * f.wtc_per_mlp;
   p.wb[1] = f.wtcT + (size_t)mt * f.wtc_per_mlp;
   p.bias[0] = f.btc + (size_t)ms * f.K * 256;

@@ -89,7 +89,7 @@ struct Tracer {
 
 struct __align__(8) Barriers {
   uint64_t full[kStages], empty[kStages];
-  uint64_t acc_full[kNS], a_ready[kMaxNA];      // (acc_full[0] only: both column halves of a layer complete together)
+  uint64_t acc_full[kNS], a_ready[kMaxNA];      // (the forward kernel uses acc_full[0 .. kFwdNS))
   uint64_t h_full[2], h_empty[2];
   uint64_t role_bar;   // persistent launch: CTA-level barrier of the epilogue + gather warps at a half-step boundary (an
                        // mbarrier, not bar.sync: arrivals are per thread, no warp convergence required)
@@ -167,6 +167,11 @@ __device__ __forceinline__ void build_bias_tiles(uint8_t* btile, float* blast, c
   if (t >= 0 && t < 2 * kNOut) blast[t] = ((t >> 4) ? bias_t : bias_s)[(K - 1) * 256 + (t & 15)];
 }
 
+// Hidden layers issue ONE N = LAT tcgen05.mma per (k-step, product): measured per half step at the bench workload,
+// two sequential N = 128 halves 0.317 ms, two N = 128 halves fed alternately (an independent MMA between two that share
+// an accumulator) 0.321 ms, one N = 256 instruction 0.290 ms -- the cost is per instruction (~20 of 84 cycles at N = 128),
+// not a read-after-write stall on the accumulator.
+//
 // PERSIST = false: one half coupling step per launch (2T launches per flow, chained by programmatic dependent launch).
 // PERSIST = true : the WHOLE flow in one cooperative launch -- every CTA keeps its tiles (same static round robin) for
 //                  all 2T half steps, a grid barrier stands where the launch boundary was, the weight ring streams
@@ -182,8 +187,7 @@ template <int LAT, int NPROD, bool BF16, int ACT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
   constexpr bool PERSIST = MODE == kModePersist;
   constexpr bool INJECT = MODE == kModeInject;
-  using G = Geo<LAT, 1>;          // epilogue view: one accumulator pass per layer, LAT / 64 conversion groups
-  using G2 = Geo<LAT, kNS>;       // weight chunk geometry: two column halves per hidden layer (shared with k_bwd_chain)
+  using G = Geo<LAT, kFwdNS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
@@ -261,13 +265,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
           const uint8_t* src = m ? w_t : w_s;
           if constexpr (!INJECT) issue(src, NPROD >= 2 ? G::L0_BYTES : G::L0_MAT_BYTES);
           src += G::L0_BYTES;
-          for (int l = 1; l < K - 1; ++l) {
-            // the image holds [half 0: kc 0..][half 1: kc 0..]; the MMA warp consumes (half 0, kc), (half 1, kc) together
-            for (int kc = 0; kc < G2::NKC; ++kc)
-              for (int ph = 0; ph < kNS; ++ph)
-                issue(src + (size_t)(ph * G2::NKC + kc) * G2::CHUNK_BYTES, NPROD >= 2 ? G2::CHUNK_BYTES : G2::MAT_BYTES);
-            src += (size_t)kNS * G2::NKC * G2::CHUNK_BYTES;
-          }
+          for (int l = 1; l < K - 1; ++l)
+            for (int c = 0; c < kFwdNS * G::NKC; ++c) {
+              issue(src, NPROD >= 2 ? G::CHUNK_BYTES : G::MAT_BYTES);
+              src += G::CHUNK_BYTES;
+            }
           issue(src, NPROD >= 2 ? G::LAST_BYTES : G::LAST_MAT_BYTES);
         }
       }
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     // ===== MMA issuer: the whole warp walks the schedule, one elected lane issues =============
     {
       constexpr uint32_t idesc_l0 = make_idesc(LAT, BF16);
-      constexpr uint32_t idesc_h = make_idesc(G2::NH, BF16);
+      constexpr uint32_t idesc_h = make_idesc(G::NH, BF16);
       constexpr uint32_t idesc_last = make_idesc(kNOut, BF16);
       const uint32_t bar_full = smem_u32(&bars->full[0]), bar_empty = smem_u32(&bars->empty[0]);
       const uint32_t bar_acc = smem_u32(&bars->acc_full[0]), bar_ready = smem_u32(&bars->a_ready[0]);
@@ -326,7 +328,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
               if (NPROD == 3) mma_ss(d, a_lo, b_hi, idesc_l0, 1);   // activation residual
               if (NPROD >= 2) mma_ss(d, a_hi, b_lo, idesc_l0, 1);   // weight residual
               tc_commit(bar_empty + 8 * stage);
-              tc_commit(bar_acc);
+#pragma unroll
+              for (int ph = 0; ph < kFwdNS; ++ph) tc_commit(bar_acc + 8 * ph);
               if (m == 1) tc_commit(bar_hempty + 8 * buf);
             }
             __syncwarp();
@@ -334,58 +337,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             region ^= 1;
           }
-          // ---- hidden layers: A from TMEM (previous region); TWO accumulators (column halves) fed alternately ------
-          // Back-to-back MMAs into the SAME accumulator wait for each other's write-back (~20 of 84 cycles per
-          // M128 N128 K16 MMA, ncu: tensor pipe 60 % active under back-to-back issue).  Alternating the two column halves
-          // puts an independent MMA between any two that share an accumulator.  Both halves complete together: one
-          // commit per layer, the epilogue converts the 64-column groups in K order.
+          // ---- hidden layers: A from TMEM (previous region), N = NH per half -----------------
           for (int l = 1; l < K - 1; ++l) {
             const uint32_t in_col = tmem_base + (region ^ 1) * LAT;
-            const uint32_t d0 = tmem_base + region * LAT, d1 = d0 + G2::NH;
+            const uint32_t out_col = tmem_base + region * LAT;
             const uint32_t sel_l = sel_u + l * 4096;
             uint32_t waited = 0;
 #pragma unroll 1
-            for (int kc = 0; kc < G2::NKC; ++kc) {
-              wait_groups(waited, (kc * G2::KC) >> 6, (kc * G2::KC + G2::KC - 1) >> 6);
-              const uint32_t st0 = stage, ph0 = phase;
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-              const uint32_t st1 = stage, ph1 = phase;
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-              mbar_wait(bar_full + 8 * st0, ph0);
-              mbar_wait(bar_full + 8 * st1, ph1);
-              tc_fence_after();
-              const uint32_t sb0 = ring_u + st0 * kStageBytes, sb1 = ring_u + st1 * kStageBytes;
-              const uint32_t a0 = in_col + a_col(kc * G2::KC);
-              tr.ev(12, m * 16 + l, kc);
-              if (elect_one()) {
-                if (kc == 0) {   // bias first: it overwrites (accumulate = 0) the stale region contents
-                  mma_ss(d0, smem_desc(sel_l, 2048, 128), smem_desc(bt, LAT * 16, 128), idesc_h, 0);
-                  mma_ss(d1, smem_desc(sel_l, 2048, 128), smem_desc(bt + G2::NH * 16, LAT * 16, 128), idesc_h, 0);
-                }
-                const uint64_t b_hi0 = smem_desc(sb0, G2::NH * 16, 128), b_hi1 = smem_desc(sb1, G2::NH * 16, 128);
-                const uint64_t b_lo0 = smem_desc(sb0 + G2::MAT_BYTES, G2::NH * 16, 128);
-                const uint64_t b_lo1 = smem_desc(sb1 + G2::MAT_BYTES, G2::NH * 16, 128);
+            for (int ph = 0; ph < kFwdNS; ++ph) {
+              const uint32_t d = out_col + ph * G::NH;
+#pragma unroll 1
+              for (int kc = 0; kc < G::NKC; ++kc) {
+                wait_groups(waited, (kc * G::KC) >> 6, (kc * G::KC + G::KC - 1) >> 6);
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sb = ring_u + stage * kStageBytes;
+                const uint32_t a0 = in_col + a_col(kc * G::KC);
+                tr.ev(12, m * 16 + l, ph * 4 + kc);
+                if (elect_one()) {
+                  if (kc == 0)   // bias first: it overwrites (accumulate = 0) the stale region contents
+                    mma_ss(d, smem_desc(sel_l, 2048, 128), smem_desc(bt + ph * G::NH * 16, LAT * 16, 128), idesc_h, 0);
+                  const uint64_t b_hi0 = smem_desc(sb, G::NH * 16, 128);
+                  const uint64_t b_lo0 = smem_desc(sb + G::MAT_BYTES, G::NH * 16, 128);
 #pragma unroll
-                for (int ks = 0; ks < G2::KC / 16; ++ks) {
-                  // K advances by 16 features = 2 core matrices = 2*LBO bytes (>>4 in the descriptor)
-                  const uint64_t koff = (uint64_t)((ks * 2 * (G2::NH * 16)) >> 4);
-                  const uint32_t a_hi = a0 + a_col(ks * 16);
-                  mma_ts(d0, a_hi, b_hi0 + koff, idesc_h, 1);
-                  mma_ts(d1, a_hi, b_hi1 + koff, idesc_h, 1);
-                  if (NPROD == 3) {
-                    mma_ts(d0, a_hi + 16, b_hi0 + koff, idesc_h, 1);
-                    mma_ts(d1, a_hi + 16, b_hi1 + koff, idesc_h, 1);
+                  for (int ks = 0; ks < G::KC / 16; ++ks) {
+                    // K advances by 16 features = 2 core matrices = 2*LBO bytes (>>4 in the descriptor)
+                    const uint64_t koff = (uint64_t)((ks * 2 * (G::NH * 16)) >> 4);
+                    const uint32_t a_hi = a0 + a_col(ks * 16);
+                    mma_ts(d, a_hi, b_hi0 + koff, idesc_h, 1);
+                    if (NPROD == 3) mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_h, 1);
+                    if (NPROD >= 2) mma_ts(d, a_hi, b_lo0 + koff, idesc_h, 1);
                   }
-                  if (NPROD >= 2) {
-                    mma_ts(d0, a_hi, b_lo0 + koff, idesc_h, 1);
-                    mma_ts(d1, a_hi, b_lo1 + koff, idesc_h, 1);
-                  }
+                  tc_commit(bar_empty + 8 * stage);
+                  if (kc == G::NKC - 1) tc_commit(bar_acc + 8 * ph);
                 }
-                tc_commit(bar_empty + 8 * st0);
-                tc_commit(bar_empty + 8 * st1);
-                if (kc == G2::NKC - 1) tc_commit(bar_acc);
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
-              __syncwarp();
             }
             region ^= 1;
           }
@@ -408,23 +396,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
                 const uint64_t b_hi0 = smem_desc(sb, kNOut * 16, 128);
                 const uint64_t b_lo0 = smem_desc(sb + G::LAST_MAT_BYTES, kNOut * 16, 128);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; k4 += 2) {
-                  // even k-steps accumulate into columns [0, 16), odd ones into [16, 32): two independent chains
-                  // (the epilogue adds the two partial sums)
+                for (int k4 = 0; k4 < 4; ++k4) {
                   const int ks = qg * 4 + k4;
-                  const uint64_t koff0 = (uint64_t)((ks * 2 * (kNOut * 16)) >> 4);
-                  const uint64_t koff1 = (uint64_t)(((ks + 1) * 2 * (kNOut * 16)) >> 4);
-                  const uint32_t a0_hi = in_col + a_col(ks * 16), a1_hi = in_col + a_col((ks + 1) * 16);
-                  mma_ts(d, a0_hi, b_hi0 + koff0, idesc_last, ks ? 1u : 0u);
-                  mma_ts(d + kNOut, a1_hi, b_hi0 + koff1, idesc_last, ks ? 1u : 0u);
-                  if (NPROD == 3) {
-                    mma_ts(d, a0_hi + 16, b_hi0 + koff0, idesc_last, 1);
-                    mma_ts(d + kNOut, a1_hi + 16, b_hi0 + koff1, idesc_last, 1);
-                  }
-                  if (NPROD >= 2) {
-                    mma_ts(d, a0_hi, b_lo0 + koff0, idesc_last, 1);
-                    mma_ts(d + kNOut, a1_hi, b_lo0 + koff1, idesc_last, 1);
-                  }
+                  const uint64_t koff = (uint64_t)((ks * 2 * (kNOut * 16)) >> 4);
+                  const uint32_t a_hi = in_col + a_col(ks * 16);
+                  mma_ts(d, a_hi, b_hi0 + koff, idesc_last, ks ? 1u : 0u);
+                  if (NPROD == 3) mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_last, 1);
+                  if (NPROD >= 2) mma_ts(d, a_hi, b_lo0 + koff, idesc_last, 1);
                 }
                 if (qg == G::NA - 1) {
                   tc_commit(bar_empty + 8 * stage);
@@ -468,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
         for (int l = 0; l < K - 1; ++l) {
           const bool from_global = INJECT && l == 0;
 #pragma unroll
-          for (int ph = 0; ph < 1; ++ph) {
+          for (int ph = 0; ph < kFwdNS; ++ph) {
             if (!from_global) {
               mbar_wait(smem_u32(&bars->acc_full[ph]), (acc_par >> ph) & 1u);
               acc_par ^= 1u << ph;
@@ -519,12 +497,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
           tc_fence_after();
           tr.ev(22, m * 16 + K - 1, 0);
           if (grp == 0) {
-            uint32_t v[32];
-            tmem_ld32(lane_base + region * LAT, v);          // [0, 16): even k-steps, [16, 32): odd k-steps
+            uint32_t v[16];
+            tmem_ld16(lane_base + region * LAT, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < kNOut; ++j)
-              st[m][j] = (__uint_as_float(v[j]) + __uint_as_float(v[kNOut + j])) + blast[m * kNOut + j];
+            for (int j = 0; j < kNOut; ++j) st[m][j] = __uint_as_float(v[j]) + blast[m * kNOut + j];
           }
           region ^= 1;
         }
@@ -719,8 +696,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
 // (the weight images are written by pack.cu: one launch for every format)
 template <int LAT>
 size_t bytes_per_mlp_t(int K) {
-  using G = Geo<LAT, kNS>;
-  return (size_t)G::L0_BYTES + (size_t)(K - 2) * kNS * G::NKC * G::CHUNK_BYTES + G::LAST_BYTES;
+  using G = Geo<LAT, kFwdNS>;
+  return (size_t)G::L0_BYTES + (size_t)(K - 2) * kFwdNS * G::NKC * G::CHUNK_BYTES + G::LAST_BYTES;
 }
 
 template <int LAT, int NPROD, bool BF16, int ACT, int MODE>
