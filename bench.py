@@ -138,8 +138,16 @@ def make_global_batch(wl, world, graphs_per_gpu):
     return concat_structures(structs, nodes=np.concatenate([b[1] for b in blocks], axis=0))
 
 
-def make_oracle_params(wl):
+def make_batch(n_graphs, seed, workload="community_medium"):
+    """One block of `n_graphs` graphs of a workload as a host GraphsTuple (tools/)."""
+    from graph_normalizing_flows_b200.graphs import concat_structures
+    structs, feats = make_block(WORKLOADS[workload], n_graphs, seed)
+    return concat_structures(structs, nodes=feats)
+
+
+def make_oracle_params(wl=None):
     from oracle import gnf_oracle as O
+    wl = wl or WORKLOADS["community_medium"]
     return O.make_params(SEED, wl["T"], D, L, K, agg="sum", block="concat", act="leaky_relu",
                          bias_init_stddev=0.1, last_layer_scale=wl["last_scale"])
 
@@ -472,7 +480,7 @@ def main():
         bytes_alg = eb * (8 + 4 * h) + 4 * nb * h                  # SURVEY §8d "THE figure"
         bytes_csr = eb * 4 + (nb + 1) * 4 + 2 * 4 * nb * h         # what the CSR form must move at least once
         ach = bytes_alg / (seg_ms * 1e-3) / 1e9
-        traffic = ncu_traffic(os.path.join(ROOT, "profiles", "r2_ncu_full_k_segment_reduce.csv"))
+        traffic = ncu_traffic(os.path.join(ROOT, "profiles", "r2_ncu_full_k_gather_segment.csv"))
         seg = {"bound": "hbm", "kernel": "k_gather_segment (gather + segment-sum, standalone)",
                "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                "traffic": traffic, "ms_per_launch": seg_ms, "algorithmic_bytes_per_launch": bytes_alg,

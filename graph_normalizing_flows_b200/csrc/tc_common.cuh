@@ -156,10 +156,10 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kGatherThreads = 128;
 constexpr int kThreads = 64 + kEpiThreads + kGatherThreads;  // warp0 producer, warp1 MMA, 8 epilogue, 4 gather
 constexpr int kNS = 2;         // accumulator column splits per hidden layer: backward chains (k_bwd_chain)
-constexpr int kFwdNS = 1;      // ... and the forward kernel (k_coupling_tc): ONE N = LAT accumulator per layer.  A TS-mode
-                               // MMA re-reads its A slice from TMEM per issue, and TMEM reads are 64 B/cycle, shared with
-                               // the epilogue's tcgen05.ld: two N = 128 halves fetch every A slice twice (64 B/cycle on
-                               // their own, 80+ cycles per MMA measured); one N = 256 MMA fetches it once
+constexpr int kFwdNS = 1;      // ... and the forward kernel (k_coupling_tc): ONE N = LAT accumulator per layer, i.e. one
+                               // N = 256 tcgen05.mma per (k-step, product).  Measured: the cost of an MMA is ~20 cycles
+                               // per INSTRUCTION on top of its M*N*K work (84 cycles at N = 128, 148 at N = 256), so the
+                               // widest instruction wins (0.317 -> 0.290 ms per half step at the bench workload)
 constexpr int kMaxNA = 4;      // a_ready barriers: one per 64 converted feature columns
 
 template <int LAT, int NS = kNS>
