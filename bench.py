@@ -184,12 +184,13 @@ class ClockSampler(threading.Thread):
         }
         while not self._halt.is_set():
             try:
+                # clocks and throttle reasons only: nvmlDeviceGetPowerUsage was seen to hold the driver for 100-200 ms
+                # now and then, which stalls the launching thread (a 10-step tc2x run lost 200 ms to it); power is
+                # logged by tools/power_trace.py instead
                 clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 if self.armed:
                     self.samples.append(clk)
-                    self.power.append(pw)
                     for bit, nm in names.items():
                         if mask & bit:
                             self.reasons.add(nm)
