@@ -93,8 +93,7 @@ __device__ __forceinline__ size_t img_off(int F, int fg, int n) {
 template <int LAT, int ACT, bool F16F>
 __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
   constexpr bool kFB = !F16F;   // forward chains: bf16 split?
-  using G = Geo<LAT>;             // epilogue view: two 128-column halves, 2 conversion groups each
-  using G1 = Geo<LAT, kFwdNS>;    // weight chunks / MMA shape: ONE N = LAT instruction per (k-step, product), as k_coupling_tc
+  using G = Geo<LAT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
@@ -189,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
   } else if (warp == 1) {
     // ===== MMA issuer ==============================================================================
     constexpr uint32_t idesc_l0_f = make_idesc(LAT, kFB), idesc_l0_b = make_idesc(LAT, kBF);
+    constexpr uint32_t idesc_h_f = make_idesc(G::NH, kFB), idesc_h_b = make_idesc(G::NH, kBF);
     constexpr uint32_t idesc_last_f = make_idesc(kNOut, kFB), idesc_last_b = make_idesc(kNOut, kBF);
     const uint32_t bar_full = smem_u32(&bars->full[0]), bar_empty = smem_u32(&bars->empty[0]);
     const uint32_t bar_acc = smem_u32(&bars->acc_full[0]), bar_ready = smem_u32(&bars->a_ready[0]);
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
         const uint32_t a0_hi = bwd ? gbuf_u + m * 8192 : hbuf_u + buf * 8192;
         const uint32_t a0_lo = a0_hi + 4096;
         const uint32_t bt = btile_u + m * (LAT * 32);
-        const uint32_t idesc_l0 = bwd ? idesc_l0_b : idesc_l0_f;
+        const uint32_t idesc_l0 = bwd ? idesc_l0_b : idesc_l0_f, idesc_h = bwd ? idesc_h_b : idesc_h_f;
         const uint32_t idesc_last = bwd ? idesc_last_b : idesc_last_f;
         // ---- chain layer 0: A from smem (K = 16), N = LAT --------------------------------------
         {
@@ -245,42 +245,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
           region ^= 1;
         }
         // ---- hidden chain layers: A from TMEM ----------------------------------------------------
+        // (two N = 128 column halves with separate commits: unlike the forward kernel, ONE N = 256 MMA per k-step was
+        //  measured slower here -- 815 vs 793 us per launch -- because this epilogue also writes the tile images and
+        //  needs the overlap of half 0's epilogue with half 1's MMAs more than it needs the cheaper instruction stream)
         for (int l = 1; l < K - 1; ++l) {
           const uint32_t in_col = tmem_base + (region ^ 1) * LAT;
           const uint32_t out_col = tmem_base + region * LAT;
           const uint32_t sel_l = sel_u + l * 4096;
           uint32_t waited = 0;
-          // one N = LAT MMA per (k-step, product): the cost of a tcgen05.mma is ~20 cycles per instruction on top of
-          // its work (coupling_tc.cu), so the widest instruction wins; both accumulator halves complete together and
-          // the epilogue (which still walks them half by half) finds both barriers already complete
-          {
-            const uint32_t d = out_col;
-            const uint32_t idesc_n = bwd ? make_idesc(G1::NH, kBF) : make_idesc(G1::NH, kFB);
 #pragma unroll 1
-            for (int kc = 0; kc < G1::NKC; ++kc) {
-              wait_groups(waited, (kc * G1::KC) >> 6, (kc * G1::KC + G1::KC - 1) >> 6);
+          for (int ph = 0; ph < kNS; ++ph) {
+            const uint32_t d = out_col + ph * G::NH;
+#pragma unroll 1
+            for (int kc = 0; kc < G::NKC; ++kc) {
+              wait_groups(waited, (kc * G::KC) >> 6, (kc * G::KC + G::KC - 1) >> 6);
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
               const uint32_t sb = ring_u + stage * kStageBytes;
-              const uint32_t a0 = in_col + a_col(kc * G1::KC);
+              const uint32_t a0 = in_col + a_col(kc * G::KC);
               if (elect_one()) {
                 if (kc == 0 && !bwd)
-                  mma_ss(d, smem_desc(sel_l, 2048, 128), smem_desc(bt, LAT * 16, 128), idesc_n, 0);
-                const uint64_t b_hi0 = smem_desc(sb, G1::NH * 16, 128);
-                const uint64_t b_lo0 = smem_desc(sb + G1::MAT_BYTES, G1::NH * 16, 128);
+                  mma_ss(d, smem_desc(sel_l, 2048, 128), smem_desc(bt + ph * G::NH * 16, LAT * 16, 128), idesc_h, 0);
+                const uint64_t b_hi0 = smem_desc(sb, G::NH * 16, 128);
+                const uint64_t b_lo0 = smem_desc(sb + G::MAT_BYTES, G::NH * 16, 128);
 #pragma unroll
-                for (int ks = 0; ks < G1::KC / 16; ++ks) {
-                  const uint64_t koff = (uint64_t)((ks * 2 * (G1::NH * 16)) >> 4);
+                for (int ks = 0; ks < G::KC / 16; ++ks) {
+                  const uint64_t koff = (uint64_t)((ks * 2 * (G::NH * 16)) >> 4);
                   const uint32_t a_hi = a0 + a_col(ks * 16);
-                  mma_ts(d, a_hi, b_hi0 + koff, idesc_n, (bwd && kc == 0 && ks == 0) ? 0u : 1u);
-                  mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_n, 1);
-                  mma_ts(d, a_hi, b_lo0 + koff, idesc_n, 1);
+                  mma_ts(d, a_hi, b_hi0 + koff, idesc_h, (bwd && kc == 0 && ks == 0) ? 0u : 1u);
+                  mma_ts(d, a_hi + 16, b_hi0 + koff, idesc_h, 1);
+                  mma_ts(d, a_hi, b_lo0 + koff, idesc_h, 1);
                 }
                 tc_commit(bar_empty + 8 * stage);
-                if (kc == G1::NKC - 1) {
-                  tc_commit(bar_acc);
-                  tc_commit(bar_acc + 8);
-                }
+                if (kc == G::NKC - 1) tc_commit(bar_acc + 8 * ph);
               }
               __syncwarp();
               if (++stage == kBStages) { stage = 0; phase ^= 1; }
@@ -1036,7 +1033,7 @@ BwdTcWs carve_bwd_tc(const Flow& f, int64_t n, void* base) {
 
 }  // namespace
 
-bool tc_bwd_supported(const Flow& f) { return f.tc_ok && f.wtcT != nullptr && f.K >= 2; }
+bool tc_bwd_supported(const Flow& f) { return f.tc_ok && f.wtcT != nullptr && f.wtcB[0] != nullptr && f.K >= 2; }
 
 size_t tc_bwd_workspace(const Flow& f, int64_t n) { return carve_bwd_tc(f, n, nullptr).bytes; }
 
@@ -1066,8 +1063,8 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
   p.xa = xa; p.xb = xb; p.gxb = gb;
   p.rowptr = rowptr; p.csr = csr_senders;
   p.n_nodes = n; p.n_tiles = n_tiles;
-  p.wf[0] = f.wtc[fwd_f16 ? 0 : 1] + (size_t)ms * f.wtc_per_mlp;
-  p.wf[1] = f.wtc[fwd_f16 ? 0 : 1] + (size_t)mt * f.wtc_per_mlp;
+  p.wf[0] = f.wtcB[fwd_f16 ? 0 : 1] + (size_t)ms * f.wtc_per_mlp;
+  p.wf[1] = f.wtcB[fwd_f16 ? 0 : 1] + (size_t)mt * f.wtc_per_mlp;
   p.wb[0] = f.wtcT + (size_t)ms * f.wtc_per_mlp;
   p.wb[1] = f.wtcT + (size_t)mt * f.wtc_per_mlp;
   p.bias[0] = f.btc + (size_t)ms * f.K * 256;

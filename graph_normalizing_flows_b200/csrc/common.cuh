@@ -103,7 +103,8 @@ struct Flow {
   int64_t wattnT_per_mlp = 0, wqT_off = 0, wkT_off = 0, wvT_off = 0, woT_off = 0;
   // tensor-core packed weights (two images: fp16 and bf16 element type), per MLP a stream of
   // shared-memory chunk images in consumption order (see coupling_tc.cu)
-  uint8_t* wtc[2] = {nullptr, nullptr};   // [0]=fp16 hi/lo, [1]=bf16 hi/lo (chunk geometry: N = LAT blocks, kFwdNS)
+  uint8_t* wtc[2] = {nullptr, nullptr};   // [0]=fp16 hi/lo, [1]=bf16 hi/lo; forward kernel's chunk geometry (kFwdNS)
+  uint8_t* wtcB[2] = {nullptr, nullptr};  // the same MLPs in the backward kernel's chunk geometry (kNS): its recompute chains
   int64_t wtc_per_mlp = 0;
   float* btc = nullptr;        // biases for the TC kernel: per MLP K*256 floats
   uint8_t* wtcT = nullptr;     // bf16 hi/lo images of the TRANSPOSED MLP chains (backward dX), same geometry

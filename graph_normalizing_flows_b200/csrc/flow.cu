@@ -1084,6 +1084,8 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
     cudaError_t e1 = cudaMalloc(&f.wtc[1], (size_t)f.n_mlps * f.wtc_per_mlp);
     cudaError_t e2 = cudaMalloc(&f.btc, (size_t)f.n_mlps * f.K * 256 * 4);
     if (e2 == cudaSuccess && f.tc_ok) e2 = cudaMalloc(&f.wtcT, (size_t)f.n_mlps * f.wtc_per_mlp);
+    if (e2 == cudaSuccess && f.tc_ok) e2 = cudaMalloc(&f.wtcB[0], (size_t)f.n_mlps * f.wtc_per_mlp);
+    if (e2 == cudaSuccess && f.tc_ok) e2 = cudaMalloc(&f.wtcB[1], (size_t)f.n_mlps * f.wtc_per_mlp);
     if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
       gnf_flow_destroy(h);
       set_error("gnf_flow_create: cudaMalloc (tc weights) failed");
@@ -1145,6 +1147,8 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.wtc[1]);
   cudaFree(h->f.btc);
   cudaFree(h->f.wtcT);
+  cudaFree(h->f.wtcB[0]);
+  cudaFree(h->f.wtcB[1]);
   cudaFree(h->f.pack_jobs);
   cudaFree(h->f.wlin[0]);
   cudaFree(h->f.wlin[1]);

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_all(const PackJob* __rest
   }
 }
 
-// NS = column blocks per hidden-layer chunk: kFwdNS = 1 (one N = LAT MMA per k-step) in both tensor-core kernels
+// NS = accumulator column splits of the consuming kernel: kFwdNS (k_coupling_tc) or kNS (k_bwd_chain)
 template <int LAT, int NS>
 void tc_layer_geometry_t(int pos, int K, int& kpad, int& npad, int& nhc, int& kcc, size_t& bytes) {
   using G = tcx::Geo<LAT, NS>;
@@ -115,11 +115,13 @@ void tc_layer_geometry_t(int pos, int K, int& kpad, int& npad, int& nhc, int& kc
   else if (pos == K - 1) { kpad = LAT; npad = tcx::kNOut; nhc = tcx::kNOut; kcc = LAT; bytes = G::LAST_BYTES; }
   else { kpad = LAT; npad = LAT; nhc = G::NH; kcc = G::KC; bytes = (size_t)NS * G::NKC * G::CHUNK_BYTES; }
 }
-void tc_layer_geometry(int L, bool /*forward_kernel: k_coupling_tc and k_bwd_chain share the chunk geometry*/, int pos, int K, int& kpad, int& npad, int& nhc, int& kcc, size_t& bytes) {
+void tc_layer_geometry(int L, bool forward_kernel, int pos, int K, int& kpad, int& npad, int& nhc, int& kcc, size_t& bytes) {
   if (L == 256) {
-    tc_layer_geometry_t<256, tcx::kFwdNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+    if (forward_kernel) tc_layer_geometry_t<256, tcx::kFwdNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+    else tc_layer_geometry_t<256, tcx::kNS>(pos, K, kpad, npad, nhc, kcc, bytes);
   } else {
-    tc_layer_geometry_t<128, tcx::kFwdNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+    if (forward_kernel) tc_layer_geometry_t<128, tcx::kFwdNS>(pos, K, kpad, npad, nhc, kcc, bytes);
+    else tc_layer_geometry_t<128, tcx::kNS>(pos, K, kpad, npad, nhc, kcc, bytes);
   }
 }
 
@@ -217,6 +219,14 @@ int pack_build_jobs(Flow& f) {
         j.d0 = f.wtc[0] + (size_t)m * f.wtc_per_mlp + tc_off[l];
         j.d1 = f.wtc[1] + (size_t)m * f.wtc_per_mlp + tc_off[l];
         if (!(l == 0 && f.tc_inject)) add(j, (int64_t)kpad * npad);
+        if (f.wtcB[0]) {   // the same layer in the backward kernel's chunk geometry (its forward recompute chains)
+          tc_layer_geometry(f.L, false, l, f.K, kpad, npad, nhc, kcc, bytes);
+          PackJob jb = j;
+          jb.p0 = kpad; jb.p1 = npad; jb.p2 = nhc; jb.p3 = kcc;
+          jb.d0 = f.wtcB[0] + (size_t)m * f.wtc_per_mlp + tc_off[l];
+          jb.d1 = f.wtcB[1] + (size_t)m * f.wtc_per_mlp + tc_off[l];
+          add(jb, (int64_t)kpad * npad);
+        }
         PackJob b{};
         b.kind = kPackBias; b.out = f.outs[l]; b.src_off = base + f.flat_b_off[l];
         b.d0 = f.btc + ((size_t)m * f.K + l) * 256;
