@@ -556,17 +556,27 @@ def main():
     def e2e_loop(k):
         """k steps; every step's shard is copied from pinned host memory (H2D of nodes, senders, receivers,
         n_node, n_edge), validated and CSR-indexed inside the timed region -- staged one step ahead on a
-        side stream, as a training input pipeline does -- and every step's 4 scalars are read back."""
+        side stream, as a training input pipeline does -- and every step's 4 scalars are copied back to pinned host
+        memory and READ by the host (one step later, so the device always has the next step queued; all k results
+        have been read when the loop returns)."""
         ticket = prefetch.submit(pinned)
-        last = None
+        host_vec = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
+        inflight, last = None, None
         for i in range(k):
             g = prefetch.wait(ticket)
             pend = sharded.log_prob_async(g)                      # enqueue this step's kernels + all-reduce first ...
             if i + 1 < k:
                 ticket = prefetch.submit(pinned)                  # ... then stage the next batch while they run
             pend.wait()
-            last = pend.vec.cpu()                                 # D2H of this step's 4 scalars (sync)
-        return last
+            host_vec[i & 1].copy_(pend.vec, non_blocking=True)    # D2H of this step's 4 scalars
+            ev_done = torch.cuda.Event()
+            ev_done.record()
+            if inflight is not None:                              # host reads step i-1 while step i runs
+                inflight[0].synchronize()
+                last = inflight[1].clone()
+            inflight = (ev_done, host_vec[i & 1])
+        inflight[0].synchronize()
+        return inflight[1].clone()
 
     e2e_loop(3)
     torch.cuda.synchronize()

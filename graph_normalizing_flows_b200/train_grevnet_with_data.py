@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import os
 import pickle
-import random
 
 import numpy as np
 import torch
@@ -19,80 +18,81 @@ from .graphs import GraphsTuple
 from .utils import senders_receivers
 
 
-def _load(path):
-    with open(path, "rb") as f:
-        d = pickle.load(f)
-    return np.asarray(d[0], dtype=np.float32), np.asarray(d[1], dtype=np.int64)
+class _EmbeddingFile:
+    """One pickle `(node_embeddings, n_node)` with a node-offset table: graphs [g0, g1) are rows
+    [node_off[g0], node_off[g1]) of the embedding matrix."""
+
+    def __init__(self, path):
+        with open(path, "rb") as f:
+            d = pickle.load(f)
+        self.node_embeddings = np.asarray(d[0], dtype=np.float32)
+        self.n_node = np.asarray(d[1], dtype=np.int64)
+        self.node_off = np.concatenate([[0], np.cumsum(self.n_node)])
+
+    def graphs(self, g0, g1):
+        return self.node_embeddings[self.node_off[g0]:self.node_off[g1]], self.n_node[g0:g1]
 
 
-class GrevnetDatasetFixed:
-    """train_grevnet_with_data.py:145-182: `train_batch_size` graphs per batch, files in os.listdir
-    order repeated `train_epochs` times, next file when the current one cannot fill a batch."""
+class _TableReader:
+    """Batches of consecutive graphs, file after file.  Every file is cut ONCE into a table of graph ranges
+    (`_cut`); `train_batch` walks the table and moves to the next file when it is used up.  Running past the last
+    file raises IndexError, as indexing the reference's file list does."""
+
+    def __init__(self, train_data_dir, files):
+        self.train_data_dir, self.files = train_data_dir, files
+        self.file_ind = -1
+        self._next_file()
+
+    def _next_file(self):
+        self.file_ind += 1
+        self._file = _EmbeddingFile(os.path.join(self.train_data_dir, self.files[self.file_ind]))
+        self._table = self._cut(self._file.n_node)
+        self._row = 0
+
+    def train_batch(self):
+        if self._row >= len(self._table):
+            self._next_file()
+        g0, g1 = self._table[self._row]
+        self._row += 1
+        return self._file.graphs(g0, g1)
+
+
+class GrevnetDatasetFixed(_TableReader):
+    """train_grevnet_with_data.py:145-182: `train_batch_size` graphs per batch, the file list repeated
+    `train_epochs` times; the graphs of a file that do not fill a batch are skipped (the reference opens the
+    next file when `prev_graph_ind + train_batch_size > len(n_node)`)."""
 
     def __init__(self, train_data_dir, train_batch_size, train_epochs=1):
-        self.files = sorted(os.listdir(train_data_dir)) * train_epochs
-        self.file_ind = 0
-        self.prev_graph_ind = 0
-        self.prev_node_embedding_ind = 0
-        self.train_batch_size = train_batch_size
-        self.train_data_dir = train_data_dir
-        self._open()
+        self.train_batch_size = int(train_batch_size)
+        super().__init__(train_data_dir, sorted(os.listdir(train_data_dir)) * train_epochs)
 
-    def _open(self):
-        self.node_embeddings, self.n_node = _load(os.path.join(self.train_data_dir, self.files[self.file_ind]))
-        self.n_node_cs = np.cumsum(self.n_node)
-        self.prev_graph_ind = 0
-        self.prev_node_embedding_ind = 0
-
-    def train_batch(self):
-        new_ind = self.prev_graph_ind + self.train_batch_size
-        if new_ind > len(self.n_node):
-            self.file_ind += 1
-            self._open()
-            new_ind = self.train_batch_size
-        node_embeddings = self.node_embeddings[self.prev_node_embedding_ind:self.n_node_cs[new_ind - 1]]
-        n_node = self.n_node[self.prev_graph_ind:new_ind]
-        self.prev_graph_ind = new_ind
-        self.prev_node_embedding_ind = self.n_node_cs[new_ind - 1]
-        return node_embeddings, n_node
+    def _cut(self, n_node):
+        b = self.train_batch_size
+        if len(n_node) < b:          # the reference indexes n_node_cs[b - 1] of the freshly opened file
+            raise IndexError(f"file {self.files[self.file_ind]} holds {len(n_node)} graphs, fewer than one batch of {b}")
+        return [(k * b, (k + 1) * b) for k in range(len(n_node) // b)]
 
 
-class GrevnetDatasetVariable:
-    """train_grevnet_with_data.py:185-234: as many consecutive graphs as stay below `max_nodes`."""
+class GrevnetDatasetVariable(_TableReader):
+    """train_grevnet_with_data.py:185-234: as many consecutive graphs as keep the node count BELOW `max_nodes`
+    (strict: a graph is added while total + n < max_nodes); the tail of a file is flushed as its own batch.
+    (A graph with >= max_nodes nodes makes the reference return empty batches forever; here it is an error.)"""
 
     def __init__(self, train_data_dir, max_nodes):
-        self.files = sorted(os.listdir(train_data_dir))
-        self.file_ind = 0
-        self.max_nodes = max_nodes
-        self.train_data_dir = train_data_dir
-        self._open()
+        self.max_nodes = int(max_nodes)
+        super().__init__(train_data_dir, sorted(os.listdir(train_data_dir)))
 
-    def _open(self):
-        self.node_embeddings, self.n_node = _load(os.path.join(self.train_data_dir, self.files[self.file_ind]))
-        self.n_node_cs = np.cumsum(self.n_node)
-        self.graph_ind = 0
-        self.prev_graph_ind = 0
-        self.prev_node_embedding_ind = 0
-
-    def train_batch(self):
-        total_nodes = 0
-        while True:
-            if self.graph_ind >= len(self.n_node):       # file exhausted: flush the tail, open the next
-                node_embeddings = self.node_embeddings[self.prev_node_embedding_ind:self.n_node_cs[self.graph_ind - 1]]
-                n_node = self.n_node[self.prev_graph_ind:self.graph_ind]
-                self.file_ind += 1
-                self._open()
-                return node_embeddings, n_node
-            if total_nodes + self.n_node[self.graph_ind] < self.max_nodes:
-                total_nodes += self.n_node[self.graph_ind]
-                self.graph_ind += 1
-            else:
-                break
-        node_embeddings = self.node_embeddings[self.prev_node_embedding_ind:self.n_node_cs[self.graph_ind - 1]]
-        n_node = self.n_node[self.prev_graph_ind:self.graph_ind]
-        self.prev_graph_ind = self.graph_ind
-        self.prev_node_embedding_ind = self.n_node_cs[self.graph_ind - 1]
-        return node_embeddings, n_node
+    def _cut(self, n_node):
+        table, g, count = [], 0, len(n_node)
+        while g < count:
+            g0, total = g, 0
+            while g < count and total + n_node[g] < self.max_nodes:
+                total += n_node[g]
+                g += 1
+            if g == g0:
+                raise ValueError(f"graph {g0} of {self.files[self.file_ind]} has {int(n_node[g0])} >= max_nodes nodes")
+            table.append((g0, g))
+        return table
 
 
 def transform_example(node_embeddings, n_node) -> GraphsTuple:

@@ -91,3 +91,61 @@ def senders_receivers(n_node):
                 receivers.append(lo + j)
         lo += n
     return np.array(senders, dtype=np.int32), np.array(receivers, dtype=np.int32)
+
+
+# --------------------------------------------------------------------------- #
+# f4  GrevnetDatasetFixed / GrevnetDatasetVariable  (train_grevnet_with_data.py:145-234)
+# State machines restated statement by statement over in-memory "files" [(node_embeddings, n_node), ...];
+# they stop (return) where the reference would index past its file list.
+# --------------------------------------------------------------------------- #
+def dataset_fixed_batches(files, train_batch_size):
+    file_ind, prev_graph_ind, prev_node_embedding_ind = 0, 0, 0          # :147-150
+    node_embeddings, n_node = files[file_ind]                            # :153-157
+    n_node_cs = np.cumsum(n_node)                                        # :158
+    while True:
+        new_ind = prev_graph_ind + train_batch_size                      # :161
+        if new_ind > len(n_node):                                        # :162
+            file_ind += 1                                                # :163
+            if file_ind >= len(files):
+                return
+            node_embeddings, n_node = files[file_ind]                    # :170-172
+            prev_graph_ind, prev_node_embedding_ind = 0, 0               # :173-174
+            n_node_cs = np.cumsum(n_node)                                # :175
+            new_ind = prev_graph_ind + train_batch_size                  # :176
+        yield (node_embeddings[prev_node_embedding_ind:n_node_cs[new_ind - 1]],   # :177-178
+               n_node[prev_graph_ind:new_ind])                                     # :179
+        prev_graph_ind = new_ind                                         # :180
+        prev_node_embedding_ind = n_node_cs[new_ind - 1]                 # :181
+
+
+def dataset_variable_batches(files, max_nodes):
+    file_ind, graph_ind, prev_graph_ind, prev_node_embedding_ind = 0, 0, 0, 0    # :188-191
+    node_embeddings, n_node = files[file_ind]
+    n_node_cs = np.cumsum(n_node)
+    while True:
+        total_nodes = 0                                                  # :203
+        flushed = False
+        while True:                                                      # :204
+            if graph_ind >= len(n_node):                                 # :205
+                out = (node_embeddings[prev_node_embedding_ind:n_node_cs[graph_ind - 1]],   # :206-208
+                       n_node[prev_graph_ind:graph_ind])                                       # :209
+                file_ind += 1                                            # :210
+                prev_graph_ind, graph_ind, prev_node_embedding_ind = 0, 0, 0   # :211-213
+                yield out
+                if file_ind >= len(files):
+                    return
+                node_embeddings, n_node = files[file_ind]                # :218-221
+                n_node_cs = np.cumsum(n_node)                            # :222
+                flushed = True                                           # :223 return
+                break
+            if total_nodes + n_node[graph_ind] < max_nodes:              # :224
+                total_nodes += n_node[graph_ind]                         # :225
+                graph_ind += 1                                           # :226
+            else:
+                break                                                    # :228
+        if flushed:
+            continue
+        yield (node_embeddings[prev_node_embedding_ind:n_node_cs[graph_ind - 1]],    # :229-231
+               n_node[prev_graph_ind:graph_ind])                                       # :232
+        prev_graph_ind = graph_ind                                       # :233
+        prev_node_embedding_ind = n_node_cs[graph_ind - 1]               # :234

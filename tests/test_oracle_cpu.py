@@ -319,6 +319,38 @@ def test_f4_embedding_pickle_readers(tmp_path):
     assert np.array_equal(g.n_edge, (n ** 2).astype(np.int32)) and g.nodes.dtype == np.float32
 
 
+def test_f4_table_readers_reproduce_the_reference_state_machines(tmp_path):
+    """The index-table readers (every file cut once into graph ranges) against statement-by-statement restatements
+    of the reference's reader state machines (oracle/data_oracle.py), batch for batch until the files run out."""
+    import pickle
+    from graph_normalizing_flows_b200 import train_grevnet_with_data as TD
+    rng = np.random.default_rng(3)
+    files = []
+    for k in range(3):
+        n_node = rng.integers(3, 12, size=int(rng.integers(9, 17)))
+        emb = rng.standard_normal((int(n_node.sum()), 4)).astype(np.float32)
+        pickle.dump((emb, n_node), open(tmp_path / f"part{k}.p", "wb"))
+        files.append((emb, n_node.astype(np.int64)))
+    for batch in (3, 4, 5):
+        ds = TD.GrevnetDatasetFixed(str(tmp_path), batch)
+        count = 0
+        for e_ref, n_ref in DO.dataset_fixed_batches(files, batch):
+            e, n = ds.train_batch()
+            assert np.array_equal(n, n_ref) and np.array_equal(e, e_ref)
+            count += 1
+        assert count == sum(len(f[1]) // batch for f in files)
+        with pytest.raises(IndexError):
+            ds.train_batch()                                   # past the last file, as the reference
+    for max_nodes in (15, 24, 40):
+        dv = TD.GrevnetDatasetVariable(str(tmp_path), max_nodes)
+        count = 0
+        for e_ref, n_ref in DO.dataset_variable_batches(files, max_nodes):
+            e, n = dv.train_batch()
+            assert np.array_equal(n, n_ref) and np.array_equal(e, e_ref), (max_nodes, count)
+            count += 1
+        assert count > len(files)
+
+
 def test_f3_oracle_pred_adj_properties():
     rng = np.random.default_rng(1)
     x = rng.standard_normal((9, 4))
