@@ -91,17 +91,24 @@ struct __align__(8) Barriers {
   uint64_t full[kStages], empty[kStages];
   uint64_t acc_full[kNS], a_ready[kMaxNA];      // (the forward kernel uses acc_full[0 .. kFwdNS))
   uint64_t h_full[2], h_empty[2];
+  uint64_t x_full[2];  // bulk-staged sender rows of the next tiles (MODE 0): one cp.async.bulk per tile and buffer
   uint64_t role_bar;   // persistent launch: CTA-level barrier of the epilogue + gather warps at a half-step boundary (an
                        // mbarrier, not bar.sync: arrivals are per thread, no warp convergence required)
   uint64_t acc_last;   // last layer's own barrier: the next MLP's layer 0 commits acc_full without waiting for the
                        // epilogue, so sharing acc_full[0] could advance it two phases past a late waiter
 };
 
+// Node-feature staging (north star: TMA / shared-memory staging of node-feature tiles): graphs are contiguous node
+// blocks, so the sender rows a 128-node tile aggregates are one compact row range [lo, hi] of the planar half; its
+// 32-byte rows are 16-byte aligned, i.e. ONE legal cp.async.bulk.  Two buffers (the gather warps run a tile ahead).
+constexpr int kXStageBytes = 8192;
+
 template <int LAT>
 constexpr size_t smem_bytes() {
   return 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * 2 * 4096 /*h tiles*/ +
          (kMaxLayers - 1) * 4096 /*selector A tiles*/ + 2 * LAT * 32 /*bias B tiles*/ +
-         2 * kNOut * 4 /*last-layer bias*/ + kGatherThreads * 17 * 4 /*h staging*/ + sizeof(Barriers) + 128;
+         2 * kNOut * 4 /*last-layer bias*/ + kGatherThreads * 17 * 4 /*h staging*/ + sizeof(Barriers) + 128 +
+         2 * kXStageBytes /*bulk-staged node-feature rows*/ + 384 /*xred + alignment of the stage buffers*/;
 }
 
 template <int ACT>
@@ -199,6 +206,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
   Barriers* bars = (Barriers*)(hstage + kGatherThreads * 17);
   uint32_t* tmem_slot = (uint32_t*)(bars + 1);
   double* ldj_red = (double*)(tmem_slot + 2);                   // [4]
+  int32_t* xred = (int32_t*)(ldj_red + 4);                      // [2][8] sender range reduction of the gather warps
+  uint8_t* xstage = (uint8_t*)(((uintptr_t)(xred + 16) + 127) & ~(uintptr_t)127);   // [2][kXStageBytes]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -215,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->h_full[i]), kGatherThreads);
       mbar_init(smem_u32(&bars->h_empty[i]), 1);
+      mbar_init(smem_u32(&bars->x_full[i]), 1);
     }
     mbar_init(smem_u32(&bars->acc_last), 1);
     mbar_init(smem_u32(&bars->role_bar), kEpiThreads + kGatherThreads);
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
     const int hp4 = p.HP >> 2;
     int it = 0;
     float amax = 0.f;
-    uint32_t role_par = 0;
+    uint32_t role_par = 0, xpar = 0;
     Tracer tr;
     tr.init(p.trace, 9, blockIdx.x == 0 && row == 0);
     for (int hs = 0; hs < (INJECT ? 0 : n_halves); ++hs) {      // INJECT: the MLP input never enters this kernel
@@ -608,6 +618,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
       float self[kNOut], agg[kNOut];
 #pragma unroll
       for (int j = 0; j < kNOut; ++j) { self[j] = 0.f; agg[j] = 0.f; }
+      // ---- stage the tile's sender rows with ONE bulk copy (MODE 0; the persistent launch keeps ld.global.cg: its
+      //      rows were written through the generic proxy by this and other CTAs one half step ago) -----------------
+      int32_t e_beg = 0, e_end = 0;
+      if (node < p.n_nodes) { e_beg = p.rowptr[node]; e_end = p.rowptr[node + 1]; }
+      bool staged = false;
+      int32_t x_lo = 0;
+      const int xbuf = it & 1;
+      if constexpr (!PERSIST) {
+        int32_t lo_t = 0x7fffffff, hi_t = -1;
+        for (int32_t e = e_beg; e < e_end; ++e) {
+          const int32_t sidx = p.csr[e];
+          lo_t = min(lo_t, sidx);
+          hi_t = max(hi_t, sidx);
+        }
+        lo_t = __reduce_min_sync(0xffffffffu, lo_t);
+        hi_t = __reduce_max_sync(0xffffffffu, hi_t);
+        int32_t* red = xred + xbuf * 8;
+        if ((row & 31) == 0) { red[row >> 5] = lo_t; red[4 + (row >> 5)] = hi_t; }
+        __syncwarp();
+        asm volatile("bar.sync 3, %0;" ::"r"(kGatherThreads) : "memory");   // all 128 gather threads, converged here
+        x_lo = min(min(red[0], red[1]), min(red[2], red[3]));
+        const int32_t x_hi = max(max(red[4], red[5]), max(red[6], red[7]));
+        const uint32_t bytes = (uint32_t)(x_hi - x_lo + 1) * (uint32_t)p.HP * 4u;
+        staged = x_hi >= x_lo && (int64_t)(x_hi - x_lo + 1) * p.HP * 4 <= kXStageBytes;
+        if (staged) {
+          const uint32_t xb = smem_u32(&bars->x_full[xbuf]);
+          if (row == 0) {
+            mbar_expect_tx(xb, bytes);
+            bulk_g2s(smem_u32(xstage + xbuf * kXStageBytes), xa_base + (int64_t)x_lo * p.HP, bytes, xb);
+          }
+          mbar_wait(xb, (xpar >> xbuf) & 1u);
+          xpar ^= 1u << xbuf;
+        }
+      }
       if (node < p.n_nodes) {
         const float* xr = xa_base + node * p.HP;
 #pragma unroll
@@ -616,10 +660,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_coupling_tc(const TcParams p) {
             float4 x = ldx(xr + g4 * 4);
             self[g4 * 4] = x.x; self[g4 * 4 + 1] = x.y; self[g4 * 4 + 2] = x.z; self[g4 * 4 + 3] = x.w;
           }
-        int32_t e = p.rowptr[node];
-        const int32_t end = p.rowptr[node + 1];
+        int32_t e = e_beg;
+        const int32_t end = e_end;
         const int32_t cnt = end - e;
-        for (; e < end; ++e) {       // ascending edge index inside the segment: TF-CPU order
+        if (staged) {
+          const float* xs = reinterpret_cast<const float*>(xstage + xbuf * kXStageBytes);
+          for (; e < end; ++e) {     // ascending edge index inside the segment: TF-CPU order
+            const float* sr = xs + (p.csr[e] - x_lo) * p.HP;
+#pragma unroll
+            for (int g4 = 0; g4 < kNOut / 4; ++g4)
+              if (g4 < hp4) {
+                const float4 x = *reinterpret_cast<const float4*>(sr + g4 * 4);
+                agg[g4 * 4] = __fadd_rn(agg[g4 * 4], x.x);
+                agg[g4 * 4 + 1] = __fadd_rn(agg[g4 * 4 + 1], x.y);
+                agg[g4 * 4 + 2] = __fadd_rn(agg[g4 * 4 + 2], x.z);
+                agg[g4 * 4 + 3] = __fadd_rn(agg[g4 * 4 + 3], x.w);
+              }
+          }
+        }
+        for (; e < end; ++e) {       // (not staged) rows straight from global memory, same order
           const float* sr = xa_base + (int64_t)p.csr[e] * p.HP;
 #pragma unroll
           for (int g4 = 0; g4 < kNOut / 4; ++g4)
