@@ -265,10 +265,11 @@ __global__ void __launch_bounds__(128)
 k_attn_bwd_recv(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
                 const float* __restrict__ gatt, int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd,
                 float inv_scale, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
-                float* __restrict__ stats, float* __restrict__ gqueries) {
+                float* __restrict__ stats, float* __restrict__ gqueries, const int32_t* __restrict__ only) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * heads) return;
   const int64_t r = i / heads;
+  if (only && !only[r >> 5]) return;       // second pass: only the 32-receiver groups k_attn_bwd_block handed back
   const int h = (int)(i - r * heads);
   const int32_t beg = rowptr[r], end = rowptr[r + 1];
   const float* qr = queries + r * qk_pad + h * kq;
@@ -318,10 +319,11 @@ k_attn_bwd_send(const float* __restrict__ keys, const float* __restrict__ querie
                 const float* __restrict__ gatt, const float* __restrict__ stats, int qk_pad, int v_pad, int hv_pad,
                 int heads, int kq, int vd, float inv_scale, const int32_t* __restrict__ rowptr_s,
                 const int32_t* __restrict__ csr_receivers, int64_t n, float* __restrict__ gkeys,
-                float* __restrict__ gvh) {
+                float* __restrict__ gvh, const int32_t* __restrict__ only) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * heads) return;
   const int64_t s = i / heads;
+  if (only && !only[s >> 5]) return;
   const int h = (int)(i - s * heads);
   const float* ks = keys + s * qk_pad + h * kq;
   const float* vs = vals + s * v_pad;
@@ -355,6 +357,193 @@ k_attn_bwd_send(const float* __restrict__ keys, const float* __restrict__ querie
 #pragma unroll
   for (int c = 0; c < VMAX; ++c)
     if (c < vd) gvh[s * hv_pad + h * vd + c] = accv[c];
+}
+
+// Block-staged attention backward (round 2), the mirror of k_dm_attn_block.  One template, two passes:
+//   SEND = 0 : a CTA owns 32 consecutive RECEIVERS r (CSR by receiver); "other" end of an edge = its sender s.
+//              dot[r,h] = sum_e w_e g_w_e  -> stats[.., 2];   g_queries[r,h,:] = sum_e g_l_e keys[s_e,h,:]
+//   SEND = 1 : a CTA owns 32 consecutive SENDERS s (CSR by sender); other end = the receiver r.
+//              g_keys[s,h,:] = sum_e g_l_e queries[r_e,h,:];  g_vh[s,h,:] = sum_e w_e g_att[r_e,h,:]
+// with, per edge and head,  l = <keys[s,h,:], queries[r,h,:]>,  w = exp(l * inv_scale - max[r,h]) / sum[r,h],
+// g_w = <g_att[r,h,:], values[s,:]>,  g_l = w (g_w - dot[r,h]) inv_scale      (k_attn_bwd_recv / k_attn_bwd_send).
+// The CTA stages its own rows and -- graphs being contiguous node blocks -- the contiguous range [lo, hi] of "other"
+// rows with coalesced loads; a warp takes own nodes in turn, 32 edges at a time: lane = edge for the per-edge terms
+// (all heads at once, odd row stride: conflict free), then lane = output column for the sums over the edges (the
+// per-edge factors pass through shared memory).  Fixed summation order, no atomics.  CTAs whose other rows are not one
+// compact range hand their 32 nodes back to the thread-per-head kernels (`fallback`).
+constexpr int kAbRecv = 32;              // own nodes per CTA (= 1 << 5: the `only` shift of the thread-per-head kernels)
+constexpr int kAbWarps = 16;
+constexpr int kAbRows = 128;             // staged "other" rows per CTA
+constexpr int kAbIdx = 2048;             // staged CSR indices per CTA
+constexpr int kAbH = 8;                  // heads (all in one register pass)
+constexpr int kAbCols = 4;               // output columns per lane: heads * kq <= 128, heads * vd <= 128
+
+__host__ __device__ inline int ab_odd(int x) { return x | 1; }
+template <int SEND>
+__host__ __device__ inline size_t attn_bwd_block_bytes(int heads, int kq, int vd) {
+  const int qk = heads * kq, hv = heads * vd;
+  const int other = SEND ? ab_odd(qk + hv + 3 * heads) : ab_odd(qk + vd);
+  const int own = SEND ? qk + vd : qk + hv + 2 * heads;
+  return ((size_t)kAbRows * other + (size_t)kAbRecv * own + (size_t)kAbWarps * 32 * kAbH * (SEND ? 2 : 1)) * sizeof(float) +
+         ((size_t)kAbIdx + kAbRecv + 1 + 2 * kAbWarps + 2) * sizeof(int32_t);
+}
+
+template <int SEND>
+__global__ void __launch_bounds__(kAbWarps * 32)
+k_attn_bwd_block(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+                 const float* __restrict__ gatt, float* __restrict__ stats, int qk_pad, int v_pad, int hv_pad, int heads,
+                 int kq, int vd, float inv_scale, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr,
+                 int64_t n, float* __restrict__ out1, float* __restrict__ out2, int32_t* __restrict__ fallback) {
+  extern __shared__ float sm_ab[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qk = heads * kq, hv = heads * vd;
+  const int o_ld = SEND ? ab_odd(qk + hv + 3 * heads) : ab_odd(qk + vd);     // "other" row stride
+  const int w_ld = SEND ? qk + vd : qk + hv + 2 * heads;                      // own row stride
+  float* o_s = sm_ab;                                     // [kAbRows][o_ld]
+  float* w_s = o_s + kAbRows * o_ld;                      // [kAbRecv][w_ld]
+  float* p_s = w_s + kAbRecv * w_ld;                      // [warps][32][kAbH] (x2 when SEND)
+  int32_t* idx_s = reinterpret_cast<int32_t*>(p_s + kAbWarps * 32 * kAbH * (SEND ? 2 : 1));   // [kAbIdx]
+  int32_t* row_s = idx_s + kAbIdx;                        // [kAbRecv + 1]
+  int32_t* red_s = row_s + kAbRecv + 1;                   // [2 * warps + 2]
+  const int64_t r0 = (int64_t)blockIdx.x * kAbRecv;
+  const int nr = (int)((n - r0) < kAbRecv ? (n - r0) : kAbRecv);
+  for (int i = tid; i <= nr; i += kAbWarps * 32) row_s[i] = rowptr[r0 + i];
+  __syncthreads();
+  const int32_t e0 = row_s[0], ne = row_s[nr] - e0;
+  int32_t lo = 0x7fffffff, hi = -1;
+  if (ne <= kAbIdx)
+    for (int i = tid; i < ne; i += kAbWarps * 32) {
+      const int32_t v = csr[e0 + i];
+      idx_s[i] = v;
+      lo = min(lo, v);
+      hi = max(hi, v);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { red_s[warp] = lo; red_s[kAbWarps + warp] = hi; }
+  __syncthreads();
+  for (int w = 0; w < kAbWarps; ++w) { lo = min(lo, red_s[w]); hi = max(hi, red_s[kAbWarps + w]); }
+  const int nrows = ne > 0 ? hi - lo + 1 : 0;
+  if (ne > kAbIdx || nrows > kAbRows) {                   // uniform: hand the CTA's nodes to the thread-per-head kernels
+    if (tid == 0) fallback[blockIdx.x] = 1;
+    return;
+  }
+  // ---- stage (a warp copies whole rows: coalesced, no index arithmetic per element) ---------------------------------
+  // receiver-side row: [queries qk | g_att hv | max heads | 1/sum heads | (SEND: dot heads)]; sender-side row: [keys qk | values vd]
+  for (int row = warp; row < nrows + nr; row += kAbWarps) {
+    const bool is_other = row < nrows;
+    const int64_t node = is_other ? (int64_t)lo + row : r0 + (row - nrows);
+    float* dst = is_other ? o_s + row * o_ld : w_s + (row - nrows) * w_ld;
+    const bool recv_side = is_other ? (SEND != 0) : (SEND == 0);
+    if (recv_side) {
+      for (int c = lane; c < qk; c += 32) dst[c] = queries[node * qk_pad + c];
+      for (int c = lane; c < hv; c += 32) dst[qk + c] = gatt[node * hv_pad + c];
+      for (int c = lane; c < heads; c += 32) {
+        const float* st = stats + (node * heads + c) * 3;
+        dst[qk + hv + c] = st[0];
+        dst[qk + hv + heads + c] = 1.f / st[1];
+        if (SEND) dst[qk + hv + 2 * heads + c] = st[2];
+      }
+    } else {
+      for (int c = lane; c < qk; c += 32) dst[c] = keys[node * qk_pad + c];
+      for (int c = lane; c < vd; c += 32) dst[qk + c] = vals[node * v_pad + c];
+    }
+  }
+  __syncthreads();
+  float* pw = p_s + warp * 32 * kAbH * (SEND ? 2 : 1);   // [32][kAbH] g_l (and, SEND, [32][kAbH] w behind it)
+  int col_h1[kAbCols], col_h2[kAbCols];                   // head of this lane's output columns (out1: / kq, out2: / vd)
+#pragma unroll
+  for (int j = 0; j < kAbCols; ++j) {
+    col_h1[j] = min((lane + 32 * j) / kq, kAbH - 1);
+    col_h2[j] = min((lane + 32 * j) / vd, kAbH - 1);
+  }
+  for (int rl = warp; rl < nr; rl += kAbWarps) {
+    const int32_t beg = row_s[rl] - e0, end = row_s[rl + 1] - e0;
+    const float* own = w_s + rl * w_ld;
+    float w[kAbH], gw[kAbH];
+    // per-edge terms of edge e (lane = edge): w[h], gw[h]; invalid lanes get zeros
+    auto edge_terms = [&](int32_t e, bool valid) {
+      const float* oth = o_s + (valid ? idx_s[e] - lo : 0) * o_ld;
+      const float* kp = SEND ? own : oth;                 // keys / values live on the sender side
+      const float* rp = SEND ? oth : own;                 // queries / g_att / statistics on the receiver side
+#pragma unroll
+      for (int h = 0; h < kAbH; ++h) {
+        float l = 0.f, g = 0.f;
+        if (h < heads) {
+          for (int d = 0; d < kq; ++d) l = fmaf(kp[h * kq + d], rp[h * kq + d], l);
+          for (int c = 0; c < vd; ++c) g = fmaf(rp[qk + h * vd + c], kp[qk + c], g);
+        }
+        const bool on = valid && h < heads;
+        w[h] = on ? expf(l * inv_scale - rp[qk + hv + h]) * rp[qk + hv + heads + h] : 0.f;
+        gw[h] = on ? g : 0.f;
+      }
+    };
+    float acc1[kAbCols], acc2[kAbCols];
+#pragma unroll
+    for (int j = 0; j < kAbCols; ++j) { acc1[j] = 0.f; acc2[j] = 0.f; }
+    float dot[kAbH];
+#pragma unroll
+    for (int h = 0; h < kAbH; ++h) dot[h] = 0.f;
+    if (!SEND) {
+      // pass A over the receiver's in-edges: dot[h] = sum_e w_e g_w_e
+      for (int32_t c0 = beg; c0 < end; c0 += 32) {
+        edge_terms(c0 + lane, c0 + lane < end);
+#pragma unroll
+        for (int h = 0; h < kAbH; ++h) dot[h] = fmaf(w[h], gw[h], dot[h]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int h = 0; h < kAbH; ++h) dot[h] += __shfl_xor_sync(0xffffffffu, dot[h], o);
+      if (lane < heads) {
+        float mine = 0.f;
+#pragma unroll
+        for (int h = 0; h < kAbH; ++h) mine = (lane == h) ? dot[h] : mine;
+        stats[((r0 + rl) * heads + lane) * 3 + 2] = mine;
+      }
+    }
+    const bool one_chunk = end - beg <= 32;
+    for (int32_t c0 = beg; c0 < end; c0 += 32) {
+      const bool valid = c0 + lane < end;
+      if (SEND || !one_chunk) edge_terms(c0 + lane, valid);          // (a single chunk still holds pass A's terms)
+      const float* oth = o_s + (valid ? idx_s[c0 + lane] - lo : 0) * o_ld;
+      float gl[kAbH];
+#pragma unroll
+      for (int h = 0; h < kAbH; ++h) {
+        const float d = SEND ? ((valid && h < heads) ? oth[qk + hv + 2 * heads + h] : 0.f) : dot[h];
+        gl[h] = w[h] * (gw[h] - d) * inv_scale;
+      }
+      *reinterpret_cast<float4*>(pw + lane * kAbH) = make_float4(gl[0], gl[1], gl[2], gl[3]);
+      *reinterpret_cast<float4*>(pw + lane * kAbH + 4) = make_float4(gl[4], gl[5], gl[6], gl[7]);
+      if (SEND) {
+        *reinterpret_cast<float4*>(pw + 32 * kAbH + lane * kAbH) = make_float4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<float4*>(pw + 32 * kAbH + lane * kAbH + 4) = make_float4(w[4], w[5], w[6], w[7]);
+      }
+      __syncwarp();
+      // lane = output column: sums over the chunk's edges, in edge order
+      const int cnt = min(32, end - c0);
+      for (int j = 0; j < cnt; ++j) {
+        const float* orow = o_s + (idx_s[c0 + j] - lo) * o_ld;
+        const float* pj = pw + j * kAbH;
+#pragma unroll
+        for (int u = 0; u < kAbCols; ++u) {
+          const int c = lane + 32 * u;
+          if (c < qk) acc1[u] = fmaf(pj[col_h1[u]], orow[c], acc1[u]);               // keys (SEND 0) / queries (SEND 1)
+          if (SEND && c < hv) acc2[u] = fmaf(pj[32 * kAbH + col_h2[u]], orow[qk + c], acc2[u]);   // g_att
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int u = 0; u < kAbCols; ++u) {
+      const int c = lane + 32 * u;
+      if (c < qk) out1[(r0 + rl) * qk_pad + c] = acc1[u];
+      if (SEND && c < hv) out2[(r0 + rl) * hv_pad + c] = acc2[u];
+    }
+  }
 }
 
 // g_v[s, c] = sum over heads of g_vh[s, h, c]   (keras.backend.repeat, gnn.py:528)
@@ -601,7 +790,7 @@ int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* h_i
 // backward of the attention front end of GNN `mlp` (m = 0: s, 1: t): w.gh holds dL/d(MLP input)
 int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_top, int gp, int64_t n,
                   const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
-                  const int32_t* csr_receivers, float* ga, float* grads, cudaStream_t stream) {
+                  const int32_t* csr_receivers, float* ga, float* grads, cudaStream_t stream, int math = GNF_MATH_FP32) {
   const AttnBufs& b = w.ab[m];
   const float* wt = f.wattnT + (int64_t)mlp * f.wattnT_per_mlp;
   float* gm = grads + (int64_t)mlp * f.params_per_mlp;
@@ -615,20 +804,53 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   int rc = run_dw_generic(b.att, f.hv_pad, hv, w.gproj, f.cho_pad, f.cho, n, w.part,
                           gm + 2ll * f.H * qk + (int64_t)f.H * f.vd, stream);                    // dWo
   if (rc) return rc;
-  rc = run_dx(w.gproj, wt + f.woT_off, nullptr, w.gatt, n, f.hv_pad, f.cho_pad, 0, 0, stream);   // g_att = g_proj Wo^T
+  if (math != GNF_MATH_FP32 && f.lin_off[6] >= 0) {                                              // g_att = g_proj Wo^T
+    const size_t off = (size_t)mlp * f.wlin_per_mlp + f.lin_off[6];
+    rc = tc_linear(f, GNF_MATH_TC3X_BF16, w.gproj, f.cho_pad, f.cho_pad, f.wlin[0] + off, f.wlin[1] + off, f.cho, hv,
+                   f.zeros, 2, w.gatt, f.hv_pad, f.hv_pad, n, stream);
+  } else {
+    rc = run_dx(w.gproj, wt + f.woT_off, nullptr, w.gatt, n, f.hv_pad, f.cho_pad, 0, 0, stream);
+  }
   if (rc) return rc;
   const unsigned blocks = (unsigned)ceil_div(n * f.heads, 128);
+  // block-staged kernels first (compact graphs); the thread-per-head kernels then serve the groups handed back, or
+  // everything when the shape does not fit the staged layout.  The receiver pass leaves dot[r,h] in stats for the
+  // sender pass, so each pass completes (staged + handed-back groups) before the next starts.
+  const size_t sm0 = attn_bwd_block_bytes<0>(f.heads, f.kq, f.vd), sm1 = attn_bwd_block_bytes<1>(f.heads, f.kq, f.vd);
+  const bool staged = b.fallback && f.heads <= kAbH && qk <= 32 * kAbCols && hv <= 32 * kAbCols && sm0 <= 200 * 1024 &&
+                      sm1 <= 200 * 1024;
+  const unsigned nblk = (unsigned)ceil_div(n, kAbRecv);
+  const int32_t* only = staged ? b.fallback : nullptr;
+  if (staged) {
+    static bool configured[kMaxDevices] = {};
+    if (first_use_on_device(configured)) {
+      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    GNF_CUDA(cudaMemsetAsync(b.fallback, 0, (size_t)nblk * 4, stream));
+    k_attn_bwd_block<0><<<nblk, kAbWarps * 32, sm0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad,
+                                                              f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
+                                                              csr_senders, n, w.gqueries, nullptr, b.fallback);
+    GNF_LAUNCH_CHECK();
+  }
   k_attn_bwd_recv<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq,
-                                              f.vd, inv_scale, rowptr, csr_senders, n, b.stats, w.gqueries);
+                                              f.vd, inv_scale, rowptr, csr_senders, n, b.stats, w.gqueries, only);
   GNF_LAUNCH_CHECK();
+  if (staged) {
+    GNF_CUDA(cudaMemsetAsync(b.fallback, 0, (size_t)nblk * 4, stream));
+    k_attn_bwd_block<1><<<nblk, kAbWarps * 32, sm1, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad,
+                                                              f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr_s,
+                                                              csr_receivers, n, w.gkeys, w.gvh, b.fallback);
+    GNF_LAUNCH_CHECK();
+  }
   if (f.vd <= 32)
     k_attn_bwd_send<32><<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
                                                     f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys,
-                                                    w.gvh);
+                                                    w.gvh, only);
   else
     k_attn_bwd_send<64><<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
                                                     f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys,
-                                                    w.gvh);
+                                                    w.gvh, only);
   GNF_LAUNCH_CHECK();
   k_sum_heads<<<(unsigned)ceil_div(n * f.v_pad, 256), 256, 0, stream>>>(w.gvh, f.hv_pad, f.heads, f.vd, f.v_pad, n, w.gv);
   GNF_LAUNCH_CHECK();
@@ -758,11 +980,77 @@ static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const f
   return GNF_OK;
 }
 
+// One reversed half step of an INJECT flow (MLP input wider than the fused kernels' 16 columns: dm_self_attn without
+// residual / layer_norm, message passing with D > 16) with the MLPs on the tensor cores:
+//   input assembly (attention front end or aggregation)      -> hin[m]          the forward's own kernels, `math`
+//   layer 0 pre-activations                                   -> pre0[m]         k_linear_tc
+//   layers 1..K-1 forward, coupling inverse, dX chain, images -> xb, g_xb, d0[m] k_bwd_chain<BINJ>
+//   dW / db of every layer                                    -> grads           k_dw_tc + k_dw_reduce
+//   g_h = d0[m] W_0^T                                         -> w.gh            k_linear_tc (K = L, bf16 hi/lo split)
+//   below layer 0: attention backward (per GNN) or the transposed aggregation (once, on the sum)
+static int bwd_half_inject(const Flow& f, const BwdWs& w, void* tc_ws, int half, int i, const float* xa, float* xb,
+                           float* ga, float* gb, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
+                           const int32_t* rowptr_by_sender, const int32_t* csr_receivers, float scale, float* grads,
+                           int math, cudaStream_t stream) {
+  const int H = f.H, gp = pad_to(f.HP, 8);
+  const int mm[2] = {f.mlp_index(0, half, i), f.mlp_index(1, half, i)};
+  const int dw_parts = (math == GNF_MATH_TC3X || math == GNF_MATH_TC3X_BF16) ? 2 : 1;
+  const int fwd_f16 = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 1 : 0;
+  float *pre0[2], *d0[2];
+  tc_bwd_inject_buffers(f, n, tc_ws, pre0, d0);
+  float* hin[2] = {w.hbuf, f.attn ? w.hbuf2 : w.hbuf};
+  int rc;
+  for (int m = 0; m < 2; ++m) {
+    if (f.attn) {
+      GNF_CUDA(cudaMemsetAsync(hin[m], 0, (size_t)n * f.in_pad * 4, stream));
+      rc = fwd_attn_input(f, mm[m], xa, n, rowptr, csr_senders, w.ab[m], hin[m], stream, math);
+      if (rc) return rc;
+    } else if (m == 0) {
+      GNF_CUDA(cudaMemsetAsync(hin[0], 0, (size_t)n * f.in_pad * 4, stream));
+      rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, hin[0], stream);
+      if (rc) return rc;
+    }
+    const float* base = f.w32 + (int64_t)mm[m] * f.w32_per_mlp;
+    const size_t off = (size_t)mm[m] * f.wlin_per_mlp + f.lin_off[4];
+    rc = tc_linear(f, math, hin[m], f.in_pads[0], f.in_pads[0], f.wlin[0] + off, f.wlin[1] + off, f.in_dim, f.L,
+                   base + f.b32_layer_off[0], 2, pre0[m], f.L, f.L, n, stream);
+    if (rc) return rc;
+  }
+  const float* const hin_c[2] = {hin[0], hin[1]};
+  rc = tc_half_backward_inject(f, mm[0], mm[1], hin_c, f.in_pads[0], xb, gb, n, scale, grads, tc_ws, dw_parts, fwd_f16,
+                               stream);
+  if (rc) return rc;
+  for (int m = 0; m < 2; ++m) {
+    const size_t off = (size_t)mm[m] * f.wlin_per_mlp + f.lin_off[5];
+    // gradients are bf16 hi/lo operands everywhere (fp16 would flush them at scale = 1/N)
+    rc = tc_linear(f, GNF_MATH_TC3X_BF16, d0[m], f.L, f.L, f.wlin[0] + off, f.wlin[1] + off, f.L, f.in_dim, f.zeros, 2, w.gh,
+                   f.in_pad, f.in_pad, n, stream, (!f.attn && m == 1) ? 1 : 0);
+    if (rc) return rc;
+    if (f.attn) {
+      // g_top of attn_backward only feeds the residual connection, which inject flows do not have
+      rc = attn_backward(f, mm[m], w, m, w.gs, gp, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, ga, grads,
+                         stream, math);
+      if (rc) return rc;
+    }
+  }
+  if (!f.attn) {
+    k_agg_bwd<<<(unsigned)ceil_div(n * H, 256), 256, 0, stream>>>(w.gh, f.in_pad, H, f.HP, rowptr_by_sender, csr_receivers,
+                                                                 rowptr, n, f.d.agg == GNF_AGG_MEAN,
+                                                                 f.d.block == GNF_BLOCK_CONCAT, f.d.eps, ga);
+    GNF_LAUNCH_CHECK();
+  }
+  return GNF_OK;
+}
+
 static bool bwd_use_tc(const Flow& f, int math) { return math != GNF_MATH_FP32 && tc_bwd_supported(f); }
+static bool bwd_use_inject(const Flow& f, int math) { return math != GNF_MATH_FP32 && tc_bwd_inject_supported(f); }
+// inject flows: the fp32 path's buffers (input assembly, attention backward) followed by the tensor-core side's
+static size_t inject_fp32_part(const Flow& f, int64_t n) { return align_up(carve_bwd(f, n, nullptr).bytes, 1024); }
 
 extern "C" size_t gnf_grevnet_backward_workspace(const gnf_flow* h, int64_t n_nodes, int32_t math) {
   if (!h || n_nodes < 0) return 0;
   if (bwd_use_tc(h->f, math)) return tc_bwd_workspace(h->f, n_nodes);
+  if (bwd_use_inject(h->f, math)) return inject_fp32_part(h->f, n_nodes) + tc_bwd_inject_workspace(h->f, n_nodes);
   return carve_bwd(h->f, n_nodes, nullptr).bytes;
 }
 
@@ -792,18 +1080,20 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
   GNF_REQUIRE(z && rowptr && rowptr_by_sender && (e == 0 || (csr_senders && csr_receivers)), GNF_EINVAL,
               "gnf_grevnet_backward: null pointer");
   const Flow& f = h->f;
-  if (math != GNF_MATH_FP32) {
+  const bool inject = bwd_use_inject(f, math);
+  if (math != GNF_MATH_FP32 && !inject) {
     GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED,
                 "gnf_grevnet_backward: the tensor-core backward needs a flow shape the fused kernel supports "
-                "(gnf_flow_supports); use GNF_MATH_FP32");
+                "(gnf_flow_supports_backward); use GNF_MATH_FP32");
     const int dw_parts = (math == GNF_MATH_TC3X || math == GNF_MATH_TC3X_BF16) ? 2 : 1;
     const int fwd_f16 = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 1 : 0;
     return tc_grevnet_backward(f, z, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, loss_scale, grads, x_out,
                                ws, ws_bytes, dw_parts, fwd_f16, stream_);
   }
-  GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0 && ws_bytes >= carve_bwd(f, n, nullptr).bytes, GNF_EWORKSPACE,
+  GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0 && ws_bytes >= gnf_grevnet_backward_workspace(h, n, math), GNF_EWORKSPACE,
               "gnf_grevnet_backward: workspace too small or misaligned");
   BwdWs w = carve_bwd(f, n, ws);
+  void* tc_ws = inject ? (void*)((uint8_t*)ws + inject_fp32_part(f, n)) : nullptr;
   const int D = f.d.node_embedding_dim, H = f.H, HP = f.HP, gp = pad_to(HP, 8);
   const float scale = (float)loss_scale;
   const unsigned eb = (unsigned)ceil_div(n * H, 256);
@@ -825,8 +1115,10 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
       float* xb = half == 0 ? w.x1 : w.x0;
       float* ga = half == 0 ? w.g0 : w.g1;
       float* gb = half == 0 ? w.g1 : w.g0;
-      int rc = bwd_half_fp32(f, w, half, i, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers,
-                             scale, grads, stream);
+      int rc = inject ? bwd_half_inject(f, w, tc_ws, half, i, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender,
+                                        csr_receivers, scale, grads, math, stream)
+                      : bwd_half_fp32(f, w, half, i, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender,
+                                      csr_receivers, scale, grads, stream);
       if (rc) return rc;
     }
   }
@@ -853,6 +1145,12 @@ extern "C" int gnf_coupling_half_backward(const gnf_flow* h, int32_t half, int32
   const Flow& f = h->f;
   GNF_REQUIRE(ws && ((uintptr_t)ws % 256) == 0 && ws_bytes >= gnf_grevnet_backward_workspace(h, n, math), GNF_EWORKSPACE,
               "gnf_coupling_half_backward: workspace too small or misaligned");
+  if (bwd_use_inject(f, math)) {
+    BwdWs w = carve_bwd(f, n, ws);
+    GNF_CUDA(cudaMemsetAsync(w.gs, 0, (size_t)n * pad_to(f.HP, 8) * 4, stream));
+    return bwd_half_inject(f, w, (uint8_t*)ws + inject_fp32_part(f, n), half, step, xa, xb, ga, gb, n, rowptr, csr_senders,
+                           rowptr_by_sender, csr_receivers, (float)loss_scale, grads, math, stream);
+  }
   if (math != GNF_MATH_FP32) {
     GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED, "gnf_coupling_half_backward: flow shape needs GNF_MATH_FP32");
     const int dw_parts = (math == GNF_MATH_TC3X || math == GNF_MATH_TC3X_BF16) ? 2 : 1;

@@ -18,6 +18,12 @@
 //                 Its epilogue warps, idle during the main loop, sum the columns of the delta operand
 //                 (read from the images through L2, in step with the ring): the bias gradients.
 //
+// Inject flows (template flag BINJ: MLP input wider than 16 columns -- dm_self_attn, message passing with D > 16): the
+// forward chains start from the layer-0 PRE-activations computed by k_linear_tc (read from global memory by the epilogue
+// warps, as k_coupling_tc MODE inject does), the backward chains stop at delta_0, which also leaves in fp32 row-major:
+// g_h = delta_0 W_0^T is a k_linear_tc call (K = latent_dim), dW_0 = h^T delta_0 a pair of the weight-gradient GEMM whose
+// B operand is an image of the MLP input built by k_make_images.  The gather warps idle.
+//
 // Image layout (one per 128-node tile, per part hi|lo): the UMMA no-swizzle MN-major canonical form,
 //   elem(f, n) = (n>>3)*(F*8) + (f>>3)*64 + (n&7)*8 + (f&7)        F = feature count (LAT or 16)
 // i.e. 8 features x 8 nodes core matrices of 128 B; SBO (feature groups) = 128 B, LBO (node groups) = F*16 B.
@@ -54,6 +60,8 @@ struct BwdParams {
   uint16_t* g_img;           // [2][tiles][2][16*128]
   float* gh;                 // [tiles*128][16]
   int write_lo;              // 0: the weight-gradient GEMM reads only the hi parts, skip the lo images
+  const float* pre0[2];      // BINJ: layer-0 pre-activations (bias included) of the s and t MLP, [n, LAT] fp32
+  float* d0[2];              // BINJ: delta_0 = dL/d(pre0) of the s and t MLP, [n, LAT] fp32
 };
 
 constexpr int kBStages = 3;          // weight ring stages (the forward kernel has 4; 32 KB go to the mask bits)
@@ -90,7 +98,7 @@ __device__ __forceinline__ size_t img_off(int F, int fg, int n) {
   return (size_t)(n >> 3) * (F * 8) + (size_t)fg * 64 + (n & 7) * 8;
 }
 
-template <int LAT, int ACT, bool F16F>
+template <int LAT, int ACT, bool F16F, bool BINJ>
 __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
   constexpr bool kFB = !F16F;   // forward chains: bf16 split?
   using G = Geo<LAT>;
@@ -174,14 +182,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < 4; ++c) {
           const uint8_t* src = c < 2 ? p.wf[c] : p.wb[c - 2];
-          issue(src, G::L0_BYTES);
+          if (!(BINJ && c < 2)) issue(src, G::L0_BYTES);      // BINJ: the forward chains' layer 0 ran in k_linear_tc
           src += G::L0_BYTES;
           for (int l = 1; l < K - 1; ++l)
             for (int cc = 0; cc < kNS * G::NKC; ++cc) {
               issue(src, G::CHUNK_BYTES);
               src += G::CHUNK_BYTES;
             }
-          issue(src, G::LAST_BYTES);
+          if (!(BINJ && c >= 2)) issue(src, G::LAST_BYTES);   // BINJ: the backward chains stop at delta_0
         }
       }
     }
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
       for (int c = 0; c < 4; ++c) {
         const bool bwd = c >= 2;
         const int m = c & 1;
-        if (c == 0) mbar_wait(bar_hfull + 8 * buf, (it >> 1) & 1);
+        if (c == 0 && !BINJ) mbar_wait(bar_hfull + 8 * buf, (it >> 1) & 1);
         if (c == 2) mbar_wait(bar_gfull, it & 1);
         const uint32_t a0_hi = bwd ? gbuf_u + m * 8192 : hbuf_u + buf * 8192;
         const uint32_t a0_lo = a0_hi + 4096;
@@ -222,7 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
         const uint32_t idesc_l0 = bwd ? idesc_l0_b : idesc_l0_f, idesc_h = bwd ? idesc_h_b : idesc_h_f;
         const uint32_t idesc_last = bwd ? idesc_last_b : idesc_last_f;
         // ---- chain layer 0: A from smem (K = 16), N = LAT --------------------------------------
-        {
+        if (BINJ && !bwd) {
+          region ^= 1;         // the epilogue warps write layer 0's activations into this region from global memory
+        } else {
           const uint32_t d = tmem_base + region * LAT;
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -286,7 +296,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
           region ^= 1;
         }
         // ---- last chain layer: N = 16, K = LAT ----------------------------------------------------
-        {
+        // (BINJ backward chains: skipped WITHOUT toggling the region -- the next chain's layer 0, which does not wait
+        //  for the epilogue, must not write the region whose delta_0 accumulator the epilogue warps are still reading)
+        if (!(BINJ && bwd)) {
           const uint32_t in_col = tmem_base + (region ^ 1) * LAT;
           const uint32_t d = tmem_base + region * LAT;
           uint32_t waited = 0;
@@ -376,16 +388,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
                 pos[ch] = bits;
               }
             }
-            mbar_wait(smem_u32(&bars->acc_full[ph]), (acc_par >> ph) & 1u);
-            acc_par ^= 1u << ph;
-            tc_fence_after();
+            // BINJ: the forward chains' layer 0 comes from global memory (pre-activations of k_linear_tc), the
+            // backward chains end at delta_0 (kept in fp32 for g_h = delta_0 W_0^T, not converted back into TMEM)
+            const bool from_global = BINJ && !bwd && l == 0;
+            const bool stop_here = BINJ && bwd && l == K - 2;
+            if (!from_global) {
+              mbar_wait(smem_u32(&bars->acc_full[ph]), (acc_par >> ph) & 1u);
+              acc_par ^= 1u << ph;
+              tc_fence_after();
+            }
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
               const int col0 = ph * G::NH + grp * 32 + ch * 64;
               const uint32_t t0 = lane_base + region * LAT + col0;
               uint32_t v[32];
-              tmem_ld32(t0, v);
-              tmem_wait_ld();
+              if (from_global) {
+                const float4* src = reinterpret_cast<const float4*>(p.pre0[m] + node * LAT + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 x = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+                  v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+                }
+              } else {
+                tmem_ld32(t0, v);
+                tmem_wait_ld();
+              }
               float d[32];
               if (!bwd) {
 #pragma unroll
@@ -405,11 +433,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) split_pair<kFB>(d[2 * j], d[2 * j + 1], hi[j], lo[j]);
               }
-              tmem_st16(t0, hi);
-              tmem_st16(t0 + 16, lo);
-              tmem_wait_st();
-              tc_fence_before();
-              mbar_arrive(smem_u32(&bars->a_ready[NCH == 2 ? ph * 2 + ch : ph]));
+              if (!stop_here) {
+                tmem_st16(t0, hi);
+                tmem_st16(t0 + 16, lo);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars->a_ready[NCH == 2 ? ph * 2 + ch : ph]));
+              } else if (valid) {
+                float4* dst = reinterpret_cast<float4*>(p.d0[m] + node * LAT + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+              }
               if (!bwd && smem_mask) {       // sign bits of a_l for the backward chains (fp16 and bf16 share bit 15)
                 uint32_t bits = 0;
                 if (ACT == GNF_ACT_LEAKY_RELU) {
@@ -442,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
           region ^= 1;
         }
         // ---- last chain layer: s / t (forward chains) or g_h (backward chains) ----------------------
-        {
+        if (!(BINJ && bwd)) {
           mbar_wait(smem_u32(&bars->acc_last), (acc_par >> 8) & 1u);
           acc_par ^= 1u << 8;
           tc_fence_after();
@@ -523,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
           fence_proxy_async();
           mbar_arrive(smem_u32(&bars->g_full));
         }
-        if (c == 3 && grp == 0 && valid) {
+        if (!BINJ && c == 3 && grp == 0 && valid) {
           float* go = p.gh + node * kK0;
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4)
@@ -537,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
     float* my = hstage + row * 17;
     const int hp4 = p.HP >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; !BINJ && tile < p.n_tiles; tile += gridDim.x, ++it) {   // BINJ: the MLP input never enters
       const int buf = it & 1;
       const int64_t node = (int64_t)tile * kTileM + row;
       float self[kNOut], agg[kNOut];
@@ -734,7 +768,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
             const uint64_t b_hi = smem_desc(sb + ks * b_step, b_lbo, b_sbo);
             const uint64_t b_lo = smem_desc(sb + b_part + ks * b_step, b_lbo, b_sbo);
             for (int mh = 0; mh < MH; ++mh) {
-              const uint32_t d = tmem_base + mh * FB;
+              const uint32_t d = tmem_base + mh * 256;      // (FB <= 256; a fixed stride keeps every FB aligned)
               const uint64_t a_hi = smem_desc(sa + ks * a_step + mh * 2048, a_lbo, a_sbo);
               mma_ss(d, a_hi, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
               if (PARTS == 2) {
@@ -835,7 +869,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
       if (FB >= 32) {
         for (int c = 0; c < FB; c += 32) {
           uint32_t v[32];
-          tmem_ld32(lane_base + mh * FB + c, v);
+          tmem_ld32(lane_base + mh * 256 + c, v);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -845,7 +879,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
         }
       } else {
         uint32_t v[16];
-        tmem_ld16(lane_base + mh * FB, v);
+        tmem_ld16(lane_base + mh * 256, v);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -901,12 +935,14 @@ __global__ void k_dw_reduce(const DwReduceParams p) {
 }
 
 // ---- debug / unit-test helper: fp32 [n, F] row-major -> bf16 hi/lo tile images ----------------
-__global__ void k_make_images(const float* __restrict__ x, int64_t n, int F, int n_tiles, uint16_t* __restrict__ img) {
+// (also the product path of inject flows: the MLP input h [n, ld] -> the B operand of dW_0 = h^T delta_0)
+__global__ void k_make_images(const float* __restrict__ x, int64_t n, int ld, int fvalid, int F, int n_tiles,
+                              uint16_t* __restrict__ img) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_tiles * 128 * F) return;
   const int64_t node = i / F;
   const int f = (int)(i - node * F);
-  const float v = node < n ? x[node * F + f] : 0.f;
+  const float v = (node < n && f < fvalid) ? x[node * ld + f] : 0.f;
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
   const int tile = (int)(node >> 7), r = (int)(node & 127);
@@ -929,9 +965,9 @@ int launch_dw(const DwParams& p, int grid, int parts, cudaStream_t stream) {
   return GNF_OK;
 }
 
-template <int LAT, int ACT, bool F16F>
+template <int LAT, int ACT, bool F16F, bool BINJ>
 int launch_chain_t(const BwdParams& p, int grid, cudaStream_t stream) {
-  auto kern = k_bwd_chain<LAT, ACT, F16F>;
+  auto kern = k_bwd_chain<LAT, ACT, F16F, BINJ>;
   static bool configured[kMaxDevices] = {};
   const size_t smem = bwd_smem_bytes<LAT>();
   if (first_use_on_device(configured))
@@ -944,9 +980,14 @@ int launch_chain_t(const BwdParams& p, int grid, cudaStream_t stream) {
 struct BwdTcWs {
   float *x0, *x1, *g0, *g1, *gh, *dw_part;
   uint16_t *act_img, *dlt_img, *h_img, *g_img;
+  float *pre0[2], *d0[2];        // inject flows: layer-0 pre-activations / delta_0 of the s and t MLP, [n, L] fp32
   size_t dw_part_floats;
   size_t bytes;
 };
+
+// feature count of the MLP-input image (B operand of dW_0): 16 for the fully fused shapes; inject flows pad to 32
+// (k_dw_tc drains its accumulator 32 columns at a time)
+int dw_in0(const Flow& f) { return f.tc_ok ? kK0 : (f.in_dim + 31) / 32 * 32; }
 
 // split plan of the weight-gradient GEMM: CTAs per pair proportional to the bytes each pair streams
 struct DwPlan {
@@ -964,10 +1005,11 @@ DwPlan plan_dw(const Flow& f, int n_tiles) {
   pl.n_pairs = 2 * K;
   double cost[kDwMaxPairs];
   double total = 0;
+  const int in0 = dw_in0(f);
   for (int m = 0; m < 2; ++m)
     for (int l = 0; l < K; ++l) {
       const bool hidden = l > 0 && l < K - 1;
-      cost[m * K + l] = hidden ? 2.0 * L : (double)L + 16;
+      cost[m * K + l] = hidden ? 2.0 * L : (double)L + (l == 0 ? in0 : 16);
       total += cost[m * K + l];
     }
   const int sms = num_sms();
@@ -990,7 +1032,7 @@ DwPlan plan_dw(const Flow& f, int n_tiles) {
   int first = 0;
   for (int i = 0; i < pl.n_pairs; ++i) {
     const int l = i % K;
-    const int fb = (l > 0 && l < K - 1) ? L : 16;
+    const int fb = (l > 0 && l < K - 1) ? L : (l == 0 ? in0 : 16);
     pl.first[i] = first;
     first += pl.splits[i];
     pl.part_off[i] = off;
@@ -1025,8 +1067,13 @@ BwdTcWs carve_bwd_tc(const Flow& f, int64_t n, void* base) {
   w.dw_part = (float*)take(pl.part_floats * 4);
   w.act_img = (uint16_t*)take((size_t)2 * (f.K - 1) * tiles * img * 2);
   w.dlt_img = (uint16_t*)take((size_t)2 * (f.K - 1) * tiles * img * 2);
-  w.h_img = (uint16_t*)take(tiles * 2 * 16 * 128 * 2);
+  w.h_img = (uint16_t*)take((f.tc_ok ? 1 : 2) * tiles * 2 * (size_t)dw_in0(f) * 128 * 2);   // inject: one per MLP
   w.g_img = (uint16_t*)take((size_t)2 * tiles * 2 * 16 * 128 * 2);
+  if (!f.tc_ok)
+    for (int m = 0; m < 2; ++m) {
+      w.pre0[m] = (float*)take(nn * f.L * 4);
+      w.d0[m] = (float*)take(nn * f.L * 4);
+    }
   w.bytes = off;
   return w;
 }
@@ -1051,49 +1098,48 @@ void tc_bwd_layout(const Flow& f, int64_t n, int64_t* out) {
   out[7] = (int64_t)w.bytes;
 }
 
-// one reversed half step: (xa, xb', g_xa, g_xb') -> (xb, g_xa += ..., g_xb), grads += ...
-static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb, float* ga, float* gb, int64_t n,
-                       const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
-                       const int32_t* csr_receivers, float scale, float* grads, const BwdTcWs& w, int dw_parts,
-                       bool fwd_f16, cudaStream_t stream) {
-  const int K = f.K, L = f.L;
-  const int n_tiles = (int)ceil_div(n, kTileM);
-  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+template <bool BINJ>
+static int launch_chain(const Flow& f, const BwdParams& p, int grid, bool fwd_f16, cudaStream_t stream) {
+  const bool leaky = f.d.act == GNF_ACT_LEAKY_RELU;
+  if (f.L == 256) {
+    if (fwd_f16) return leaky ? launch_chain_t<256, GNF_ACT_LEAKY_RELU, true, BINJ>(p, grid, stream)
+                              : launch_chain_t<256, GNF_ACT_RELU, true, BINJ>(p, grid, stream);
+    return leaky ? launch_chain_t<256, GNF_ACT_LEAKY_RELU, false, BINJ>(p, grid, stream)
+                 : launch_chain_t<256, GNF_ACT_RELU, false, BINJ>(p, grid, stream);
+  }
+  if (fwd_f16) return leaky ? launch_chain_t<128, GNF_ACT_LEAKY_RELU, true, BINJ>(p, grid, stream)
+                            : launch_chain_t<128, GNF_ACT_RELU, true, BINJ>(p, grid, stream);
+  return leaky ? launch_chain_t<128, GNF_ACT_LEAKY_RELU, false, BINJ>(p, grid, stream)
+               : launch_chain_t<128, GNF_ACT_RELU, false, BINJ>(p, grid, stream);
+}
+
+static BwdParams chain_params(const Flow& f, int ms, int mt, float* xb, float* gb, int64_t n, float scale,
+                              const BwdTcWs& w, int dw_parts, bool fwd_f16) {
   BwdParams p{};
-  p.xa = xa; p.xb = xb; p.gxb = gb;
-  p.rowptr = rowptr; p.csr = csr_senders;
-  p.n_nodes = n; p.n_tiles = n_tiles;
+  p.xb = xb; p.gxb = gb;
+  p.n_nodes = n; p.n_tiles = (int)ceil_div(n, kTileM);
   p.wf[0] = f.wtcB[fwd_f16 ? 0 : 1] + (size_t)ms * f.wtc_per_mlp;
   p.wf[1] = f.wtcB[fwd_f16 ? 0 : 1] + (size_t)mt * f.wtc_per_mlp;
   p.wb[0] = f.wtcT + (size_t)ms * f.wtc_per_mlp;
   p.wb[1] = f.wtcT + (size_t)mt * f.wtc_per_mlp;
   p.bias[0] = f.btc + (size_t)ms * f.K * 256;
   p.bias[1] = f.btc + (size_t)mt * f.K * 256;
-  p.K = K; p.H = f.H; p.HP = f.HP;
+  p.K = f.K; p.H = f.H; p.HP = f.HP;
   p.concat = f.d.block == GNF_BLOCK_CONCAT;
   p.mean = f.d.agg == GNF_AGG_MEAN;
   p.eps = f.d.eps; p.scale = scale;
   p.act_img = w.act_img; p.dlt_img = w.dlt_img; p.h_img = w.h_img; p.g_img = w.g_img;
   p.gh = w.gh;
   p.write_lo = dw_parts == 2;
-  int rc;
-  const bool leaky = f.d.act == GNF_ACT_LEAKY_RELU;
-  if (L == 256) {
-    if (fwd_f16) rc = leaky ? launch_chain_t<256, GNF_ACT_LEAKY_RELU, true>(p, grid, stream)
-                            : launch_chain_t<256, GNF_ACT_RELU, true>(p, grid, stream);
-    else rc = leaky ? launch_chain_t<256, GNF_ACT_LEAKY_RELU, false>(p, grid, stream)
-                    : launch_chain_t<256, GNF_ACT_RELU, false>(p, grid, stream);
-  } else {
-    if (fwd_f16) rc = leaky ? launch_chain_t<128, GNF_ACT_LEAKY_RELU, true>(p, grid, stream)
-                            : launch_chain_t<128, GNF_ACT_RELU, true>(p, grid, stream);
-    else rc = leaky ? launch_chain_t<128, GNF_ACT_LEAKY_RELU, false>(p, grid, stream)
-                    : launch_chain_t<128, GNF_ACT_RELU, false>(p, grid, stream);
-  }
-  if (rc) return rc;
-  rc = bwd_agg_transpose(f, w.gh, kK0, rowptr_s, csr_receivers, rowptr, n, ga, stream);
-  if (rc) return rc;
+  return p;
+}
 
-  // ---- weight gradients ---------------------------------------------------------------------
+// weight (and bias) gradients of the s and t MLP from the tile images of one half step.  h_img[m]: image of MLP m's
+// input with dw_in0(f) features (the fully fused shapes share one image)
+static int dw_half(const Flow& f, int ms, int mt, int n_tiles, const BwdTcWs& w, const uint16_t* const h_img[2],
+                   float* grads, int dw_parts, cudaStream_t stream) {
+  const int K = f.K, L = f.L;
+  const int in0 = dw_in0(f);
   const DwPlan pl = plan_dw(f, n_tiles);
   DwParams dp{};
   DwReduceParams rp{};
@@ -1114,8 +1160,8 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
       pr.a_feats = L;
       if (l == 0) {                       // dW_0^T = delta_0^T h
         pr.A = w.dlt_img + ((size_t)m * (K - 1) + 0) * layer_stride;
-        pr.B = w.h_img;
-        pr.b_feats = 16;
+        pr.B = h_img[m];
+        pr.b_feats = in0;
         pr.a_bf16 = 1; pr.b_bf16 = 1;
         pr.db_mode = 2;                   // db_0 = column sums of delta_0 (the A operand)
       } else if (l == K - 1) {            // dW_{K-1} = a_{K-2}^T g_top
@@ -1145,14 +1191,30 @@ static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb
       rr.grad_b = gm + f.flat_b_off[l];
     }
   }
-  rc = launch_dw(dp, pl.grid, dw_parts, stream);
+  int rc = launch_dw(dp, pl.grid, dw_parts, stream);
   if (rc) return rc;
-  {
-    dim3 rg((unsigned)ceil_div((int64_t)L * L, 256), (unsigned)pl.n_pairs);
-    k_dw_reduce<<<rg, 256, 0, stream>>>(rp);
-    GNF_LAUNCH_CHECK();
-  }
+  dim3 rg((unsigned)ceil_div((int64_t)L * L, 256), (unsigned)pl.n_pairs);
+  k_dw_reduce<<<rg, 256, 0, stream>>>(rp);
+  GNF_LAUNCH_CHECK();
   return GNF_OK;
+}
+
+// one reversed half step: (xa, xb', g_xa, g_xb') -> (xb, g_xa += ..., g_xb), grads += ...
+static int bwd_half_tc(const Flow& f, int ms, int mt, const float* xa, float* xb, float* ga, float* gb, int64_t n,
+                       const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
+                       const int32_t* csr_receivers, float scale, float* grads, const BwdTcWs& w, int dw_parts,
+                       bool fwd_f16, cudaStream_t stream) {
+  const int n_tiles = (int)ceil_div(n, kTileM);
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  BwdParams p = chain_params(f, ms, mt, xb, gb, n, scale, w, dw_parts, fwd_f16);
+  p.xa = xa;
+  p.rowptr = rowptr; p.csr = csr_senders;
+  int rc = launch_chain<false>(f, p, grid, fwd_f16, stream);
+  if (rc) return rc;
+  rc = bwd_agg_transpose(f, w.gh, kK0, rowptr_s, csr_receivers, rowptr, n, ga, stream);
+  if (rc) return rc;
+  const uint16_t* const h_img[2] = {w.h_img, w.h_img};
+  return dw_half(f, ms, mt, n_tiles, w, h_img, grads, dw_parts, stream);
 }
 
 int tc_grevnet_backward(const Flow& f, const float* z, int64_t n, const int32_t* rowptr, const int32_t* csr_senders,
@@ -1196,6 +1258,45 @@ int tc_half_backward(const Flow& f, int half, int step, const float* xa, float* 
                      grads, w, dw_parts, fwd_f16 != 0, (cudaStream_t)stream_);
 }
 
+// ---- inject flows (MLP input wider than 16 columns) ---------------------------------------------------------------
+// The caller (backward.cu) owns the input assembly and everything below layer 0; this side runs the MLP chains.
+bool tc_bwd_inject_supported(const Flow& f) {
+  return f.tc_inject && f.wtcT != nullptr && f.wtcB[0] != nullptr && f.K >= 2 && f.lin_off[4] >= 0 && f.lin_off[5] >= 0 &&
+         (!f.attn || f.lin_off[6] >= 0) && dw_in0(f) <= 128;
+}
+
+size_t tc_bwd_inject_workspace(const Flow& f, int64_t n) { return carve_bwd_tc(f, n, nullptr).bytes; }
+
+void tc_bwd_inject_buffers(const Flow& f, int64_t n, void* ws, float* pre0[2], float* d0[2]) {
+  const BwdTcWs w = carve_bwd_tc(f, n, ws);
+  for (int m = 0; m < 2; ++m) { pre0[m] = w.pre0[m]; d0[m] = w.d0[m]; }
+}
+
+// MLP chains of one reversed half step.  In: the layer-0 pre-activations (workspace buffers pre0[m], bias included),
+// the MLP inputs hin[m] ([n, in_ld] fp32; the same pointer twice when s and t share their input), xb', g_xb'.
+// Out: xb, g_xb, the workspace buffers d0[m] = dL/d(pre0[m]); grads += dW, db of every layer (layer 0 included).
+int tc_half_backward_inject(const Flow& f, int ms, int mt, const float* const hin[2], int in_ld, float* xb, float* gb,
+                            int64_t n, double loss_scale, float* grads, void* ws, int dw_parts, int fwd_f16,
+                            void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const BwdTcWs w = carve_bwd_tc(f, n, ws);
+  const int n_tiles = (int)ceil_div(n, kTileM);
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  const int in0 = dw_in0(f);
+  const size_t h_elems = (size_t)n_tiles * 2 * in0 * 128;
+  uint16_t* h_img[2] = {w.h_img, hin[1] == hin[0] ? w.h_img : w.h_img + h_elems};
+  for (int m = 0; m < (hin[1] == hin[0] ? 1 : 2); ++m) {
+    k_make_images<<<(unsigned)ceil_div((int64_t)n_tiles * 128 * in0, 256), 256, 0, stream>>>(hin[m], n, in_ld, in_ld, in0,
+                                                                                             n_tiles, h_img[m]);
+    GNF_LAUNCH_CHECK();
+  }
+  BwdParams p = chain_params(f, ms, mt, xb, gb, n, (float)loss_scale, w, dw_parts, fwd_f16 != 0);
+  for (int m = 0; m < 2; ++m) { p.pre0[m] = w.pre0[m]; p.d0[m] = w.d0[m]; }
+  int rc = launch_chain<true>(f, p, grid, fwd_f16 != 0, stream);
+  if (rc) return rc;
+  return dw_half(f, ms, mt, n_tiles, w, h_img, grads, dw_parts, stream);
+}
+
 // unit-test entry: out[fa][fb] = A^T B for fp32 A [n, fa], B [n, fb] through the image format + k_dw_tc
 int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, int parts, int n_splits, float* out,
                     void* ws, size_t ws_bytes, void* stream_) {
@@ -1212,9 +1313,9 @@ int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, i
   uint16_t* ai = (uint16_t*)ws;
   uint16_t* bi = (uint16_t*)((uint8_t*)ws + a_bytes);
   float* part = (float*)((uint8_t*)ws + a_bytes + b_bytes);
-  k_make_images<<<(unsigned)ceil_div((int64_t)n_tiles * 128 * fa, 256), 256, 0, stream>>>(A, n, fa, n_tiles, ai);
+  k_make_images<<<(unsigned)ceil_div((int64_t)n_tiles * 128 * fa, 256), 256, 0, stream>>>(A, n, fa, fa, fa, n_tiles, ai);
   GNF_LAUNCH_CHECK();
-  k_make_images<<<(unsigned)ceil_div((int64_t)n_tiles * 128 * fb, 256), 256, 0, stream>>>(B, n, fb, n_tiles, bi);
+  k_make_images<<<(unsigned)ceil_div((int64_t)n_tiles * 128 * fb, 256), 256, 0, stream>>>(B, n, fb, fb, fb, n_tiles, bi);
   GNF_LAUNCH_CHECK();
   DwParams dp{};
   dp.n_pairs = 1;

@@ -109,13 +109,14 @@ struct Flow {
   float* btc = nullptr;        // biases for the TC kernel: per MLP K*256 floats
   uint8_t* wtcT = nullptr;     // bf16 hi/lo images of the TRANSPOSED MLP chains (backward dX), same geometry
   bool tc_ok = false;          // fully fused tcgen05 kernel (MLP input <= 16)
-  bool tc_inject = false;      // layer 0 in the fp32 kernels, layers 1..K-1 + coupling in the tcgen05 kernel (MODE inject)
+  bool tc_inject = false;      // layer 0 in k_linear_tc, layers 1..K-1 + coupling in the tcgen05 kernel (MODE inject)
   void* pack_jobs = nullptr;   // device job table of the one-launch re-pack (pack.cu)
   int n_pack_jobs = 0, pack_blocks = 0;
   // stand-alone tensor-core linears (linear_tc.cu): fp16 / bf16 hi-lo images per GNN of Wq, Wk, Wv, Wo (attention) and
   // of layer 0 (inject flows); offset < 0: that matrix stays on the fp32 kernels
   uint8_t* wlin[2] = {nullptr, nullptr};
-  int64_t wlin_per_mlp = 0, lin_off[5] = {-1, -1, -1, -1, -1};     // q, k, v, o, layer 0
+  int64_t wlin_per_mlp = 0;
+  int64_t lin_off[7] = {-1, -1, -1, -1, -1, -1, -1};   // q, k, v, o, layer 0; backward dX: W0^T (L -> in), Wo^T (cho -> heads*v)
   void* half_tables = nullptr; // device HalfDesc[2 images][2 directions][2T] of the persistent launch (coupling_tc.cu)
   int* range_flag = nullptr;   // sticky device flag: an fp16-split operand left the fp16 range (gnf_flow_range_flag)
 
@@ -157,7 +158,8 @@ int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp,
 bool tc_linear_shape_ok(int k, int n);
 size_t tc_linear_image_bytes(int k, int n);
 int tc_linear(const Flow& f, int math, const float* A, int lda, int kvalid, const uint8_t* img_f16, const uint8_t* img_bf16,
-              int k, int n, const float* bias, int act, float* C, int ldc, int nvalid, int64_t M, cudaStream_t stream);
+              int k, int n, const float* bias, int act, float* C, int ldc, int nvalid, int64_t M, cudaStream_t stream,
+              int accumulate = 0);
 
 // backward_tc.cu
 bool tc_bwd_supported(const Flow& f);
@@ -170,6 +172,11 @@ int tc_half_backward(const Flow& f, int half, int step, const float* xa, float* 
                      const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_s,
                      const int32_t* csr_receivers, double loss_scale, float* grads, void* ws, int dw_parts, int fwd_f16,
                      void* stream);
+bool tc_bwd_inject_supported(const Flow& f);
+size_t tc_bwd_inject_workspace(const Flow& f, int64_t n);
+void tc_bwd_inject_buffers(const Flow& f, int64_t n, void* ws, float* pre0[2], float* d0[2]);
+int tc_half_backward_inject(const Flow& f, int ms, int mt, const float* const hin[2], int in_ld, float* xb, float* gb,
+                            int64_t n, double loss_scale, float* grads, void* ws, int dw_parts, int fwd_f16, void* stream);
 int tc_dw_gemm_test(const float* A, const float* B, int64_t n, int fa, int fb, int parts, int n_splits, float* out,
                     void* ws, size_t ws_bytes, void* stream);
 

@@ -1083,9 +1083,10 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
     cudaError_t e0 = cudaMalloc(&f.wtc[0], (size_t)f.n_mlps * f.wtc_per_mlp);
     cudaError_t e1 = cudaMalloc(&f.wtc[1], (size_t)f.n_mlps * f.wtc_per_mlp);
     cudaError_t e2 = cudaMalloc(&f.btc, (size_t)f.n_mlps * f.K * 256 * 4);
-    if (e2 == cudaSuccess && f.tc_ok) e2 = cudaMalloc(&f.wtcT, (size_t)f.n_mlps * f.wtc_per_mlp);
-    if (e2 == cudaSuccess && f.tc_ok) e2 = cudaMalloc(&f.wtcB[0], (size_t)f.n_mlps * f.wtc_per_mlp);
-    if (e2 == cudaSuccess && f.tc_ok) e2 = cudaMalloc(&f.wtcB[1], (size_t)f.n_mlps * f.wtc_per_mlp);
+    // backward chains (inject flows too: their layer-0 / last-position images are packed but never read)
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&f.wtcT, (size_t)f.n_mlps * f.wtc_per_mlp);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&f.wtcB[0], (size_t)f.n_mlps * f.wtc_per_mlp);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&f.wtcB[1], (size_t)f.n_mlps * f.wtc_per_mlp);
     if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
       gnf_flow_destroy(h);
       set_error("gnf_flow_create: cudaMalloc (tc weights) failed");
@@ -1108,6 +1109,8 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
       want(3, f.heads * f.vd, f.cho);
     }
     want(4, f.in_dim, f.L);
+    want(5, f.L, f.in_dim);                        // backward: g_h = delta_0 W0^T
+    if (f.attn) want(6, f.cho, f.heads * f.vd);    // backward: g_att = g_proj Wo^T
     f.wlin_per_mlp = off;
     if (off > 0) {
       cudaError_t e0 = cudaMalloc(&f.wlin[0], (size_t)f.n_mlps * off);
@@ -1167,7 +1170,7 @@ extern "C" int gnf_flow_supports(const gnf_flow* h, int32_t math) {
 extern "C" int gnf_flow_supports_backward(const gnf_flow* h, int32_t math) {
   if (!h) return 0;
   if (math == GNF_MATH_FP32) return 1;
-  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && tc_bwd_supported(h->f)) ? 1 : 0;
+  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && (tc_bwd_supported(h->f) || tc_bwd_inject_supported(h->f))) ? 1 : 0;
 }
 
 extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* stream_) {

@@ -168,16 +168,19 @@ int pack_build_jobs(Flow& f) {
     }
     if (f.wlin[0]) {      // images of the stand-alone tensor-core linears (linear_tc.cu): chunk geometry kcc = 16, one N block
       const int qk = f.heads * f.kq, hv = f.heads * f.vd;
-      struct Lin { int slot; int64_t src; int k, n; };
-      const Lin lins[5] = {{0, 0, f.H, qk},
-                           {1, (int64_t)f.H * qk, f.H, qk},
-                           {2, 2ll * f.H * qk, f.H, f.vd},
-                           {3, 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho},
-                           {4, f.flat_w_off[0], f.in_dim, f.L}};
+      // (k, n) = logical GEMM dims; transposed: the parameter block is stored [n, k] row-major (the backward's W^T)
+      struct Lin { int slot; int64_t src; int k, n, transposed; };
+      const Lin lins[7] = {{0, 0, f.H, qk, 0},
+                           {1, (int64_t)f.H * qk, f.H, qk, 0},
+                           {2, 2ll * f.H * qk, f.H, f.vd, 0},
+                           {3, 2ll * f.H * qk + (int64_t)f.H * f.vd, hv, f.cho, 0},
+                           {4, f.flat_w_off[0], f.in_dim, f.L, 0},
+                           {5, f.flat_w_off[0], f.L, f.in_dim, 1},
+                           {6, 2ll * f.H * qk + (int64_t)f.H * f.vd, f.cho, hv, 1}};
       for (const Lin& q : lins) {
         if (f.lin_off[q.slot] < 0) continue;
         PackJob j{};
-        j.kind = kPackTc; j.transposed = 0; j.in = q.k; j.out = q.n;
+        j.kind = kPackTc; j.transposed = q.transposed; j.in = q.k; j.out = q.n;
         j.p0 = pad16(q.k); j.p1 = pad16(q.n); j.p2 = pad16(q.n); j.p3 = 16;
         j.src_off = base + q.src;
         j.d0 = f.wlin[0] + (size_t)m * f.wlin_per_mlp + f.lin_off[q.slot];

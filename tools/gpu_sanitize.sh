@@ -50,6 +50,12 @@ for math in ("tc3x", "tc3x_bf16", "fp32"):
 g24 = H.random_batch(rng, 10, 5, 40, D=24)
 net24 = H.make_grevnet(O.make_params(2, 2, 24, 128, 3, last_layer_scale=0.05), 128, 3)
 print("inject mp", net24.math, float(G.loss.log_prob(net24, H.to_device_graph(g24))["log_prob_xs"]))
+# backward of the inject flows: k_linear_tc (K = 256 in two passes), k_bwd_chain<BINJ>, k_dw_tc with a 32/96-column
+# input image, block-staged attention backward (both passes) + the thread-per-head kernels behind it
+for bm in ("tc3x", "bf16", "fp32"):
+    _, ga = neta.loss_and_grad(dfc, backward_math=bm)
+    _, g24g = net24.loss_and_grad(H.to_device_graph(g24), backward_math=bm)
+    print("inject backward", bm, float(ga.norm()), float(g24g.norm()))
 st = G.graphs.structure_of(dg)
 for h in (7, 8, 20):
     xs = torch.randn(dg.nodes.shape[0], h, device="cuda")
