@@ -378,17 +378,21 @@ constexpr int kAbIdx = 2048;             // staged CSR indices per CTA
 constexpr int kAbH = 8;                  // heads (all in one register pass)
 constexpr int kAbCols = 4;               // output columns per lane: heads * kq <= 128, heads * vd <= 128
 
-__host__ __device__ inline int ab_odd(int x) { return x | 1; }
+// "other" row stride: odd (scalar loads, lane = row: conflict free); specialised shapes (vec): 4 mod 8 words, which
+// keeps 16-byte loads of 8 consecutive rows on 8 different bank groups
+__host__ __device__ inline int ab_ld(int x, bool vec) { return vec ? ((x + 3) / 4 * 4) + (((x + 3) / 4) % 2 ? 0 : 4) : (x | 1); }
 template <int SEND>
-__host__ __device__ inline size_t attn_bwd_block_bytes(int heads, int kq, int vd) {
+__host__ __device__ inline size_t attn_bwd_block_bytes(int heads, int kq, int vd, bool vec) {
   const int qk = heads * kq, hv = heads * vd;
-  const int other = SEND ? ab_odd(qk + hv + 3 * heads) : ab_odd(qk + vd);
-  const int own = SEND ? qk + vd : qk + hv + 2 * heads;
+  const int other = SEND ? ab_ld(qk + hv + 3 * heads, vec) : ab_ld(qk + (vec ? (vd + 3) / 4 * 4 : vd), vec);
+  const int own = SEND ? qk + (vec ? (vd + 3) / 4 * 4 : vd) : qk + hv + 2 * heads;
   return ((size_t)kAbRows * other + (size_t)kAbRecv * own + (size_t)kAbWarps * 32 * kAbH * (SEND ? 2 : 1)) * sizeof(float) +
          ((size_t)kAbIdx + kAbRecv + 1 + 2 * kAbWarps + 2) * sizeof(int32_t);
 }
 
-template <int SEND>
+// KQ > 0: specialised on (heads, kq, vd) = (NH, KQ, VD) -- the run_grevnet.py defaults 8 x 10, 10 -- with the per-edge
+// loops fully unrolled over 16-byte shared-memory loads; the sender-side value row is then padded to a multiple of 4.
+template <int SEND, int KQ, int NH, int VD>
 __global__ void __launch_bounds__(kAbWarps * 32)
 k_attn_bwd_block(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
                  const float* __restrict__ gatt, float* __restrict__ stats, int qk_pad, int v_pad, int hv_pad, int heads,
@@ -396,9 +400,11 @@ k_attn_bwd_block(const float* __restrict__ keys, const float* __restrict__ queri
                  int64_t n, float* __restrict__ out1, float* __restrict__ out2, int32_t* __restrict__ fallback) {
   extern __shared__ float sm_ab[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr bool VEC = KQ > 0;
   const int qk = heads * kq, hv = heads * vd;
-  const int o_ld = SEND ? ab_odd(qk + hv + 3 * heads) : ab_odd(qk + vd);     // "other" row stride
-  const int w_ld = SEND ? qk + vd : qk + hv + 2 * heads;                      // own row stride
+  const int vdp = VEC ? (vd + 3) / 4 * 4 : vd;            // sender-side rows: [keys qk | values vdp]
+  const int o_ld = SEND ? ab_ld(qk + hv + 3 * heads, VEC) : ab_ld(qk + vdp, VEC);     // "other" row stride
+  const int w_ld = SEND ? qk + vdp : qk + hv + 2 * heads;                               // own row stride
   float* o_s = sm_ab;                                     // [kAbRows][o_ld]
   float* w_s = o_s + kAbRows * o_ld;                      // [kAbRecv][w_ld]
   float* p_s = w_s + kAbRecv * w_ld;                      // [warps][32][kAbH] (x2 when SEND)
@@ -449,7 +455,7 @@ k_attn_bwd_block(const float* __restrict__ keys, const float* __restrict__ queri
       }
     } else {
       for (int c = lane; c < qk; c += 32) dst[c] = keys[node * qk_pad + c];
-      for (int c = lane; c < vd; c += 32) dst[qk + c] = vals[node * v_pad + c];
+      for (int c = lane; c < vdp; c += 32) dst[qk + c] = c < vd ? vals[node * v_pad + c] : 0.f;
     }
   }
   __syncthreads();
@@ -469,16 +475,65 @@ k_attn_bwd_block(const float* __restrict__ keys, const float* __restrict__ queri
       const float* oth = o_s + (valid ? idx_s[e] - lo : 0) * o_ld;
       const float* kp = SEND ? own : oth;                 // keys / values live on the sender side
       const float* rp = SEND ? oth : own;                 // queries / g_att / statistics on the receiver side
+      // (opaque to the optimiser: hoisting the own row's ~170 loop-invariant loads out of the edge loop spills)
+      asm volatile("" : "+l"(kp), "+l"(rp));
+      if constexpr (VEC) {
+        static_assert(!VEC || ((KQ * NH) % 4 == 0 && (VD * NH) % 4 == 0 && NH <= kAbH && NH % 4 == 0), "");
+        float l[kAbH], g[kAbH];
 #pragma unroll
-      for (int h = 0; h < kAbH; ++h) {
-        float l = 0.f, g = 0.f;
-        if (h < heads) {
-          for (int d = 0; d < kq; ++d) l = fmaf(kp[h * kq + d], rp[h * kq + d], l);
-          for (int c = 0; c < vd; ++c) g = fmaf(rp[qk + h * vd + c], kp[qk + c], g);
+        for (int h = 0; h < kAbH; ++h) { l[h] = 0.f; g[h] = 0.f; }
+        const float4* k4 = reinterpret_cast<const float4*>(kp);
+        const float4* q4 = reinterpret_cast<const float4*>(rp);
+#pragma unroll
+        for (int i4 = 0; i4 < KQ * NH / 4; ++i4) {            // same FMA order per head as the generic loop
+          const float4 kv = k4[i4], qv = q4[i4];
+          l[(4 * i4) / KQ] = fmaf(kv.x, qv.x, l[(4 * i4) / KQ]);
+          l[(4 * i4 + 1) / KQ] = fmaf(kv.y, qv.y, l[(4 * i4 + 1) / KQ]);
+          l[(4 * i4 + 2) / KQ] = fmaf(kv.z, qv.z, l[(4 * i4 + 2) / KQ]);
+          l[(4 * i4 + 3) / KQ] = fmaf(kv.w, qv.w, l[(4 * i4 + 3) / KQ]);
         }
-        const bool on = valid && h < heads;
-        w[h] = on ? expf(l * inv_scale - rp[qk + hv + h]) * rp[qk + hv + heads + h] : 0.f;
-        gw[h] = on ? g : 0.f;
+        float vv[(VD + 3) / 4 * 4];
+        const float4* v4 = reinterpret_cast<const float4*>(kp + KQ * NH);
+#pragma unroll
+        for (int i4 = 0; i4 < (VD + 3) / 4; ++i4) {
+          const float4 x = v4[i4];
+          vv[4 * i4] = x.x; vv[4 * i4 + 1] = x.y; vv[4 * i4 + 2] = x.z; vv[4 * i4 + 3] = x.w;
+        }
+        const float4* g4 = reinterpret_cast<const float4*>(rp + KQ * NH);
+#pragma unroll
+        for (int i4 = 0; i4 < VD * NH / 4; ++i4) {
+          const float4 x = g4[i4];
+          g[(4 * i4) / VD] = fmaf(x.x, vv[(4 * i4) % VD], g[(4 * i4) / VD]);
+          g[(4 * i4 + 1) / VD] = fmaf(x.y, vv[(4 * i4 + 1) % VD], g[(4 * i4 + 1) / VD]);
+          g[(4 * i4 + 2) / VD] = fmaf(x.z, vv[(4 * i4 + 2) % VD], g[(4 * i4 + 2) / VD]);
+          g[(4 * i4 + 3) / VD] = fmaf(x.w, vv[(4 * i4 + 3) % VD], g[(4 * i4 + 3) / VD]);
+        }
+        const float4* s4 = reinterpret_cast<const float4*>(rp + KQ * NH + VD * NH);    // max[NH] then 1/sum[NH]
+        float mxv[kAbH], rsv[kAbH];
+#pragma unroll
+        for (int i4 = 0; i4 < NH / 4; ++i4) {
+          const float4 a = s4[i4], b = s4[NH / 4 + i4];
+          mxv[4 * i4] = a.x; mxv[4 * i4 + 1] = a.y; mxv[4 * i4 + 2] = a.z; mxv[4 * i4 + 3] = a.w;
+          rsv[4 * i4] = b.x; rsv[4 * i4 + 1] = b.y; rsv[4 * i4 + 2] = b.z; rsv[4 * i4 + 3] = b.w;
+        }
+#pragma unroll
+        for (int h = 0; h < kAbH; ++h) {
+          const bool on = valid && h < NH;
+          w[h] = on ? expf(l[h] * inv_scale - mxv[h]) * rsv[h] : 0.f;
+          gw[h] = on ? g[h] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < kAbH; ++h) {
+          float l = 0.f, g = 0.f;
+          if (h < heads) {
+            for (int d = 0; d < kq; ++d) l = fmaf(kp[h * kq + d], rp[h * kq + d], l);
+            for (int c = 0; c < vd; ++c) g = fmaf(rp[qk + h * vd + c], kp[qk + c], g);
+          }
+          const bool on = valid && h < heads;
+          w[h] = on ? expf(l * inv_scale - rp[qk + hv + h]) * rp[qk + hv + heads + h] : 0.f;
+          gw[h] = on ? g : 0.f;
+        }
       }
     };
     float acc1[kAbCols], acc2[kAbCols];
@@ -816,7 +871,8 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   // block-staged kernels first (compact graphs); the thread-per-head kernels then serve the groups handed back, or
   // everything when the shape does not fit the staged layout.  The receiver pass leaves dot[r,h] in stats for the
   // sender pass, so each pass completes (staged + handed-back groups) before the next starts.
-  const size_t sm0 = attn_bwd_block_bytes<0>(f.heads, f.kq, f.vd), sm1 = attn_bwd_block_bytes<1>(f.heads, f.kq, f.vd);
+  const bool vec = f.heads == 8 && f.kq == 10 && f.vd == 10;      // the specialised instantiation (run_grevnet.py defaults)
+  const size_t sm0 = attn_bwd_block_bytes<0>(f.heads, f.kq, f.vd, vec), sm1 = attn_bwd_block_bytes<1>(f.heads, f.kq, f.vd, vec);
   const bool staged = b.fallback && f.heads <= kAbH && qk <= 32 * kAbCols && hv <= 32 * kAbCols && sm0 <= 200 * 1024 &&
                       sm1 <= 200 * 1024;
   const unsigned nblk = (unsigned)ceil_div(n, kAbRecv);
@@ -824,13 +880,15 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   if (staged) {
     static bool configured[kMaxDevices] = {};
     if (first_use_on_device(configured)) {
-      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<1, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<0, 10, 8, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GNF_CUDA(cudaFuncSetAttribute(k_attn_bwd_block<1, 10, 8, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     GNF_CUDA(cudaMemsetAsync(b.fallback, 0, (size_t)nblk * 4, stream));
-    k_attn_bwd_block<0><<<nblk, kAbWarps * 32, sm0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad,
-                                                              f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
-                                                              csr_senders, n, w.gqueries, nullptr, b.fallback);
+    auto k0 = vec ? k_attn_bwd_block<0, 10, 8, 10> : k_attn_bwd_block<0, 0, 0, 0>;
+    k0<<<nblk, kAbWarps * 32, sm0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad, f.heads,
+                                             f.kq, f.vd, inv_scale, rowptr, csr_senders, n, w.gqueries, nullptr, b.fallback);
     GNF_LAUNCH_CHECK();
   }
   k_attn_bwd_recv<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq,
@@ -838,9 +896,9 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   GNF_LAUNCH_CHECK();
   if (staged) {
     GNF_CUDA(cudaMemsetAsync(b.fallback, 0, (size_t)nblk * 4, stream));
-    k_attn_bwd_block<1><<<nblk, kAbWarps * 32, sm1, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad,
-                                                              f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr_s,
-                                                              csr_receivers, n, w.gkeys, w.gvh, b.fallback);
+    auto k1 = vec ? k_attn_bwd_block<1, 10, 8, 10> : k_attn_bwd_block<1, 0, 0, 0>;
+    k1<<<nblk, kAbWarps * 32, sm1, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad, f.heads,
+                                             f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys, w.gvh, b.fallback);
     GNF_LAUNCH_CHECK();
   }
   if (f.vd <= 32)

@@ -296,9 +296,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
           region ^= 1;
         }
         // ---- last chain layer: N = 16, K = LAT ----------------------------------------------------
-        // (BINJ backward chains: skipped WITHOUT toggling the region -- the next chain's layer 0, which does not wait
-        //  for the epilogue, must not write the region whose delta_0 accumulator the epilogue warps are still reading)
-        if (!(BINJ && bwd)) {
+        // BINJ backward chains stop at delta_0: no MMA here, but the issuer still waits until the epilogue warps have
+        // drained the delta_0 accumulator (they arrive on a_ready as if they had converted it).  Without that wait the
+        // next chain's layer 0 -- which needs nothing from the epilogue -- could commit acc_full a second time before the
+        // epilogue has seen the first commit (a barrier two phases ahead of its waiter: deadlock), and could overwrite
+        // the accumulator region still being read.  The region is not toggled.
+        if (BINJ && bwd) {
+          uint32_t waited = 0;
+          wait_groups(waited, 0, G::NA - 1);
+        } else {
           const uint32_t in_col = tmem_base + (region ^ 1) * LAT;
           const uint32_t d = tmem_base + region * LAT;
           uint32_t waited = 0;
@@ -439,10 +445,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_bwd_chain(const BwdParams p) {
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars->a_ready[NCH == 2 ? ph * 2 + ch : ph]));
-              } else if (valid) {
-                float4* dst = reinterpret_cast<float4*>(p.d0[m] + node * LAT + col0);
+              } else {
+                tc_fence_before();        // accumulator chunk read (tcgen05.wait::ld above): release it to the issuer
+                mbar_arrive(smem_u32(&bars->a_ready[NCH == 2 ? ph * 2 + ch : ph]));
+                if (valid) {
+                  float4* dst = reinterpret_cast<float4*>(p.d0[m] + node * LAT + col0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+                  for (int j = 0; j < 8; ++j) dst[j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+                }
               }
               if (!bwd && smem_mask) {       // sign bits of a_l for the backward chains (fp16 and bf16 share bit 15)
                 uint32_t bits = 0;

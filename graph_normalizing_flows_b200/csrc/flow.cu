@@ -186,14 +186,20 @@ constexpr int kAttnIdx = 2048;           // staged CSR indices per CTA
 constexpr int kAttnH = 8;                // heads per register pass
 
 __host__ __device__ inline int attn_odd(int x) { return x | 1; }
-__host__ __device__ inline size_t attn_block_bytes(int heads, int kq, int vd) {
+// key row stride: odd (scalar loads, lane = row: conflict free), or -- specialised shapes, qk a multiple of 4 -- 4 mod 8
+// words, which keeps 16-byte loads of 8 consecutive rows on 8 different bank groups
+__host__ __device__ inline int attn_key_ld(int qk, bool vec) { return vec ? ((qk + 3) / 4 * 4) + (((qk + 3) / 4) % 2 ? 0 : 4) : attn_odd(qk); }
+__host__ __device__ inline size_t attn_block_bytes(int heads, int kq, int vd, bool vec = false) {
   const int qk = heads * kq;
-  return ((size_t)kAttnRows * attn_odd(qk) + (size_t)kAttnRows * attn_odd(vd) + (size_t)kAttnRecv * qk +
+  return ((size_t)kAttnRows * attn_key_ld(qk, vec) + (size_t)kAttnRows * attn_odd(vd) + (size_t)kAttnRecv * qk +
           (size_t)kAttnWarps * 32 * kAttnH) * sizeof(float) +
          ((size_t)kAttnIdx + kAttnRecv + 1 + 2 * kAttnWarps + 2) * sizeof(int32_t);
 }
 
-__global__ void __launch_bounds__(kAttnWarps * 32)
+// KQ > 0: specialised on (heads, kq) = (NH, KQ) -- the run_grevnet.py defaults 8 x 10 -- with the logit loop fully
+// unrolled over 16-byte shared-memory loads (40 loads + 80 FMAs per edge instead of ~500 instructions)
+template <int KQ, int NH, int MINB>
+__global__ void __launch_bounds__(kAttnWarps * 32, MINB)
 k_dm_attn_block(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
                 int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
@@ -201,7 +207,7 @@ k_dm_attn_block(const float* __restrict__ keys, const float* __restrict__ querie
   extern __shared__ float sm_attn[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qk = heads * kq;
-  const int ks_ld = attn_odd(qk), v_ld = attn_odd(vd);
+  const int ks_ld = attn_key_ld(qk, KQ > 0), v_ld = attn_odd(vd);
   float* k_s = sm_attn;                                   // [kAttnRows][ks_ld]
   float* v_s = k_s + kAttnRows * ks_ld;                   // [kAttnRows][v_ld]
   float* q_s = v_s + kAttnRows * v_ld;                    // [kAttnRecv][qk]
@@ -236,24 +242,22 @@ k_dm_attn_block(const float* __restrict__ keys, const float* __restrict__ querie
     return;
   }
   // ---- stage: contiguous global rows [lo, hi] of keys / values, rows [r0, r0 + nr) of queries ------------------
-  for (int i = tid; i < nrows * qk; i += kAttnWarps * 32) {
-    const int row = i / qk, col = i - row * qk;
-    k_s[row * ks_ld + col] = keys[(int64_t)(lo + row) * qk_pad + col];
-  }
-  for (int i = tid; i < nrows * vd; i += kAttnWarps * 32) {
-    const int row = i / vd, col = i - row * vd;
-    v_s[row * v_ld + col] = vals[(int64_t)(lo + row) * v_pad + col];
-  }
-  for (int i = tid; i < nr * qk; i += kAttnWarps * 32) {
-    const int row = i / qk, col = i - row * qk;
-    q_s[i] = queries[(r0 + row) * qk_pad + col];
+  for (int row = warp; row < nrows + nr; row += kAttnWarps) {      // a warp copies whole rows: coalesced, no division
+    if (row < nrows) {
+      const int64_t node = (int64_t)lo + row;
+      for (int c = lane; c < qk; c += 32) k_s[row * ks_ld + c] = keys[node * qk_pad + c];
+      for (int c = lane; c < vd; c += 32) v_s[row * v_ld + c] = vals[node * v_pad + c];
+    } else {
+      const int rr = row - nrows;
+      for (int c = lane; c < qk; c += 32) q_s[rr * qk + c] = queries[(r0 + rr) * qk_pad + c];
+    }
   }
   __syncthreads();
   float* pw = p_s + warp * 32 * kAttnH;
   const int vc = lane % 10, vg = lane / 10;               // value phase: column vc (< vd <= 10), edge residue vg (0..2)
   for (int rl = warp; rl < nr; rl += kAttnWarps) {
     const int32_t beg = row_s[rl] - e0, end = row_s[rl + 1] - e0;
-    const float* qr = q_s + rl * qk;
+    const float* qr = q_s + rl * qk;   // (not const-qualified pointer value: see the asm below)
     for (int h0 = 0; h0 < heads; h0 += kAttnH) {          // up to 8 heads per register pass
       const int nh = min(kAttnH, heads - h0);
       float mx[kAttnH], sum[kAttnH], acc[kAttnH];
@@ -264,13 +268,33 @@ k_dm_attn_block(const float* __restrict__ keys, const float* __restrict__ querie
         const bool valid = e < end;
         const int row = valid ? idx_s[e] - lo : 0;
         const float* kr = k_s + row * ks_ld + h0 * kq;
+        if constexpr (KQ > 0) asm volatile("" : "+l"(qr));     // keep the query row's loads inside the loop (registers)
         float l[kAttnH];
+        if constexpr (KQ > 0) {
+          static_assert((KQ * NH) % 4 == 0 && NH <= kAttnH, "");
+          float a[kAttnH];
 #pragma unroll
-        for (int h = 0; h < kAttnH; ++h) {
-          float a = 0.f;
-          if (h < nh)
-            for (int d = 0; d < kq; ++d) a = fmaf(kr[h * kq + d], qr[(h0 + h) * kq + d], a);
-          l[h] = (valid && h < nh) ? a * inv_scale : -INFINITY;
+          for (int h = 0; h < kAttnH; ++h) a[h] = 0.f;
+          const float4* k4 = reinterpret_cast<const float4*>(kr);
+          const float4* q4 = reinterpret_cast<const float4*>(qr);
+#pragma unroll
+          for (int i4 = 0; i4 < KQ * NH / 4; ++i4) {          // same FMA order per head as the generic loop
+            const float4 kv = k4[i4], qv = q4[i4];
+            a[(4 * i4) / KQ] = fmaf(kv.x, qv.x, a[(4 * i4) / KQ]);
+            a[(4 * i4 + 1) / KQ] = fmaf(kv.y, qv.y, a[(4 * i4 + 1) / KQ]);
+            a[(4 * i4 + 2) / KQ] = fmaf(kv.z, qv.z, a[(4 * i4 + 2) / KQ]);
+            a[(4 * i4 + 3) / KQ] = fmaf(kv.w, qv.w, a[(4 * i4 + 3) / KQ]);
+          }
+#pragma unroll
+          for (int h = 0; h < kAttnH; ++h) l[h] = (valid && h < NH) ? a[h] * inv_scale : -INFINITY;
+        } else {
+#pragma unroll
+          for (int h = 0; h < kAttnH; ++h) {
+            float a = 0.f;
+            if (h < nh)
+              for (int d = 0; d < kq; ++d) a = fmaf(kr[h * kq + d], qr[(h0 + h) * kq + d], a);
+            l[h] = (valid && h < nh) ? a * inv_scale : -INFINITY;
+          }
         }
         float m[kAttnH];
 #pragma unroll
@@ -886,18 +910,27 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   rc = linear_any(f, mlp, math, 2, w.xq, f.hp8, f.H, wa + f.wv_off, f.zeros, w.vbuf, f.v_pad, f.vd, n, stream);      // project_v  gnn.py:525-528
   if (rc) return rc;
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
-  const size_t attn_smem = attn_block_bytes(f.heads, f.kq, f.vd);
+  const bool vec = f.heads == 8 && f.kq == 10;            // the specialised instantiation (run_grevnet.py defaults)
+  const size_t attn_smem = attn_block_bytes(f.heads, f.kq, f.vd, vec);
   const bool staged = w.fallback && f.vd <= 10 && attn_smem <= 200 * 1024;
   const int32_t* only = nullptr;
   if (staged) {
     static bool attn_configured[kMaxDevices] = {};
-    if (first_use_on_device(attn_configured))
-      GNF_CUDA(cudaFuncSetAttribute(k_dm_attn_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    auto kern = k_dm_attn_block<0, 0, 3>;
+    if (vec) {
+      // 3 CTAs per SM at 80 registers with a few spilled values, or 2 at 96 without: GNF_ATTN_MINB picks (A/B knob)
+      const char* mb = getenv("GNF_ATTN_MINB");
+      kern = (mb && mb[0] == '2') ? k_dm_attn_block<10, 8, 2> : k_dm_attn_block<10, 8, 3>;
+    }
+    if (first_use_on_device(attn_configured)) {
+      GNF_CUDA(cudaFuncSetAttribute(k_dm_attn_block<0, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GNF_CUDA(cudaFuncSetAttribute(k_dm_attn_block<10, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GNF_CUDA(cudaFuncSetAttribute(k_dm_attn_block<10, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
     const unsigned nblk = (unsigned)ceil_div(n, kAttnRecv);
     GNF_CUDA(cudaMemsetAsync(w.fallback, 0, (size_t)nblk * 4, stream));
-    k_dm_attn_block<<<nblk, kAttnWarps * 32, attn_smem, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad, f.hv_pad,
-                                                                 f.heads, f.kq, f.vd, inv_scale, rowptr, csr_senders, n,
-                                                                 w.att, w.stats, w.fallback);
+    kern<<<nblk, kAttnWarps * 32, attn_smem, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq,
+                                                       f.vd, inv_scale, rowptr, csr_senders, n, w.att, w.stats, w.fallback);
     GNF_LAUNCH_CHECK();
     only = w.fallback;                  // receiver groups whose senders are not one compact row range
   }
