@@ -149,5 +149,9 @@ def stream_ptr(device=None):
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    # torch's caching allocator returns >=512-byte aligned blocks
+    # torch's caching allocator returns >=512-byte aligned blocks.  GNF_POISON_WORKSPACE=1 (set by the GPU tests) fills
+    # the block with 0xFF bytes -- NaN as fp32/fp64, -1 as int32 -- so a kernel that reads a workspace word nobody wrote
+    # fails its test every time instead of whenever the caching allocator hands back a dirty block
+    if os.environ.get("GNF_POISON_WORKSPACE") == "1":
+        return torch.full((max(int(nbytes), 256),), 255, dtype=torch.uint8, device=device)
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

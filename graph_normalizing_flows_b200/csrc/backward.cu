@@ -868,6 +868,10 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   }
   if (rc) return rc;
   const unsigned blocks = (unsigned)ceil_div(n * f.heads, 128);
+  if (f.qk_pad != qk) {       // dX reads qk_pad columns of these (zero weight rows under the pad): pad columns = 0, not NaN
+    GNF_CUDA(cudaMemsetAsync(w.gkeys, 0, (size_t)n * f.qk_pad * 4, stream));
+    GNF_CUDA(cudaMemsetAsync(w.gqueries, 0, (size_t)n * f.qk_pad * 4, stream));
+  }
   // block-staged kernels first (compact graphs); the thread-per-head kernels then serve the groups handed back, or
   // everything when the shape does not fit the staged layout.  The receiver pass leaves dot[r,h] in stats for the
   // sender pass, so each pass completes (staged + handed-back groups) before the next starts.

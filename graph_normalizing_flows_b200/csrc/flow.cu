@@ -910,6 +910,9 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   rc = linear_any(f, mlp, math, 2, w.xq, f.hp8, f.H, wa + f.wv_off, f.zeros, w.vbuf, f.v_pad, f.vd, n, stream);      // project_v  gnn.py:525-528
   if (rc) return rc;
   const float inv_scale = (f.attn_flags & GNF_ATTN_KQ_DIV) ? 1.f / sqrtf((float)f.kq) : 1.f;
+  // the output projection reads hv_pad columns per row (zero weight rows under the pad): the pad columns, which no
+  // attention kernel writes, must hold zeros, not whatever the workspace held before (0 * NaN = NaN)
+  if (f.hv_pad != f.heads * f.vd) GNF_CUDA(cudaMemsetAsync(w.att, 0, (size_t)n * f.hv_pad * 4, stream));
   const bool vec = f.heads == 8 && f.kq == 10;            // the specialised instantiation (run_grevnet.py defaults)
   const size_t attn_smem = attn_block_bytes(f.heads, f.kq, f.vd, vec);
   const bool staged = w.fallback && f.vd <= 10 && attn_smem <= 200 * 1024;

@@ -9,6 +9,11 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 
+# every library workspace the tests hand out is pre-filled with 0xFF bytes (NaN / -1): reading a word nobody wrote fails
+# deterministically instead of depending on what the caching allocator's block held before (_lib.workspace)
+os.environ.setdefault("GNF_POISON_WORKSPACE", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -1,0 +1,12 @@
+#!/bin/bash
+# re-entry verification of HEAD: the inject-backward paths first (short timeouts), f1 timing, whole suite, default bench,
+# f1 launch list
+set -x
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests -q -m gpu -x -k "inject or wide_graphs or f1_dm" -o timeout=100 > gpurun_out/r2_pytest_call17a.log 2>&1; rc=$?
+tail -15 gpurun_out/r2_pytest_call17a.log
+if [ $rc -ne 0 ]; then echo "new-path tests failed (rc=$rc): stopping here"; exit 1; fi
+timeout 200 python tools/bench_next_rows.py tc3x skip 2>&1 | tail -1 | tee gpurun_out/r2_next_rows_f1_b.jsonl
+timeout 500 python -m pytest tests -q -m gpu -o timeout=100 2>&1 | tail -15 > gpurun_out/r2_pytest_gpu.log; tail -15 gpurun_out/r2_pytest_gpu.log
+timeout 200 python bench.py 2>gpurun_out/bench_err.log | tail -1 | tee gpurun_out/r2_bench_n1.json
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_f1_fwd_bwd.csv python tools/profile_f1.py > gpurun_out/ncu_f1.log 2>&1; tail -2 gpurun_out/ncu_f1.log
