@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgnf_b200.so")
 
 GNF_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 GNF_EINVAL, GNF_ECUDA, GNF_EUNSUPPORTED, GNF_EWORKSPACE = -1, -2, -3, -4
 AGG = {"sum": 0, "mean": 1}
 BLOCK = {"concat": 0, "agg_then": 1, "dm_attn": 2}
@@ -81,6 +81,8 @@ SIGNATURES = {
     "gnf_grevnet_backward": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, C.c_double, _p, _p, _i32, _p, _sz, _p]),
     "gnf_debug_bwd_layout": (C.c_int, [_p, _i64, _p]),
     "gnf_debug_dw_gemm": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _sz, _p]),
+    "gnf_debug_linear_tc_workspace": (_sz, [_i32, _i32]),
+    "gnf_debug_linear_tc": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "gnf_pred_adj": (C.c_int, [_p, _i32, _p, _p, _i64, C.c_float, C.c_float, _p, _p]),
     "gnf_log_prob_workspace": (_sz, [_i64, _i32]),
     "gnf_log_prob": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),

@@ -117,6 +117,12 @@ struct Flow {
   uint8_t* wlin[2] = {nullptr, nullptr};
   int64_t wlin_per_mlp = 0;
   int64_t lin_off[7] = {-1, -1, -1, -1, -1, -1, -1};   // q, k, v, o, layer 0; backward dX: W0^T (L -> in), Wo^T (cho -> heads*v)
+  // layered tensor-core path (gemm_tc.cu) for the shapes the fused kernels do not take (latent_dim not in {128, 256},
+  // residual / layer_norm attention variants): fp16 / bf16 hi-lo images of every MLP layer, k_gemm_tc geometry
+  uint8_t* wgemm[2] = {nullptr, nullptr};
+  int64_t wgemm_per_mlp = 0;
+  int64_t gemm_off[kMaxLayers];
+  bool tc_layered = false;     // MLP layers in k_gemm_tc, input assembly / coupling update in the fp32 path's kernels
   void* half_tables = nullptr; // device HalfDesc[2 images][2 directions][2T] of the persistent launch (coupling_tc.cu)
   int* range_flag = nullptr;   // sticky device flag: an fp16-split operand left the fp16 range (gnf_flow_range_flag)
 
@@ -145,6 +151,8 @@ int fwd_agg_input(const Flow& f, const float* xa, int64_t n, const int32_t* rowp
 // pack.cu
 int pack_build_jobs(Flow& f);
 int pack_all(const Flow& f, const float* params, cudaStream_t stream);
+int pack_tc_image(const float* W, int k, int n, int kpad, int npad, int nhc, int kcc, uint8_t* img_f16, uint8_t* img_bf16,
+                  void* job_scratch, cudaStream_t stream);
 
 // backward.cu (shared with backward_tc.cu)
 int bwd_agg_transpose(const Flow& f, const float* gh, int gh_stride, const int32_t* rowptr_s,
@@ -155,6 +163,11 @@ int bwd_split_scale(const float* z, int64_t n, int d, int h, int hp, float scale
 int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp, float* x, cudaStream_t stream);
 
 // linear_tc.cu
+// gemm_tc.cu
+void tc_gemm_geometry(int k, int n, int& kpad, int& npad, int& nb);
+size_t tc_gemm_image_bytes(int k, int n);
+int tc_gemm(const Flow& f, int math, const float* A, int lda, int kvalid, const uint8_t* img_f16, const uint8_t* img_bf16,
+            int k, int n, const float* bias, int act, float* C, int ldc, int nvalid, int64_t M, cudaStream_t stream);
 bool tc_linear_shape_ok(int k, int n);
 size_t tc_linear_image_bytes(int k, int n);
 int tc_linear(const Flow& f, int math, const float* A, int lda, int kvalid, const uint8_t* img_f16, const uint8_t* img_bf16,

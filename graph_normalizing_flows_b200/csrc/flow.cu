@@ -167,6 +167,79 @@ k_dm_attn(const float* __restrict__ keys, const float* __restrict__ queries, con
   }
 }
 
+// Warp per (receiver, head): the shapes of the embedding flow (train_grevnet_with_data.py:41-47: 1 head, kq = v = 64, fully
+// connected graphs of 100..400 nodes), where a thread per (receiver, head) leaves the GPU almost empty (N threads in
+// all, each walking hundreds of edges x 128 scalar loads).  32 in-edges at a time:
+//   logits : lane = edge, <keys[s_e, h, :], queries[r, h, :]> with the query row broadcast out of shared memory
+//   softmax: running (max, sum), two warp reductions per chunk
+//   values : lane = value column (and column + 32); the chunk's edges in ascending order, p_e and s_e by shuffle -- every
+//            value row is one coalesced read
+// Same mathematics and summation order over a segment as k_dm_attn (serial in edge order, rescaled when the max moves).
+__global__ void __launch_bounds__(256)
+k_dm_attn_warp(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+               int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd, float inv_scale,
+               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders, int64_t n,
+               float* __restrict__ att, float* __restrict__ stats, const int32_t* __restrict__ only, int only_shift) {
+  __shared__ __align__(16) float q_s[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= n * heads) return;
+  const int64_t r = i / heads;
+  if (only && !only[r >> only_shift]) return;
+  const int h = (int)(i - r * heads);
+  const int32_t beg = rowptr[r], end = rowptr[r + 1];
+  const float* qr = queries + r * qk_pad + h * kq;
+  for (int d = lane; d < kq; d += 32) q_s[warp][d] = qr[d];
+  __syncwarp();
+  const bool vec = (kq & 3) == 0 && (qk_pad & 3) == 0;      // key rows of head h start 16-byte aligned
+  float mx = -INFINITY, sum = 0.f, acc0 = 0.f, acc1 = 0.f;
+  for (int32_t c0 = beg; c0 < end; c0 += 32) {
+    const int32_t e = c0 + lane;
+    const bool valid = e < end;
+    const int32_t s = valid ? csr_senders[e] : 0;
+    float l = -INFINITY;
+    if (valid) {
+      const float* ks = keys + (int64_t)s * qk_pad + h * kq;
+      float a = 0.f;
+      if (vec) {
+        for (int d = 0; d < kq; d += 4) {
+          const float4 kv = *reinterpret_cast<const float4*>(ks + d);
+          const float4 qv = *reinterpret_cast<const float4*>(&q_s[warp][d]);
+          a = fmaf(kv.x, qv.x, a); a = fmaf(kv.y, qv.y, a); a = fmaf(kv.z, qv.z, a); a = fmaf(kv.w, qv.w, a);
+        }
+      } else {
+        for (int d = 0; d < kq; ++d) a = fmaf(ks[d], q_s[warp][d], a);
+      }
+      l = a * inv_scale;
+    }
+    float m = l;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float m_new = fmaxf(mx, m);
+    const float sc = expf(mx - m_new);                   // exp(-inf) = 0 on the first chunk
+    const float p = valid ? expf(l - m_new) : 0.f;
+    // the segment sums in ascending edge order, like the thread-per-head kernel (every lane keeps the same `sum`)
+    sum *= sc; acc0 *= sc; acc1 *= sc;
+    mx = m_new;
+    const int cnt = min(32, end - c0);
+    for (int j = 0; j < cnt; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      const int32_t sj = __shfl_sync(0xffffffffu, s, j);
+      const float* vs = vals + (int64_t)sj * v_pad;
+      sum += pj;
+      if (lane < vd) acc0 = fmaf(vs[lane], pj, acc0);
+      if (lane + 32 < vd) acc1 = fmaf(vs[lane + 32], pj, acc1);
+    }
+  }
+  const float inv = end > beg ? 1.f / sum : 0.f;          // empty segments give 0
+  if (lane < vd) att[r * hv_pad + h * vd + lane] = acc0 * inv;
+  if (lane + 32 < vd) att[r * hv_pad + h * vd + lane + 32] = acc1 * inv;
+  if (stats && lane == 0) {
+    stats[i * 3] = end > beg ? mx : 0.f;
+    stats[i * 3 + 1] = end > beg ? sum : 1.f;
+  }
+}
+
 // Block-staged attention (round 2).  A CTA owns kAttnRecv consecutive receivers; like k_gather_segment it stages what
 // they need ONCE in shared memory with coalesced loads: their CSR index range and -- graphs being contiguous node
 // blocks -- the sender rows [lo, hi] of the key and value matrices, plus their own query rows.  Every warp then takes
@@ -738,7 +811,8 @@ Workspace carve(const Flow& f, int64_t n, int math, void* base) {
   w.partials = (double*)take((size_t)w.n_partials_cap * 8);
   w.counter = (unsigned int*)take(256);
   const bool inject = math != GNF_MATH_FP32 && f.tc_inject;
-  if (math == GNF_MATH_FP32 || inject) {
+  const bool layered = math != GNF_MATH_FP32 && f.tc_layered;       // the fp32 path's buffers, MLP layers in k_gemm_tc
+  if (math == GNF_MATH_FP32 || inject || layered) {
     const int lp = pad_to(f.L, 8);
     w.hbuf = (float*)take(nn * f.in_pad * 4);
     w.act0 = (float*)take(nn * lp * 4);        // inject: layer-0 pre-activations of the s MLP
@@ -781,13 +855,21 @@ int run_linear(const float* A, const float* W, const float* b, float* C, int64_t
 }
 
 // fp32 layered MLP: hbuf -> out (uses act0/act1 ping-pong)
-int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n, cudaStream_t stream) {
+int run_mlp32(const Flow& f, int mlp, const Workspace& w, float* out, int64_t n, cudaStream_t stream,
+              int math = GNF_MATH_FP32) {
   const float* base = f.w32 + (int64_t)mlp * f.w32_per_mlp;
   const float* in = w.hbuf;
+  const bool tc = math != GNF_MATH_FP32 && f.tc_layered;      // layer by layer on the tensor cores (gemm_tc.cu)
   for (int l = 0; l < f.K; ++l) {
     const bool last = (l == f.K - 1);
     float* dst = last ? out : ((l & 1) ? w.act1 : w.act0);
-    int rc = run_linear(in, base + f.w32_layer_off[l], base + f.b32_layer_off[l], dst, n,
+    int rc;
+    if (tc) {
+      const size_t off = (size_t)mlp * f.wgemm_per_mlp + f.gemm_off[l];
+      rc = tc_gemm(f, math, in, f.in_pads[l], f.in_pads[l], f.wgemm[0] + off, f.wgemm[1] + off, f.ins[l], f.outs[l],
+                   base + f.b32_layer_off[l], last ? 2 : f.d.act, dst, f.out_pads[l], f.out_pads[l], n, stream);
+    } else
+    rc = run_linear(in, base + f.w32_layer_off[l], base + f.b32_layer_off[l], dst, n,
                         f.out_pads[l], f.in_pads[l], last ? 2 : f.d.act, stream);
     if (rc) return rc;
     in = dst;
@@ -803,10 +885,11 @@ int build_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const i
 }
 
 int gnn_forward32(const Flow& f, int mlp, bool build_agg, const float* xa, int64_t n, const int32_t* rowptr,
-                  const int32_t* csr_senders, const Workspace& w, float* out, cudaStream_t stream) {
+                  const int32_t* csr_senders, const Workspace& w, float* out, cudaStream_t stream,
+                  int math = GNF_MATH_FP32) {
   int rc = GNF_OK;
   if (f.attn) {
-    rc = build_attn_input(f, mlp, xa, n, rowptr, csr_senders, w, stream);
+    rc = build_attn_input(f, mlp, xa, n, rowptr, csr_senders, w, stream, math);
   } else if (build_agg) {
     k_agg_input<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(
         xa, f.H, f.HP, rowptr, csr_senders, n, f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps,
@@ -814,7 +897,7 @@ int gnn_forward32(const Flow& f, int mlp, bool build_agg, const float* xa, int64
     GNF_LAUNCH_CHECK();
   }
   if (rc) return rc;
-  rc = run_mlp32(f, mlp, w, out, n, stream);
+  rc = run_mlp32(f, mlp, w, out, n, stream, math);
   if (rc) return rc;
   if (f.attn && (f.attn_flags & GNF_ATTN_RESIDUAL)) {                                          // gnn.py:551-552
     k_add_rows<<<(unsigned)ceil_div(n * f.H, 256), 256, 0, stream>>>(out, xa, f.H, f.HP, n);
@@ -830,12 +913,14 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
                   int math, const Workspace& w, cudaStream_t stream) {
   const int ms = f.mlp_index(0, half, step), mt = f.mlp_index(1, half, step);
   if (n == 0) return GNF_OK;
-  if (math == GNF_MATH_FP32) {
+  if (math == GNF_MATH_FP32 || f.tc_layered) {
+    // fp32 kernels layer by layer; tc_layered flows under a tensor-core `math`: same skeleton, the Linears in k_gemm_tc
+    // (MLP layers) and k_linear_tc (attention projections)
     const int64_t total = n * f.H;
     const unsigned blocks = (unsigned)ceil_div(total, 256);
-    int rc = gnn_forward32(f, ms, true, xa, n, rowptr, csr_senders, w, w.sbuf, stream);
+    int rc = gnn_forward32(f, ms, true, xa, n, rowptr, csr_senders, w, w.sbuf, stream, math);
     if (rc) return rc;
-    rc = gnn_forward32(f, mt, false, xa, n, rowptr, csr_senders, w, w.tbuf, stream);   // aggregation input is shared
+    rc = gnn_forward32(f, mt, false, xa, n, rowptr, csr_senders, w, w.tbuf, stream, math);   // aggregation input is shared
     if (rc) return rc;
     const bool want_ldj = (!inverse && ldj_accum);
     k_coupling_update<<<blocks, 256, 0, stream>>>(xb, w.sbuf, w.tbuf, n, f.H, f.HP, f.HP, inverse,
@@ -871,9 +956,9 @@ int coupling_half(const Flow& f, int half, int step, int inverse, const float* x
 int check_math(const Flow& f, int math, const char* who) {
   GNF_REQUIRE(math >= GNF_MATH_FP32 && math <= GNF_MATH_TC2X, GNF_EINVAL, "%s: bad math %d", who, math);
   if (math != GNF_MATH_FP32)
-    GNF_REQUIRE(f.tc_ok || f.tc_inject, GNF_EUNSUPPORTED,
-                "%s: the tcgen05 kernels need latent_dim in {128,256}, D/2 <= 16, 2 <= num_layers <= %d and, for "
-                "dm_self_attn, residual = layer_norm = False (got L=%d in=%d H=%d K=%d); use GNF_MATH_FP32",
+    GNF_REQUIRE(f.tc_ok || f.tc_inject || f.tc_layered, GNF_EUNSUPPORTED,
+                "%s: no tensor-core path for this flow (its layer images would exceed the memory budget of the layered "
+                "kernels; num_layers <= %d, got L=%d in=%d H=%d K=%d); use GNF_MATH_FP32",
                 who, kMaxLayers, f.L, f.in_dim, f.H, f.K);
   return GNF_OK;
 }
@@ -937,7 +1022,11 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
     GNF_LAUNCH_CHECK();
     only = w.fallback;                  // receiver groups whose senders are not one compact row range
   }
-  if (f.vd <= 32)
+  if (!staged && (f.vd >= 16 || f.kq >= 32) && f.vd <= 64 && f.kq <= 64)
+    k_dm_attn_warp<<<(unsigned)ceil_div(n * f.heads, 8), 256, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
+                                                                          f.hv_pad, f.heads, f.kq, f.vd, inv_scale, rowptr,
+                                                                          csr_senders, n, w.att, w.stats, only, 5);
+  else if (f.vd <= 32)
     k_dm_attn<32><<<(unsigned)ceil_div(n * f.heads, 128), 128, 0, stream>>>(w.qbuf, w.kbuf, w.vbuf, f.qk_pad, f.v_pad,
                                                                             f.hv_pad, f.heads, f.kq, f.vd, inv_scale,
                                                                             rowptr, csr_senders, n, w.att, w.stats, only, 5);
@@ -1129,8 +1218,28 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
       return GNF_ECUDA;
     }
   }
-  if (f.tc_inject) {
-    // stand-alone tensor-core linears of the inject path: layer 0 and, for dm_self_attn, the four projections
+  if (!f.tc_ok && !f.tc_inject) {
+    // every other shape: the MLP layers one by one in k_gemm_tc (images of all K layers, fp16 and bf16 element type);
+    // flows whose images would not fit a sane share of HBM stay on the fp32 kernels
+    int64_t goff = 0;
+    for (int l = 0; l < f.K; ++l) {
+      f.gemm_off[l] = goff;
+      goff += (int64_t)align_up(tc_gemm_image_bytes(f.ins[l], f.outs[l]), 256);
+    }
+    f.wgemm_per_mlp = goff;
+    if ((double)goff * f.n_mlps * 2 <= 24e9) {
+      cudaError_t e0 = cudaMalloc(&f.wgemm[0], (size_t)f.n_mlps * goff);
+      cudaError_t e1 = cudaMalloc(&f.wgemm[1], (size_t)f.n_mlps * goff);
+      if (e0 != cudaSuccess || e1 != cudaSuccess) {
+        gnf_flow_destroy(h);
+        set_error("gnf_flow_create: cudaMalloc (gemm images) failed");
+        return GNF_ECUDA;
+      }
+      f.tc_layered = true;
+    }
+  }
+  if (f.tc_inject || f.tc_layered) {
+    // stand-alone tensor-core linears: layer 0 (inject flows) and, for dm_self_attn, the four projections
     int64_t off = 0;
     auto want = [&](int slot, int k, int n) {
       if (tc_linear_shape_ok(k, n)) {
@@ -1144,9 +1253,11 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
       want(2, f.H, f.vd);
       want(3, f.heads * f.vd, f.cho);
     }
-    want(4, f.in_dim, f.L);
-    want(5, f.L, f.in_dim);                        // backward: g_h = delta_0 W0^T
-    if (f.attn) want(6, f.cho, f.heads * f.vd);    // backward: g_att = g_proj Wo^T
+    if (f.tc_inject) {
+      want(4, f.in_dim, f.L);
+      want(5, f.L, f.in_dim);                        // backward: g_h = delta_0 W0^T
+      if (f.attn) want(6, f.cho, f.heads * f.vd);    // backward: g_att = g_proj Wo^T
+    }
     f.wlin_per_mlp = off;
     if (off > 0) {
       cudaError_t e0 = cudaMalloc(&f.wlin[0], (size_t)f.n_mlps * off);
@@ -1191,6 +1302,8 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.pack_jobs);
   cudaFree(h->f.wlin[0]);
   cudaFree(h->f.wlin[1]);
+  cudaFree(h->f.wgemm[0]);
+  cudaFree(h->f.wgemm[1]);
   cudaFree(h->f.half_tables);
   cudaFree(h->f.range_flag);
   delete h;
@@ -1200,7 +1313,7 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
 extern "C" int gnf_flow_supports(const gnf_flow* h, int32_t math) {
   if (!h) return 0;
   if (math == GNF_MATH_FP32) return 1;
-  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && (h->f.tc_ok || h->f.tc_inject)) ? 1 : 0;
+  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && (h->f.tc_ok || h->f.tc_inject || h->f.tc_layered)) ? 1 : 0;
 }
 
 extern "C" int gnf_flow_supports_backward(const gnf_flow* h, int32_t math) {

@@ -188,6 +188,18 @@ int pack_build_jobs(Flow& f) {
         add(j, (int64_t)j.p0 * j.p1);
       }
     }
+    if (f.wgemm[0])       // layered path (gemm_tc.cu): every MLP layer, column blocks of <= 256, k16 slabs
+      for (int l = 0; l < f.K; ++l) {
+        int kpad, npad, nb;
+        tc_gemm_geometry(f.ins[l], f.outs[l], kpad, npad, nb);
+        PackJob j{};
+        j.kind = kPackTc; j.transposed = 0; j.in = f.ins[l]; j.out = f.outs[l];
+        j.p0 = kpad; j.p1 = npad; j.p2 = nb; j.p3 = 16;
+        j.src_off = base + f.flat_w_off[l];
+        j.d0 = f.wgemm[0] + (size_t)m * f.wgemm_per_mlp + f.gemm_off[l];
+        j.d1 = f.wgemm[1] + (size_t)m * f.wgemm_per_mlp + f.gemm_off[l];
+        add(j, (int64_t)kpad * npad);
+      }
     size_t tc_off[kMaxLayers + 1] = {0};
     if (f.tc_ok || f.tc_inject)
       for (int pos = 0; pos < f.K; ++pos) {
@@ -252,6 +264,23 @@ int pack_build_jobs(Flow& f) {
   f.pack_blocks = blocks;
   GNF_CUDA(cudaMalloc(&f.pack_jobs, jobs.size() * sizeof(PackJob)));
   GNF_CUDA(cudaMemcpy(f.pack_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  return GNF_OK;
+}
+
+// one kPackTc image of a row-major W [k, n] on its own (debug entry of gemm_tc.cu); job_scratch: device, >= 256 bytes
+int pack_tc_image(const float* W, int k, int n, int kpad, int npad, int nhc, int kcc, uint8_t* img_f16, uint8_t* img_bf16,
+                  void* job_scratch, cudaStream_t stream) {
+  static_assert(sizeof(PackJob) <= 256, "");
+  PackJob j{};
+  j.kind = kPackTc; j.transposed = 0; j.in = k; j.out = n;
+  j.p0 = kpad; j.p1 = npad; j.p2 = nhc; j.p3 = kcc;
+  j.src_off = 0; j.d0 = img_f16; j.d1 = img_bf16;
+  j.first_block = 0;
+  j.n_blocks = (int)ceil_div((int64_t)kpad * npad, kPackThreads);
+  GNF_CUDA(cudaMemcpyAsync(job_scratch, &j, sizeof(j), cudaMemcpyHostToDevice, stream));
+  GNF_CUDA(cudaStreamSynchronize(stream));       // `j` lives on this stack frame
+  k_pack_all<<<(unsigned)j.n_blocks, kPackThreads, 0, stream>>>((const PackJob*)job_scratch, 1, W);
+  GNF_LAUNCH_CHECK();
   return GNF_OK;
 }
 

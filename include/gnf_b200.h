@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GNF_ABI_VERSION 4
+#define GNF_ABI_VERSION 5
 
 /* status codes */
 #define GNF_OK            0
@@ -312,6 +312,15 @@ int gnf_coupling_half_backward(const gnf_flow* flow, int32_t half, int32_t step,
 int gnf_debug_bwd_layout(const gnf_flow* flow, int64_t n_nodes, int64_t* out8);
 int gnf_debug_dw_gemm(const float* a, const float* b, int64_t n, int32_t fa, int32_t fb, int32_t parts,
                       int32_t n_splits, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One Sonnet Linear of the layered tensor-core path on its own (unit tests, profiling; gnn.py:143-180 make_mlp_model
+ * layers of any width, e.g. the 2048-wide MLPs of train_grevnet_with_data.py:41-47):
+ * c[m, n] = act(a[m, k] @ w[k, n] + bias[n]), row-major fp32, k % 4 == 0, n % 4 == 0, act = GNF_ACT_* or 2 (none),
+ * math = GNF_MATH_TC3X / TC3X_BF16 / BF16.  The entry packs w into the kernel's image format inside the workspace
+ * (>= gnf_debug_linear_tc_workspace(k, n) bytes) and runs k_gemm_tc (csrc/gemm_tc.cu). */
+size_t gnf_debug_linear_tc_workspace(int32_t k, int32_t n);
+int gnf_debug_linear_tc(const float* a, const float* w, const float* bias, int64_t m, int32_t k, int32_t n, int32_t act,
+                        int32_t math, float* c, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * f3  Decode tail of the sampling pass (train_grevnet_with_data.py:414-416):

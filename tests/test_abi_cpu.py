@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gnf_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.gnf_abi_version() == 4
+    assert lib.gnf_abi_version() == 5
 
 
 def test_param_count_matches_reference_formula():

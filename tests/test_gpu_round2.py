@@ -115,9 +115,17 @@ def test_embedding_flow_default_shape_runs_and_matches_oracle():
     want = O.log_prob(z64, ldj64, n_node)["log_prob_xs"]
     net = H.make_grevnet(params, 2048, 3, device=DEV)
     dg = dev_graph(g)
+    # round 2: the 2048-wide MLP layers run on the tensor cores (k_gemm_tc, layer by layer), the attention projections
+    # in k_linear_tc; math=None picks that path
+    assert net.math == "tc3x"
     out = G.loss.log_prob(net, dg, return_z=True)
     assert H.rel_err(out["log_prob_xs"], want) < LOGPROB_RTOL
     assert np.abs(out["z"].nodes.cpu().numpy() - z64).max() < 2e-4
+    net.check_numerics()
+    net32 = H.make_grevnet(params, 2048, 3, device=DEV, math="fp32")          # the FFMA kernels, same flow
+    out32 = G.loss.log_prob(net32, dg, return_z=True)
+    assert H.rel_err(out32["log_prob_xs"], want) < LOGPROB_RTOL
+    assert float((out32["z"].nodes - out["z"].nodes).abs().max()) < 2e-4
     x_back = net(out["z"], inverse=False).nodes
     assert float((x_back - dg.nodes).abs().max()) < 1e-3
     # and it trains: reversible backward vs autograd of the fp64 restatement
@@ -358,3 +366,71 @@ def test_attention_kernels_hand_wide_graphs_back(bmath):
     assert abs(float(scal["loss_per_node"]) - loss_ref) <= 1e-5 * abs(loss_ref)
     assert np.abs(got - grad_ref).max() <= (5e-4 if bmath == "tc3x" else 2e-4) * np.abs(grad_ref).max()
     assert float(got @ grad_ref) / (np.linalg.norm(got) * np.linalg.norm(grad_ref)) > 1 - 1e-6
+
+
+# ------------------------------------------------- layered tensor-core Linear (gemm_tc.cu) on its own ---
+@pytest.mark.parametrize("shape", [(300, 164, 2048), (300, 2048, 2048), (517, 2048, 100), (129, 16, 16), (1, 40, 300),
+                                   (700, 100, 104), (256, 32, 512), (40000, 176, 512)])
+@pytest.mark.parametrize("math,tol", [("tc3x", 2e-6), ("tc3x_bf16", 4e-5), ("bf16", 2e-2)])
+def test_layered_tensor_core_linear(shape, math, tol):
+    """k_gemm_tc (gnf_debug_linear_tc): act(a @ w + b) for the widths the fused kernels do not take -- the 2048-wide
+    layers of train_grevnet_with_data.py:41-47, ragged K / N (not multiples of 16 or of the 256-column block), row
+    counts below one tile and far above one wave -- against a float64 matmul; the error bound scales with
+    (|a| @ |w|), the sum a rounding error is relative to."""
+    from graph_normalizing_flows_b200 import _lib
+    lib = _lib.load()
+    m, k, n = shape
+    if m > 10000 and math != "tc3x":
+        pytest.skip("the many-items case runs once")
+    gen = torch.Generator(device="cpu").manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=gen)
+    w = torch.randn(k, n, generator=gen) / np.sqrt(k)
+    b = torch.randn(n, generator=gen)
+    dev = torch.device(DEV)
+    ad, wd, bd = a.to(dev), w.to(dev), b.to(dev)
+    pre = a.double() @ w.double() + b.double()
+    scale = (a.double().abs() @ w.double().abs()).max().item() + b.abs().max().item()
+    wsb = lib.gnf_debug_linear_tc_workspace(k, n)
+    for act, fn in ((2, lambda x: x), (0, lambda x: torch.nn.functional.leaky_relu(x, 0.2)), (1, torch.relu)):
+        c = torch.full((m, n), float("nan"), device=dev)
+        ws = _lib.workspace(wsb, dev)
+        _lib.check(lib.gnf_debug_linear_tc(_lib.ptr(ad), _lib.ptr(wd), _lib.ptr(bd), m, k, n, act, _lib.MATH[math],
+                                           _lib.ptr(c), _lib.ptr(ws), wsb, _lib.stream_ptr(dev)), "gnf_debug_linear_tc")
+        got = c.double().cpu()
+        assert torch.isfinite(got).all(), (shape, math, act)
+        assert float((got - fn(pre)).abs().max()) <= tol * scale, (shape, math, act)
+
+
+# ---------------------------------------------- warp-per-(receiver, head) attention (k_dm_attn_warp) ---
+@pytest.mark.parametrize("shape", [(3, 33, 40), (1, 64, 64), (2, 32, 16)])
+def test_attention_warp_kernel_shapes(shape):
+    """Wide keys / values (beyond the block-staged kernel's 10 value columns) on fully connected graphs with more than
+    32 in-edges per node (several chunks, running max moves) next to tiny graphs: kq not a multiple of 4 (scalar key
+    loads), v_dim above 32 (second value column per lane), several heads.  Density pass vs the fp64 oracle under every
+    arithmetic; reversible backward vs autograd."""
+    from graph_normalizing_flows_b200 import utils as U
+    from oracle import gnf_oracle_torch as OT
+    heads, kq, vd = shape
+    rng = np.random.default_rng(heads * 100 + kq)
+    D, T, L, K = 8, 1, 64, 3
+    n_node = np.array([70, 3, 45, 1], np.int32)
+    senders, receivers = U.senders_receivers(n_node)
+    n = int(n_node.sum())
+    nodes = rng.standard_normal((n, D)).astype(np.float32)
+    g = O.GraphsTuple(nodes, None, np.asarray(receivers, np.int32), np.asarray(senders, np.int32), None, n_node,
+                      (n_node.astype(np.int64) ** 2).astype(np.int32))
+    attn = dict(num_heads=heads, kq_dim=kq, v_dim=vd, out_dim=24, concat=True, residual=False, kq_dim_division=True)
+    params = O.make_params(5, T, D, L, K, block="dm_attn", act="leaky_relu", attn=attn, last_layer_scale=0.1)
+    z64, ldj64 = O.grevnet_f(nodes.astype(np.float64), g.senders, g.receivers, O.cast_params(params, np.float64))
+    want = O.log_prob(z64, ldj64, n_node)["log_prob_xs"]
+    dg = dev_graph(g)
+    for math in ("tc3x", "fp32"):
+        net = H.make_grevnet(params, L, K, device=DEV, math=math)
+        out = G.loss.log_prob(net, dg, return_z=True)
+        assert np.abs(out["z"].nodes.cpu().numpy() - z64).max() < 1e-4 * max(1.0, np.abs(z64).max()), math
+        assert H.rel_err(out["log_prob_xs"], want) < LOGPROB_RTOL, math
+    loss_ref, grad_ref = OT.loss_and_grads(nodes, g.senders, g.receivers, params, 1.0 / n)
+    scal, grads = net.loss_and_grad(dg, per_node=True)
+    got = grads.double().cpu().numpy()
+    assert abs(float(scal["loss_per_node"]) - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert np.abs(got - grad_ref).max() <= 2e-4 * np.abs(grad_ref).max()
