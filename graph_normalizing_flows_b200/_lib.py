@@ -71,6 +71,11 @@ SIGNATURES = {
     "gnf_bn_moments": (C.c_int, [_p, _i64, _i32, _p, _p, _sz, _p]),
     "gnf_affine_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "gnf_bn_finalize": (C.c_int, [_p, _i32, _p, _p, C.c_double, C.c_double, _p, _p, _p, _p, _p, C.c_float, _p]),
+    "gnf_grevnet_bn_workspace": (_sz, [_p]),
+    "gnf_grevnet_forward_bn": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, C.c_double, C.c_float, _p, _p, _p,
+                                         _i32, _p, _sz, _p, _sz, _p]),
+    "gnf_grevnet_inverse_bn": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, C.c_double, _p, _i32, _p, _sz, _p,
+                                         _sz, _p]),
     "gnf_bn_backward_coef": (C.c_int, [_p, _p, _i32, _p, _p, C.c_double, C.c_double, _p, _p, _p, _p, _p]),
     "gnf_bn_backward_sums": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "gnf_bn_backward_apply": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),

@@ -149,6 +149,48 @@ k_dw(const float* __restrict__ A, int lda, const float* __restrict__ D, int ldd,
   }
 }
 
+// dW for a NARROW left operand (A has MR <= 16 columns: the attention projections q / k / v when D/2 is small, where the
+// 128 x 128 register tiles of k_dw multiply mostly zeros on a third of the SMs).  Block (z, c): node range z, 128
+// columns of D, two row slots; a thread keeps MR sums for its column over every other row of the range (D read
+// coalesced, the A row broadcast), the two slots are added in fixed order.  part[z][m][col] as k_dw writes it.
+template <int MR>
+__global__ void __launch_bounds__(256)
+k_dw_skinny(const float* __restrict__ A, const float* __restrict__ D, int ldd, int64_t n_nodes, float* __restrict__ part) {
+  __shared__ float red[MR][128];
+  const int cl = threadIdx.x & 127, rs = threadIdx.x >> 7;
+  const int col = blockIdx.y * 128 + cl;
+  const int64_t per = (n_nodes + gridDim.x - 1) / gridDim.x;
+  const int64_t beg = (int64_t)blockIdx.x * per;
+  const int64_t end = beg + per < n_nodes ? beg + per : n_nodes;
+  float acc[MR];
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+  if (col < ldd) {
+#pragma unroll 4
+    for (int64_t r = beg + rs; r < end; r += 2) {
+      const float d = D[r * ldd + col];
+      const float4* ar = reinterpret_cast<const float4*>(A + r * MR);
+#pragma unroll
+      for (int m4 = 0; m4 < MR / 4; ++m4) {
+        const float4 a = __ldg(ar + m4);
+        acc[4 * m4] = fmaf(a.x, d, acc[4 * m4]);
+        acc[4 * m4 + 1] = fmaf(a.y, d, acc[4 * m4 + 1]);
+        acc[4 * m4 + 2] = fmaf(a.z, d, acc[4 * m4 + 2]);
+        acc[4 * m4 + 3] = fmaf(a.w, d, acc[4 * m4 + 3]);
+      }
+    }
+  }
+  if (rs == 1) {
+#pragma unroll
+    for (int m = 0; m < MR; ++m) red[m][cl] = acc[m];
+  }
+  __syncthreads();
+  if (rs == 0 && col < ldd) {
+#pragma unroll
+    for (int m = 0; m < MR; ++m) part[((int64_t)blockIdx.x * MR + m) * ldd + col] = acc[m] + red[m][cl];
+  }
+}
+
 // column sums of D over a node range: part[z][n].  Block (z, c): 32 columns, 8 warps stride the rows of range z
 // (one coalesced 128-byte read per warp and row); the 8 partial sums are combined in warp order (fixed order).
 __global__ void __launch_bounds__(256)
@@ -685,6 +727,7 @@ struct BwdWs {
   AttnBufs ab[2];
   float *hbuf2, *gproj, *gatt, *gkeys, *gqueries, *gvh, *gv, *gxq;
   float *preln[2], *lnt;       // GNF_ATTN_LAYER_NORM: pre-LayerNorm GNN outputs, gy * xhat
+  size_t part_floats;          // capacity of `part`
   size_t bytes;
 };
 
@@ -743,6 +786,7 @@ BwdWs carve_bwd(const Flow& f, int64_t n, void* base) {
     if (a2 > part_elems) part_elems = a2;
   }
   w.part = take((size_t)kSplit * part_elems * 4);
+  w.part_floats = (size_t)kSplit * part_elems;
   w.bytes = off;
   return w;
 }
@@ -785,7 +829,22 @@ int run_dw(const Flow& f, int l, const float* a_in, int lda, const float* delta,
 
 // part/grad of one bias-free projection: grad[in, out] += a_in^T delta
 int run_dw_generic(const float* a_in, int lda, int in_real, const float* delta, int ldd, int out_real, int64_t n,
-                   float* part, float* grad, cudaStream_t stream) {
+                   float* part, float* grad, cudaStream_t stream, size_t part_capacity = 0) {
+  if ((lda == 8 || lda == 16) && part_capacity >= (size_t)lda * ldd) {
+    // narrow left operand: many small node ranges (the part buffer holds part_capacity floats)
+    int64_t nz = (int64_t)(part_capacity / ((size_t)lda * ldd));
+    if (nz > 296) nz = 296;
+    if (nz > ceil_div(n, 32)) nz = ceil_div(n, 32);
+    if (nz < 1) nz = 1;
+    dim3 grid((unsigned)nz, (unsigned)ceil_div(ldd, 128));
+    if (lda == 8) k_dw_skinny<8><<<grid, 256, 0, stream>>>(a_in, delta, ldd, n, part);
+    else k_dw_skinny<16><<<grid, 256, 0, stream>>>(a_in, delta, ldd, n, part);
+    GNF_LAUNCH_CHECK();
+    k_reduce_split<<<(unsigned)ceil_div((int64_t)in_real * out_real, 256), 256, 0, stream>>>(part, (int)nz, lda, ldd,
+                                                                                            in_real, out_real, grad);
+    GNF_LAUNCH_CHECK();
+    return GNF_OK;
+  }
   if (ldd <= 16) {
     dim3 grid((unsigned)ceil_div(lda, BM), 1, kSplit);
     k_dw<16><<<grid, 256, 0, stream>>>(a_in, lda, delta, ldd, n, lda, ldd, part);
@@ -917,11 +976,11 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
   k_sum_heads<<<(unsigned)ceil_div(n * f.v_pad, 256), 256, 0, stream>>>(w.gvh, f.hv_pad, f.heads, f.vd, f.v_pad, n, w.gv);
   GNF_LAUNCH_CHECK();
   // keys = project_q, queries = project_k (gnn.py:531-532)
-  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gkeys, f.qk_pad, qk, n, w.part, gm, stream);                          // dWq
+  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gkeys, f.qk_pad, qk, n, w.part, gm, stream, w.part_floats);           // dWq
   if (rc) return rc;
-  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gqueries, f.qk_pad, qk, n, w.part, gm + (int64_t)f.H * qk, stream);   // dWk
+  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gqueries, f.qk_pad, qk, n, w.part, gm + (int64_t)f.H * qk, stream, w.part_floats);   // dWk
   if (rc) return rc;
-  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gv, f.v_pad, f.vd, n, w.part, gm + 2ll * f.H * qk, stream);           // dWv
+  rc = run_dw_generic(b.xq, f.hp8, f.H, w.gv, f.v_pad, f.vd, n, w.part, gm + 2ll * f.H * qk, stream, w.part_floats);           // dWv
   if (rc) return rc;
   rc = run_dx(w.gkeys, wt + f.wqT_off, nullptr, w.gxq, n, f.hp8, f.qk_pad, 0, 0, stream);
   if (rc) return rc;

@@ -635,6 +635,18 @@ __global__ void k_affine_rows(float* __restrict__ x, int64_t n, int h, int hp, c
   if (f < h) x[i] = __fadd_rn(__fmul_rn(x[i], scale[f]), shift[f]);
 }
 
+// bn.forward (sampling direction, gnn.py:356-358,369-371): de-normalise with the MOVING statistics.
+// scale = sqrt(moving_var + eps) / gamma, shift = moving_mean - beta * scale, each a separately rounded fp32 operation
+__global__ void k_bn_moving_scale_shift(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const float* __restrict__ mm, const float* __restrict__ mv, float eps, int h,
+                                        float* __restrict__ scale_shift) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= h) return;
+  const float sc = __fdiv_rn(__fsqrt_rn(__fadd_rn(mv[f], eps)), gamma[f]);
+  scale_shift[f] = sc;
+  scale_shift[h + f] = __fsub_rn(mm[f], __fmul_rn(beta[f], sc));
+}
+
 // backward of the batch-norm bijector, phase 1: per-feature sums of G_y and G_y * xhat, xhat = (y - beta) / gamma
 __global__ void k_bn_bwd_partial(const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ beta,
                                  const float* __restrict__ inv_gamma, int64_t total, int h, int hp,
@@ -1580,6 +1592,110 @@ extern "C" int gnf_affine_rows(float* x, int64_t n, int32_t hh, const float* sca
   GNF_REQUIRE(x && scale && shift, GNF_EINVAL, "gnf_affine_rows: null pointer");
   const int hp = gnf_padded_half(hh);
   k_affine_rows<<<(unsigned)ceil_div(n * hp, 256), 256, 0, stream>>>(x, n, hh, hp, scale, shift);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+// ---- a9, chained: the whole batch-norm flow in one call (single-rank batches; sharded runs all-reduce the moment sums
+// between gnf_bn_moments and gnf_bn_finalize and therefore stay on the per-half-step entries) -------------------------
+static size_t bn_chain_sums_off(int32_t h) { return align_up(gnf_bn_moments_workspace(h), 256); }
+static size_t bn_chain_ss_off(int32_t h) { return bn_chain_sums_off(h) + align_up((size_t)(2 * h + 1) * 8, 256); }
+extern "C" size_t gnf_grevnet_bn_workspace(const gnf_flow* h) {
+  if (!h) return 0;
+  return bn_chain_ss_off(h->f.H) + align_up((size_t)2 * h->f.H * 4, 256);
+}
+
+static int check_bn_chain(const gnf_flow* h, const float* gamma, const float* beta, const float* mm, const float* mv,
+                          void* bn_ws, size_t bn_ws_bytes, const char* who) {
+  GNF_REQUIRE(gamma && beta && mm && mv, GNF_EINVAL, "%s: null batch-norm parameter", who);
+  GNF_REQUIRE(gnf_padded_half(h->f.H) <= 256, GNF_EINVAL, "%s: batch norm needs D/2 <= 256", who);
+  GNF_REQUIRE(bn_ws && ((uintptr_t)bn_ws % 256) == 0 && bn_ws_bytes >= gnf_grevnet_bn_workspace(h), GNF_EWORKSPACE,
+              "%s: batch-norm workspace too small or misaligned", who);
+  return GNF_OK;
+}
+
+extern "C" int gnf_grevnet_forward_bn(const gnf_flow* h, const float* x, int64_t n, int64_t e, const int32_t* rowptr,
+                                      const int32_t* csr, const float* gamma, const float* beta, float* moving_mean,
+                                      float* moving_var, double eps, float momentum, float* z, double* ldj,
+                                      double* stats, int32_t math, void* ws, size_t ws_bytes, void* bn_ws,
+                                      size_t bn_ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_common(h, n, e, rowptr, csr, ws, ws_bytes, math, "gnf_grevnet_forward_bn");
+  if (rc) return rc;
+  GNF_REQUIRE(ldj && stats, GNF_EINVAL, "gnf_grevnet_forward_bn: null ldj/stats");
+  rc = check_bn_chain(h, gamma, beta, moving_mean, moving_var, bn_ws, bn_ws_bytes, "gnf_grevnet_forward_bn");
+  if (rc) return rc;
+  GNF_CUDA(cudaMemsetAsync(ldj, 0, 8, stream));
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_forward_bn: null x/z");
+  const Flow& f = h->f;
+  const int H = f.H, T = f.d.num_timesteps, D = f.d.node_embedding_dim;
+  Workspace w = carve(f, n, math, ws);
+  double* sums = (double*)((uint8_t*)bn_ws + bn_chain_sums_off(H));
+  float* ss = (float*)((uint8_t*)bn_ws + bn_chain_ss_off(H));
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 256, stream));
+  if (w.hbuf) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(x, n, D, H, f.HP, w.x0, w.x1);
+  GNF_LAUNCH_CHECK();
+  for (int i = 0; i < T; ++i)                                    // gnn.py:309-338
+    for (int half = 0; half < 2; ++half) {
+      float* xa = half ? w.x1 : w.x0;
+      float* xb = half ? w.x0 : w.x1;
+      const int64_t po = ((int64_t)half * T + i) * H;
+      // bn.inverse + its log-det on the conditioning half (gnn.py:310-313,325-328), batch statistics
+      rc = gnf_bn_moments(xa, n, H, sums, bn_ws, bn_chain_sums_off(H), stream_);
+      if (rc) return rc;
+      rc = gnf_bn_finalize(sums, H, gamma + po, beta + po, eps, (double)n, ldj, ss,
+                           stats + ((int64_t)half * T + i) * (2 * H + 1), moving_mean + po, moving_var + po, momentum,
+                           stream_);
+      if (rc) return rc;
+      rc = gnf_affine_rows(xa, n, H, ss, ss + H, stream_);
+      if (rc) return rc;
+      GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
+      rc = coupling_half(f, half, i, 0, xa, xb, n, rowptr, csr, ldj, math, w, stream);
+      if (rc) return rc;
+    }
+  k_merge<<<(unsigned)ceil_div(n * D, 256), 256, 0, stream>>>(w.x0, w.x1, n, D, H, f.HP, z);
+  GNF_LAUNCH_CHECK();
+  return GNF_OK;
+}
+
+extern "C" int gnf_grevnet_inverse_bn(const gnf_flow* h, const float* z, int64_t n, int64_t e, const int32_t* rowptr,
+                                      const int32_t* csr, const float* gamma, const float* beta,
+                                      const float* moving_mean, const float* moving_var, double eps, float* x,
+                                      int32_t math, void* ws, size_t ws_bytes, void* bn_ws, size_t bn_ws_bytes,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_common(h, n, e, rowptr, csr, ws, ws_bytes, math, "gnf_grevnet_inverse_bn");
+  if (rc) return rc;
+  rc = check_bn_chain(h, gamma, beta, moving_mean, moving_var, bn_ws, bn_ws_bytes, "gnf_grevnet_inverse_bn");
+  if (rc) return rc;
+  if (n == 0) return GNF_OK;
+  GNF_REQUIRE(x && z, GNF_EINVAL, "gnf_grevnet_inverse_bn: null x/z");
+  const Flow& f = h->f;
+  const int H = f.H, T = f.d.num_timesteps, D = f.d.node_embedding_dim;
+  Workspace w = carve(f, n, math, ws);
+  float* ss = (float*)((uint8_t*)bn_ws + bn_chain_ss_off(H));
+  GNF_CUDA(cudaMemsetAsync(w.counter, 0, 256, stream));
+  if (w.hbuf) GNF_CUDA(cudaMemsetAsync(w.hbuf, 0, (size_t)n * f.in_pad * 4, stream));
+  k_split<<<(unsigned)ceil_div(n * f.HP, 256), 256, 0, stream>>>(z, n, D, H, f.HP, w.x0, w.x1);
+  GNF_LAUNCH_CHECK();
+  for (int i = T - 1; i >= 0; --i)                               // gnn.py:347-372
+    for (int half = 1; half >= 0; --half) {
+      float* xa = half ? w.x1 : w.x0;
+      float* xb = half ? w.x0 : w.x1;
+      const int64_t po = ((int64_t)half * T + i) * H;
+      GNF_CUDA(cudaMemsetAsync(w.counter, 0, 4, stream));
+      rc = coupling_half(f, half, i, 1, xa, xb, n, rowptr, csr, nullptr, math, w, stream);
+      if (rc) return rc;
+      // bn.forward on the conditioning half: de-normalise with the moving statistics (gnn.py:356-358,369-371)
+      k_bn_moving_scale_shift<<<(unsigned)ceil_div(H, 128), 128, 0, stream>>>(gamma + po, beta + po, moving_mean + po,
+                                                                              moving_var + po, (float)eps, H, ss);
+      GNF_LAUNCH_CHECK();
+      rc = gnf_affine_rows(xa, n, H, ss, ss + H, stream_);
+      if (rc) return rc;
+    }
+  k_merge<<<(unsigned)ceil_div(n * D, 256), 256, 0, stream>>>(w.x0, w.x1, n, D, H, f.HP, x);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
 }

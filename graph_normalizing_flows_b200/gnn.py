@@ -513,6 +513,7 @@ class GRevNet(nn.Module):
         self._bn_saved = {}                   # (half, step) -> (mean, var, N) of the last density pass
         self.bn_group = None                  # process group for cross-rank batch statistics (sharding.py)
         self.bn_sync = True                   # all-reduce the batch statistics when running sharded
+        self.bn_chain = True                  # single-rank batches: whole batch-norm flow in one library call
 
     # -- parameter plumbing -------------------------------------------------------------------
     def _rebind(self):
@@ -671,6 +672,36 @@ class GRevNet(nn.Module):
         wsb = lib.gnf_grevnet_workspace(handle, n, m)
         ws = _lib.workspace(wsb, dev)
         stream = _lib.stream_ptr(dev)
+        dist = torch.distributed
+        sharded = self.bn_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.bn_group) > 1
+        if self.bn_chain and not sharded:
+            # single-rank batch: the whole chain in one library call (no per-half-step host work)
+            H, T = D // 2, self.num_timesteps
+            bwsb = lib.gnf_grevnet_bn_workspace(handle)
+            bws = _lib.workspace(bwsb, dev)
+            out = torch.empty_like(nodes)
+            gamma, beta = self.bn_gamma.detach(), self.bn_beta.detach()
+            for t in (gamma, beta, self.bn_moving_mean, self.bn_moving_var):
+                _lib.require_cuda(t, "batch-norm parameter", torch.float32)
+            if not inverse_kernel:
+                ldj = torch.empty(1, dtype=torch.float64, device=dev)
+                stats = torch.empty(2, T, 2 * H + 1, dtype=torch.float64, device=dev)
+                _lib.check(lib.gnf_grevnet_forward_bn(
+                    handle, _lib.ptr(nodes), n, st.n_edges, _lib.ptr(st.rowptr), _lib.ptr(st.csr_senders), _lib.ptr(gamma),
+                    _lib.ptr(beta), _lib.ptr(self.bn_moving_mean), _lib.ptr(self.bn_moving_var), float(self.bn_epsilon),
+                    float(self.bn_momentum) if self.bn_update_moving else -1.0, _lib.ptr(out), _lib.ptr(ldj),
+                    _lib.ptr(stats), m, _lib.ptr(ws), wsb, _lib.ptr(bws), bwsb, stream), "gnf_grevnet_forward_bn")
+                for half in range(2):
+                    for i in range(T):
+                        self._bn_saved[(half, i)] = stats[half, i]
+                self._arm_range_guard(handle, math_name, dev)
+                return out, ldj
+            _lib.check(lib.gnf_grevnet_inverse_bn(
+                handle, _lib.ptr(nodes), n, st.n_edges, _lib.ptr(st.rowptr), _lib.ptr(st.csr_senders), _lib.ptr(gamma),
+                _lib.ptr(beta), _lib.ptr(self.bn_moving_mean), _lib.ptr(self.bn_moving_var), float(self.bn_epsilon),
+                _lib.ptr(out), m, _lib.ptr(ws), wsb, _lib.ptr(bws), bwsb, stream), "gnf_grevnet_inverse_bn")
+            self._arm_range_guard(handle, math_name, dev)
+            return out, None
         x0 = torch.empty(max(n, 1), hp, dtype=torch.float32, device=dev)
         x1 = torch.empty(max(n, 1), hp, dtype=torch.float32, device=dev)
         _lib.check(lib.gnf_split_halves(_lib.ptr(nodes), n, D, _lib.ptr(x0), _lib.ptr(x1), stream), "gnf_split_halves")

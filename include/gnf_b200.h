@@ -231,6 +231,26 @@ int gnf_bn_finalize(const double* sums, int32_t h, const float* gamma, const flo
                     double n_local, double* ldj_accum, float* scale_shift, double* stats,
                     float* moving_mean, float* moving_var, float momentum, void* stream);
 int gnf_affine_rows(float* x, int64_t n_nodes, int32_t h, const float* scale, const float* shift, void* stream);
+/* The whole batch-norm flow in ONE call (single-rank batches: GRevNet(use_batch_norm=True), the default of both scripts,
+ * run_grevnet.py:83 / train_grevnet_with_data.py:109): the chain the host mirror would otherwise drive half step by half
+ * step -- density direction gnn.py:309-338 (per half step: gnf_bn_moments, gnf_bn_finalize, gnf_affine_rows on the
+ * conditioning half, then gnf_coupling_half), sampling direction gnn.py:347-372 (gnf_coupling_half inverse, then the
+ * de-normalisation with the moving statistics).  gamma, beta, moving_mean, moving_var: device float [2, T, H] (half,
+ * step, feature); stats: device double [2, T, 2H+1] = {mean, var, N} of every half step (kept for the backward);
+ * momentum < 0 leaves the moving statistics alone.  bn_workspace >= gnf_grevnet_bn_workspace(flow) bytes, workspace as
+ * gnf_grevnet_forward.  Sharded runs all-reduce the moment sums between gnf_bn_moments and gnf_bn_finalize and keep
+ * using the per-half-step entries. */
+size_t gnf_grevnet_bn_workspace(const gnf_flow* flow);
+int gnf_grevnet_forward_bn(const gnf_flow* flow, const float* x, int64_t n_nodes, int64_t n_edges,
+                           const int32_t* rowptr, const int32_t* csr_senders, const float* gamma, const float* beta,
+                           float* moving_mean, float* moving_var, double eps, float momentum, float* z, double* ldj,
+                           double* stats, int32_t math, void* workspace, size_t workspace_bytes, void* bn_workspace,
+                           size_t bn_workspace_bytes, void* stream);
+int gnf_grevnet_inverse_bn(const gnf_flow* flow, const float* z, int64_t n_nodes, int64_t n_edges,
+                           const int32_t* rowptr, const int32_t* csr_senders, const float* gamma, const float* beta,
+                           const float* moving_mean, const float* moving_var, double eps, float* x, int32_t math,
+                           void* workspace, size_t workspace_bytes, void* bn_workspace, size_t bn_workspace_bytes,
+                           void* stream);
 /* Backward of the bijector in training mode (batch statistics depend on x), for loss = -loss_scale * log_prob_xs:
  *   gnf_bn_backward_sums : sums[0:H] = sum_n G_y[n,f], sums[H:2H] = sum_n G_y[n,f] * xhat[n,f],
  *                          xhat = (y - beta) * inv_gamma   (device double[2H]; all-reduce across ranks before use;

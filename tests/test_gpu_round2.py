@@ -434,3 +434,33 @@ def test_attention_warp_kernel_shapes(shape):
     got = grads.double().cpu().numpy()
     assert abs(float(scal["loss_per_node"]) - loss_ref) <= 1e-5 * abs(loss_ref)
     assert np.abs(got - grad_ref).max() <= 2e-4 * np.abs(grad_ref).max()
+
+
+# ------------------------------------------- batch-norm flow: one library call vs the per-half-step chain ---
+@pytest.mark.parametrize("math", ["tc3x", "fp32"])
+def test_batch_norm_chained_entry_equals_per_half_step_calls(math):
+    """gnf_grevnet_forward_bn / gnf_grevnet_inverse_bn run the same kernels in the same order as the host mirror's
+    half-step-by-half-step loop (the path sharded runs keep): z, log-det, saved batch statistics, moving statistics and
+    the sampling direction agree bit for bit; the training step works from the statistics the chained call saved."""
+    rng = np.random.default_rng(3)
+    g = H.random_batch(rng, 20, 4, 25, D=14)
+    g = g._replace(nodes=(g.nodes * 1.3 - 0.2).astype(np.float32))
+    params = O.make_params(8, 2, 14, 128, 3, last_layer_scale=0.05)
+    dg = dev_graph(g)
+    res = {}
+    for chain in (True, False):
+        net = H.make_grevnet(params, 128, 3, device=DEV, math=math)
+        net.use_batch_norm = True
+        net.bn_chain = chain
+        with torch.no_grad():
+            net.bn_gamma.copy_(1.0 + 0.1 * torch.arange(net.bn_gamma.numel(), device=DEV).reshape(net.bn_gamma.shape) / 20)
+            net.bn_beta.copy_(0.05 * torch.ones_like(net.bn_beta))
+        out = G.loss.log_prob(net, dg, return_z=True)
+        out2 = G.loss.log_prob(net, dg, return_z=True)            # second pass: moving statistics moved once already
+        x_back = net(out2["z"], inverse=False).nodes
+        saved = torch.stack([net._bn_saved[(h, i)].clone() for h in range(2) for i in range(2)])
+        scal, grads = net.loss_and_grad(dg, per_node=True)
+        res[chain] = (out["z"].nodes, out["log_det_jacobian"], out2["z"].nodes, x_back, saved,
+                      net.bn_moving_mean.clone(), net.bn_moving_var.clone(), grads, net.bn_gamma.grad.clone())
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)

@@ -24,3 +24,12 @@ for B in (64, 256, 1024):
     graphed = timeit(lambda: runner())
     print(json.dumps({"family": "protein_4_128", "graphs": B, "nodes": n, "eager_us": eager * 1e6, "cuda_graph_us": graphed * 1e6,
                       "node_updates_per_s_graphed": n * 12 / graphed}))
+    # use_batch_norm=True (the scripts' default): the whole chain in one library call vs the host mirror driving it half
+    # step by half step (what sharded runs do)
+    bn = H.make_grevnet(params, 256, 5, device="cuda", math="tc3x")
+    bn.use_batch_norm = True
+    row = {"family": "protein_4_128", "graphs": B, "nodes": n, "what": "use_batch_norm density pass"}
+    for chain in (True, False):
+        bn.bn_chain = chain
+        row["chained_us" if chain else "per_half_step_us"] = timeit(lambda: G.loss.log_prob(bn, g)) * 1e6
+    print(json.dumps(row))
