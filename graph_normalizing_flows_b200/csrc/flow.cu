@@ -1010,7 +1010,9 @@ int fwd_attn_input(const Flow& f, int mlp, const float* xa, int64_t n, const int
   // the output projection reads hv_pad columns per row (zero weight rows under the pad): the pad columns, which no
   // attention kernel writes, must hold zeros, not whatever the workspace held before (0 * NaN = NaN)
   if (f.hv_pad != f.heads * f.vd) GNF_CUDA(cudaMemsetAsync(w.att, 0, (size_t)n * f.hv_pad * 4, stream));
-  const bool vec = f.heads == 8 && f.kq == 10;            // the specialised instantiation (run_grevnet.py defaults)
+  // the specialised instantiation (run_grevnet.py defaults); GNF_ATTN_SPECIAL=0 keeps the generic one (A/B knob)
+  const char* spec = getenv("GNF_ATTN_SPECIAL");
+  const bool vec = f.heads == 8 && f.kq == 10 && !(spec && spec[0] == '0');
   const size_t attn_smem = attn_block_bytes(f.heads, f.kq, f.vd, vec);
   const bool staged = w.fallback && f.vd <= 10 && attn_smem <= 200 * 1024;
   const int32_t* only = nullptr;

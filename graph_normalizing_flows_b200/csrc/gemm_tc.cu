@@ -14,12 +14,20 @@
 //   warp 0   weight producer: one cp.async.bulk per k16 slab of the column block (the image -- pack.cu, kPackTc geometry
 //            nhc = block width, kcc = 16 -- IS the K-major no-swizzle UMMA layout), 6-stage ring, mbarrier expect_tx
 //   warp 1   MMA issuer: per slab 2 row tiles x 3 products of M128 x N<=256 x K16; tcgen05.commit frees the slab / A stage
-//   warps 2-9 converters, then epilogue: read the fp32 A rows (a lane owns 8 consecutive k of a row: full 32-byte sectors,
-//            the stage after next already in flight), split them and write the K-major A tile of a 32-k stage (3 stages);
-//            after the last slab they drain both accumulators (tcgen05.ld, + bias, activation) into fp32 rows of C.
+//   warps 2-9 converters, then epilogue: take the fp32 A rows of a 32-k stage, split them and write the K-major A tile
+//            (a lane owns 8 consecutive k of a row); after the last slab they drain both accumulators (tcgen05.ld,
+//            + bias, activation) into fp32 rows of C.
+// How the fp32 A rows reach the converters (template flag TMA):
+//   TMA = true (default): the producer warp issues ONE cp.async.bulk.tensor.2d per stage through a tensor map of A
+//            (box = 32 floats x 256 rows, SWIZZLE_128B, zero fill past M / past the readable row width) into a raw
+//            shared-memory ring; the converters read it back with conflict-free 16-byte loads (chunk index XOR row).
+//            Measured: the per-lane global loads of the other path kept the L1 request path 58 % busy and were the
+//            kernel's limiter (profiles/r2_ncu_full_k_gemm_tc.csv, GNF_GEMM_VARIANT experiments).
+//   TMA = false (GNF_GEMM_TMA=0): per-lane LDG.128, three stages of loads in flight in registers.
 // The A tile of a row block is converted once per column block (re-read from L2, not from HBM); sharing each weight slab
 // between two row tiles halves the weight stream per FLOP (the fused kernel's figure is ~43 B/cycle/SM).
 #include <stdlib.h>
+#include <cuda.h>              // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no -lcuda)
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,12 +40,17 @@ constexpr int kGemmThreads = 320;
 constexpr int kGemmConv = 256;           // converter / epilogue threads (warps 2..9)
 constexpr int kGemmRows = 256;           // rows per work item (two UMMA tiles)
 constexpr int kGemmNB = 256;             // widest column block
-constexpr int kGemmWS = 6;               // weight ring stages (one k16 slab each)
-constexpr int kGemmWStage = kGemmNB * 64;   // hi + lo, 16 k x 256 columns x 2 B
-constexpr int kGemmAS = 3;               // A stages of 32 k
-constexpr int kGemmAK = 32;
-constexpr int kGemmAStage = kGemmRows * kGemmAK * 2 * 2;   // hi + lo: 32 KB
-constexpr size_t kGemmSmem = 1024 + (size_t)kGemmWS * kGemmWStage + (size_t)kGemmAS * kGemmAStage + 256;
+constexpr int kGemmWStage = kGemmNB * 64;   // one k16 slab: hi + lo, 16 k x 256 columns x 2 B
+constexpr int kGemmAK = 32;              // k per A stage
+constexpr int kGemmAStage = kGemmRows * kGemmAK * 2 * 2;   // converted stage, hi + lo: 32 KB
+constexpr int kGemmRawStage = kGemmRows * kGemmAK * 4;     // raw fp32 stage (TMA path): 32 KB
+constexpr int kGemmMaxRing = 6;
+// ring depths: weight slabs, converted A stages, raw A stages
+template <bool TMA>
+struct GemmCfg {
+  static constexpr int WS = TMA ? 5 : 6, AS = TMA ? 2 : 3, RS = TMA ? 2 : 0;
+  static constexpr size_t kSmem = 1024 + (size_t)WS * kGemmWStage + (size_t)AS * kGemmAStage + (size_t)RS * kGemmRawStage + 256;
+};
 
 struct GemmParams {
   const float* A;
@@ -49,6 +62,7 @@ struct GemmParams {
   int ldc, nvalid;          // row stride of C; floats of a row that may be written (multiple of 4)
   int Kp;                   // K padded to 16
   int nb, n_blocks;         // column block width (multiple of 16, <= 256) and count
+  int rows;                 // rows per work item: 256 (two row tiles per weight slab), or 128 when that leaves SMs idle
   int act;                  // GNF_ACT_* or 2 = none
   int n_items;              // row blocks x column blocks
   int variant;              // GNF_GEMM_VARIANT (timing experiments only; results are wrong for bits 1, 2)
@@ -56,10 +70,19 @@ struct GemmParams {
 };
 
 struct GemmBars {
-  uint64_t w_full[kGemmWS], w_empty[kGemmWS];
-  uint64_t a_full[kGemmAS], a_empty[kGemmAS];
+  uint64_t w_full[kGemmMaxRing], w_empty[kGemmMaxRing];
+  uint64_t a_full[kGemmMaxRing], a_empty[kGemmMaxRing];
+  uint64_t raw_full[kGemmMaxRing], raw_empty[kGemmMaxRing];
   uint64_t acc_full, acc_empty;
 };
+
+// one box of the tensor map into shared memory, completion on an mbarrier (coordinates: innermost first)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
 
 __device__ __forceinline__ float gemm_act(float v, int act) {
   if (act == GNF_ACT_LEAKY_RELU) return fmaxf(v, 0.2f * v);
@@ -75,11 +98,13 @@ __device__ __forceinline__ int stage_offset(const GemmParams& p, int rb, int cb,
   return (int)(((unsigned)rb * 7u + (unsigned)cb * 3u) % (unsigned)n_astages);
 }
 
-template <int NPROD, bool BF16>
-__global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p) {
+template <int NPROD, bool BF16, bool TMA>
+__global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int kGemmWS = GemmCfg<TMA>::WS, kGemmAS = GemmCfg<TMA>::AS, kGemmRS = GemmCfg<TMA>::RS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* wring = smem;
+  uint8_t* rawring = smem;                                  // (TMA path; 1024-byte aligned stages: SWIZZLE_128B atoms)
+  uint8_t* wring = rawring + kGemmRS * kGemmRawStage;
   uint8_t* aring = wring + kGemmWS * kGemmWStage;
   GemmBars* bars = (GemmBars*)(aring + kGemmAS * kGemmAStage);
   uint32_t* tmem_slot = (uint32_t*)(bars + 1);
@@ -98,6 +123,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
       mbar_init(smem_u32(&bars->a_full[i]), kGemmConv / 32);
       mbar_init(smem_u32(&bars->a_empty[i]), 1);
     }
+    for (int i = 0; i < kGemmRS; ++i) {
+      mbar_init(smem_u32(&bars->raw_full[i]), 1);
+      mbar_init(smem_u32(&bars->raw_empty[i]), kGemmConv / 32);
+    }
     mbar_init(smem_u32(&bars->acc_full), 1);
     mbar_init(smem_u32(&bars->acc_empty), kGemmConv / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -115,8 +144,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
   if (warp == 0) {
     // ===== weight producer ===================================================================================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, rstage = 0;
+      uint32_t phase = 0, rphase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int rb = item / p.n_blocks, cb = item - rb * p.n_blocks;
         const uint8_t* src = p.wimg + (size_t)cb * n_slabs * slab_bytes;
@@ -124,6 +153,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
         for (int as = 0; as < n_astages; ++as) {
           const int asr = as + off < n_astages ? as + off : as + off - n_astages;
           const int ksteps = (Kp - asr * kGemmAK) >= kGemmAK ? 2 : 1;
+          if constexpr (TMA) {      // the stage's fp32 rows: one box (32 floats x p.rows rows), zero filled out of bounds
+            mbar_wait(smem_u32(&bars->raw_empty[rstage]), rphase ^ 1);
+            const uint32_t fb = smem_u32(&bars->raw_full[rstage]);
+            mbar_expect_tx(fb, (uint32_t)p.rows * (kGemmAK * 4));
+            tma_load_2d(smem_u32(rawring + rstage * kGemmRawStage), &tmap, asr * kGemmAK, rb * p.rows, fb);
+            if (++rstage == kGemmRS) { rstage = 0; rphase ^= 1; }
+          }
           for (int ks = 0; ks < ksteps; ++ks) {
             const int s = asr * 2 + ks;
             mbar_wait(smem_u32(&bars->w_empty[stage]), phase ^ 1);
@@ -143,7 +179,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int rb = item / p.n_blocks, cb = item - rb * p.n_blocks;
       const int off = stage_offset(p, rb, cb, n_astages);
-      const int n_rt = ((int64_t)rb * kGemmRows + kTileM < p.M) ? 2 : 1;     // second row tile entirely past M: skipped
+      const int n_rt = (p.rows > kTileM && (int64_t)rb * p.rows + kTileM < p.M) ? 2 : 1;   // second row tile past M: skipped
       mbar_wait(smem_u32(&bars->acc_empty), (it & 1u) ^ 1u);                 // previous item's accumulators drained
       tc_fence_after();
       for (int as = 0; as < n_astages; ++as) {
@@ -193,9 +229,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
     const int q = warp & 3, chalf = cw >> 2;             // epilogue: TMEM lane quarter (warp id mod 4), column chunk parity
     float amax = 0.f;
     uint32_t astage = 0, aphase = 0, it = 0;
+    [[maybe_unused]] uint32_t rstage = 0, rphase = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int rb = item / p.n_blocks, cb = item - rb * p.n_blocks;
-      const int64_t row0 = (int64_t)rb * kGemmRows;
+      const int64_t row0 = (int64_t)rb * p.rows;
       const int off = stage_offset(p, rb, cb, n_astages);
       auto real_stage = [&](int as) { return as + off < n_astages ? as + off : as + off - n_astages; };
       // a converter thread serves rows (j * 8 + cw) * 8 + r8, j = 0..3, k group g of every stage
@@ -209,7 +246,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int64_t r = row0 + (j * 8 + cw) * 8 + r8;
+          const int rl = (j * 8 + cw) * 8 + r8;
+          const int64_t r = rl < p.rows ? row0 + rl : p.M;          // 128-row items: the upper half of the tile is zeros
           const float* ar = p.A + r * p.lda + k;
           v[2 * j] = (r < p.M && k + 4 <= p.kvalid) ? __ldg(reinterpret_cast<const float4*>(ar)) : make_float4(0.f, 0.f, 0.f, 0.f);
           v[2 * j + 1] = (r < p.M && k + 8 <= p.kvalid) ? __ldg(reinterpret_cast<const float4*>(ar + 4))
@@ -241,7 +279,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
         if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[astage]));
         if (++astage == kGemmAS) { astage = 0; aphase ^= 1; }
       };
-      if (p.variant & 2) {            // experiment: no loads, no conversion -- the converters only keep the ring going
+      if constexpr (TMA) {
+        // raw stage [row][128 B] with the 16-byte chunks of a row XOR-swizzled by (row & 7): the 8 lanes of a quarter
+        // warp (8 rows, same k group) read 8 different chunk positions -- no bank conflicts
+        for (int as = 0; as < n_astages; ++as) {
+          float4 v[8];
+          mbar_wait(smem_u32(&bars->raw_full[rstage]), rphase);
+          const uint8_t* raw = rawring + rstage * kGemmRawStage;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rl = (j * 8 + cw) * 8 + r8;
+            if (rl < p.rows) {
+              const uint8_t* rr = raw + rl * 128;
+              v[2 * j] = *reinterpret_cast<const float4*>(rr + (((2 * g) ^ r8) << 4));
+              v[2 * j + 1] = *reinterpret_cast<const float4*>(rr + (((2 * g + 1) ^ r8) << 4));
+            } else {
+              v[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              v[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->raw_empty[rstage]));     // values are in registers: refill the slot
+          if (++rstage == kGemmRS) { rstage = 0; rphase ^= 1; }
+          convert_stage(as, v);
+        }
+      } else if (p.variant & 2) {     // experiment: no loads, no conversion -- the converters only keep the ring going
         for (int as = 0; as < n_astages; ++as) {
           mbar_wait(smem_u32(&bars->a_empty[astage]), aphase ^ 1);
           if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[astage]));
@@ -266,7 +328,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
       // ---- epilogue: both accumulators, 16-column chunks of parity chalf --------------------------------------
       mbar_wait(smem_u32(&bars->acc_full), it & 1u);
       tc_fence_after();
-      const int n_rt = (row0 + kTileM < p.M) ? 2 : 1;
+      const int n_rt = (p.rows > kTileM && row0 + kTileM < p.M) ? 2 : 1;
       const int col_base = cb * nb;
       for (int rt = 0; rt < n_rt; ++rt) {
         const int64_t orow = row0 + rt * kTileM + q * 32 + lane;
@@ -306,16 +368,55 @@ __global__ void __launch_bounds__(kGemmThreads, 1) k_gemm_tc(const GemmParams p)
   }
 }
 
-template <int NPROD, bool BF16>
-int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  auto kern = k_gemm_tc<NPROD, BF16>;
+// tensor map of A [M, lda] fp32: dim 0 = the kvalid readable floats of a row, dim 1 = rows; box = 32 floats x `rows`
+// rows; SWIZZLE_128B (a box row is exactly one 128-byte swizzle span); elements out of bounds read as zero
+int encode_a_map(CUtensorMap* map, const float* A, int64_t M, int lda, int kvalid, int rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GNF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    GNF_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, GNF_ECUDA, "tc_gemm: cuTensorMapEncodeTiled not available");
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)kvalid, (cuuint64_t)M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)lda * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kGemmAK, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)A, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GNF_REQUIRE(r == CUDA_SUCCESS, GNF_ECUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d) for M=%lld lda=%d kvalid=%d", (int)r,
+              (long long)M, lda, kvalid);
+  return GNF_OK;
+}
+
+template <int NPROD, bool BF16, bool TMA>
+int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
+  auto kern = k_gemm_tc<NPROD, BF16, TMA>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured))
-    GNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    GNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<TMA>::kSmem));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (TMA) {
+    int rc = encode_a_map(&map, p.A, p.M, p.lda, p.kvalid, p.rows);
+    if (rc) return rc;
+  }
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
-  kern<<<grid, kGemmThreads, kGemmSmem, stream>>>(p);
+  kern<<<grid, kGemmThreads, GemmCfg<TMA>::kSmem, stream>>>(p, map);
   GNF_LAUNCH_CHECK();
   return GNF_OK;
+}
+
+template <int NPROD, bool BF16>
+int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  const char* t = getenv("GNF_GEMM_TMA");
+  if (t && t[0] == '0') return launch_gemm_t<NPROD, BF16, false>(p, stream);
+  return launch_gemm_t<NPROD, BF16, true>(p, stream);
 }
 
 }  // namespace
@@ -358,7 +459,9 @@ int tc_gemm(const Flow& f, int math, const float* A, int lda, int kvalid, const 
   p.nb = nb;
   p.n_blocks = npad / nb;
   p.act = act;
-  p.n_items = (int)ceil_div(M, kGemmRows) * p.n_blocks;
+  // two row tiles share every weight slab (half the weight stream per FLOP) unless that leaves SMs without an item
+  p.rows = (ceil_div(M, kGemmRows) * p.n_blocks < num_sms()) ? kTileM : kGemmRows;
+  p.n_items = (int)ceil_div(M, p.rows) * p.n_blocks;
   p.range_flag = f.range_flag;
   const char* var = getenv("GNF_GEMM_VARIANT");
   p.variant = var ? atoi(var) : 0;

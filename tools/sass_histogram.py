@@ -1,12 +1,13 @@
 """cuobjdump -sass of the in-tree libgnf_b200.so -> per-kernel instruction histogram (profiles/<tag>_sass_histogram.csv).
 Runs without a GPU.  The columns that prove the tcgen05 / TMEM / bulk-copy path: UTCHMMA (tcgen05.mma), UTCBAR
-(tcgen05.commit), LDTM / STTM (tcgen05.ld / .st), UBLKCP (cp.async.bulk), SYNCS (mbarrier)."""
+(tcgen05.commit), LDTM / STTM (tcgen05.ld / .st), UBLKCP (cp.async.bulk), UTMALDG (cp.async.bulk.tensor through a
+tensor map), SYNCS (mbarrier)."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 so = os.path.join(ROOT, "graph_normalizing_flows_b200", "libgnf_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-COLS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "LDL", "STL", "FFMA", "FADD",
+COLS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "LDG", "STG", "LDS", "STS", "LDL", "STL", "FFMA", "FADD",
         "DADD", "MUFU", "ATOMG", "RED", "SHFL", "BAR", "ELECT"]
 rows, cur, hist = [], None, None
 for line in txt.splitlines():
@@ -33,4 +34,4 @@ with open(out, "w") as f:
 tot = collections.Counter()
 for _, h in rows:
     tot.update(h)
-print(out, "kernels:", len(rows), {c: tot[c] for c in COLS[:6]})
+print(out, "kernels:", len(rows), {c: tot[c] for c in COLS[:7]})
