@@ -231,6 +231,21 @@ __global__ void k_reduce_split(const float* __restrict__ part, int splits, int M
   grad[i] += s;
 }
 
+// the same fold for MANY node ranges and few outputs (k_dw_skinny: up to 296 ranges, as few as 80 outputs): a warp per
+// output element, lanes stride the ranges, fixed shuffle tree -- same bits on every run
+__global__ void __launch_bounds__(256)
+k_reduce_split_warp(const float* __restrict__ part, int splits, int Mpad, int Npad, int M, int N, float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= M * N) return;
+  const int m = w / N, n = w - m * N;
+  float s = 0.f;
+  for (int z = lane; z < splits; z += 32) s += part[((int64_t)z * Mpad + m) * Npad + n];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) grad[w] += s;
+}
+
 // ---- element-wise backward of the affine update ---------------------------------------------
 // xb: in = xb' (post-update), out = xb (pre-update).  gxb: in = dL/dxb', out = dL/dxb.
 __global__ void k_coupling_bwd(float* __restrict__ xb, float* __restrict__ gxb, const float* __restrict__ s,
@@ -840,8 +855,8 @@ int run_dw_generic(const float* a_in, int lda, int in_real, const float* delta, 
     if (lda == 8) k_dw_skinny<8><<<grid, 256, 0, stream>>>(a_in, delta, ldd, n, part);
     else k_dw_skinny<16><<<grid, 256, 0, stream>>>(a_in, delta, ldd, n, part);
     GNF_LAUNCH_CHECK();
-    k_reduce_split<<<(unsigned)ceil_div((int64_t)in_real * out_real, 256), 256, 0, stream>>>(part, (int)nz, lda, ldd,
-                                                                                            in_real, out_real, grad);
+    k_reduce_split_warp<<<(unsigned)ceil_div((int64_t)in_real * out_real, 8), 256, 0, stream>>>(part, (int)nz, lda, ldd,
+                                                                                               in_real, out_real, grad);
     GNF_LAUNCH_CHECK();
     return GNF_OK;
   }
