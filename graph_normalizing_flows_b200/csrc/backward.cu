@@ -416,6 +416,136 @@ k_attn_bwd_send(const float* __restrict__ keys, const float* __restrict__ querie
     if (c < vd) gvh[s * hv_pad + h * vd + c] = accv[c];
 }
 
+// Warp per (node, head) forms of the two passes for wide keys / values (the embedding flow: 1 head, kq = v = 64, fully
+// connected graphs of 100..400 nodes -- a thread per (node, head) is N threads in all, each walking hundreds of edges x
+// 256 scalar loads, and took two thirds of that flow's training step).  32 edges at a time: lane = edge for the per-edge
+// terms (l, w, g_w, g_l: the own row broadcast out of shared memory, the other end's row as 16-byte loads), then lane =
+// output column for the sums over the edges, g_l / w and the other end's index handed round by shuffle so that every
+// row is one coalesced read.  Same formulas as k_attn_bwd_recv / k_attn_bwd_send; sums in ascending edge order per column.
+__device__ __forceinline__ float attn_row_dot(const float* __restrict__ g, const float* s, int len, bool vec) {
+  float a = 0.f;
+  if (vec) {
+    for (int d = 0; d < len; d += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(g + d);
+      const float4 y = *reinterpret_cast<const float4*>(s + d);
+      a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+    }
+  } else {
+    for (int d = 0; d < len; ++d) a = fmaf(g[d], s[d], a);
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(256)
+k_attn_bwd_recv_warp(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+                     const float* __restrict__ gatt, int qk_pad, int v_pad, int hv_pad, int heads, int kq, int vd,
+                     float inv_scale, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_senders,
+                     int64_t n, float* __restrict__ stats, float* __restrict__ gqueries, const int32_t* __restrict__ only) {
+  __shared__ __align__(16) float q_s[8][64];
+  __shared__ __align__(16) float g_s[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= n * heads) return;
+  const int64_t r = i / heads;
+  if (only && !only[r >> 5]) return;
+  const int h = (int)(i - r * heads);
+  const int32_t beg = rowptr[r], end = rowptr[r + 1];
+  const float* qr = queries + r * qk_pad + h * kq;
+  const float* ga = gatt + r * hv_pad + h * vd;
+  for (int d = lane; d < kq; d += 32) q_s[warp][d] = qr[d];
+  for (int c = lane; c < vd; c += 32) g_s[warp][c] = ga[c];
+  __syncwarp();
+  const bool veck = (kq & 3) == 0 && (qk_pad & 3) == 0, vecv = (vd & 3) == 0 && (v_pad & 3) == 0;
+  const float mx = stats[i * 3], rsum = 1.f / stats[i * 3 + 1];      // segment max / sum from the recomputed forward
+  float dot = 0.f;
+  for (int32_t c0 = beg; c0 < end; c0 += 32) {
+    const int32_t e = c0 + lane;
+    if (e < end) {
+      const int64_t s = csr_senders[e];
+      const float w = expf(attn_row_dot(keys + s * qk_pad + h * kq, q_s[warp], kq, veck) * inv_scale - mx) * rsum;
+      dot = fmaf(w, attn_row_dot(vals + s * v_pad, g_s[warp], vd, vecv), dot);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int32_t c0 = beg; c0 < end; c0 += 32) {
+    const int32_t e = c0 + lane;
+    const bool valid = e < end;
+    const int32_t s = valid ? csr_senders[e] : 0;
+    float gl = 0.f;
+    if (valid) {
+      const float w = expf(attn_row_dot(keys + (int64_t)s * qk_pad + h * kq, q_s[warp], kq, veck) * inv_scale - mx) * rsum;
+      const float gw = attn_row_dot(vals + (int64_t)s * v_pad, g_s[warp], vd, vecv);
+      gl = w * (gw - dot) * inv_scale;
+    }
+    const int cnt = min(32, end - c0);
+    for (int j = 0; j < cnt; ++j) {
+      const float glj = __shfl_sync(0xffffffffu, gl, j);
+      const int32_t sj = __shfl_sync(0xffffffffu, s, j);
+      const float* kr = keys + (int64_t)sj * qk_pad + h * kq;
+      if (lane < kq) acc0 = fmaf(glj, kr[lane], acc0);
+      if (lane + 32 < kq) acc1 = fmaf(glj, kr[lane + 32], acc1);
+    }
+  }
+  if (lane == 0) stats[i * 3 + 2] = dot;
+  if (lane < kq) gqueries[r * qk_pad + h * kq + lane] = acc0;
+  if (lane + 32 < kq) gqueries[r * qk_pad + h * kq + lane + 32] = acc1;
+}
+
+__global__ void __launch_bounds__(256)
+k_attn_bwd_send_warp(const float* __restrict__ keys, const float* __restrict__ queries, const float* __restrict__ vals,
+                     const float* __restrict__ gatt, const float* __restrict__ stats, int qk_pad, int v_pad, int hv_pad,
+                     int heads, int kq, int vd, float inv_scale, const int32_t* __restrict__ rowptr_s,
+                     const int32_t* __restrict__ csr_receivers, int64_t n, float* __restrict__ gkeys,
+                     float* __restrict__ gvh, const int32_t* __restrict__ only) {
+  __shared__ __align__(16) float k_s[8][64];
+  __shared__ __align__(16) float v_s[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= n * heads) return;
+  const int64_t s = i / heads;
+  if (only && !only[s >> 5]) return;
+  const int h = (int)(i - s * heads);
+  const float* ks = keys + s * qk_pad + h * kq;
+  const float* vs = vals + s * v_pad;
+  for (int d = lane; d < kq; d += 32) k_s[warp][d] = ks[d];
+  for (int c = lane; c < vd; c += 32) v_s[warp][c] = vs[c];
+  __syncwarp();
+  const bool veck = (kq & 3) == 0 && (qk_pad & 3) == 0, vecg = (vd & 3) == 0 && (hv_pad & 3) == 0;
+  float acck0 = 0.f, acck1 = 0.f, accv0 = 0.f, accv1 = 0.f;
+  const int32_t beg = rowptr_s[s], end = rowptr_s[s + 1];
+  for (int32_t c0 = beg; c0 < end; c0 += 32) {
+    const int32_t e = c0 + lane;
+    const bool valid = e < end;
+    const int32_t r = valid ? csr_receivers[e] : 0;
+    float w = 0.f, gl = 0.f;
+    if (valid) {
+      const float* st = stats + ((int64_t)r * heads + h) * 3;
+      const float l = attn_row_dot(queries + (int64_t)r * qk_pad + h * kq, k_s[warp], kq, veck);
+      w = expf(l * inv_scale - st[0]) / st[1];
+      const float gw = attn_row_dot(gatt + (int64_t)r * hv_pad + h * vd, v_s[warp], vd, vecg);
+      gl = w * (gw - st[2]) * inv_scale;
+    }
+    const int cnt = min(32, end - c0);
+    for (int j = 0; j < cnt; ++j) {
+      const float glj = __shfl_sync(0xffffffffu, gl, j);
+      const float wj = __shfl_sync(0xffffffffu, w, j);
+      const int32_t rj = __shfl_sync(0xffffffffu, r, j);
+      const float* qrow = queries + (int64_t)rj * qk_pad + h * kq;
+      const float* grow = gatt + (int64_t)rj * hv_pad + h * vd;
+      if (lane < kq) acck0 = fmaf(glj, qrow[lane], acck0);
+      if (lane + 32 < kq) acck1 = fmaf(glj, qrow[lane + 32], acck1);
+      if (lane < vd) accv0 = fmaf(wj, grow[lane], accv0);
+      if (lane + 32 < vd) accv1 = fmaf(wj, grow[lane + 32], accv1);
+    }
+  }
+  if (lane < kq) gkeys[s * qk_pad + h * kq + lane] = acck0;
+  if (lane + 32 < kq) gkeys[s * qk_pad + h * kq + lane + 32] = acck1;
+  if (lane < vd) gvh[s * hv_pad + h * vd + lane] = accv0;
+  if (lane + 32 < vd) gvh[s * hv_pad + h * vd + lane + 32] = accv1;
+}
+
 // Block-staged attention backward (round 2), the mirror of k_dm_attn_block.  One template, two passes:
 //   SEND = 0 : a CTA owns 32 consecutive RECEIVERS r (CSR by receiver); "other" end of an edge = its sender s.
 //              dot[r,h] = sum_e w_e g_w_e  -> stats[.., 2];   g_queries[r,h,:] = sum_e g_l_e keys[s_e,h,:]
@@ -969,6 +1099,14 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
                                              f.kq, f.vd, inv_scale, rowptr, csr_senders, n, w.gqueries, nullptr, b.fallback);
     GNF_LAUNCH_CHECK();
   }
+  // wide keys / values: warp per (node, head) for whatever the staged kernels do not serve (everything, or the groups
+  // they handed back); otherwise the thread-per-(node, head) kernels
+  const bool warp_k = (f.vd >= 16 || f.kq >= 32) && f.vd <= 64 && f.kq <= 64;
+  const unsigned wblocks = (unsigned)ceil_div(n * f.heads, 8);
+  if (warp_k)
+    k_attn_bwd_recv_warp<<<wblocks, 256, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, f.qk_pad, f.v_pad, f.hv_pad, f.heads,
+                                                      f.kq, f.vd, inv_scale, rowptr, csr_senders, n, b.stats, w.gqueries, only);
+  else
   k_attn_bwd_recv<<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, f.qk_pad, f.v_pad, f.hv_pad, f.heads, f.kq,
                                               f.vd, inv_scale, rowptr, csr_senders, n, b.stats, w.gqueries, only);
   GNF_LAUNCH_CHECK();
@@ -979,7 +1117,11 @@ int attn_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* g_
                                              f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys, w.gvh, b.fallback);
     GNF_LAUNCH_CHECK();
   }
-  if (f.vd <= 32)
+  if (warp_k)
+    k_attn_bwd_send_warp<<<wblocks, 256, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
+                                                      f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys,
+                                                      w.gvh, only);
+  else if (f.vd <= 32)
     k_attn_bwd_send<32><<<blocks, 128, 0, stream>>>(b.qbuf, b.kbuf, b.vbuf, w.gatt, b.stats, f.qk_pad, f.v_pad, f.hv_pad,
                                                     f.heads, f.kq, f.vd, inv_scale, rowptr_s, csr_receivers, n, w.gkeys,
                                                     w.gvh, only);
