@@ -1006,13 +1006,20 @@ int run_dw_generic(const float* a_in, int lda, int in_real, const float* delta, 
 
 // forward of one MLP keeping every hidden activation
 int mlp_forward_keep(const Flow& f, int mlp, const BwdWs& w, int m, const float* h_in, float* out, int64_t n,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int math = GNF_MATH_FP32) {
   const float* base = f.w32 + (int64_t)mlp * f.w32_per_mlp;
   const float* in = h_in;
+  const bool tc = math != GNF_MATH_FP32 && f.tc_layered;      // layered flows: the recompute in k_gemm_tc, as the forward
   for (int l = 0; l < f.K; ++l) {
     const bool last = l == f.K - 1;
     float* dst = last ? out : w.act[m][l];
-    int rc = fwd_linear(in, base + f.w32_layer_off[l], base + f.b32_layer_off[l], dst, n, f.out_pads[l],
+    int rc;
+    if (tc) {
+      const size_t off = (size_t)mlp * f.wgemm_per_mlp + f.gemm_off[l];
+      rc = tc_gemm(f, math, in, f.in_pads[l], f.in_pads[l], f.wgemm[0] + off, f.wgemm[1] + off, f.ins[l], f.outs[l],
+                   base + f.b32_layer_off[l], last ? 2 : f.d.act, dst, f.out_pads[l], f.out_pads[l], n, stream);
+    } else
+    rc = fwd_linear(in, base + f.w32_layer_off[l], base + f.b32_layer_off[l], dst, n, f.out_pads[l],
                         f.in_pads[l], last ? 2 : f.d.act, stream);
     if (rc) return rc;
     in = dst;
@@ -1186,9 +1193,12 @@ int bwd_merge(const float* x0, const float* x1, int64_t n, int d, int h, int hp,
 using namespace gnf;
 
 // one reversed half step on the fp32 FFMA path: (xa, xb', g_xa, g_xb') -> (xb, g_xa += ..., g_xb), grads += ...
+// (`math` != FP32, layered flows only: the forward recompute -- attention projections and MLP layers -- runs in
+//  k_linear_tc / k_gemm_tc exactly as the density pass did; the dX / dW GEMMs and the attention backward stay here)
 static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const float* xa, float* xb, float* ga, float* gb,
                          int64_t n, const int32_t* rowptr, const int32_t* csr_senders, const int32_t* rowptr_by_sender,
-                         const int32_t* csr_receivers, float scale, float* grads, cudaStream_t stream) {
+                         const int32_t* csr_receivers, float scale, float* grads, cudaStream_t stream,
+                         int math = GNF_MATH_FP32) {
   const int H = f.H, HP = f.HP, gp = pad_to(HP, 8);
   const unsigned eb = (unsigned)ceil_div(n * H, 256);
   const int ms = f.mlp_index(0, half, i), mt = f.mlp_index(1, half, i);
@@ -1200,9 +1210,9 @@ static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const f
     const int mm[2] = {ms, mt};
     for (int m = 0; m < 2; ++m) {
       GNF_CUDA(cudaMemsetAsync(hin[m], 0, (size_t)n * f.in_pad * 4, stream));
-      rc = fwd_attn_input(f, mm[m], xa, n, rowptr, csr_senders, w.ab[m], hin[m], stream);
+      rc = fwd_attn_input(f, mm[m], xa, n, rowptr, csr_senders, w.ab[m], hin[m], stream, math);
       if (rc) return rc;
-      rc = mlp_forward_keep(f, mm[m], w, m, hin[m], outs[m], n, stream);
+      rc = mlp_forward_keep(f, mm[m], w, m, hin[m], outs[m], n, stream, math);
       if (rc) return rc;
       if (f.attn_flags & GNF_ATTN_RESIDUAL) {                                     // gnn.py:551-552
         k_add_rows_p<<<eb, 256, 0, stream>>>(outs[m], xa, H, HP, n);
@@ -1242,9 +1252,9 @@ static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const f
   }
   rc = fwd_agg_input(f, xa, n, rowptr, csr_senders, w.hbuf, stream);
   if (rc) return rc;
-  rc = mlp_forward_keep(f, ms, w, 0, w.hbuf, w.sbuf, n, stream);
+  rc = mlp_forward_keep(f, ms, w, 0, w.hbuf, w.sbuf, n, stream, math);
   if (rc) return rc;
-  rc = mlp_forward_keep(f, mt, w, 1, w.hbuf, w.tbuf, n, stream);
+  rc = mlp_forward_keep(f, mt, w, 1, w.hbuf, w.tbuf, n, stream, math);
   if (rc) return rc;
   k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
   GNF_LAUNCH_CHECK();
@@ -1359,7 +1369,8 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
               "gnf_grevnet_backward: null pointer");
   const Flow& f = h->f;
   const bool inject = bwd_use_inject(f, math);
-  if (math != GNF_MATH_FP32 && !inject) {
+  const bool layered = math != GNF_MATH_FP32 && !inject && !tc_bwd_supported(f) && f.tc_layered;
+  if (math != GNF_MATH_FP32 && !inject && !layered) {
     GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED,
                 "gnf_grevnet_backward: the tensor-core backward needs a flow shape the fused kernel supports "
                 "(gnf_flow_supports_backward); use GNF_MATH_FP32");
@@ -1396,7 +1407,7 @@ extern "C" int gnf_grevnet_backward(const gnf_flow* h, const float* z, int64_t n
       int rc = inject ? bwd_half_inject(f, w, tc_ws, half, i, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender,
                                         csr_receivers, scale, grads, math, stream)
                       : bwd_half_fp32(f, w, half, i, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender,
-                                      csr_receivers, scale, grads, stream);
+                                      csr_receivers, scale, grads, stream, layered ? math : GNF_MATH_FP32);
       if (rc) return rc;
     }
   }
@@ -1429,7 +1440,8 @@ extern "C" int gnf_coupling_half_backward(const gnf_flow* h, int32_t half, int32
     return bwd_half_inject(f, w, (uint8_t*)ws + inject_fp32_part(f, n), half, step, xa, xb, ga, gb, n, rowptr, csr_senders,
                            rowptr_by_sender, csr_receivers, (float)loss_scale, grads, math, stream);
   }
-  if (math != GNF_MATH_FP32) {
+  const bool layered = math != GNF_MATH_FP32 && !tc_bwd_supported(f) && f.tc_layered;
+  if (math != GNF_MATH_FP32 && !layered) {
     GNF_REQUIRE(tc_bwd_supported(f), GNF_EUNSUPPORTED, "gnf_coupling_half_backward: flow shape needs GNF_MATH_FP32");
     const int dw_parts = (math == GNF_MATH_TC3X || math == GNF_MATH_TC3X_BF16) ? 2 : 1;
     const int fwd_f16 = (math == GNF_MATH_TC3X || math == GNF_MATH_TC2X) ? 1 : 0;
@@ -1442,5 +1454,5 @@ extern "C" int gnf_coupling_half_backward(const gnf_flow* h, int32_t half, int32
   GNF_CUDA(cudaMemsetAsync(w.gs, 0, (size_t)n * gp * 4, stream));
   GNF_CUDA(cudaMemsetAsync(w.gt, 0, (size_t)n * gp * 4, stream));
   return bwd_half_fp32(f, w, half, step, xa, xb, ga, gb, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers,
-                       (float)loss_scale, grads, stream);
+                       (float)loss_scale, grads, stream, layered ? math : GNF_MATH_FP32);
 }

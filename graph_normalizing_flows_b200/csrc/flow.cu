@@ -1333,7 +1333,9 @@ extern "C" int gnf_flow_supports(const gnf_flow* h, int32_t math) {
 extern "C" int gnf_flow_supports_backward(const gnf_flow* h, int32_t math) {
   if (!h) return 0;
   if (math == GNF_MATH_FP32) return 1;
-  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X && (tc_bwd_supported(h->f) || tc_bwd_inject_supported(h->f))) ? 1 : 0;
+  // layered flows: forward recompute on the tensor cores, dX / dW on the fp32 kernels (backward.cu::bwd_half_fp32)
+  return (math >= GNF_MATH_TC3X && math <= GNF_MATH_TC2X &&
+          (tc_bwd_supported(h->f) || tc_bwd_inject_supported(h->f) || h->f.tc_layered)) ? 1 : 0;
 }
 
 extern "C" int gnf_flow_set_params(gnf_flow* h, const float* params, void* stream_) {
