@@ -1027,9 +1027,17 @@ int mlp_forward_keep(const Flow& f, int mlp, const BwdWs& w, int m, const float*
   return GNF_OK;
 }
 
-// backward of one MLP: top gradient g_top [n, gp]; accumulates into gh and the flat grads
+// x *= act'(a) elementwise (a = the stored activation): what k_dx does in its epilogue, for the dX GEMMs run in k_gemm_tc
+__global__ void k_mask_rows(float* __restrict__ x, const float* __restrict__ a, int64_t total, int mask) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < total && !(a[i] > 0.f)) x[i] *= (mask == 1 ? 0.2f : 0.f);
+}
+
+// backward of one MLP: top gradient g_top [n, gp]; accumulates into gh and the flat grads.  `math` != FP32 (layered
+// flows): dX = delta W_l^T in k_gemm_tc from the transposed bf16 hi/lo images (gradients would flush in fp16), the
+// activation derivative applied by k_mask_rows; dW stays on the FFMA kernels
 int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* h_in, const float* g_top, int gp, int64_t n,
-                 int accumulate_gh, float* grads, cudaStream_t stream) {
+                 int accumulate_gh, float* grads, cudaStream_t stream, int math = GNF_MATH_FP32) {
   const float* wt = f.w32T + (int64_t)mlp * f.w32T_per_mlp;
   float* grad_mlp = grads + (int64_t)mlp * f.params_per_mlp;
   const int mask = f.d.act == GNF_ACT_LEAKY_RELU ? 1 : 2;
@@ -1043,6 +1051,20 @@ int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* h_i
     int rc = run_dw(f, l, a_in, lda, delta, ldd, n, w.part, grad_mlp, stream);
     if (rc) return rc;
     float* dst = l == 0 ? w.gh : ((l & 1) ? w.d1 : w.d0);
+    if (math != GNF_MATH_FP32 && f.wgemmT && !(l == 0 && accumulate_gh)) {
+      const uint8_t* img = f.wgemmT + (size_t)mlp * f.wgemmT_per_mlp + f.gemmT_off[l];
+      rc = tc_gemm(f, GNF_MATH_TC3X_BF16, delta, ldd, ldd, img, img, f.outs[l], f.ins[l], f.zeros, 2, dst, f.in_pads[l],
+                   f.in_pads[l], n, stream);
+      if (rc) return rc;
+      if (l > 0) {
+        const int64_t total = n * f.in_pads[l];
+        k_mask_rows<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(dst, a_in, total, mask);
+        GNF_LAUNCH_CHECK();
+      }
+      delta = dst;
+      ldd = f.in_pads[l];
+      continue;
+    }
     // K of this GEMM = leading dimension of delta (zero-padded rows of W^T beyond out)
     rc = run_dx(delta, wt + f.w32T_layer_off[l], l == 0 ? nullptr : a_in, dst, n, f.in_pads[l],
                 l == f.K - 1 ? f.out_pad8[l] : ldd, l == 0 ? 0 : mask, l == 0 ? accumulate_gh : 0, stream);
@@ -1242,7 +1264,7 @@ static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const f
         k_reduce_split<<<1, 256, 0, stream>>>(w.part, kSplit, 1, gp, 1, H, gln);
         GNF_LAUNCH_CHECK();
       }
-      rc = mlp_backward(f, mm[m], w, m, hin[m], gtop[m], gp, n, 0, grads, stream);
+      rc = mlp_backward(f, mm[m], w, m, hin[m], gtop[m], gp, n, 0, grads, stream, math);
       if (rc) return rc;
       rc = attn_backward(f, mm[m], w, m, gtop[m], gp, n, rowptr, csr_senders, rowptr_by_sender, csr_receivers, ga,
                          grads, stream);
@@ -1258,9 +1280,9 @@ static int bwd_half_fp32(const Flow& f, const BwdWs& w, int half, int i, const f
   if (rc) return rc;
   k_coupling_bwd<<<eb, 256, 0, stream>>>(xb, gb, w.sbuf, w.tbuf, n, H, HP, HP, gp, scale, w.gs, w.gt);
   GNF_LAUNCH_CHECK();
-  rc = mlp_backward(f, ms, w, 0, w.hbuf, w.gs, gp, n, 0, grads, stream);
+  rc = mlp_backward(f, ms, w, 0, w.hbuf, w.gs, gp, n, 0, grads, stream, math);
   if (rc) return rc;
-  rc = mlp_backward(f, mt, w, 1, w.hbuf, w.gt, gp, n, 1, grads, stream);
+  rc = mlp_backward(f, mt, w, 1, w.hbuf, w.gt, gp, n, 1, grads, stream, math);
   if (rc) return rc;
   k_agg_bwd<<<eb, 256, 0, stream>>>(w.gh, f.in_pad, H, HP, rowptr_by_sender, csr_receivers, rowptr, n,
                                     f.d.agg == GNF_AGG_MEAN, f.d.block == GNF_BLOCK_CONCAT, f.d.eps, ga);

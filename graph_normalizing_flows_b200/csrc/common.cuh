@@ -123,6 +123,9 @@ struct Flow {
   int64_t wgemm_per_mlp = 0;
   int64_t gemm_off[kMaxLayers];
   bool tc_layered = false;     // MLP layers in k_gemm_tc, input assembly / coupling update in the fp32 path's kernels
+  uint8_t* wgemmT = nullptr;   // bf16 hi-lo images of every W_l^T (backward dX = delta W_l^T of the layered flows)
+  int64_t wgemmT_per_mlp = 0;
+  int64_t gemmT_off[kMaxLayers];
   void* half_tables = nullptr; // device HalfDesc[2 images][2 directions][2T] of the persistent launch (coupling_tc.cu)
   int* range_flag = nullptr;   // sticky device flag: an fp16-split operand left the fp16 range (gnf_flow_range_flag)
 

@@ -1241,9 +1241,16 @@ extern "C" int gnf_flow_create(gnf_flow** out, const gnf_flow_desc* d) {
       goff += (int64_t)align_up(tc_gemm_image_bytes(f.ins[l], f.outs[l]), 256);
     }
     f.wgemm_per_mlp = goff;
-    if ((double)goff * f.n_mlps * 2 <= 24e9) {
+    int64_t goffT = 0;
+    for (int l = 0; l < f.K; ++l) {
+      f.gemmT_off[l] = goffT;
+      goffT += (int64_t)align_up(tc_gemm_image_bytes(f.outs[l], f.ins[l]), 256);
+    }
+    f.wgemmT_per_mlp = goffT;
+    if (((double)goff * 2 + (double)goffT) * f.n_mlps <= 24e9) {
       cudaError_t e0 = cudaMalloc(&f.wgemm[0], (size_t)f.n_mlps * goff);
       cudaError_t e1 = cudaMalloc(&f.wgemm[1], (size_t)f.n_mlps * goff);
+      if (e1 == cudaSuccess) e1 = cudaMalloc(&f.wgemmT, (size_t)f.n_mlps * goffT);
       if (e0 != cudaSuccess || e1 != cudaSuccess) {
         gnf_flow_destroy(h);
         set_error("gnf_flow_create: cudaMalloc (gemm images) failed");
@@ -1318,6 +1325,7 @@ extern "C" int gnf_flow_destroy(gnf_flow* h) {
   cudaFree(h->f.wlin[1]);
   cudaFree(h->f.wgemm[0]);
   cudaFree(h->f.wgemm[1]);
+  cudaFree(h->f.wgemmT);
   cudaFree(h->f.half_tables);
   cudaFree(h->f.range_flag);
   delete h;

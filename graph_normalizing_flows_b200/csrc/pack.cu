@@ -199,6 +199,16 @@ int pack_build_jobs(Flow& f) {
         j.d0 = f.wgemm[0] + (size_t)m * f.wgemm_per_mlp + f.gemm_off[l];
         j.d1 = f.wgemm[1] + (size_t)m * f.wgemm_per_mlp + f.gemm_off[l];
         add(j, (int64_t)kpad * npad);
+        if (f.wgemmT) {     // W_l^T for the backward's dX: logical [outs, ins], parameter block stored [ins, outs]; bf16 only
+          tc_gemm_geometry(f.outs[l], f.ins[l], kpad, npad, nb);
+          PackJob t{};
+          t.kind = kPackTc; t.transposed = 1; t.in = f.outs[l]; t.out = f.ins[l];
+          t.p0 = kpad; t.p1 = npad; t.p2 = nb; t.p3 = 16;
+          t.src_off = base + f.flat_w_off[l];
+          t.d0 = nullptr;
+          t.d1 = f.wgemmT + (size_t)m * f.wgemmT_per_mlp + f.gemmT_off[l];
+          add(t, (int64_t)kpad * npad);
+        }
       }
     size_t tc_off[kMaxLayers + 1] = {0};
     if (f.tc_ok || f.tc_inject)
