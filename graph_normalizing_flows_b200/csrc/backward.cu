@@ -950,20 +950,106 @@ int run_dx(const float* A, const float* Wt, const float* aux, float* C, int64_t 
 }
 
 // dW (+db) of one layer into the flat gradient
+// ---- dW of a wide layer on the tensor cores (layered flows): dW = a^T delta as ONE k_gemm_tc call -------------------
+// k_gemm_tc multiplies a row-major A [M, K] by a weight IMAGE [K, N]; here M = input features, K = nodes, N = output
+// features, so a is transposed into aT [in, n] (rows padded to 4 with zeros) and delta [n, out] is packed into the
+// kernel's bf16 hi/lo image format (the same arithmetic k_dw_tc uses for the fused flows: both operands bf16 hi/lo).
+__global__ void __launch_bounds__(256)
+k_transpose_pad(const float* __restrict__ a, int lda, int64_t n, int cols, float* __restrict__ aT, int64_t n4) {
+  __shared__ float t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                 // 32 x 8
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t r = r0 + ty + 8 * j;
+    t[ty + 8 * j][tx] = (r < n && c0 + tx < cols) ? a[r * lda + c0 + tx] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < n4) aT[(int64_t)c * n4 + r] = t[tx][ty + 8 * j];
+  }
+}
+
+// delta [n, >= cols] row-major -> bf16 hi/lo image of the logical weight [k = node, n' = column] in k_gemm_tc's geometry
+// (pack.cu kPackTc: column blocks of nb, k16 slabs, K-major 8 x 16-byte core matrices); zero beyond n / cols
+__global__ void __launch_bounds__(256)
+k_pack_rows_image(const float* __restrict__ D, int ldd, int64_t n, int cols, int kpad, int npad, int nb,
+                  uint8_t* __restrict__ img) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)kpad * npad) return;
+  const int64_t k = i / npad;
+  const int c = (int)(i - k * npad);
+  const float v = (k < n && c < cols) ? D[k * ldd + c] : 0.f;
+  const int ph = c / nb, nl = c - ph * nb, kl = (int)(k & 15);
+  const size_t mat_bytes = (size_t)nb * 32;
+  const size_t off = ((size_t)ph * (kpad / 16) + (size_t)(k >> 4)) * (2 * mat_bytes) + (size_t)(kl >> 3) * (nb * 16) +
+                     (nl >> 3) * 128 + (nl & 7) * 16 + (kl & 7) * 2;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
+  *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(img + off + mat_bytes) = lo;
+}
+
+__global__ void k_add_mat(float* __restrict__ grad, const float* __restrict__ c, int rows, int cols, int ldc) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * cols) return;
+  const int r = (int)(i / cols), col = (int)(i - (int64_t)r * cols);
+  grad[i] += c[(int64_t)r * ldc + col];
+}
+
+// returns 1 when the layer was done here, 0 when the caller should use the FFMA kernels, < 0 on error
+int run_dw_tc(const Flow& f, int l, const float* a_in, int lda, const float* delta, int ldd, int64_t n, float* part,
+              size_t part_floats, float* grad_mlp, cudaStream_t stream) {
+  const int in = f.ins[l], out = f.outs[l];
+  if (in < 64 || out < 64 || n < 16 || n > (1ll << 30)) return 0;      // narrow layers: the FFMA kernels are cheap there
+  const int64_t n4 = (n + 3) / 4 * 4;
+  int kpad, npad, nb;
+  tc_gemm_geometry((int)n, out, kpad, npad, nb);
+  const int outp = (out + 3) / 4 * 4;
+  const size_t at_floats = align_up((size_t)in * n4, 64), img_floats = align_up((size_t)kpad * npad, 64),
+               c_floats = align_up((size_t)in * outp, 64);
+  if (at_floats + img_floats + c_floats > part_floats) return 0;       // scratch = the split-K partial buffer
+  float* aT = part;
+  uint8_t* img = (uint8_t*)(part + at_floats);
+  float* ctmp = part + at_floats + img_floats;
+  k_transpose_pad<<<dim3((unsigned)ceil_div(n4, 32), (unsigned)ceil_div(in, 32)), 256, 0, stream>>>(a_in, lda, n, in, aT, n4);
+  GNF_LAUNCH_CHECK();
+  k_pack_rows_image<<<(unsigned)ceil_div((int64_t)kpad * npad, 256), 256, 0, stream>>>(delta, ldd, n, out, kpad, npad, nb, img);
+  GNF_LAUNCH_CHECK();
+  int rc = tc_gemm(f, GNF_MATH_TC3X_BF16, aT, (int)n4, (int)n4, img, img, (int)n, out, f.zeros, 2, ctmp, outp, outp, in, stream);
+  if (rc) return rc;
+  k_add_mat<<<(unsigned)ceil_div((int64_t)in * out, 256), 256, 0, stream>>>(grad_mlp + f.flat_w_off[l], ctmp, in, out, outp);
+  GNF_LAUNCH_CHECK();
+  return 1;
+}
+
 int run_dw(const Flow& f, int l, const float* a_in, int lda, const float* delta, int ldd, int64_t n, float* part,
-           float* grad_mlp, cudaStream_t stream) {
+           float* grad_mlp, cudaStream_t stream, int math = GNF_MATH_FP32, size_t part_floats = 0) {
   const int Mdim = f.in_pads[l], Ndim = ldd;
-  if (Ndim <= 16) {
+  int done = 0;
+  if (math != GNF_MATH_FP32 && f.tc_layered) {
+    done = run_dw_tc(f, l, a_in, lda, delta, ldd, n, part, part_floats, grad_mlp, stream);
+    if (done < 0) return done;
+  }
+  if (done) {
+    // weight gradient done on the tensor cores; the bias gradient below
+  } else if (Ndim <= 16) {
     dim3 grid((unsigned)ceil_div(Mdim, BM), 1, kSplit);
     k_dw<16><<<grid, 256, 0, stream>>>(a_in, lda, delta, ldd, n, Mdim, Ndim, part);
   } else {
     dim3 grid((unsigned)ceil_div(Mdim, BM), (unsigned)ceil_div(Ndim, 128), kSplit);
     k_dw<128><<<grid, 256, 0, stream>>>(a_in, lda, delta, ldd, n, Mdim, Ndim, part);
   }
-  GNF_LAUNCH_CHECK();
-  k_reduce_split<<<(unsigned)ceil_div((int64_t)f.ins[l] * f.outs[l], 256), 256, 0, stream>>>(
-      part, kSplit, Mdim, Ndim, f.ins[l], f.outs[l], grad_mlp + f.flat_w_off[l]);
-  GNF_LAUNCH_CHECK();
+  if (!done) {
+    GNF_LAUNCH_CHECK();
+    k_reduce_split<<<(unsigned)ceil_div((int64_t)f.ins[l] * f.outs[l], 256), 256, 0, stream>>>(
+        part, kSplit, Mdim, Ndim, f.ins[l], f.outs[l], grad_mlp + f.flat_w_off[l]);
+    GNF_LAUNCH_CHECK();
+  }
   k_db<<<dim3(kSplit, (unsigned)ceil_div(Ndim, 32)), 256, 0, stream>>>(delta, ldd, n, Ndim, part);
   GNF_LAUNCH_CHECK();
   k_reduce_split<<<(unsigned)ceil_div(f.outs[l], 256), 256, 0, stream>>>(part, kSplit, 1, Ndim, 1, f.outs[l],
@@ -1048,7 +1134,7 @@ int mlp_backward(const Flow& f, int mlp, const BwdWs& w, int m, const float* h_i
     const int lda = f.in_pads[l];
     // weight gradient needs delta with leading dimension == out_pads[l]: the top gradient buffer is
     // [n, gp] with gp = pad8(HP) >= HP; its extra columns are zero, so Ndim = ldd works for both
-    int rc = run_dw(f, l, a_in, lda, delta, ldd, n, w.part, grad_mlp, stream);
+    int rc = run_dw(f, l, a_in, lda, delta, ldd, n, w.part, grad_mlp, stream, math, w.part_floats);
     if (rc) return rc;
     float* dst = l == 0 ? w.gh : ((l & 1) ? w.d1 : w.d0);
     if (math != GNF_MATH_FP32 && f.wgemmT && !(l == 0 && accumulate_gh)) {
