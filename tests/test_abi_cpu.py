@@ -124,6 +124,21 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.gnf_debug_dw_gemm(null, null, 0, 256, 256, 2, 1, null, null, 0, null) == _lib.GNF_EINVAL
     assert lib.gnf_debug_bwd_layout(null, 10, null) == _lib.GNF_EINVAL
     assert lib.gnf_debug_kernel_timing(0) == _lib.GNF_OK        # switching the (unused) event brackets off is a no-op
+    # round-2 additions: chained batch-norm entries, the layered tensor-core Linear on its own
+    assert lib.gnf_grevnet_bn_workspace(null) == 0
+    assert lib.gnf_grevnet_forward_bn(null, null, 0, 0, null, null, null, null, null, null, 1e-3, 0.99, null, null, null, 1,
+                                      null, 0, null, 0, null) == _lib.GNF_EINVAL
+    assert b"null flow" in lib.gnf_last_error()
+    assert lib.gnf_grevnet_inverse_bn(null, null, 0, 0, null, null, null, null, null, null, 1e-3, null, 1, null, 0, null, 0,
+                                      null) == _lib.GNF_EINVAL
+    # image = K padded to 16 x N padded to column blocks of <= 256, hi + lo of 2 bytes, in two element types, + job scratch
+    assert lib.gnf_debug_linear_tc_workspace(2048, 2048) == 2 * 2048 * 2048 * 4 + 256
+    assert lib.gnf_debug_linear_tc_workspace(164, 300) == 2 * 176 * 512 * 4 + 256
+    assert lib.gnf_debug_linear_tc_workspace(40, 100) == 2 * 48 * 112 * 4 + 256
+    assert lib.gnf_debug_linear_tc_workspace(0, 4) == 0
+    assert lib.gnf_debug_linear_tc(null, null, null, 4, 8, 8, 2, 1, null, null, 0, null) == _lib.GNF_EINVAL
+    assert lib.gnf_debug_linear_tc(C.c_void_p(256), C.c_void_p(256), C.c_void_p(256), 4, 6, 8, 2, 1, C.c_void_p(256), null, 0,
+                                   null) == _lib.GNF_EINVAL            # k not a multiple of 4
 
 
 def test_attention_gnn_parameter_layout_and_layer_norm():
