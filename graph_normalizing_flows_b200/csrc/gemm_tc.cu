@@ -22,7 +22,7 @@
 //            (box = 32 floats x 256 rows, SWIZZLE_128B, zero fill past M / past the readable row width) into a raw
 //            shared-memory ring; the converters read it back with conflict-free 16-byte loads (chunk index XOR row).
 //            Measured: the per-lane global loads of the other path kept the L1 request path 58 % busy and were the
-//            kernel's limiter (profiles/r2_ncu_full_k_gemm_tc.csv, GNF_GEMM_VARIANT experiments).
+//            kernel's limiter (profiles/r2_ncu_full_k_gemm_tc_ldg.csv, GNF_GEMM_VARIANT experiments).
 //   TMA = false (GNF_GEMM_TMA=0): per-lane LDG.128, three stages of loads in flight in registers.
 // The A tile of a row block is converted once per column block (re-read from L2, not from HBM); sharing each weight slab
 // between two row tiles halves the weight stream per FLOP (the fused kernel's figure is ~43 B/cycle/SM).
